@@ -1,0 +1,173 @@
+/* b2l.h — C ABI of libb2l.so, the B200 (sm_100a) replacement for librosa's FFT time-frequency path.
+ *
+ * librosa has no FFI: its boundary for this path is the public Python API.  The Python package
+ * `librosa_b200` mirrors those signatures and makes one call into this library per public function;
+ * INTEGRATION.md shows the ctypes binding.  Each entry point names the reference code it replaces
+ * (paths relative to the librosa checkout, commit b7e7bf4).
+ *
+ * Conventions
+ *   - every function returns an int status (B2L_OK == 0); b2l_last_error() gives the message of the
+ *     last failure on the calling thread;
+ *   - plain pointers and sizes only; device pointers are marked d_, host pointers h_;
+ *   - all work is enqueued on the context's stream; b2l_ctx_sync() waits for it;
+ *   - a context is bound to one CUDA device and is not thread-safe; use one context per thread / GPU;
+ *   - there is no CPU fallback: without a usable sm_100 device b2l_ctx_create fails.
+ */
+#ifndef B2L_H_
+#define B2L_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2L_VERSION 100 /* 0.1.0 */
+
+enum b2l_status {
+  B2L_OK = 0,
+  B2L_ERR_INVALID = 1,     /* bad argument (the Python layer raises ParameterError before calling) */
+  B2L_ERR_CUDA = 2,        /* CUDA runtime / launch failure */
+  B2L_ERR_UNSUPPORTED = 3, /* valid for librosa, not built for the GPU yet (never a silent fallback) */
+  B2L_ERR_OOM = 4,
+  B2L_ERR_NCCL = 5
+};
+
+/* np.pad modes accepted by librosa.stft (librosa/_typing.py:60-71, core/spectrum.py:252-265). */
+enum b2l_pad_mode {
+  B2L_PAD_CONSTANT = 0,
+  B2L_PAD_EDGE = 1,
+  B2L_PAD_REFLECT = 2,
+  B2L_PAD_SYMMETRIC = 3,
+  B2L_PAD_LINEAR_RAMP = 4,
+  B2L_PAD_EMPTY = 5
+};
+
+typedef struct b2l_ctx b2l_ctx;
+typedef struct b2l_plan b2l_plan;
+typedef struct b2l_event b2l_event;
+
+/* Constants of one transform configuration.  Built on the host by the Python layer with the same
+ * float64 expressions as the reference (filters.get_window + util.pad_center, filters.mel, the
+ * scipy.fft.dct matrix), uploaded once per plan. */
+typedef struct b2l_plan_desc {
+  int32_t n_fft;             /* power of two, 8 .. 4096                     core/spectrum.py:58-69   */
+  int32_t hop_length;        /* >= 1                                        core/spectrum.py:235-237 */
+  int32_t center;            /* 0 / 1                                       core/spectrum.py:252     */
+  int32_t pad_mode;          /* enum b2l_pad_mode                           core/spectrum.py:287     */
+  const double* h_window;    /* [n_fft] window after pad_center             core/spectrum.py:243-249 */
+  int32_t n_mels;            /* 0: no mel stage                             feature/spectral.py:2158 */
+  const float* h_mel_basis;  /* [n_mels][1 + n_fft/2] float32 (filters.mel) filters.py:117-251       */
+  float power;               /* exponent of |STFT|                          core/spectrum.py:3000    */
+  int32_t n_mfcc;            /* 0: no mfcc stage                            feature/spectral.py:2005 */
+  const float* h_dct_basis;  /* [n_mfcc][n_mels] DCT rows (lifter folded in) feature/spectral.py:2005-2015 */
+  float amin;                /* power_to_db amin                            core/spectrum.py:1875    */
+  float ref_value;           /* power_to_db |ref|                           core/spectrum.py:1876    */
+  float top_db;              /* < 0 means None                              core/spectrum.py:1878-1881 */
+} b2l_plan_desc;
+
+/* ---- library / device ---------------------------------------------------------------------- */
+int b2l_version(void);
+const char* b2l_last_error(void);
+int b2l_device_count(int* count);
+
+int b2l_ctx_create(int device, b2l_ctx** ctx);
+int b2l_ctx_destroy(b2l_ctx* ctx);
+int b2l_ctx_sync(b2l_ctx* ctx);
+int b2l_ctx_device(const b2l_ctx* ctx, int* device);
+int b2l_ctx_sm_count(const b2l_ctx* ctx, int* sms);
+/* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
+int b2l_ctx_launch_count(const b2l_ctx* ctx, uint64_t* launches);
+
+/* ---- memory --------------------------------------------------------------------------------- */
+int b2l_alloc(b2l_ctx* ctx, size_t bytes, void** d_ptr);
+int b2l_free(b2l_ctx* ctx, void* d_ptr);
+int b2l_memset(b2l_ctx* ctx, void* d_ptr, int value, size_t bytes);
+int b2l_h2d(b2l_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on the ctx stream */
+int b2l_d2h(b2l_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async on the ctx stream */
+int b2l_d2d(b2l_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+int b2l_host_alloc(size_t bytes, void** h_ptr);                          /* pinned host memory */
+int b2l_host_free(void* h_ptr);
+int b2l_mem_info(b2l_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+
+/* ---- timing (CUDA events on the ctx stream) -------------------------------------------------- */
+int b2l_event_create(b2l_ctx* ctx, b2l_event** ev);
+int b2l_event_record(b2l_ctx* ctx, b2l_event* ev);
+int b2l_event_elapsed_ms(b2l_event* start, b2l_event* stop, float* ms); /* syncs on stop */
+int b2l_event_destroy(b2l_event* ev);
+
+/* ---- plans ------------------------------------------------------------------------------------ */
+int b2l_plan_create(b2l_ctx* ctx, const b2l_plan_desc* desc, b2l_plan** plan);
+int b2l_plan_destroy(b2l_plan* plan);
+/* frame count for a clip of n samples: 1 + (n + 2*pad - n_fft) / hop   (core/spectrum.py:277-355) */
+int b2l_plan_n_frames(const b2l_plan* plan, int64_t n, int64_t* n_frames);
+
+/* ---- the hot path ------------------------------------------------------------------------------
+ * Layouts (device memory, float32 / complex64):
+ *   y      [n_clips][y_stride]               first n samples of each row are the clip
+ *   D      [n_clips][n_frames][1 + n_fft/2]  bins contiguous; viewed by NumPy as (..., bin, frame),
+ *                                            which for a single clip is exactly the reference's
+ *                                            Fortran-ordered stft matrix (core/spectrum.py:356)
+ *   mel    [n_clips][n_mels][n_frames]       C order, like the reference einsum output
+ *   mfcc   [n_clips][n_mfcc][n_frames]
+ */
+
+/* librosa.stft — core/spectrum.py:58-391 (frame, window, rfft). */
+int b2l_stft(b2l_ctx* ctx, const b2l_plan* plan, const float* d_y, int64_t n_clips, int64_t n,
+             int64_t y_stride, void* d_D /* complex64 */);
+
+/* np.abs(stft)**power — core/spectrum.py:2920-3015 (_spectrogram); out [n_clips][n_frames][bins]. */
+int b2l_spectrogram(b2l_ctx* ctx, const b2l_plan* plan, const float* d_y, int64_t n_clips, int64_t n,
+                    int64_t y_stride, float* d_S);
+
+/* librosa.feature.melspectrogram(y=...) — feature/spectral.py:2022-2161, fused with stft. */
+int b2l_melspectrogram(b2l_ctx* ctx, const b2l_plan* plan, const float* d_y, int64_t n_clips, int64_t n,
+                       int64_t y_stride, float* d_mel);
+
+/* librosa.feature.mfcc(y=...) — feature/spectral.py:1843-2019 incl. power_to_db
+ * (core/spectrum.py:1735-1883, per-clip top_db reference max).  d_logmel is scratch of
+ * n_clips*n_mels*n_frames floats (NULL: allocated and freed internally). */
+int b2l_mfcc(b2l_ctx* ctx, const b2l_plan* plan, const float* d_y, int64_t n_clips, int64_t n,
+             int64_t y_stride, float* d_mfcc, float* d_logmel);
+
+/* librosa.istft — core/spectrum.py:395-626 (+ __overlap_add :629-643).  n_frames_stored is the frame
+ * count of D; n_frames_used <= stored is what the reference would use for `length` (:523-531).
+ * d_inv_wss: [out_len] reciprocal of the trimmed window-sum-square where > tiny, else 1
+ * (filters.window_sumsquare, filters.py:1268-1339; core/spectrum.py:606-624). */
+int b2l_istft(b2l_ctx* ctx, const b2l_plan* plan, const void* d_D, int64_t n_clips, int64_t n_frames_stored,
+              int64_t n_frames_used, const float* d_inv_wss, int64_t out_len, float* d_y, int64_t y_stride);
+
+/* ---- pieces of the path for S= inputs (device arrays in the layouts above) -------------------- */
+/* mel_basis . S for a given spectrogram S [n_clips][n_frames][bins] (feature/spectral.py:2160). */
+int b2l_mel_project(b2l_ctx* ctx, const b2l_plan* plan, const float* d_S, int64_t n_clips,
+                    int64_t n_frames, float* d_mel);
+/* power_to_db over [n_clips][rows][cols] blocks, top_db reference max per clip
+ * (core/spectrum.py:1839-1883); in place when d_out == d_in. */
+int b2l_power_to_db(b2l_ctx* ctx, const float* d_in, int64_t n_clips, int64_t per_clip, float amin,
+                    float ref_value, float top_db, float* d_out);
+/* DCT rows applied along the mel axis of S [n_clips][n_mels][n_frames] (feature/spectral.py:2005). */
+int b2l_dct_project(b2l_ctx* ctx, const b2l_plan* plan, const float* d_S, int64_t n_clips,
+                    int64_t n_frames, float* d_mfcc);
+/* [n_clips][rows][cols] -> [n_clips][cols][rows], elem_bytes 4 or 8 (layout adapter for NumPy
+ * arrays that arrive as C-ordered (..., bin, frame)). */
+int b2l_transpose(b2l_ctx* ctx, const void* d_in, int64_t n_clips, int64_t rows, int64_t cols,
+                  int32_t elem_bytes, void* d_out);
+
+/* ---- multi-GPU split / join (one process per GPU; NCCL over NVLink) --------------------------- */
+/* 128-byte NCCL unique id, created on rank 0 and handed to the other ranks by the launcher. */
+int b2l_comm_unique_id(void* id128);
+int b2l_comm_init(b2l_ctx* ctx, const void* id128, int rank, int world);
+int b2l_comm_destroy(b2l_ctx* ctx);
+/* broadcast `bytes` from root's d_buf into every rank's d_buf (plan constants, small) */
+int b2l_comm_broadcast(b2l_ctx* ctx, void* d_buf, size_t bytes, int root);
+/* root holds world*shard_bytes at d_full; every rank receives its shard into d_shard */
+int b2l_comm_scatter(b2l_ctx* ctx, const void* d_full, void* d_shard, size_t shard_bytes, int root);
+/* inverse of scatter */
+int b2l_comm_gather(b2l_ctx* ctx, const void* d_shard, void* d_full, size_t shard_bytes, int root);
+int b2l_comm_barrier(b2l_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2L_H_ */

@@ -1,0 +1,36 @@
+"""librosa_b200 — B200 (sm_100a) implementation of librosa's FFT time-frequency hot path.
+
+Drop-in for this path only: ``import librosa_b200 as librosa`` gives ``stft``, ``istft``,
+``power_to_db``, ``feature.melspectrogram``, ``feature.mfcc``, ``filters.mel / get_window /
+window_sumsquare``, ``util.frame`` (and the small helpers around them) with librosa's signatures,
+shapes, dtypes, warnings and exceptions.  The arithmetic runs in hand-written CUDA kernels reached
+through a C ABI (``include/b2l.h``) with ctypes — no PyTorch, no Triton, no CPU fallback.
+"""
+from . import core, feature, filters, util
+from ._native import (
+    Context,
+    DeviceArray,
+    NativeLibraryError,
+    UnsupportedOnGPU,
+    default_context,
+    device_count,
+    pinned_empty,
+)
+from .core.convert import fft_frequencies, hz_to_mel, mel_frequencies, mel_to_hz
+from .core.spectrum import _spectrogram, istft, power_to_db, stft
+from .util.exceptions import LibrosaError, ParameterError
+
+__version__ = "0.1.0"
+
+
+def to_device(arr, device=None):
+    """Copy a NumPy array to the GPU; device-resident inputs make every function return DeviceArrays."""
+    return default_context(device).to_device(arr)
+
+
+__all__ = [
+    "stft", "istft", "power_to_db", "_spectrogram", "feature", "filters", "util", "core",
+    "hz_to_mel", "mel_to_hz", "mel_frequencies", "fft_frequencies", "ParameterError", "LibrosaError",
+    "Context", "DeviceArray", "default_context", "device_count", "pinned_empty", "to_device",
+    "NativeLibraryError", "UnsupportedOnGPU",
+]

@@ -1,0 +1,416 @@
+"""ctypes binding of ``libb2l.so`` (C ABI declared in ``include/b2l.h``).
+
+No PyTorch, no CuPy: device memory, streams and launches all live behind the C ABI.  There is no
+CPU fallback — if the shared library is missing or no sm_100 GPU is present, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+import weakref
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb2l.so")
+
+B2L_OK = 0
+B2L_ERR_INVALID = 1
+B2L_ERR_CUDA = 2
+B2L_ERR_UNSUPPORTED = 3
+B2L_ERR_OOM = 4
+B2L_ERR_NCCL = 5
+
+PAD_MODES = {"constant": 0, "edge": 1, "reflect": 2, "symmetric": 3, "linear_ramp": 4, "empty": 5}
+
+
+class NativeLibraryError(RuntimeError):
+    """libb2l.so is missing / failed, or a CUDA / NCCL call failed."""
+
+
+class UnsupportedOnGPU(NotImplementedError):
+    """Valid for librosa but not built for the sm_100a path yet (never a silent CPU fallback)."""
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [
+        ("n_fft", C.c_int32),
+        ("hop_length", C.c_int32),
+        ("center", C.c_int32),
+        ("pad_mode", C.c_int32),
+        ("h_window", C.POINTER(C.c_double)),
+        ("n_mels", C.c_int32),
+        ("h_mel_basis", C.POINTER(C.c_float)),
+        ("power", C.c_float),
+        ("n_mfcc", C.c_int32),
+        ("h_dct_basis", C.POINTER(C.c_float)),
+        ("amin", C.c_float),
+        ("ref_value", C.c_float),
+        ("top_db", C.c_float),
+    ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+
+
+def _declare(lib):
+    P = C.POINTER
+    sig = {
+        "b2l_version": (C.c_int, []),
+        "b2l_last_error": (C.c_char_p, []),
+        "b2l_device_count": (C.c_int, [P(C.c_int)]),
+        "b2l_ctx_create": (C.c_int, [C.c_int, P(_vp)]),
+        "b2l_ctx_destroy": (C.c_int, [_vp]),
+        "b2l_ctx_sync": (C.c_int, [_vp]),
+        "b2l_ctx_device": (C.c_int, [_vp, P(C.c_int)]),
+        "b2l_ctx_sm_count": (C.c_int, [_vp, P(C.c_int)]),
+        "b2l_ctx_launch_count": (C.c_int, [_vp, P(C.c_uint64)]),
+        "b2l_alloc": (C.c_int, [_vp, C.c_size_t, P(_vp)]),
+        "b2l_free": (C.c_int, [_vp, _vp]),
+        "b2l_memset": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t]),
+        "b2l_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+        "b2l_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+        "b2l_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+        "b2l_host_alloc": (C.c_int, [C.c_size_t, P(_vp)]),
+        "b2l_host_free": (C.c_int, [_vp]),
+        "b2l_mem_info": (C.c_int, [_vp, P(C.c_size_t), P(C.c_size_t)]),
+        "b2l_event_create": (C.c_int, [_vp, P(_vp)]),
+        "b2l_event_record": (C.c_int, [_vp, _vp]),
+        "b2l_event_elapsed_ms": (C.c_int, [_vp, _vp, P(C.c_float)]),
+        "b2l_event_destroy": (C.c_int, [_vp]),
+        "b2l_plan_create": (C.c_int, [_vp, P(PlanDesc), P(_vp)]),
+        "b2l_plan_destroy": (C.c_int, [_vp]),
+        "b2l_plan_n_frames": (C.c_int, [_vp, _i64, P(_i64)]),
+        "b2l_stft": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+        "b2l_spectrogram": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+        "b2l_melspectrogram": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+        "b2l_mfcc": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+        "b2l_istft": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64]),
+        "b2l_mel_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+        "b2l_power_to_db": (C.c_int, [_vp, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp]),
+        "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+        "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),
+        "b2l_comm_unique_id": (C.c_int, [_vp]),
+        "b2l_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+        "b2l_comm_destroy": (C.c_int, [_vp]),
+        "b2l_comm_broadcast": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int]),
+        "b2l_comm_scatter": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int]),
+        "b2l_comm_gather": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int]),
+        "b2l_comm_barrier": (C.c_int, [_vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+EXPORTED_SYMBOLS: Tuple[str, ...] = ()
+
+
+def lib():
+    """Load libb2l.so once (raises NativeLibraryError with build instructions if absent)."""
+    global _lib, EXPORTED_SYMBOLS
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeLibraryError(
+                        f"{LIB_PATH} not found: build it with `make -C librosa_b200/csrc` or "
+                        "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback."
+                    )
+                try:
+                    handle = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+                except OSError as exc:  # pragma: no cover
+                    raise NativeLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+                EXPORTED_SYMBOLS = tuple(_declare(handle))
+                _lib = handle
+    return _lib
+
+
+def check(status: int):
+    if status == B2L_OK:
+        return
+    msg = lib().b2l_last_error().decode("utf-8", "replace")
+    if status == B2L_ERR_INVALID:
+        from .util.exceptions import ParameterError
+
+        raise ParameterError(msg)
+    if status == B2L_ERR_UNSUPPORTED:
+        raise UnsupportedOnGPU(msg)
+    if status == B2L_ERR_OOM:
+        raise MemoryError(msg)
+    raise NativeLibraryError(msg)
+
+
+# --------------------------------------------------------------------------------------------- context
+class Context:
+    """One CUDA device + stream.  Not thread-safe; create one per thread / per GPU."""
+
+    def __init__(self, device: int = 0):
+        self._h = _vp()
+        check(lib().b2l_ctx_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+        self._plans = {}
+        self._wss = {}
+        self._finalizer = weakref.finalize(self, Context._destroy, self._h, self._plans, self._wss)
+
+    @staticmethod
+    def _destroy(h, plans, wss):
+        try:
+            L = lib()
+            for p in plans.values():
+                L.b2l_plan_destroy(p.handle)
+            plans.clear()
+            for arr in wss.values():
+                L.b2l_free(h, arr)
+            wss.clear()
+            L.b2l_ctx_destroy(h)
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        check(lib().b2l_ctx_sync(self._h))
+
+    @property
+    def sm_count(self) -> int:
+        v = C.c_int()
+        check(lib().b2l_ctx_sm_count(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        check(lib().b2l_ctx_launch_count(self._h, C.byref(v)))
+        return int(v.value)
+
+    def mem_info(self):
+        f, t = C.c_size_t(), C.c_size_t()
+        check(lib().b2l_mem_info(self._h, C.byref(f), C.byref(t)))
+        return int(f.value), int(t.value)
+
+    # ---- memory
+    def alloc(self, nbytes: int) -> int:
+        p = _vp()
+        check(lib().b2l_alloc(self._h, int(nbytes), C.byref(p)))
+        return p.value
+
+    def free(self, ptr: int):
+        if ptr:
+            check(lib().b2l_free(self._h, _vp(ptr)))
+
+    def empty(self, shape, dtype, layout: str = "c") -> "DeviceArray":
+        return DeviceArray.empty(self, shape, dtype, layout=layout)
+
+    def to_device(self, arr: np.ndarray) -> "DeviceArray":
+        arr = np.ascontiguousarray(arr)
+        out = DeviceArray.empty(self, arr.shape, arr.dtype)
+        check(lib().b2l_h2d(self._h, _vp(out.ptr), arr.ctypes.data_as(_vp), arr.nbytes))
+        self.synchronize()
+        return out
+
+    # ---- events
+    def event(self) -> "Event":
+        return Event(self)
+
+
+_default_ctx: dict = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    """Process-wide context of a device (device defaults to $B2L_DEVICE, then $LOCAL_RANK, then 0)."""
+    if device is None:
+        device = int(os.environ.get("B2L_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        _default_ctx[device] = ctx
+    return ctx
+
+
+def device_count() -> int:
+    n = C.c_int()
+    check(lib().b2l_device_count(C.byref(n)))
+    return n.value
+
+
+class Event:
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._h = _vp()
+        check(lib().b2l_event_create(ctx.handle, C.byref(self._h)))
+        self._finalizer = weakref.finalize(self, lambda h: lib().b2l_event_destroy(h), self._h)
+
+    def record(self):
+        check(lib().b2l_event_record(self.ctx.handle, self._h))
+        return self
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float()
+        check(lib().b2l_event_elapsed_ms(self._h, stop._h, C.byref(ms)))
+        return float(ms.value)
+
+
+# --------------------------------------------------------------------------------------------- arrays
+class DeviceArray:
+    """A device buffer with a logical NumPy-style shape.
+
+    ``layout``:
+      * ``"c"``   — memory is C-ordered in the logical shape;
+      * ``"ft"``  — logical shape is ``(..., bins, frames)`` (what librosa returns) while memory is
+        ``[...][frames][bins]`` (bins contiguous) — the kernels' native spectrogram layout, and for a
+        single clip exactly the Fortran order librosa.stft produces.
+    """
+
+    def __init__(self, ctx: Context, ptr: int, shape, dtype, layout: str = "c", owner: bool = True):
+        self.ctx = ctx
+        self.ptr = ptr
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.layout = layout
+        self._finalizer = weakref.finalize(self, DeviceArray._release, ctx, ptr) if owner and ptr else None
+
+    @staticmethod
+    def _release(ctx, ptr):
+        try:
+            lib().b2l_free(ctx.handle, _vp(ptr))
+        except Exception:  # pragma: no cover
+            pass
+
+    @classmethod
+    def empty(cls, ctx: Context, shape, dtype, layout: str = "c") -> "DeviceArray":
+        shape = tuple(int(s) for s in shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        return cls(ctx, ctx.alloc(max(nbytes, 16)), shape, dtype, layout=layout)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64))
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
+
+    def free(self):
+        if self._finalizer is not None and self._finalizer.alive:
+            self._finalizer()
+        self.ptr = 0
+
+    def _mem_shape(self):
+        if self.layout == "ft":
+            return self.shape[:-2] + (self.shape[-1], self.shape[-2])
+        return self.shape
+
+    def get(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Copy to the host; returns an array of the logical shape (a transposed view for "ft")."""
+        mem_shape = self._mem_shape()
+        if out is None:
+            host = np.empty(mem_shape, dtype=self.dtype)
+        else:
+            host = out
+            if host.shape != mem_shape or host.dtype != self.dtype or not host.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous array of the memory shape and dtype")
+        if self.nbytes:
+            check(lib().b2l_d2h(self.ctx.handle, host.ctypes.data_as(_vp), _vp(self.ptr), self.nbytes))
+            self.ctx.synchronize()
+        if self.layout == "ft":
+            return np.swapaxes(host, -1, -2)
+        return host
+
+    def set(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        if arr.shape != self._mem_shape():
+            raise ValueError(f"shape mismatch: {arr.shape} vs memory shape {self._mem_shape()}")
+        check(lib().b2l_h2d(self.ctx.handle, _vp(self.ptr), arr.ctypes.data_as(_vp), arr.nbytes))
+        self.ctx.synchronize()
+        return self
+
+    def __repr__(self):
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, layout={self.layout!r}, device={self.ctx.device})"
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """NumPy array backed by page-locked host memory (fast, truly asynchronous H2D / D2H)."""
+    shape = tuple(int(s) for s in np.atleast_1d(shape)) if not isinstance(shape, tuple) else shape
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    p = _vp()
+    check(lib().b2l_host_alloc(max(nbytes, 16), C.byref(p)))
+    buf = (C.c_char * max(nbytes, 16)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    weakref.finalize(buf, lambda addr: lib().b2l_host_free(_vp(addr)), p.value)
+    return arr
+
+
+# --------------------------------------------------------------------------------------------- plans
+class Plan:
+    def __init__(self, ctx: Context, handle, n_fft, hop, center, n_mels, n_mfcc):
+        self.ctx = ctx
+        self.handle = handle
+        self.n_fft = n_fft
+        self.hop = hop
+        self.center = center
+        self.n_mels = n_mels
+        self.n_mfcc = n_mfcc
+
+    def n_frames(self, n: int) -> int:
+        v = _i64()
+        check(lib().b2l_plan_n_frames(self.handle, int(n), C.byref(v)))
+        return int(v.value)
+
+
+def make_plan(ctx: Context, key, *, n_fft: int, hop_length: int, center: bool, pad_mode: str,
+              window: np.ndarray, mel_basis: Optional[np.ndarray] = None, power: float = 2.0,
+              dct_basis: Optional[np.ndarray] = None, amin: float = 1e-10, ref_value: float = 1.0,
+              top_db: Optional[float] = 80.0) -> Plan:
+    """Create (or fetch from the context's cache) the device constants of one configuration."""
+    plan = ctx._plans.get(key)
+    if plan is not None:
+        return plan
+    win = np.ascontiguousarray(window, dtype=np.float64)
+    desc = PlanDesc()
+    desc.n_fft = int(n_fft)
+    desc.hop_length = int(hop_length)
+    desc.center = 1 if center else 0
+    desc.pad_mode = PAD_MODES[pad_mode]
+    desc.h_window = win.ctypes.data_as(C.POINTER(C.c_double))
+    keep = [win]
+    n_mels = n_mfcc = 0
+    if mel_basis is not None:
+        mb = np.ascontiguousarray(mel_basis, dtype=np.float32)
+        keep.append(mb)
+        n_mels = mb.shape[0]
+        desc.n_mels = n_mels
+        desc.h_mel_basis = mb.ctypes.data_as(C.POINTER(C.c_float))
+    desc.power = float(power)
+    if dct_basis is not None:
+        db = np.ascontiguousarray(dct_basis, dtype=np.float32)
+        keep.append(db)
+        n_mfcc = db.shape[0]
+        desc.n_mfcc = n_mfcc
+        desc.h_dct_basis = db.ctypes.data_as(C.POINTER(C.c_float))
+    desc.amin = float(amin)
+    desc.ref_value = float(ref_value)
+    desc.top_db = -1.0 if top_db is None else float(top_db)
+    h = _vp()
+    check(lib().b2l_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+    plan = Plan(ctx, h, int(n_fft), int(hop_length), bool(center), n_mels, n_mfcc)
+    if len(ctx._plans) > 64:  # bound the cache
+        _, old = ctx._plans.popitem()
+        lib().b2l_plan_destroy(old.handle)
+    ctx._plans[key] = plan
+    return plan

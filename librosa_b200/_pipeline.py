@@ -1,0 +1,150 @@
+"""Shared host logic between the public functions and the C ABI: argument normalisation, plan keys,
+device staging of inputs / outputs.  Everything numeric happens in libb2l.so."""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import warnings
+from functools import lru_cache
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from . import filters
+from .util.exceptions import ParameterError
+from .util.utils import is_positive_int, pad_center, valid_audio
+
+_UNSUPPORTED_PAD = ("wrap", "maximum", "mean", "median", "minimum")   # librosa/core/spectrum.py:253
+
+
+def float64_policy() -> str:
+    """``B2L_FLOAT64``: "error" (default) refuses float64 / complex128 requests — the kernels compute in
+    float32 and silently lowering precision would not be a drop-in; "downcast" computes in float32 and
+    returns arrays of the requested dtype."""
+    return os.environ.get("B2L_FLOAT64", "error").lower()
+
+
+def check_real_dtype(dtype, what: str) -> np.dtype:
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return dtype
+    if dtype == np.float64 and float64_policy() == "downcast":
+        return dtype
+    if dtype == np.float64:
+        raise nat.UnsupportedOnGPU(
+            f"{what}: float64 data is not supported by the float32 sm_100a kernels; cast to float32 or set "
+            "B2L_FLOAT64=downcast to compute in float32 (there is no CPU fallback)")
+    if np.issubdtype(dtype, np.floating):
+        if float64_policy() == "downcast":
+            return dtype
+        raise nat.UnsupportedOnGPU(f"{what}: dtype {dtype} is not supported (float32 only)")
+    raise ParameterError(f"{what}: data must be floating-point, got {dtype}")
+
+
+def digest(arr: np.ndarray) -> str:
+    return hashlib.blake2b(np.ascontiguousarray(arr).tobytes(), digest_size=16).hexdigest()
+
+
+def resolve_window(window, win_length: int, n_fft: int) -> Tuple[np.ndarray, str]:
+    """get_window + pad_center exactly as librosa.stft does (core/spectrum.py:243-246)."""
+    w = filters.get_window(window, win_length, fftbins=True)
+    w = pad_center(np.asarray(w, dtype=np.float64), size=n_fft)
+    return w, digest(w)
+
+
+@lru_cache(maxsize=64)
+def _mel_cached(sr, n_fft, items):
+    kwargs = dict(items)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        basis = filters.mel(sr=sr, n_fft=n_fft, **kwargs)
+    basis.setflags(write=False)
+    return basis, digest(basis), tuple(str(w.message) for w in caught)
+
+
+def mel_basis(sr, n_fft, kwargs) -> Tuple[np.ndarray, str]:
+    """filters.mel with memoisation (the reference recomputes it on every call, feature/spectral.py:2158)."""
+    items = []
+    for k, v in sorted(kwargs.items()):
+        if k == "dtype":
+            v = np.dtype(v).str
+        items.append((k, v))
+    try:
+        basis, dg, msgs = _mel_cached(float(sr), int(n_fft), tuple(items))
+    except TypeError:  # unhashable kwarg -> no memoisation
+        basis = filters.mel(sr=sr, n_fft=n_fft, **kwargs)
+        return basis, digest(basis)
+    for m in msgs:
+        warnings.warn(m, stacklevel=3)
+    return basis, dg
+
+
+def frame_params(n_fft, hop_length, win_length):
+    """Defaults and the hop check of librosa/core/spectrum.py:231-237."""
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    elif not is_positive_int(hop_length):
+        raise ParameterError(f"hop_length={hop_length} must be a positive integer")
+    return int(hop_length), int(win_length)
+
+
+def check_stft_geometry(n: int, n_fft: int, center: bool, pad_mode):
+    """Padding-mode and length checks of librosa/core/spectrum.py:252-271, 329-333."""
+    if center:
+        if callable(pad_mode):
+            raise nat.UnsupportedOnGPU("callable pad_mode cannot run on the GPU (no CPU fallback)")
+        if pad_mode in _UNSUPPORTED_PAD:
+            raise ParameterError(f"pad_mode='{pad_mode}' is not supported by librosa.stft")
+        if pad_mode not in nat.PAD_MODES:
+            raise ValueError(f"mode '{pad_mode}' is not supported")   # what np.pad raises
+        if n_fft > n:
+            warnings.warn(f"n_fft={n_fft} is too large for input signal of length={n}", stacklevel=4)
+    elif n_fft > n:
+        raise ParameterError(
+            f"n_fft={n_fft} is too large for uncentered analysis of input signal of length={n}")
+    return pad_mode if (center and isinstance(pad_mode, str)) else "constant"
+
+
+class StagedInput:
+    """A batch of clips resident on the device as ``[n_clips][n]`` float32."""
+
+    def __init__(self, ctx, y):
+        self.ctx = ctx
+        if isinstance(y, nat.DeviceArray):
+            if y.dtype != np.float32 or y.layout != "c":
+                raise ParameterError("device input must be a C-ordered float32 DeviceArray")
+            if y.ndim == 0:
+                raise ParameterError("Audio data must be at least one-dimensional")
+            if y.ctx is not ctx:
+                raise ParameterError("DeviceArray belongs to a different context")
+            self.dev = y
+            self.on_device = True
+            self.req_dtype = np.dtype(np.float32)
+        else:
+            valid_audio(y)
+            self.req_dtype = check_real_dtype(y.dtype, "input signal")
+            host = np.ascontiguousarray(y, dtype=np.float32)
+            self.dev = nat.DeviceArray.empty(ctx, host.shape, np.float32)
+            if host.nbytes:
+                nat.check(nat.lib().b2l_h2d(ctx.handle, C.c_void_p(self.dev.ptr), host.ctypes.data_as(C.c_void_p),
+                                            host.nbytes))
+            self._host = host   # keep alive until the stream has consumed it
+            self.on_device = False
+        self.lead = self.dev.shape[:-1]
+        self.n = self.dev.shape[-1]
+        self.n_clips = int(np.prod(self.lead, dtype=np.int64)) if self.lead else 1
+
+
+def finish(ctx, dev_out: nat.DeviceArray, to_host: bool, host_dtype=None):
+    """Return the device array itself (device-resident pipelines) or copy it to a fresh NumPy array."""
+    if not to_host:
+        return dev_out
+    arr = dev_out.get()
+    dev_out.free()
+    if host_dtype is not None and arr.dtype != host_dtype:
+        arr = arr.astype(host_dtype)
+    return arr

@@ -1,0 +1,284 @@
+"""``stft`` / ``istft`` / ``_spectrogram`` / ``power_to_db`` with librosa's signatures, executed by
+libb2l.so on a B200 (reference: librosa/core/spectrum.py:58-391, 395-626, 2920-3015, 1735-1883).
+
+Inputs may be NumPy arrays (results come back as NumPy arrays with librosa's shapes and dtypes) or
+``DeviceArray`` objects (results stay on the device, so ``stft -> istft`` or ``melspectrogram`` chains
+never touch the host).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Optional
+
+import numpy as np
+
+from .. import _native as nat
+from .. import _pipeline as pl
+from .. import filters
+from ..util.exceptions import ParameterError
+from ..util.utils import dtype_c2r, dtype_r2c, fix_length, tiny
+
+_vp = C.c_void_p
+
+
+def _stft_plan(ctx, n_fft, hop_length, center, pad_mode, window, win_length):
+    win, wkey = pl.resolve_window(window, win_length, n_fft)
+    key = ("stft", n_fft, hop_length, bool(center), pad_mode, wkey)
+    return nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=pad_mode,
+                         window=win)
+
+
+def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: Optional[int] = None,
+         window="hann", center: bool = True, dtype=None, pad_mode="constant", out=None):
+    """Short-time Fourier transform; same contract as ``librosa.stft`` (core/spectrum.py:58-391).
+
+    Returns ``(..., 1 + n_fft/2, n_frames)`` complex64.  For a NumPy input the result is a view whose
+    memory is ``[..., frame, bin]`` — for a 1-D signal that is the Fortran order librosa returns.
+    """
+    hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
+    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
+    staged = pl.StagedInput(ctx, y)
+    # window first (its errors precede the padding checks in the reference)
+    win, wkey = pl.resolve_window(window, win_length, n_fft)
+    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    if dtype is None:
+        dtype = dtype_r2c(staged.req_dtype)
+    dtype = np.dtype(dtype)
+    if dtype != np.complex64 and not (dtype.kind == "c" and pl.float64_policy() == "downcast"):
+        raise nat.UnsupportedOnGPU(f"stft dtype={dtype}: only complex64 is computed on the GPU "
+                                   "(set B2L_FLOAT64=downcast to get float32 results in a wider dtype)")
+    key = ("stft", n_fft, hop_length, bool(center), mode, wkey)
+    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win)
+    T = plan.n_frames(staged.n)
+    F = 1 + n_fft // 2
+    shape = staged.lead + (F, T)
+    if out is not None:
+        if isinstance(out, nat.DeviceArray):
+            raise ParameterError("out= must be a NumPy array")
+        if not (tuple(out.shape[:-1]) == tuple(shape[:-1]) and out.shape[-1] >= shape[-1]):
+            raise ParameterError(f"Shape mismatch for provided output array out.shape={out.shape} and "
+                                 f"target shape={list(shape)}")
+        if not np.iscomplexobj(out):
+            raise ParameterError(f"output with dtype={out.dtype} is not of complex type")
+    D = nat.DeviceArray.empty(ctx, shape, np.complex64, layout="ft")
+    nat.check(nat.lib().b2l_stft(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n, staged.n,
+                                 _vp(D.ptr)))
+    if staged.on_device and out is None:
+        return D
+    res = pl.finish(ctx, D, True, dtype)
+    if out is None:
+        return res
+    target = out if out.shape[-1] == shape[-1] else out[..., : shape[-1]]
+    target[...] = res
+    return target
+
+
+def _inv_wss(ctx, window, n_frames, win_length, n_fft, hop_length, start, out_len, wkey):
+    """Reciprocal window-sum-square, trimmed as istft does (core/spectrum.py:606-624), cached on device."""
+    key = ("wss", wkey, n_frames, n_fft, hop_length, start, out_len)
+    ptr = ctx._wss.get(key)
+    if ptr is None:
+        wss = filters.window_sumsquare(window=window, n_frames=n_frames, win_length=win_length, n_fft=n_fft,
+                                       hop_length=hop_length, dtype=np.float32)
+        wss = fix_length(wss[start:], size=out_len)
+        inv = np.ones(out_len, dtype=np.float32)
+        nz = wss > tiny(wss)
+        inv[nz] = (np.float32(1.0) / wss[nz]).astype(np.float32)
+        if len(ctx._wss) > 32:
+            _, old = ctx._wss.popitem()
+            ctx.free(old)
+        ptr = ctx.alloc(max(inv.nbytes, 16))
+        nat.check(nat.lib().b2l_h2d(ctx.handle, _vp(ptr), inv.ctypes.data_as(_vp), inv.nbytes))
+        ctx.synchronize()
+        ctx._wss[key] = ptr
+    return ptr
+
+
+def istft(stft_matrix, *, hop_length: Optional[int] = None, win_length: Optional[int] = None,
+          n_fft: Optional[int] = None, window="hann", center: bool = True, dtype=None,
+          length: Optional[int] = None, out=None):
+    """Inverse STFT; same contract as ``librosa.istft`` (core/spectrum.py:395-626)."""
+    on_device = isinstance(stft_matrix, nat.DeviceArray)
+    if not on_device:
+        stft_matrix = np.asarray(stft_matrix)
+    if stft_matrix.ndim < 2:
+        raise ParameterError("stft_matrix must have at least two dimensions (bins, frames)")
+    F, T_stored = stft_matrix.shape[-2], stft_matrix.shape[-1]
+    if n_fft is None:
+        n_fft = 2 * (F - 1)
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    win, wkey = pl.resolve_window(window, win_length, n_fft)
+    if F != n_fft // 2 + 1:
+        raise nat.UnsupportedOnGPU(f"istft: n_fft={n_fft} does not match {F} frequency bins")
+    if length:
+        padded = length + 2 * (n_fft // 2) if center else length
+        n_frames = min(T_stored, int(np.ceil(padded / hop_length)))
+    else:
+        n_frames = T_stored
+    in_dtype = np.dtype(stft_matrix.dtype)
+    if in_dtype != np.complex64:
+        if in_dtype.kind == "c" and pl.float64_policy() == "downcast":
+            pass
+        elif in_dtype.kind == "c":
+            raise nat.UnsupportedOnGPU("istft: only complex64 input is computed on the GPU "
+                                       "(set B2L_FLOAT64=downcast to compute in float32)")
+        else:
+            raise ParameterError(f"stft_matrix must be complex, got {in_dtype}")
+    if dtype is None:
+        dtype = dtype_c2r(in_dtype)
+    dtype = pl.check_real_dtype(dtype, "istft dtype")
+    full_len = n_fft + hop_length * (n_frames - 1)
+    if length:
+        out_len = int(length)
+    elif center:
+        out_len = full_len - 2 * (n_fft // 2)
+    else:
+        out_len = full_len
+    lead = tuple(stft_matrix.shape[:-2])
+    shape = lead + (out_len,)
+    if out is not None:
+        if isinstance(out, nat.DeviceArray):
+            raise ParameterError("out= must be a NumPy array")
+        if tuple(out.shape) != shape:
+            raise ParameterError(f"Shape mismatch for provided output array out.shape={out.shape} != {list(shape)}")
+    ctx = stft_matrix.ctx if on_device else nat.default_context()
+    n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    key = ("stft", n_fft, hop_length, bool(center), "constant", wkey)
+    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode="constant",
+                         window=win)
+    L = nat.lib()
+    tmp = None
+    if on_device:
+        if stft_matrix.dtype != np.complex64:
+            raise ParameterError("device stft_matrix must be complex64")
+        if stft_matrix.layout == "ft":
+            d_ptr = stft_matrix.ptr
+        else:   # C-ordered (..., bin, frame) on the device -> native [frame][bin]
+            tmp = nat.DeviceArray.empty(ctx, stft_matrix.shape, np.complex64, layout="ft")
+            nat.check(L.b2l_transpose(ctx.handle, _vp(stft_matrix.ptr), n_clips, F, T_stored, 8, _vp(tmp.ptr)))
+            d_ptr = tmp.ptr
+    else:
+        Dt = np.swapaxes(stft_matrix, -1, -2)
+        if Dt.flags.c_contiguous and Dt.dtype == np.complex64:
+            host = Dt                                   # already [.., frame, bin] in memory
+            tmp = nat.DeviceArray.empty(ctx, stft_matrix.shape, np.complex64, layout="ft")
+            nat.check(L.b2l_h2d(ctx.handle, _vp(tmp.ptr), host.ctypes.data_as(_vp), host.nbytes))
+        else:
+            host = np.ascontiguousarray(stft_matrix, dtype=np.complex64)
+            raw = nat.DeviceArray.empty(ctx, stft_matrix.shape, np.complex64)
+            nat.check(L.b2l_h2d(ctx.handle, _vp(raw.ptr), host.ctypes.data_as(_vp), host.nbytes))
+            tmp = nat.DeviceArray.empty(ctx, stft_matrix.shape, np.complex64, layout="ft")
+            nat.check(L.b2l_transpose(ctx.handle, _vp(raw.ptr), n_clips, F, T_stored, 8, _vp(tmp.ptr)))
+            ctx.synchronize()
+            raw.free()
+        d_ptr = tmp.ptr
+    start = n_fft // 2 if center else 0
+    inv_ptr = _inv_wss(ctx, window, n_frames, win_length, n_fft, hop_length, start, out_len, wkey)
+    y = nat.DeviceArray.empty(ctx, shape, np.float32)
+    nat.check(L.b2l_istft(ctx.handle, plan.handle, _vp(d_ptr), n_clips, T_stored, n_frames, _vp(inv_ptr), out_len,
+                          _vp(y.ptr), out_len))
+    if on_device and out is None:
+        if tmp is not None:
+            ctx.synchronize()
+            tmp.free()
+        return y
+    res = pl.finish(ctx, y, True, dtype)
+    if tmp is not None:
+        tmp.free()
+    if out is None:
+        return res
+    out[...] = res
+    return out
+
+
+def _spectrogram(*, y=None, S=None, n_fft: Optional[int] = 2048, hop_length: Optional[int] = 512,
+                 power: float = 1, win_length: Optional[int] = None, window="hann", center: bool = True,
+                 pad_mode="constant"):
+    """``|stft|**power`` (or pass ``S`` through); mirror of core/spectrum.py:2920-3015."""
+    if S is not None:
+        if n_fft is None or n_fft // 2 + 1 != S.shape[-2]:
+            n_fft = 2 * (S.shape[-2] - 1)
+        return S, n_fft
+    if n_fft is None:
+        raise ParameterError(f"Unable to compute spectrogram with n_fft={n_fft}")
+    if y is None:
+        raise ParameterError("Input signal must be provided to compute a spectrogram")
+    hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
+    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
+    staged = pl.StagedInput(ctx, y)
+    win, wkey = pl.resolve_window(window, win_length, n_fft)
+    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    key = ("spec", n_fft, hop_length, bool(center), mode, wkey, float(power))
+    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
+                         power=float(power))
+    T = plan.n_frames(staged.n)
+    Sd = nat.DeviceArray.empty(ctx, staged.lead + (1 + n_fft // 2, T), np.float32, layout="ft")
+    nat.check(nat.lib().b2l_spectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
+                                        staged.n, _vp(Sd.ptr)))
+    return pl.finish(ctx, Sd, not staged.on_device, staged.req_dtype), n_fft
+
+
+def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80.0, axes="auto"):
+    """``10*log10(S/ref)`` with the ``top_db`` floor; mirror of core/spectrum.py:1735-1883.
+
+    The reference maximum of ``top_db`` is taken per leading index over the last two axes
+    (``axes="auto"``), which is what ``mfcc`` relies on for multichannel input."""
+    on_device = isinstance(S, nat.DeviceArray)
+    if not on_device:
+        S = np.asarray(S)
+    if amin <= 0:
+        raise ParameterError("amin must be strictly positive")
+    if not on_device and np.issubdtype(S.dtype, np.complexfloating):
+        warnings.warn("power_to_db was called on complex input so phase information will be discarded. "
+                      "To suppress this warning, call power_to_db(np.abs(D)**2) instead.", stacklevel=2)
+        S = np.abs(S)
+    if axes != "auto":
+        raise nat.UnsupportedOnGPU("power_to_db: only axes='auto' is computed on the GPU")
+    if top_db is not None and top_db < 0:
+        raise ParameterError("top_db must be non-negative")
+    ctx = S.ctx if on_device else nat.default_context()
+    if on_device:
+        if S.dtype != np.float32:
+            raise ParameterError("device input must be float32")
+        dev = S
+        req = np.dtype(np.float32)
+    else:
+        if not np.issubdtype(S.dtype, np.floating):
+            S = S.astype(np.float32) if pl.float64_policy() != "downcast" else S.astype(np.float64)
+        req = pl.check_real_dtype(S.dtype, "power_to_db input")
+        dev = ctx.to_device(np.ascontiguousarray(S, dtype=np.float32))
+    ndim = len(dev.shape)
+    if ndim >= 2:
+        lead = dev.shape[:-2]
+        per = dev.shape[-2] * dev.shape[-1]
+    else:
+        lead = ()
+        per = dev.size
+    n_lead = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    out = nat.DeviceArray.empty(ctx, dev.shape, np.float32, layout=dev.layout)
+    tdb = -1.0 if top_db is None else float(top_db)
+    L = nat.lib()
+    if callable(ref):
+        if on_device:
+            raise nat.UnsupportedOnGPU("callable ref needs a host array")
+        ax = (-2, -1) if ndim >= 2 else ((-1,) if ndim == 1 else None)
+        try:
+            ref_value = np.asarray(ref(S, axis=ax, keepdims=True), dtype=np.float64).reshape(-1)
+        except TypeError as exc:
+            raise ParameterError("The provided reference function must support 'axis' and 'keepdims' "
+                                 "arguments for proper multichannel processing.") from exc
+        for i in range(n_lead):   # one reference level per leading index
+            nat.check(L.b2l_power_to_db(ctx.handle, _vp(dev.ptr + 4 * i * per), 1, per, float(amin),
+                                        float(ref_value[i if ref_value.size > 1 else 0]), tdb,
+                                        _vp(out.ptr + 4 * i * per)))
+    else:
+        nat.check(L.b2l_power_to_db(ctx.handle, _vp(dev.ptr), n_lead, per, float(amin), float(np.abs(ref)), tdb,
+                                    _vp(out.ptr)))
+    if on_device:
+        return out
+    res = pl.finish(ctx, out, True, req)
+    return res[()]

@@ -1,0 +1,861 @@
+// api.cu — C ABI of libb2l.so (see include/b2l.h): contexts, memory, plans and the launch logic for
+// the forward (stft / spectrogram / melspectrogram / mfcc) and inverse (istft) kernels.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b2l.h"
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "internal.h"
+
+using namespace b2l;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      cudaGetLastError();                                                                     \
+      return fail(_e == cudaErrorMemoryAllocation ? B2L_ERR_OOM : B2L_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(_e), __FILE__, __LINE__);                                \
+    }                                                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------ NCCL (loaded on demand)
+// Only the handful of entry points needed for the batch split / join; resolved from libnccl.so.2 with
+// dlopen so that single-GPU use has no NCCL dependency.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclChar = 0 };
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.handle) return B2L_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(B2L_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                       \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                   \
+  if (!g_nccl.field) return fail(B2L_ERR_NCCL, "libnccl is missing %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Broadcast, "ncclBroadcast")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.handle = h;
+  return B2L_OK;
+}
+#define NCCL_TRY(expr)                                                                            \
+  do {                                                                                            \
+    ncclResult_t _r = (expr);                                                                     \
+    if (_r != 0) return fail(B2L_ERR_NCCL, "%s: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+  } while (0)
+
+// ------------------------------------------------------------------ objects
+struct b2l_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  unsigned int* d_clip_max = nullptr;   // scratch for per-clip maxima
+  size_t clip_max_cap = 0;
+};
+
+struct b2l_event {
+  cudaEvent_t ev;
+  int device;
+};
+
+struct b2l_plan {
+  b2l_ctx* ctx = nullptr;
+  int n_fft = 0, hop = 0, center = 0, pad_mode = 0, log2m = 0;
+  float* d_win_fwd = nullptr;   // window * 1/2
+  float* d_win_inv = nullptr;   // window * 1/n_fft
+  float2* d_tw = nullptr;
+  float2* d_twn = nullptr;
+  int tw_count = 0;
+  // mel
+  int n_mels = 0, mel_w_count = 0;
+  float* d_mel_w = nullptr;
+  MelBand* d_band = nullptr;
+  int power_mode = 2;
+  float power = 2.0f;
+  // mfcc
+  int n_mfcc = 0;
+  float* d_dct = nullptr;
+  float amin = 1e-10f, ref_value = 1.0f, top_db = 80.0f;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ library / device
+extern "C" int b2l_version(void) { return B2L_VERSION; }
+extern "C" const char* b2l_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int b2l_device_count(int* count) {
+  if (!count) return fail(B2L_ERR_INVALID, "count is NULL");
+  CUDA_TRY(cudaGetDeviceCount(count));
+  return B2L_OK;
+}
+
+extern "C" int b2l_ctx_create(int device, b2l_ctx** out) {
+  if (!out) return fail(B2L_ERR_INVALID, "ctx out pointer is NULL");
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(B2L_ERR_INVALID, "device %d out of range (have %d)", device, n);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(B2L_ERR_UNSUPPORTED, "device %d is sm_%d%d; libb2l is built for sm_100a only (no fallback path)",
+                device, prop.major, prop.minor);
+  DeviceGuard g(device);
+  b2l_ctx* c = new b2l_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(B2L_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return B2L_OK;
+}
+
+extern "C" int b2l_ctx_destroy(b2l_ctx* c) {
+  if (!c) return B2L_OK;
+  DeviceGuard g(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->d_clip_max) cudaFree(c->d_clip_max);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return B2L_OK;
+}
+
+extern "C" int b2l_ctx_sync(b2l_ctx* c) {
+  if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_ctx_device(const b2l_ctx* c, int* device) {
+  if (!c || !device) return fail(B2L_ERR_INVALID, "NULL argument");
+  *device = c->device;
+  return B2L_OK;
+}
+extern "C" int b2l_ctx_sm_count(const b2l_ctx* c, int* sms) {
+  if (!c || !sms) return fail(B2L_ERR_INVALID, "NULL argument");
+  *sms = c->sm_count;
+  return B2L_OK;
+}
+extern "C" int b2l_ctx_launch_count(const b2l_ctx* c, uint64_t* launches) {
+  if (!c || !launches) return fail(B2L_ERR_INVALID, "NULL argument");
+  *launches = c->launches;
+  return B2L_OK;
+}
+
+// ------------------------------------------------------------------ memory
+extern "C" int b2l_alloc(b2l_ctx* c, size_t bytes, void** d_ptr) {
+  if (!c || !d_ptr) return fail(B2L_ERR_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  *d_ptr = nullptr;
+  if (bytes == 0) bytes = 16;
+  CUDA_TRY(cudaMalloc(d_ptr, bytes));
+  return B2L_OK;
+}
+extern "C" int b2l_free(b2l_ctx* c, void* d_ptr) {
+  if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
+  if (!d_ptr) return B2L_OK;
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFree(d_ptr));
+  return B2L_OK;
+}
+extern "C" int b2l_memset(b2l_ctx* c, void* d_ptr, int value, size_t bytes) {
+  if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemsetAsync(d_ptr, value, bytes, c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_h2d(b2l_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
+  if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_d2h(b2l_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+  if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_d2d(b2l_ctx* c, void* d_dst, const void* d_src, size_t bytes) {
+  if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_host_alloc(size_t bytes, void** h_ptr) {
+  if (!h_ptr) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (bytes == 0) bytes = 16;
+  CUDA_TRY(cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable));
+  return B2L_OK;
+}
+extern "C" int b2l_host_free(void* h_ptr) {
+  if (!h_ptr) return B2L_OK;
+  CUDA_TRY(cudaFreeHost(h_ptr));
+  return B2L_OK;
+}
+extern "C" int b2l_mem_info(b2l_ctx* c, size_t* free_bytes, size_t* total_bytes) {
+  if (!c || !free_bytes || !total_bytes) return fail(B2L_ERR_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemGetInfo(free_bytes, total_bytes));
+  return B2L_OK;
+}
+
+// ------------------------------------------------------------------ events
+extern "C" int b2l_event_create(b2l_ctx* c, b2l_event** ev) {
+  if (!c || !ev) return fail(B2L_ERR_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  b2l_event* e = new b2l_event();
+  e->device = c->device;
+  cudaError_t r = cudaEventCreate(&e->ev);
+  if (r != cudaSuccess) {
+    delete e;
+    return fail(B2L_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(r));
+  }
+  *ev = e;
+  return B2L_OK;
+}
+extern "C" int b2l_event_record(b2l_ctx* c, b2l_event* ev) {
+  if (!c || !ev) return fail(B2L_ERR_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaEventRecord(ev->ev, c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_event_elapsed_ms(b2l_event* start, b2l_event* stop, float* ms) {
+  if (!start || !stop || !ms) return fail(B2L_ERR_INVALID, "NULL argument");
+  DeviceGuard g(stop->device);
+  CUDA_TRY(cudaEventSynchronize(stop->ev));
+  CUDA_TRY(cudaEventElapsedTime(ms, start->ev, stop->ev));
+  return B2L_OK;
+}
+extern "C" int b2l_event_destroy(b2l_event* ev) {
+  if (!ev) return B2L_OK;
+  DeviceGuard g(ev->device);
+  cudaEventDestroy(ev->ev);
+  delete ev;
+  return B2L_OK;
+}
+
+// ------------------------------------------------------------------ plans
+static int ilog2_exact(int x) {
+  int l = 0;
+  while ((1 << l) < x) ++l;
+  return (1 << l) == x ? l : -1;
+}
+
+template <class T>
+static int upload(b2l_ctx* c, const std::vector<T>& h, T** d) {
+  *d = nullptr;
+  size_t bytes = h.size() * sizeof(T);
+  CUDA_TRY(cudaMalloc((void**)d, bytes ? bytes : 16));
+  if (bytes) CUDA_TRY(cudaMemcpy(*d, h.data(), bytes, cudaMemcpyHostToDevice));
+  return B2L_OK;
+}
+
+extern "C" int b2l_plan_destroy(b2l_plan* p) {
+  if (!p) return B2L_OK;
+  DeviceGuard g(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  cudaFree(p->d_win_fwd);
+  cudaFree(p->d_win_inv);
+  cudaFree(p->d_tw);
+  cudaFree(p->d_twn);
+  cudaFree(p->d_mel_w);
+  cudaFree(p->d_band);
+  cudaFree(p->d_dct);
+  delete p;
+  return B2L_OK;
+}
+
+extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** out) {
+  if (!c || !d || !out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (d->n_fft < 1) return fail(B2L_ERR_INVALID, "n_fft=%d must be positive", d->n_fft);
+  if (d->hop_length < 1) return fail(B2L_ERR_INVALID, "hop_length=%d must be a positive integer", d->hop_length);
+  int l2n = ilog2_exact(d->n_fft);
+  if (l2n < 0 || l2n - 1 < kMinLog2M || l2n - 1 > kMaxLog2M)
+    return fail(B2L_ERR_UNSUPPORTED,
+                "n_fft=%d: the sm_100a kernels are built for powers of two from %d to %d (no CPU fallback)",
+                d->n_fft, 2 << kMinLog2M, 2 << kMaxLog2M);
+  if (!d->h_window) return fail(B2L_ERR_INVALID, "window is NULL");
+  if (d->pad_mode < 0 || d->pad_mode > B2L_PAD_EMPTY) return fail(B2L_ERR_INVALID, "bad pad_mode %d", d->pad_mode);
+  if (d->n_mels < 0 || d->n_mfcc < 0) return fail(B2L_ERR_INVALID, "negative n_mels / n_mfcc");
+  if (d->n_mels > 0 && !d->h_mel_basis) return fail(B2L_ERR_INVALID, "mel basis is NULL");
+  if (d->n_mfcc > 0 && (!d->h_dct_basis || d->n_mels == 0))
+    return fail(B2L_ERR_INVALID, "mfcc stage needs a mel stage and a DCT basis");
+  if (d->n_mfcc > 0 && !(d->amin > 0.0f)) return fail(B2L_ERR_INVALID, "amin must be strictly positive");
+
+  DeviceGuard g(c->device);
+  b2l_plan* p = new b2l_plan();
+  p->ctx = c;
+  p->n_fft = d->n_fft;
+  p->hop = d->hop_length;
+  p->center = d->center ? 1 : 0;
+  p->pad_mode = d->pad_mode;
+  p->log2m = l2n - 1;
+  p->power = d->power;
+  p->power_mode = d->power == 2.0f ? 2 : (d->power == 1.0f ? 1 : 0);
+  p->amin = d->amin;
+  p->ref_value = d->ref_value;
+  p->top_db = d->top_db;
+  const int N = d->n_fft, M = N / 2;
+  HostFftCfg cfg(p->log2m);
+
+  int rc = B2L_OK;
+  {
+    std::vector<float> wf(N), wi(N);
+    for (int i = 0; i < N; ++i) {
+      wf[i] = (float)(d->h_window[i] * 0.5);
+      wi[i] = (float)(d->h_window[i] / (double)N);
+    }
+    if ((rc = upload(c, wf, &p->d_win_fwd)) || (rc = upload(c, wi, &p->d_win_inv))) goto bad;
+  }
+  {
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<float2> tw((size_t)cfg.tw_count());
+    for (int s = 1; s < cfg.npass; ++s) {
+      const int R = cfg.radix(s), pl = cfg.sublen(s), off = cfg.tw_offset(s);
+      for (int r = 1; r < R; ++r)
+        for (int k = 0; k < pl; ++k) {
+          // exp(-2*pi*i * r*k / (p*R)); reduce the integer phase first to keep the argument small
+          long long num = ((long long)r * k) % ((long long)pl * R);
+          double ang = -two_pi * (double)num / (double)((long long)pl * R);
+          tw[(size_t)off + (size_t)(r - 1) * pl + k] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    }
+    p->tw_count = cfg.tw_count();
+    std::vector<float2> twn((size_t)M / 2 + 1);
+    for (int k = 0; k <= M / 2; ++k) {
+      double ang = -two_pi * (double)k / (double)N;
+      twn[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    if ((rc = upload(c, tw, &p->d_tw)) || (rc = upload(c, twn, &p->d_twn))) goto bad;
+  }
+  if (d->n_mels > 0) {
+    const int F = M + 1;
+    std::vector<MelBand> bands(d->n_mels);
+    std::vector<float> w;
+    for (int m = 0; m < d->n_mels; ++m) {
+      const float* row = d->h_mel_basis + (size_t)m * F;
+      int lo = -1, hi = -1;
+      for (int k = 0; k < F; ++k)
+        if (row[k] != 0.0f) {
+          if (lo < 0) lo = k;
+          hi = k;
+        }
+      MelBand b;
+      b.off = (int)w.size();
+      b.pad = 0;
+      if (lo < 0) {
+        b.lo = 0;
+        b.len = 0;
+      } else {
+        b.lo = lo;
+        b.len = hi - lo + 1;
+        w.insert(w.end(), row + lo, row + hi + 1);
+      }
+      bands[m] = b;
+    }
+    p->n_mels = d->n_mels;
+    p->mel_w_count = (int)w.size();
+    if ((rc = upload(c, w, &p->d_mel_w)) || (rc = upload(c, bands, &p->d_band))) goto bad;
+  }
+  if (d->n_mfcc > 0) {
+    std::vector<float> dct(d->h_dct_basis, d->h_dct_basis + (size_t)d->n_mfcc * d->n_mels);
+    p->n_mfcc = d->n_mfcc;
+    if ((rc = upload(c, dct, &p->d_dct))) goto bad;
+  }
+  *out = p;
+  return B2L_OK;
+bad:
+  b2l_plan_destroy(p);
+  return rc;
+}
+
+static long long plan_frames(const b2l_plan* p, long long n) {
+  long long padded = n + (p->center ? 2LL * (p->n_fft / 2) : 0);
+  if (padded < p->n_fft) return 0;
+  return 1 + (padded - p->n_fft) / p->hop;
+}
+
+extern "C" int b2l_plan_n_frames(const b2l_plan* p, int64_t n, int64_t* n_frames) {
+  if (!p || !n_frames) return fail(B2L_ERR_INVALID, "NULL argument");
+  *n_frames = plan_frames(p, n);
+  return B2L_OK;
+}
+
+// ------------------------------------------------------------------ forward launches
+typedef cudaError_t (*fwd_op_fn)(int, int, int, const FwdArgs*, int, size_t, cudaStream_t, int*);
+typedef cudaError_t (*inv_op_fn)(int, int, const InvArgs*, int, size_t, cudaStream_t, int*);
+static fwd_op_fn fwd_table(int log2m) {
+  switch (log2m) {
+    case 2: return fwd_op_2; case 3: return fwd_op_3; case 4: return fwd_op_4; case 5: return fwd_op_5;
+    case 6: return fwd_op_6; case 7: return fwd_op_7; case 8: return fwd_op_8; case 9: return fwd_op_9;
+    case 10: return fwd_op_10; case 11: return fwd_op_11;
+  }
+  return nullptr;
+}
+static inv_op_fn inv_table(int log2m) {
+  switch (log2m) {
+    case 2: return inv_op_2; case 3: return inv_op_3; case 4: return inv_op_4; case 5: return inv_op_5;
+    case 6: return inv_op_6; case 7: return inv_op_7; case 8: return inv_op_8; case 9: return inv_op_9;
+    case 10: return inv_op_10; case 11: return inv_op_11;
+  }
+  return nullptr;
+}
+
+static int ensure_clip_max(b2l_ctx* c, size_t n_clips) {
+  if (c->clip_max_cap < n_clips) {
+    if (c->d_clip_max) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      CUDA_TRY(cudaFree(c->d_clip_max));
+      c->d_clip_max = nullptr;
+      c->clip_max_cap = 0;
+    }
+    size_t cap = n_clips < 1024 ? 1024 : n_clips;
+    CUDA_TRY(cudaMalloc((void**)&c->d_clip_max, cap * sizeof(unsigned int)));
+    c->clip_max_cap = cap;
+  }
+  return B2L_OK;
+}
+
+static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const float* d_y, int64_t n_clips,
+                       int64_t n, int64_t y_stride, float2* out_c, float* out_r) {
+  if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
+  if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
+  if (n_clips < 0 || n < 0 || y_stride < n) return fail(B2L_ERR_INVALID, "bad clip geometry");
+  if (n > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "clips longer than 2^31-1 samples are not supported");
+  const long long T = plan_frames(p, n);
+  if (T <= 0)
+    return fail(B2L_ERR_INVALID, "n_fft=%d is too large for input signal of length=%lld", p->n_fft, (long long)n);
+  if (n_clips == 0) return B2L_OK;
+  if (!d_y || (mode == MODE_STFT ? (void*)out_c : (void*)out_r) == nullptr)
+    return fail(B2L_ERR_INVALID, "NULL device pointer");
+  if (mode == MODE_MEL && p->n_mels == 0) return fail(B2L_ERR_INVALID, "plan has no mel stage");
+  DeviceGuard g(c->device);
+
+  HostFftCfg cfg(p->log2m);
+  const int N = p->n_fft, M = N / 2;
+  fwd_op_fn op = fwd_table(p->log2m);
+  int nws[2];
+  const int n_opt = cfg.nw_options(nws);
+  FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  int nw = 0;
+  size_t smem = 0;
+  for (int i = 0; i < n_opt; ++i) {
+    const int w = nws[i];
+    const int ft = w * 32 / cfg.tpf;
+    size_t off = 0;
+    a.off_win = (int)off; off = align_up(off + (size_t)N * 4, 16);
+    a.off_tw = (int)off; off = align_up(off + (size_t)cfg.tw_count() * 8, 16);
+    a.off_twn = (int)off; off = align_up(off + (size_t)(M / 2 + 1) * 8, 16);
+    a.off_bar = (int)off; off = align_up(off + 8, 16);
+    if (mode == MODE_MEL) {
+      a.off_melw = (int)off; off = align_up(off + (size_t)p->mel_w_count * 4, 16);
+      a.off_melband = (int)off; off = align_up(off + (size_t)p->n_mels * sizeof(MelBand), 16);
+    }
+    const long long span = (long long)(ft - 1) * p->hop + N;
+    a.off_in = (int)(off = align_up(off, 128)); off += (size_t)align_up((size_t)span * 4, 16);
+    a.off_xbuf = (int)(off = align_up(off, 128));
+    size_t xbytes = (size_t)ft * cfg.xbuf_f2() * 8;
+    size_t pbytes = mode == MODE_MEL ? (size_t)(M + 1) * ft * 4 : 0;
+    off += xbytes > pbytes ? xbytes : pbytes;
+    if (span > 0x3fffffff) continue;
+    a.in_floats = (int)span;
+    if (off <= c->smem_optin) {
+      nw = w;
+      smem = off;
+      break;
+    }
+  }
+  if (nw == 0)
+    return fail(B2L_ERR_UNSUPPORTED, "hop_length=%d with n_fft=%d needs more shared memory than one SM has", p->hop,
+                p->n_fft);
+  const int ft = nw * 32 / cfg.tpf;
+
+  a.y = d_y;
+  a.clip_stride = y_stride;
+  a.n = (int)n;
+  a.n_clips = (int)n_clips;
+  a.n_fft = N;
+  a.hop = p->hop;
+  a.pad = p->center ? N / 2 : 0;
+  a.pad_mode = p->pad_mode;
+  a.n_frames = (int)T;
+  a.tiles_per_clip = (int)((T + ft - 1) / ft);
+  a.total_tiles = (long long)a.tiles_per_clip * n_clips;
+  a.tma_ok = (((uintptr_t)d_y & 15) == 0) && (y_stride % 4 == 0) && (a.in_floats % 4 == 0);
+  a.window = p->d_win_fwd;
+  a.tw = p->d_tw;
+  a.twn = p->d_twn;
+  a.out_c = out_c;
+  a.out_r = out_r;
+  a.power_mode = p->power_mode;
+  a.power = p->power;
+  a.n_mels = p->n_mels;
+  a.mel_w_count = p->mel_w_count;
+  a.mel_w = p->d_mel_w;
+  a.mel_band = p->d_band;
+  a.log_mode = log_mode;
+  a.amin = p->amin;
+  a.db_sub = 10.0f * log10f(fmaxf(p->amin, fabsf(p->ref_value)));
+  a.clip_max = c->d_clip_max;
+
+  CUDA_TRY(op(OP_SET_SMEM, nw, mode, &a, 0, smem, c->stream, nullptr));
+  int occ = 0;
+  CUDA_TRY(op(OP_OCCUPANCY, nw, mode, &a, 0, smem, c->stream, &occ));
+  if (occ < 1) return fail(B2L_ERR_CUDA, "forward kernel does not fit on an SM (smem %zu)", smem);
+  long long grid = (long long)c->sm_count * occ;
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  CUDA_TRY(op(OP_LAUNCH, nw, mode, &a, (int)grid, smem, c->stream, nullptr));
+  c->launches++;
+  return B2L_OK;
+}
+
+extern "C" int b2l_stft(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
+                        void* d_D) {
+  return run_forward(c, p, MODE_STFT, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
+}
+extern "C" int b2l_spectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
+                               int64_t y_stride, float* d_S) {
+  return run_forward(c, p, MODE_SPEC, 0, d_y, n_clips, n, y_stride, nullptr, d_S);
+}
+extern "C" int b2l_melspectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
+                                  int64_t y_stride, float* d_mel) {
+  return run_forward(c, p, MODE_MEL, 0, d_y, n_clips, n, y_stride, nullptr, d_mel);
+}
+
+static int launch_dct(b2l_ctx* c, const b2l_plan* p, const float* d_L, int64_t n_clips, int64_t T, int clamp,
+                      float* d_out) {
+  const int KG = (p->n_mfcc + 7) / 8;
+  if (KG > 32) return fail(B2L_ERR_UNSUPPORTED, "n_mfcc=%d > 256 is not supported", p->n_mfcc);
+  size_t smem = ((size_t)p->n_mels * DCT_TILE + (size_t)p->n_mels * 8 * KG) * 4;
+  if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_mels=%d is too large for the DCT kernel", p->n_mels);
+  CUDA_TRY(cudaFuncSetAttribute(dct_clamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (int)((T + DCT_TILE - 1) / DCT_TILE);
+  const long long grid = (long long)tiles * n_clips;
+  if (grid > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many DCT tiles");
+  dct_clamp_kernel<<<(int)grid, KG * 32, smem, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
+                                                            clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, (int)T,
+                                                            tiles, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
+extern "C" int b2l_mfcc(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
+                        float* d_mfcc, float* d_logmel) {
+  if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
+  if (p->n_mfcc == 0) return fail(B2L_ERR_INVALID, "plan has no mfcc stage");
+  if (n_clips <= 0) return n_clips == 0 ? B2L_OK : fail(B2L_ERR_INVALID, "negative n_clips");
+  DeviceGuard g(c->device);
+  const long long T = plan_frames(p, n);
+  if (T <= 0) return fail(B2L_ERR_INVALID, "n_fft=%d is too large for input signal of length=%lld", p->n_fft, (long long)n);
+  int rc = ensure_clip_max(c, (size_t)n_clips);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(c->d_clip_max, 0, (size_t)n_clips * sizeof(unsigned int), c->stream));
+  float* scratch = d_logmel;
+  if (!scratch) CUDA_TRY(cudaMalloc((void**)&scratch, (size_t)n_clips * p->n_mels * T * sizeof(float)));
+  rc = run_forward(c, p, MODE_MEL, 1, d_y, n_clips, n, y_stride, nullptr, scratch);
+  if (rc == B2L_OK) rc = launch_dct(c, p, scratch, n_clips, T, 1, d_mfcc);
+  if (!d_logmel) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(scratch);
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------ inverse launch
+extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t n_clips, int64_t n_frames_stored,
+                         int64_t n_frames_used, const float* d_inv_wss, int64_t out_len, float* d_y,
+                         int64_t y_stride) {
+  if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
+  if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
+  if (n_clips < 0 || n_frames_used < 1 || n_frames_used > n_frames_stored || out_len < 0 || y_stride < out_len)
+    return fail(B2L_ERR_INVALID, "bad istft geometry");
+  if (n_clips == 0 || out_len == 0) return B2L_OK;
+  if (!d_D || !d_inv_wss || !d_y) return fail(B2L_ERR_INVALID, "NULL device pointer");
+  if (out_len > 0x7fffffffLL || n_frames_stored > 0x7fffffffLL)
+    return fail(B2L_ERR_UNSUPPORTED, "istft output longer than 2^31-1 samples is not supported");
+  DeviceGuard g(c->device);
+  HostFftCfg cfg(p->log2m);
+  const int N = p->n_fft, M = N / 2;
+  inv_op_fn op = inv_table(p->log2m);
+  int nws[2];
+  const int n_opt = cfg.nw_options(nws);
+  InvArgs a;
+  memset(&a, 0, sizeof(a));
+  int nw = 0;
+  size_t smem = 0;
+  const int clen = N > p->hop ? N - p->hop : 0;
+  for (int i = 0; i < n_opt; ++i) {
+    const int w = nws[i];
+    const int G = w * 32 / cfg.tpf;
+    size_t off = 0;
+    a.off_win = (int)off; off = align_up(off + (size_t)N * 4, 16);
+    a.off_tw = (int)off; off = align_up(off + (size_t)cfg.tw_count() * 8, 16);
+    a.off_twn = (int)off; off = align_up(off + (size_t)(M / 2 + 1) * 8, 16);
+    a.off_acc = (int)off; off = align_up(off + (size_t)2 * clen * 4, 16);
+    a.off_xbuf = (int)(off = align_up(off, 128));
+    off += (size_t)G * cfg.xbuf_f2() * 8;
+    if (off <= c->smem_optin) {
+      nw = w;
+      smem = off;
+      break;
+    }
+  }
+  if (nw == 0) return fail(B2L_ERR_UNSUPPORTED, "istft configuration does not fit in shared memory");
+  const int G = nw * 32 / cfg.tpf;
+  a.acc_floats = 2 * clen;
+  a.D = (const float2*)d_D;
+  a.d_clip_stride = (long long)n_frames_stored * (M + 1);
+  a.n_clips = (int)n_clips;
+  a.n_frames = (int)n_frames_used;
+  a.n_fft = N;
+  a.hop = p->hop;
+  a.start = p->center ? N / 2 : 0;
+  a.out_len = (int)out_len;
+  a.y_clip_stride = y_stride;
+  a.y = d_y;
+  a.window = p->d_win_inv;
+  a.inv_wss = d_inv_wss;
+  a.tw = p->d_tw;
+  a.twn = p->d_twn;
+  // segments: enough CTAs to fill the machine twice; each at least 4 rounds long so the halo frames
+  // (recomputed at every segment start) stay a small fraction
+  {
+    const long long want = 2LL * c->sm_count;
+    long long segs = (want + n_clips - 1) / n_clips;
+    const long long max_segs = (n_frames_used + 4LL * G - 1) / (4LL * G);
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+    long long fps = (n_frames_used + segs - 1) / segs;
+    fps = (fps + G - 1) / G * G;
+    segs = (n_frames_used + fps - 1) / fps;
+    a.segs_per_clip = (int)segs;
+    a.frames_per_seg = (int)fps;
+  }
+  const long long grid = (long long)a.segs_per_clip * n_clips;
+  if (grid > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many istft segments");
+  CUDA_TRY(op(OP_SET_SMEM, nw, &a, 0, smem, c->stream, nullptr));
+  CUDA_TRY(op(OP_LAUNCH, nw, &a, (int)grid, smem, c->stream, nullptr));
+  c->launches++;
+  return B2L_OK;
+}
+
+// ------------------------------------------------------------------ S= pieces
+extern "C" int b2l_mel_project(b2l_ctx* c, const b2l_plan* p, const float* d_S, int64_t n_clips, int64_t n_frames,
+                               float* d_mel) {
+  if (!c || !p || !d_S || !d_mel) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (p->n_mels == 0) return fail(B2L_ERR_INVALID, "plan has no mel stage");
+  if (n_clips <= 0 || n_frames <= 0) return B2L_OK;
+  DeviceGuard g(c->device);
+  const int F = p->n_fft / 2 + 1;
+  size_t smem = (size_t)F * 33 * 4;
+  if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_fft too large for mel_project");
+  CUDA_TRY(cudaFuncSetAttribute(mel_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (int)((n_frames + 31) / 32);
+  const long long grid = (long long)tiles * n_clips;
+  if (grid > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many tiles");
+  mel_project_kernel<<<(int)grid, 256, smem, c->stream>>>(d_S, p->d_mel_w, p->d_band, p->n_mels, F, (int)n_frames,
+                                                          tiles, d_mel);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
+extern "C" int b2l_power_to_db(b2l_ctx* c, const float* d_in, int64_t n_clips, int64_t per_clip, float amin,
+                               float ref_value, float top_db, float* d_out) {
+  if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (!(amin > 0.0f)) return fail(B2L_ERR_INVALID, "amin must be strictly positive");
+  if (n_clips <= 0 || per_clip <= 0) return B2L_OK;
+  if (n_clips > 65535) return fail(B2L_ERR_UNSUPPORTED, "power_to_db: more than 65535 leading indices");
+  DeviceGuard g(c->device);
+  int rc = ensure_clip_max(c, (size_t)n_clips);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(c->d_clip_max, 0, (size_t)n_clips * sizeof(unsigned int), c->stream));
+  long long bx = (per_clip + 256LL * 8 - 1) / (256LL * 8);
+  long long cap = (4LL * c->sm_count + n_clips - 1) / n_clips;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)n_clips);
+  const float db_sub = 10.0f * log10f(fmaxf(amin, fabsf(ref_value)));
+  db_kernel<<<grid, 256, 0, c->stream>>>(d_in, per_clip, amin, db_sub, c->d_clip_max, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  if (top_db >= 0.0f) {
+    db_clamp_kernel<<<grid, 256, 0, c->stream>>>(d_out, per_clip, c->d_clip_max, top_db);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  return B2L_OK;
+}
+
+extern "C" int b2l_dct_project(b2l_ctx* c, const b2l_plan* p, const float* d_S, int64_t n_clips, int64_t n_frames,
+                               float* d_mfcc) {
+  if (!c || !p || !d_S || !d_mfcc) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (p->n_mfcc == 0) return fail(B2L_ERR_INVALID, "plan has no mfcc stage");
+  if (n_clips <= 0 || n_frames <= 0) return B2L_OK;
+  DeviceGuard g(c->device);
+  return launch_dct(c, p, d_S, n_clips, n_frames, 0, d_mfcc);
+}
+
+extern "C" int b2l_transpose(b2l_ctx* c, const void* d_in, int64_t n_clips, int64_t rows, int64_t cols,
+                             int32_t elem_bytes, void* d_out) {
+  if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (n_clips <= 0 || rows <= 0 || cols <= 0) return B2L_OK;
+  if (n_clips > 65535) return fail(B2L_ERR_UNSUPPORTED, "transpose: more than 65535 leading indices");
+  DeviceGuard g(c->device);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)n_clips);
+  dim3 block(32, 8);
+  if (elem_bytes == 4)
+    transpose_kernel<float><<<grid, block, 0, c->stream>>>((const float*)d_in, (int)rows, (int)cols, (float*)d_out);
+  else if (elem_bytes == 8)
+    transpose_kernel<float2><<<grid, block, 0, c->stream>>>((const float2*)d_in, (int)rows, (int)cols, (float2*)d_out);
+  else
+    return fail(B2L_ERR_INVALID, "elem_bytes must be 4 or 8");
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU split / join
+extern "C" int b2l_comm_unique_id(void* id128) {
+  if (!id128) return fail(B2L_ERR_INVALID, "NULL argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return B2L_OK;
+}
+extern "C" int b2l_comm_init(b2l_ctx* c, const void* id128, int rank, int world) {
+  if (!c || !id128) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(B2L_ERR_INVALID, "bad rank %d / world %d", rank, world);
+  int rc = nccl_load();
+  if (rc) return rc;
+  DeviceGuard g(c->device);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_TRY(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  c->rank = rank;
+  c->world = world;
+  return B2L_OK;
+}
+extern "C" int b2l_comm_destroy(b2l_ctx* c) {
+  if (!c || !c->comm) return B2L_OK;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  NCCL_TRY(g_nccl.CommDestroy(c->comm));
+  c->comm = nullptr;
+  c->world = 1;
+  c->rank = 0;
+  return B2L_OK;
+}
+extern "C" int b2l_comm_broadcast(b2l_ctx* c, void* d_buf, size_t bytes, int root) {
+  if (!c || !c->comm) return fail(B2L_ERR_INVALID, "communicator not initialised");
+  DeviceGuard g(c->device);
+  NCCL_TRY(g_nccl.Broadcast(d_buf, d_buf, bytes, ncclChar, root, c->comm, c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_comm_scatter(b2l_ctx* c, const void* d_full, void* d_shard, size_t shard_bytes, int root) {
+  if (!c || !c->comm) return fail(B2L_ERR_INVALID, "communicator not initialised");
+  DeviceGuard g(c->device);
+  NCCL_TRY(g_nccl.GroupStart());
+  if (c->rank == root)
+    for (int r = 0; r < c->world; ++r)
+      NCCL_TRY(g_nccl.Send((const char*)d_full + (size_t)r * shard_bytes, shard_bytes, ncclChar, r, c->comm, c->stream));
+  NCCL_TRY(g_nccl.Recv(d_shard, shard_bytes, ncclChar, root, c->comm, c->stream));
+  NCCL_TRY(g_nccl.GroupEnd());
+  return B2L_OK;
+}
+extern "C" int b2l_comm_gather(b2l_ctx* c, const void* d_shard, void* d_full, size_t shard_bytes, int root) {
+  if (!c || !c->comm) return fail(B2L_ERR_INVALID, "communicator not initialised");
+  DeviceGuard g(c->device);
+  NCCL_TRY(g_nccl.GroupStart());
+  if (c->rank == root)
+    for (int r = 0; r < c->world; ++r)
+      NCCL_TRY(g_nccl.Recv((char*)d_full + (size_t)r * shard_bytes, shard_bytes, ncclChar, r, c->comm, c->stream));
+  NCCL_TRY(g_nccl.Send(d_shard, shard_bytes, ncclChar, root, c->comm, c->stream));
+  NCCL_TRY(g_nccl.GroupEnd());
+  return B2L_OK;
+}
+extern "C" int b2l_comm_barrier(b2l_ctx* c) {
+  if (!c || !c->comm) return fail(B2L_ERR_INVALID, "communicator not initialised");
+  DeviceGuard g(c->device);
+  int rc = ensure_clip_max(c, 1);
+  if (rc) return rc;
+  NCCL_TRY(g_nccl.AllReduce(c->d_clip_max, c->d_clip_max, 1, ncclChar, 0 /* ncclSum */, c->comm, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return B2L_OK;
+}

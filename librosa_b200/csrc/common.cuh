@@ -1,0 +1,90 @@
+// common.cuh — shared declarations for the b2l kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2l {
+
+enum PadMode : int {   // librosa/_typing.py:60-71 (_PadModeSTFT); callables are rejected on the host
+  PAD_CONSTANT = 0,
+  PAD_EDGE = 1,
+  PAD_REFLECT = 2,
+  PAD_SYMMETRIC = 3,
+  PAD_LINEAR_RAMP = 4,
+  PAD_EMPTY = 5,       // values undefined in NumPy; zeros here
+};
+
+enum FwdMode : int {
+  MODE_STFT = 0,   // complex64 [clip][frame][bin]
+  MODE_MEL = 1,    // |X|^power -> band-sparse mel projection -> float32 [clip][mel][frame]
+  MODE_SPEC = 2,   // |X|^power -> float32 [clip][frame][bin]
+};
+
+struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at mel_w[off ..]
+
+struct FwdArgs {
+  // input
+  const float* y;            // [n_clips][clip_stride] (first n samples of each row are valid)
+  long long clip_stride;
+  int n, n_clips;
+  int n_fft, hop, pad, pad_mode, n_frames;
+  int tiles_per_clip;
+  long long total_tiles;
+  int tma_ok;                // host-checked alignment of base pointer / stride / span
+  // constants (device)
+  const float* window;       // [n_fft] float32, already scaled by 1/2 for the packed real FFT
+  const float2* tw;          // inter-pass twiddles, FftCfg::tw_offset layout
+  const float2* twn;         // exp(-2*pi*i*k/n_fft), k = 0 .. n_fft/4
+  // outputs
+  float2* out_c;             // MODE_STFT
+  float* out_r;              // MODE_MEL / MODE_SPEC
+  // power / mel / dB epilogue
+  int power_mode;            // 2: re^2+im^2, 1: sqrt, 0: powf(|X|, power)
+  float power;
+  int n_mels, mel_w_count;
+  const float* mel_w;
+  const MelBand* mel_band;
+  int log_mode;              // 1: write 10*log10(max(amin, S)) - db_sub and track the per-clip max
+  float amin, db_sub;
+  unsigned int* clip_max;    // order-preserving uint keys of the per-clip max (log_mode)
+  // dynamic shared-memory layout (byte offsets)
+  int off_win, off_tw, off_twn, off_in, off_xbuf, off_melw, off_melband, off_bar;
+  int in_floats;             // staged span length (floats)
+};
+
+struct InvArgs {
+  const float2* D;           // [n_clips][n_frames_total][n_bins]
+  long long d_clip_stride;   // in float2 elements
+  int n_clips, n_frames;     // frames actually used (<= frames stored)
+  int n_fft, hop, start;     // start = n_fft/2 when center else 0
+  int out_len;
+  long long y_clip_stride;
+  float* y;                  // [n_clips][y_clip_stride]
+  const float* window;       // [n_fft] float32 scaled by 1/n_fft
+  const float* inv_wss;      // [out_len] 1/wss where wss > tiny else 1
+  const float2* tw;
+  const float2* twn;
+  int segs_per_clip, frames_per_seg;
+  int off_win, off_tw, off_twn, off_xbuf, off_acc;
+  int acc_floats;
+};
+
+// order-preserving float <-> uint mapping for atomicMax on floats
+__host__ __device__ inline unsigned int float_to_key(float f) {
+#ifdef __CUDA_ARCH__
+  unsigned int u = __float_as_uint(f);
+#else
+  union { float f; unsigned int u; } c; c.f = f; unsigned int u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float key_to_float(unsigned int k) {
+  unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; unsigned int u; } c; c.u = u; return c.f;
+#endif
+}
+
+}  // namespace b2l

@@ -1,0 +1,261 @@
+// fft_engine.cuh — register-resident Stockham complex FFT for sm_100a.
+//
+// One "frame group" of TPF threads transforms M = 2^LOG2M complex points; every thread keeps
+// PPT = M / TPF points (32 for all production sizes) in registers.  Each pass is a radix-R DFT done
+// entirely in registers (decimation-in-time, compile-time twiddles folded into FFMA immediates);
+// passes exchange data through a padded shared-memory buffer that belongs to the group alone,
+// so a warp-sized group synchronises with __syncwarp only.
+//
+// Stockham pass (radix R, sub-transform length p, T = M / R butterflies, butterfly i):
+//     k = i mod p ;  u[r] = x[i + r*T] * exp(-2*pi*i * r*k / (p*R)) ;  v = DFT_R(u)
+//     y[(i - k)*R + k + q*p] = v[q]
+// After the last pass y is the DFT in natural order.
+//
+// The real-input transform of length N = 2M packs even/odd samples as re/im (z[n] = x[2n] + i x[2n+1])
+// and un-mixes the result with one twiddled butterfly per bin pair (k, M-k); see r2c_pair().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+#include <utility>
+
+namespace b2l {
+
+// ------------------------------------------------------------------ compile-time helpers
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(static_cast<F&&>(f));
+  }
+}
+
+__host__ __device__ constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
+__host__ __device__ constexpr int bitrevc(int x, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+
+// cos / sin of 2*pi*j/n evaluated by the host compiler (octant reduction keeps 0, +-1, sqrt(1/2) exact)
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double taylor_sin(double x) {
+  double x2 = x * x, term = x, sum = x;
+  for (int i = 1; i < 14; ++i) { term *= -x2 / double((2 * i) * (2 * i + 1)); sum += term; }
+  return sum;
+}
+constexpr double taylor_cos(double x) {
+  double x2 = x * x, term = 1.0, sum = 1.0;
+  for (int i = 1; i < 14; ++i) { term *= -x2 / double((2 * i - 1) * (2 * i)); sum += term; }
+  return sum;
+}
+struct cpair { double c, s; };
+constexpr cpair cossin2pi(long j, long n) {   // (cos, sin) of 2*pi*j/n
+  long t = ((j % n) + n) % n;
+  long o = (8 * t) / n;          // octant
+  long r = 8 * t - o * n;        // position inside the octant, in units of 2*pi/(8n)
+  bool odd = (o & 1) != 0;
+  long rr = odd ? (n - r) : r;
+  double a = kPi * double(rr) / (4.0 * double(n));
+  double c = taylor_cos(a), s = taylor_sin(a);
+  switch (o) {
+    case 0: return {c, s};
+    case 1: return {s, c};
+    case 2: return {-s, c};
+    case 3: return {-c, s};
+    case 4: return {-c, -s};
+    case 5: return {-s, -c};
+    case 6: return {s, -c};
+    default: return {c, -s};
+  }
+}
+template <int J, int N>
+struct TwC {   // W_N^J = exp(-2*pi*i*J/N)
+  static constexpr float re = float(cossin2pi(J, N).c);
+  static constexpr float im = float(-cossin2pi(J, N).s);
+};
+
+// ------------------------------------------------------------------ complex helpers
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// DIT butterfly  (a, b) <- (a + w b, a - w b)  with a compile-time twiddle.
+template <int J, int N>
+__device__ __forceinline__ void bfly(float2& a, float2& b) {
+  constexpr int j = ((J % N) + N) % N;
+  if constexpr (j == 0) {
+    float2 s = make_float2(a.x + b.x, a.y + b.y);
+    b = make_float2(a.x - b.x, a.y - b.y);
+    a = s;
+  } else if constexpr (4 * j == N) {            // w = -i
+    float2 s = make_float2(a.x + b.y, a.y - b.x);
+    b = make_float2(a.x - b.y, a.y + b.x);
+    a = s;
+  } else {
+    constexpr float wr = TwC<j, N>::re, wi = TwC<j, N>::im;
+    float sr = fmaf(wr, b.x, a.x);
+    sr = fmaf(-wi, b.y, sr);
+    float si = fmaf(wr, b.y, a.y);
+    si = fmaf(wi, b.x, si);
+    b = make_float2(fmaf(2.0f, a.x, -sr), fmaf(2.0f, a.y, -si));
+    a = make_float2(sr, si);
+  }
+}
+
+// In-register radix-R DFT on v[BASE .. BASE+R): input in bit-reversed slots, output natural.
+template <int R, int BASE, int N>
+__device__ __forceinline__ void dft_reg(float2 (&v)[N]) {
+  constexpr int LOGR = ilog2c(R);
+  static_for<0, LOGR>([&](auto S) {
+    constexpr int h = 1 << decltype(S)::value;
+    static_for<0, R / 2>([&](auto I) {
+      constexpr int i = decltype(I)::value;
+      constexpr int blk = i / h, j = i % h;
+      constexpr int ia = BASE + blk * 2 * h + j;
+      bfly<j, 2 * h>(v[ia], v[ia + h]);
+    });
+  });
+}
+
+// ------------------------------------------------------------------ schedule
+template <int LOG2M_, int TPF_>
+struct FftCfg {
+  static constexpr int LOG2M = LOG2M_;
+  static constexpr int M = 1 << LOG2M_;
+  static constexpr int TPF = TPF_;
+  static constexpr int PPT = M / TPF_;
+  static_assert(PPT >= 1 && PPT <= 32, "points per thread must be 1..32");
+  static constexpr int LOGP = ilog2c(PPT);
+  static constexpr int NPASS = PPT == 1 ? 1 : (LOG2M_ + LOGP - 1) / LOGP;
+  // greedy: every pass uses radix PPT except the last, which takes what is left
+  __host__ __device__ static constexpr int log_radix(int s) {
+    int left = LOG2M_ - s * LOGP;
+    return left >= LOGP ? LOGP : left;
+  }
+  __host__ __device__ static constexpr int radix(int s) { return 1 << log_radix(s); }
+  __host__ __device__ static constexpr int sublen(int s) { return 1 << (s * LOGP); }   // p before pass s
+  // twiddle table: pass s >= 1 stores (R_s - 1) rows of p_s entries: tw[s][(r-1)*p + k]
+  __host__ __device__ static constexpr int tw_offset(int s) {
+    int off = 0;
+    for (int q = 1; q < s; ++q) off += (radix(q) - 1) * sublen(q);
+    return off;
+  }
+  static constexpr int TW_COUNT = tw_offset(NPASS);
+  // exchange buffer: M complex values, one pad slot per 32
+  static constexpr int XBUF_F2 = M + M / 32;
+};
+
+__device__ __forceinline__ int xphys(int e) { return e + (e >> 5); }
+
+// Group barrier: warp-sized (or smaller) groups use __syncwarp, larger ones a named barrier.
+template <int TPF>
+__device__ __forceinline__ void group_sync(int group_in_cta) {
+  if constexpr (TPF <= 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(group_in_cta + 1), "n"(TPF) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ the transform
+// Pass-0 operand fetch: v[slot] = load_in(e) for the elements thread t owns in the first pass
+// (bit-reversed slots, as dft_reg expects).  Kept separate from fft_forward so callers can pick an
+// aligned / unaligned / global-memory loader without duplicating the transform body.
+template <class Cfg, class LoadIn>
+__device__ __forceinline__ void load_pass0(float2 (&v)[Cfg::PPT], int t, LoadIn&& load_in) {
+  constexpr int R = Cfg::radix(0), LOGR = Cfg::log_radix(0), T = Cfg::M / R, NB = Cfg::PPT / R;
+  static_for<0, NB>([&](auto B) {
+    constexpr int b = decltype(B)::value;
+    const int i = t + Cfg::TPF * b;
+    static_for<0, R>([&](auto Rr) {
+      constexpr int r = decltype(Rr)::value;
+      v[b * R + bitrevc(r, LOGR)] = load_in(i + r * T);
+    });
+  });
+}
+
+// v[] must hold the pass-0 operands (see load_pass0) and receives the spectrum:
+//   v[b*RL + q] = Z[t + TPF*b + q*pL]   (RL, pL = radix / sub-length of the last pass, b = 0 .. PPT/RL-1).
+template <class Cfg>
+__device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int group_in_cta,
+                                            float2* __restrict__ xbuf, const float2* __restrict__ tw) {
+  constexpr int M = Cfg::M, TPF = Cfg::TPF, PPT = Cfg::PPT;
+  static_for<0, Cfg::NPASS>([&](auto S) {
+    constexpr int s = decltype(S)::value;
+    constexpr int R = Cfg::radix(s);
+    constexpr int LOGR = Cfg::log_radix(s);
+    constexpr int p = Cfg::sublen(s);
+    constexpr int T = M / R;
+    constexpr int NB = PPT / R;
+    // ---- load (+ inter-pass twiddle)
+    static_for<0, NB>([&](auto B) {
+      constexpr int b = decltype(B)::value;
+      const int i = t + TPF * b;
+      static_for<0, R>([&](auto Rr) {
+        constexpr int r = decltype(Rr)::value;
+        constexpr int slot = b * R + bitrevc(r, LOGR);
+        if constexpr (s > 0) {
+          float2 x = xbuf[xphys(i + r * T)];
+          if constexpr (r > 0) {
+            const int k = i & (p - 1);
+            x = cmul(x, tw[Cfg::tw_offset(s) + (r - 1) * p + k]);
+          }
+          v[slot] = x;
+        }
+      });
+    });
+    // ---- radix-R DFTs in registers
+    static_for<0, NB>([&](auto B) { dft_reg<R, decltype(B)::value * R>(v); });
+    // ---- store for the next pass
+    if constexpr (s + 1 < Cfg::NPASS) {
+      if constexpr (s > 0) group_sync<TPF>(group_in_cta);   // everyone finished reading pass s-1 data
+      static_for<0, NB>([&](auto B) {
+        constexpr int b = decltype(B)::value;
+        const int i = t + TPF * b;
+        const int k = i & (p - 1);
+        const int j = (i - k) * R + k;
+        static_for<0, R>([&](auto Q) {
+          constexpr int q = decltype(Q)::value;
+          xbuf[xphys(j + q * p)] = v[b * R + q];
+        });
+      });
+      group_sync<TPF>(group_in_cta);
+    }
+  });
+}
+
+// Index of the spectrum element held in v[slot] after fft_forward.
+template <class Cfg>
+__device__ __forceinline__ int spectrum_index(int t, int slot) {
+  constexpr int RL = Cfg::radix(Cfg::NPASS - 1);
+  constexpr int pL = Cfg::sublen(Cfg::NPASS - 1);
+  int b = slot / RL, q = slot % RL;
+  return t + Cfg::TPF * b + q * pL;
+}
+
+// One bin pair of the real-input un-mix.  A = Z[k], B = Z[M-k] (Z computed from a window that already
+// carries the factor 1/2), w = exp(-2*pi*i*k/N).  Returns X[k] in xa and X[M-k] in xb.
+__device__ __forceinline__ void r2c_pair(float2 A, float2 B, float2 w, float2& xa, float2& xb) {
+  float er = A.x + B.x, ei = A.y - B.y;
+  float orr = A.y + B.y, oi = B.x - A.x;
+  float pr = fmaf(w.x, orr, -w.y * oi);
+  float pi = fmaf(w.x, oi, w.y * orr);
+  xa = make_float2(er + pr, ei + pi);
+  xb = make_float2(er - pr, pi - ei);
+}
+
+// Inverse of r2c_pair: from X[k], X[M-k] rebuild Z[k], Z[M-k] (scaled by 2; caller folds 1/2 into its
+// window).  w = exp(-2*pi*i*k/N) as above.
+__device__ __forceinline__ void c2r_pair(float2 xa, float2 xb, float2 w, float2& A, float2& B) {
+  // E = (Xa + conj(Xb)), P = (Xa - conj(Xb)) = w*O  ->  O = conj(w) * P
+  float er = xa.x + xb.x, ei = xa.y - xb.y;
+  float pr = xa.x - xb.x, pi = xa.y + xb.y;
+  float orr = fmaf(w.x, pr, w.y * pi);
+  float oi = fmaf(w.x, pi, -w.y * pr);
+  // Z[k] = E + i*O ; Z[M-k] = conj(E) + i*conj(O)
+  A = make_float2(er - oi, ei + orr);
+  B = make_float2(er + oi, orr - ei);
+}
+
+}  // namespace b2l

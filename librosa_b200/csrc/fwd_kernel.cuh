@@ -1,0 +1,310 @@
+// fwd_kernel.cuh — fused frame + pad + window + real FFT kernel with three epilogues
+// (complex STFT / power spectrogram / band-sparse mel projection with optional dB + per-clip max).
+//
+// Replaces, per frame, the reference's  util.frame -> float64 window product -> scipy.fft.rfft
+// (librosa/core/spectrum.py:341-390),  np.abs(.)**power (:3000-3013) and the mel einsum
+// (librosa/feature/spectral.py:2160).
+//
+// Work decomposition: a persistent CTA walks tiles of FT consecutive frames of one clip.  The
+// contiguous sample span of a tile, (FT-1)*hop + n_fft floats, is staged once into shared memory
+// (frames overlap *inside* shared memory) — by a single 1-D TMA bulk copy (cp.async.bulk + mbarrier)
+// for interior tiles, prefetched one tile ahead, or by a cooperative gather with the pad-mode index
+// map for tiles that touch the clip edges.  Each group of TPF threads then transforms one frame in
+// registers (fft_engine.cuh).
+#pragma once
+#include "common.cuh"
+#include "fft_engine.cuh"
+
+namespace b2l {
+
+// ------------------------------------------------------------------ mbarrier / TMA (PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------------ padded sample fetch
+// Virtual sample j of a clip of n samples under np.pad semantics (librosa/core/spectrum.py:252-328,
+// equivalence to np.pad(y, n_fft//2, mode) per SURVEY Appendix A.2).
+__device__ __forceinline__ float load_padded(const float* __restrict__ y, int n, long long j, int mode, int pad) {
+  if (j >= 0 && j < n) return __ldg(y + j);
+  switch (mode) {
+    case PAD_EDGE:
+      return __ldg(y + (j < 0 ? 0 : n - 1));
+    case PAD_REFLECT: {
+      if (n == 1) return __ldg(y);
+      long long P = 2LL * (n - 1);
+      long long m = j % P;
+      if (m < 0) m += P;
+      if (m >= n) m = P - m;
+      return __ldg(y + m);
+    }
+    case PAD_SYMMETRIC: {
+      long long P = 2LL * n;
+      long long m = j % P;
+      if (m < 0) m += P;
+      if (m >= n) m = P - 1 - m;
+      return __ldg(y + m);
+    }
+    case PAD_LINEAR_RAMP: {
+      long long d = j < 0 ? -j : j - (n - 1);          // distance from the edge sample, 1..pad
+      float edge = __ldg(y + (j < 0 ? 0 : n - 1));
+      long long i = pad - d;                           // np.linspace(0, edge, pad, endpoint=False)[i]
+      if (i <= 0) return 0.0f;
+      return (float)((double)i * ((double)edge / (double)pad));
+    }
+    default:
+      return 0.0f;
+  }
+}
+
+__device__ __forceinline__ float apply_power(float2 x, int power_mode, float power) {
+  float p2 = fmaf(x.x, x.x, x.y * x.y);
+  if (power_mode == 2) return p2;
+  float mag = sqrtf(p2);
+  if (power_mode == 1) return mag;
+  return powf(mag, power);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int LOG2M, int TPF, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
+  using Cfg = FftCfg<LOG2M, TPF>;
+  constexpr int M = Cfg::M, N = 2 * M, PPT = Cfg::PPT;
+  constexpr int NT = NW * 32;
+  constexpr int FT = NT / TPF;                 // frames per tile == frame groups per CTA
+  static_assert(FT >= 1 && FT <= 32, "tile must hold 1..32 frames");
+  constexpr int H = 32 / FT;                   // bin interleave of the mel phase
+  constexpr int NPAIR = PPT / 2;               // bin pairs (k, M-k) per thread
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* s_win = reinterpret_cast<float*>(smem + a.off_win);
+  float2* s_tw = reinterpret_cast<float2*>(smem + a.off_tw);
+  float2* s_twn = reinterpret_cast<float2*>(smem + a.off_twn);
+  float* s_in = reinterpret_cast<float*>(smem + a.off_in);
+  float2* s_xall = reinterpret_cast<float2*>(smem + a.off_xbuf);
+  float* s_p = reinterpret_cast<float*>(smem + a.off_xbuf);     // P[k][FT] aliases the exchange area
+  float* s_melw = reinterpret_cast<float*>(smem + a.off_melw);
+  MelBand* s_band = reinterpret_cast<MelBand*>(smem + a.off_melband);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+
+  const int tid = threadIdx.x;
+  const int grp = tid / TPF;                   // frame group == local frame index
+  const int t = tid % TPF;
+  float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
+
+  // ---- one-time table staging
+  for (int i = tid; i < N; i += NT) s_win[i] = a.window[i];
+  for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.tw[i];
+  for (int i = tid; i <= M / 2; i += NT) s_twn[i] = a.twn[i];
+  if constexpr (MODE == MODE_MEL) {
+    for (int i = tid; i < a.mel_w_count; i += NT) s_melw[i] = a.mel_w[i];
+    for (int i = tid; i < a.n_mels; i += NT) s_band[i] = a.mel_band[i];
+  }
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int span = a.in_floats;
+  const bool hop_even = (a.hop & 1) == 0;
+
+  auto tile_origin = [&](long long tile, int& clip, int& t0, long long& s0) {
+    clip = (int)(tile / a.tiles_per_clip);
+    t0 = (int)(tile % a.tiles_per_clip) * FT;
+    s0 = (long long)t0 * a.hop - a.pad;
+  };
+  auto tile_is_tma = [&](long long tile) -> bool {
+    int clip, t0;
+    long long s0;
+    tile_origin(tile, clip, t0, s0);
+    return a.tma_ok && s0 >= 0 && s0 + span <= a.n && (s0 & 3) == 0;
+  };
+  auto issue_tma = [&](long long tile) {
+    int clip, t0;
+    long long s0;
+    tile_origin(tile, clip, t0, s0);
+    fence_proxy_async();
+    mbar_expect_tx(s_bar, (uint32_t)span * 4u);
+    tma_load_1d(s_in, a.y + (long long)clip * a.clip_stride + s0, (uint32_t)span * 4u, s_bar);
+  };
+
+  long long tile = blockIdx.x;
+  uint32_t phase = 0;
+  if (tile < a.total_tiles && tid == 0 && tile_is_tma(tile)) issue_tma(tile);
+
+  for (; tile < a.total_tiles; tile += gridDim.x) {
+    int clip, t0;
+    long long s0;
+    tile_origin(tile, clip, t0, s0);
+    // ---------------- stage the tile's sample span
+    if (tile_is_tma(tile)) {
+      mbar_wait(s_bar, phase);
+      phase ^= 1;
+    } else {
+      const float* yc = a.y + (long long)clip * a.clip_stride;
+      for (int i = tid; i < span; i += NT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
+      __syncthreads();
+    }
+
+    // ---------------- windowed frame -> registers (pass-0 operands)
+    float2 v[PPT];
+    {
+      const float* fr = s_in + grp * a.hop;
+      if (hop_even) {
+        load_pass0<Cfg>(v, t, [&](int e) {
+          float2 x = *reinterpret_cast<const float2*>(fr + 2 * e);
+          float2 w = *reinterpret_cast<const float2*>(s_win + 2 * e);
+          return make_float2(x.x * w.x, x.y * w.y);
+        });
+      } else {
+        load_pass0<Cfg>(v, t, [&](int e) {
+          float2 w = *reinterpret_cast<const float2*>(s_win + 2 * e);
+          return make_float2(fr[2 * e] * w.x, fr[2 * e + 1] * w.y);
+        });
+      }
+    }
+    __syncthreads();   // B0: staging buffer consumed -> prefetch the next tile behind the math
+    {
+      long long nxt = tile + gridDim.x;
+      if (tid == 0 && nxt < a.total_tiles && tile_is_tma(nxt)) issue_tma(nxt);
+    }
+
+    // ---------------- M-point complex FFT, then publish Z for the pair un-mix
+    fft_forward<Cfg>(v, t, grp, xbuf, s_tw);
+    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp);
+    static_for<0, PPT>([&](auto S) {
+      constexpr int slot = decltype(S)::value;
+      xbuf[xphys(spectrum_index<Cfg>(t, slot))] = v[slot];
+    });
+    group_sync<TPF>(grp);
+
+    const int frame = t0 + grp;
+    const bool frame_ok = frame < a.n_frames;
+
+    if constexpr (MODE == MODE_STFT) {
+      float2* orow = a.out_c + ((long long)clip * a.n_frames + frame) * (M + 1);
+      static_for<0, NPAIR>([&](auto C) {
+        const int k = t + TPF * decltype(C)::value;
+        float2 xa, xb;
+        r2c_pair(xbuf[xphys(k)], xbuf[xphys((M - k) & (M - 1))], s_twn[k], xa, xb);
+        if (frame_ok) {
+          orow[k] = xa;
+          orow[M - k] = xb;
+        }
+      });
+      if (t == 0) {
+        float2 xa, xb;
+        float2 zc = xbuf[xphys(M / 2)];
+        r2c_pair(zc, zc, s_twn[M / 2], xa, xb);
+        if (frame_ok) orow[M / 2] = xa;
+      }
+      group_sync<TPF>(grp);   // pair reads done before the next tile's exchange writes
+    } else {
+      float pw[PPT + 1];
+      static_for<0, NPAIR>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        const int k = t + TPF * c;
+        float2 xa, xb;
+        r2c_pair(xbuf[xphys(k)], xbuf[xphys((M - k) & (M - 1))], s_twn[k], xa, xb);
+        pw[2 * c] = apply_power(xa, a.power_mode, a.power);
+        pw[2 * c + 1] = apply_power(xb, a.power_mode, a.power);
+      });
+      pw[PPT] = 0.0f;
+      if (t == 0) {
+        float2 xa, xb;
+        float2 zc = xbuf[xphys(M / 2)];
+        r2c_pair(zc, zc, s_twn[M / 2], xa, xb);
+        pw[PPT] = apply_power(xa, a.power_mode, a.power);
+      }
+      if constexpr (MODE == MODE_SPEC) {
+        float* orow = a.out_r + ((long long)clip * a.n_frames + frame) * (M + 1);
+        if (frame_ok) {
+          static_for<0, NPAIR>([&](auto C) {
+            constexpr int c = decltype(C)::value;
+            const int k = t + TPF * c;
+            orow[k] = pw[2 * c];
+            orow[M - k] = pw[2 * c + 1];
+          });
+          if (t == 0) orow[M / 2] = pw[PPT];
+        }
+        group_sync<TPF>(grp);
+      } else {
+        // ---------------- band-sparse mel projection over the tile
+        __syncthreads();   // B1: every group finished reading its Z
+        auto paddr = [&](int k, int f) { return k * FT + (f ^ ((k / H) & (FT - 1))); };
+        static_for<0, NPAIR>([&](auto C) {
+          constexpr int c = decltype(C)::value;
+          const int k = t + TPF * c;
+          s_p[paddr(k, grp)] = pw[2 * c];
+          s_p[paddr(M - k, grp)] = pw[2 * c + 1];
+        });
+        if (t == 0) s_p[paddr(M / 2, grp)] = pw[PPT];
+        __syncthreads();   // B2
+        {
+          const int warp = tid >> 5, lane = tid & 31;
+          const int f = lane & (FT - 1), h = lane / FT;
+          const bool ok = (t0 + f) < a.n_frames;
+          float wmax = -INFINITY;
+          for (int m = warp; m < a.n_mels; m += NW) {
+            const MelBand band = s_band[m];
+            const float* wrow = s_melw + band.off;
+            float acc = 0.0f;
+            for (int kx = h; kx < band.len; kx += H) {
+              const int k = band.lo + kx;
+              acc = fmaf(wrow[kx], s_p[paddr(k, f)], acc);
+            }
+#pragma unroll
+            for (int o = FT; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (a.log_mode) {
+              acc = 10.0f * log10f(fmaxf(a.amin, acc)) - a.db_sub;
+              if (ok) wmax = fmaxf(wmax, acc);
+            }
+            if (h == 0 && ok) a.out_r[((long long)clip * a.n_mels + m) * a.n_frames + t0 + f] = acc;
+          }
+          if (a.log_mode) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+            if (lane == 0 && wmax > -INFINITY) atomicMax(a.clip_max + clip, float_to_key(wmax));
+          }
+        }
+        __syncthreads();   // B3: P reads done before the next tile's exchange writes
+      }
+    }
+  }
+}
+
+}  // namespace b2l

@@ -1,0 +1,136 @@
+// inv_kernel.cuh — fused inverse real FFT + window + gather-form overlap-add + WOLA normalisation.
+//
+// Replaces librosa.istft's per-block  win * scipy.fft.irfft(D)  (librosa/core/spectrum.py:566, :598),
+// the numba __overlap_add loop (:629-643) and the window-sum-square division (:606-624).
+//
+// A CTA owns one (clip, segment of frames).  It walks its frames G at a time (one frame per thread
+// group): each group rebuilds the packed half-length spectrum from bin pairs (c2r_pair), runs the
+// same register FFT as the forward path with re/im swapped (== inverse transform), multiplies by
+// the window (which carries 1/n_fft) and parks the frame in its exchange region.  The CTA then
+// *gathers*: every output sample sums the frames that cover it in increasing frame order — the
+// order the reference adds them — plus the carry of the previous rounds, and is written exactly once,
+// already divided by the window-sum-square.  No atomics, bit-reproducible.
+#pragma once
+#include "common.cuh"
+#include "fft_engine.cuh"
+
+namespace b2l {
+
+template <int LOG2M, int TPF, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
+  using Cfg = FftCfg<LOG2M, TPF>;
+  constexpr int M = Cfg::M, N = 2 * M, PPT = Cfg::PPT;
+  constexpr int NT = NW * 32;
+  constexpr int G = NT / TPF;
+  constexpr int NPAIR = PPT / 2;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* s_win = reinterpret_cast<float*>(smem + a.off_win);
+  float2* s_tw = reinterpret_cast<float2*>(smem + a.off_tw);
+  float2* s_twn = reinterpret_cast<float2*>(smem + a.off_twn);
+  float2* s_xall = reinterpret_cast<float2*>(smem + a.off_xbuf);
+  float* s_carry = reinterpret_cast<float*>(smem + a.off_acc);   // two buffers of clen floats
+
+  const int tid = threadIdx.x;
+  const int grp = tid / TPF;
+  const int t = tid % TPF;
+  float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
+
+  for (int i = tid; i < N; i += NT) s_win[i] = a.window[i];
+  for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.tw[i];
+  for (int i = tid; i <= M / 2; i += NT) s_twn[i] = a.twn[i];
+  const int clen = a.n_fft > a.hop ? a.n_fft - a.hop : 0;
+  for (int i = tid; i < 2 * clen; i += NT) s_carry[i] = 0.0f;
+  __syncthreads();
+
+  const int clip = blockIdx.x / a.segs_per_clip;
+  const int seg = blockIdx.x % a.segs_per_clip;
+  const int fs = seg * a.frames_per_seg;
+  const int fe = min(a.n_frames, fs + a.frames_per_seg);
+  if (fs >= fe) return;
+  const bool last_seg = (fe == a.n_frames);
+  const int overlap = (a.n_fft + a.hop - 1) / a.hop;          // frames covering one sample
+  const int fh = max(0, fs - (overlap - 1));                  // halo frames rebuild the carry
+  const long long emit_lo = (long long)fs * a.hop;
+  const long long emit_hi = last_seg ? (1LL << 62) : (long long)fe * a.hop;
+
+  const float2* Dclip = a.D + (long long)clip * a.d_clip_stride;
+  float* yclip = a.y + (long long)clip * a.y_clip_stride;
+  float* carry_cur = s_carry;
+  float* carry_nxt = s_carry + clen;
+
+  int fr0 = fh;
+  for (; fr0 < fe; fr0 += G) {
+    const int frame = fr0 + grp;
+    if (frame < fe) {
+      // ---- bin pairs -> packed spectrum Z (re/im swapped for the inverse transform)
+      const float2* Drow = Dclip + (long long)frame * (M + 1);
+      static_for<0, NPAIR>([&](auto C) {
+        const int k = t + TPF * decltype(C)::value;
+        float2 xa = __ldg(Drow + k), xb = __ldg(Drow + M - k);
+        if (k == 0) { xa.y = 0.0f; xb.y = 0.0f; }    // irfft ignores Im of DC and Nyquist
+        float2 A, B;
+        c2r_pair(xa, xb, s_twn[k], A, B);
+        xbuf[xphys(k)] = make_float2(A.y, A.x);
+        if (k != 0) xbuf[xphys(M - k)] = make_float2(B.y, B.x);
+      });
+      if (t == 0) {
+        float2 xc = __ldg(Drow + M / 2), A, B;
+        c2r_pair(xc, xc, s_twn[M / 2], A, B);
+        xbuf[xphys(M / 2)] = make_float2(A.y, A.x);
+      }
+      group_sync<TPF>(grp);
+      float2 v[PPT];
+      load_pass0<Cfg>(v, t, [&](int e) { return xbuf[xphys(e)]; });
+      group_sync<TPF>(grp);           // operands fetched before the exchange area is overwritten
+      fft_forward<Cfg>(v, t, grp, xbuf, s_tw);
+      if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp);
+      // ---- un-swap, window (carries 1/n_fft), park the frame: ybuf[j], j = 0 .. n_fft-1
+      float2* ybuf = xbuf;
+      static_for<0, PPT>([&](auto S) {
+        constexpr int slot = decltype(S)::value;
+        const int e = spectrum_index<Cfg>(t, slot);
+        const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * e);
+        ybuf[e] = make_float2(v[slot].y * w.x, v[slot].x * w.y);
+      });
+    }
+    __syncthreads();
+
+    // ---- gather: emit positions [fr0*hop, (fr0+G)*hop), then rebuild the carry
+    const int ng = min(G, fe - fr0);                 // valid frames in this round
+    const long long u0 = (long long)fr0 * a.hop;
+    const int emit_n = G * a.hop;
+    for (int x = tid; x < emit_n + clen; x += NT) {
+      float val = (x < clen) ? carry_cur[x] : 0.0f;
+      int g_hi = x / a.hop;
+      if (g_hi > ng - 1) g_hi = ng - 1;
+      int g_lo = x - a.n_fft + 1;
+      g_lo = g_lo <= 0 ? 0 : (g_lo + a.hop - 1) / a.hop;
+      for (int g = g_lo; g <= g_hi; ++g) {
+        const float* yb = reinterpret_cast<const float*>(s_xall + g * Cfg::XBUF_F2);
+        val += yb[x - g * a.hop];
+      }
+      if (x < emit_n) {
+        const long long u = u0 + x;
+        const long long o = u - a.start;
+        if (u >= emit_lo && u < emit_hi && o >= 0 && o < a.out_len) yclip[o] = val * __ldg(a.inv_wss + o);
+      } else {
+        carry_nxt[x - emit_n] = val;
+      }
+    }
+    __syncthreads();
+    float* tmp = carry_cur; carry_cur = carry_nxt; carry_nxt = tmp;
+  }
+  // ---- flush: samples past the last round that only the carry reaches, then zero-fill the rest
+  if (last_seg) {
+    const long long u0 = (long long)fr0 * a.hop;     // fr0 == first frame index past the last round
+    for (int x = tid; x < clen; x += NT) {
+      const long long o = u0 + x - a.start;
+      if (o >= 0 && o < a.out_len) yclip[o] = carry_cur[x] * __ldg(a.inv_wss + o);
+    }
+    for (long long o = u0 + clen - a.start + tid; o < a.out_len; o += NT)
+      if (o >= 0) yclip[o] = 0.0f;
+  }
+}
+
+}  // namespace b2l

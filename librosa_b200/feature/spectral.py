@@ -1,0 +1,155 @@
+"""``melspectrogram`` and ``mfcc`` with librosa's signatures (reference:
+librosa/feature/spectral.py:2022-2161 and :1843-2019), fused on the GPU:
+
+* ``melspectrogram(y=...)`` is ONE kernel — frame, window, real FFT, ``|.|**power`` and the band-sparse
+  mel projection; the STFT and power spectrogram never exist in HBM;
+* ``mfcc(y=...)`` adds the dB conversion (per-clip ``top_db`` reference maximum) and the DCT.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import scipy.fft
+
+from .. import _native as nat
+from .. import _pipeline as pl
+from ..core.spectrum import power_to_db
+from ..util.exceptions import ParameterError
+
+_vp = C.c_void_p
+
+
+def _spec_to_device(ctx, S):
+    """Host/device spectrogram-like array (..., rows, frames) -> DeviceArray (C layout or native "ft")."""
+    if isinstance(S, nat.DeviceArray):
+        if S.dtype != np.float32:
+            raise ParameterError("device spectrogram must be float32")
+        return S, np.dtype(np.float32), True
+    S = np.asarray(S)
+    if np.iscomplexobj(S):
+        raise ParameterError("spectrogram input must be real")
+    req = pl.check_real_dtype(S.dtype if np.issubdtype(S.dtype, np.floating) else np.float32, "S")
+    return ctx.to_device(np.ascontiguousarray(S, dtype=np.float32)), req, False
+
+
+def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_length: int = 512,
+                   win_length: Optional[int] = None, window="hann", center: bool = True,
+                   pad_mode="constant", power: float = 2.0, **kwargs):
+    """Mel-scaled spectrogram, shape ``(..., n_mels, n_frames)``; same contract as
+    ``librosa.feature.melspectrogram``.  ``kwargs`` go to ``filters.mel`` (n_mels, fmin, fmax, htk, norm, dtype)."""
+    if S is not None:
+        # mel_basis . S for a caller-supplied spectrogram (feature/spectral.py:2158-2160)
+        ctx = S.ctx if isinstance(S, nat.DeviceArray) else nat.default_context()
+        Sd, req, on_device = _spec_to_device(ctx, S)
+        F, T = Sd.shape[-2], Sd.shape[-1]
+        if n_fft is None or n_fft // 2 + 1 != F:
+            n_fft = 2 * (F - 1)
+        basis, bkey = pl.mel_basis(sr, n_fft, kwargs)
+        plan = nat.make_plan(ctx, ("melproj", n_fft, bkey), n_fft=n_fft, hop_length=1, center=True,
+                             pad_mode="constant", window=np.ones(n_fft), mel_basis=basis)
+        lead = Sd.shape[:-2]
+        n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+        L = nat.lib()
+        if Sd.layout == "ft":
+            src = Sd
+        else:
+            src = nat.DeviceArray.empty(ctx, Sd.shape, np.float32, layout="ft")
+            nat.check(L.b2l_transpose(ctx.handle, _vp(Sd.ptr), n_clips, F, T, 4, _vp(src.ptr)))
+        out = nat.DeviceArray.empty(ctx, lead + (basis.shape[0], T), np.float32)
+        nat.check(L.b2l_mel_project(ctx.handle, plan.handle, _vp(src.ptr), n_clips, T, _vp(out.ptr)))
+        res = pl.finish(ctx, out, not on_device, np.result_type(req, basis.dtype))
+        if src is not Sd:
+            ctx.synchronize()
+            src.free()
+        return res
+    if n_fft is None:
+        raise ParameterError(f"Unable to compute spectrogram with n_fft={n_fft}")
+    if y is None:
+        raise ParameterError("Input signal must be provided to compute a spectrogram")
+    hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
+    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
+    staged = pl.StagedInput(ctx, y)
+    win, wkey = pl.resolve_window(window, win_length, n_fft)
+    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    basis, bkey = pl.mel_basis(sr, n_fft, kwargs)
+    key = ("mel", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power))
+    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
+                         mel_basis=basis, power=float(power))
+    T = plan.n_frames(staged.n)
+    out = nat.DeviceArray.empty(ctx, staged.lead + (basis.shape[0], T), np.float32)
+    nat.check(nat.lib().b2l_melspectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
+                                           staged.n, _vp(out.ptr)))
+    return pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype))
+
+
+def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float) -> np.ndarray:
+    """Rows 0..n_mfcc-1 of the DCT applied along the mel axis, as an explicit matrix, with the
+    sinusoidal lifter ``1 + (lifter/2) sin(pi (k+1) / lifter)`` folded in
+    (feature/spectral.py:2005-2015).  Built in float64 from scipy.fft.dct itself, so every
+    type / norm combination SciPy accepts is covered."""
+    basis = scipy.fft.dct(np.eye(n_mels, dtype=np.float64), axis=0, type=dct_type, norm=norm)[:n_mfcc]
+    if lifter > 0:
+        lift = 1 + (lifter / 2) * np.sin(np.pi * np.arange(1, 1 + basis.shape[0], dtype=np.float64) / lifter)
+        basis = basis * lift[:, np.newaxis]
+    return np.ascontiguousarray(basis, dtype=np.float32)
+
+
+def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int = 2, norm="ortho",
+         lifter: float = 0, mel_norm="slaney", **kwargs):
+    """Mel-frequency cepstral coefficients, shape ``(..., n_mfcc, n_frames)``; same contract as
+    ``librosa.feature.mfcc``."""
+    if not (lifter >= 0):   # also catches NaN, like the reference's final else-branch
+        raise ParameterError(f"MFCC lifter={lifter} must be a non-negative number")
+    if S is not None:
+        ctx = S.ctx if isinstance(S, nat.DeviceArray) else nat.default_context()
+        Sd, req, on_device = _spec_to_device(ctx, S)
+        if Sd.layout != "c":
+            raise ParameterError("device log-mel input must be C-ordered (..., n_mels, frames)")
+        n_mels, T = Sd.shape[-2], Sd.shape[-1]
+        dct = _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter)
+        plan = nat.make_plan(ctx, ("dct", n_mels, pl.digest(dct)), n_fft=8, hop_length=1, center=True,
+                             pad_mode="constant", window=np.ones(8),
+                             mel_basis=np.zeros((n_mels, 5), dtype=np.float32), dct_basis=dct)
+        lead = Sd.shape[:-2]
+        n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+        out = nat.DeviceArray.empty(ctx, lead + (dct.shape[0], T), np.float32)
+        nat.check(nat.lib().b2l_dct_project(ctx.handle, plan.handle, _vp(Sd.ptr), n_clips, T, _vp(out.ptr)))
+        return pl.finish(ctx, out, not on_device, req)
+    # y path: fused stft -> |.|^power -> mel -> dB (+ per-clip max), then clamp + DCT
+    n_fft = kwargs.pop("n_fft", 2048)
+    hop_length = kwargs.pop("hop_length", 512)
+    win_length = kwargs.pop("win_length", None)
+    window = kwargs.pop("window", "hann")
+    center = kwargs.pop("center", True)
+    pad_mode = kwargs.pop("pad_mode", "constant")
+    power = kwargs.pop("power", 2.0)
+    if n_fft is None:
+        raise ParameterError(f"Unable to compute spectrogram with n_fft={n_fft}")
+    if y is None:
+        raise ParameterError("Input signal must be provided to compute a spectrogram")
+    hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
+    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
+    staged = pl.StagedInput(ctx, y)
+    win, wkey = pl.resolve_window(window, win_length, n_fft)
+    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    mel_kwargs = dict(kwargs)
+    mel_kwargs["norm"] = mel_norm
+    basis, bkey = pl.mel_basis(sr, n_fft, mel_kwargs)
+    n_mels = basis.shape[0]
+    dct = _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter)
+    key = ("mfcc", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power), pl.digest(dct))
+    # power_to_db defaults used by mfcc: ref=1.0, amin=1e-10, top_db=80 (feature/spectral.py:2001)
+    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
+                         mel_basis=basis, power=float(power), dct_basis=dct, amin=1e-10, ref_value=1.0, top_db=80.0)
+    T = plan.n_frames(staged.n)
+    out = nat.DeviceArray.empty(ctx, staged.lead + (dct.shape[0], T), np.float32)
+    scratch = nat.DeviceArray.empty(ctx, (staged.n_clips, n_mels, T), np.float32)
+    nat.check(nat.lib().b2l_mfcc(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n, staged.n,
+                                 _vp(out.ptr), _vp(scratch.ptr)))
+    res = pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype))
+    if staged.on_device:
+        ctx.synchronize()
+    scratch.free()
+    return res

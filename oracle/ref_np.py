@@ -1,0 +1,391 @@
+"""CPU oracle: NumPy/SciPy restatement of librosa's stft / istft / melspectrogram / mfcc path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``librosa_b200/`` imports this module; it is used by
+``tests/``, by ``__graft_entry__.smoke()`` and by ``bench.py``'s CPU-baseline / ``--impl reference``
+legs as the checker and as the timed CPU port.  The product path is the CUDA library and fails
+loudly if it is missing.
+
+Parity status: PINNED.  Every function below is checked (a) against the unmodified reference
+imported from /root/reference in the build container (``tests/test_oracle_vs_reference.py``, via
+``tools/ref_shim.py``) and (b) against committed fixtures generated from that reference
+(``tests/golden/*.npz`` written by ``tools/make_golden.py``), which travel to the GPU box.
+
+The reference is pure Python; its arithmetic lives in third-party libraries that are not under
+/root/reference and are called here exactly as the reference calls them:
+``scipy.fft.rfft / irfft / dct`` (SciPy >= 1.15, ducc0 backend; this image: 1.18.1),
+``numpy.einsum`` -> OpenBLAS sgemm (NumPy >= 2.1; this image: 2.3.5) and
+``scipy.signal.get_window``.  ``numba`` (used by the reference only to JIT two serial loops)
+is not needed: the loops are restated with NumPy slices.
+
+Each function cites the reference lines it restates (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import scipy.fft
+import scipy.signal
+
+MAX_MEM_BLOCK = 2 ** 8 * 2 ** 10  # librosa/util/utils.py:41 (256 KiB column-block bound)
+
+
+class ParameterError(Exception):
+    """librosa/util/exceptions.py:11-15."""
+
+
+# --------------------------------------------------------------------------- small helpers
+def tiny(x):
+    """Smallest positive normal of x's dtype (librosa/util/utils.py:1935-2001)."""
+    x = np.asarray(x)
+    if np.issubdtype(x.dtype, np.floating) or np.issubdtype(x.dtype, np.complexfloating):
+        dtype = x.dtype
+    else:
+        dtype = np.dtype(np.float32)
+    return np.finfo(dtype).tiny
+
+
+def dtype_r2c(d, default=np.complex64):
+    """float32->complex64, float64->complex128 (librosa/util/utils.py:2362-2417)."""
+    mapping = {np.dtype(np.float32): np.complex64, np.dtype(np.float64): np.complex128}
+    dt = np.dtype(d)
+    if dt.kind == "c":
+        return dt
+    return np.dtype(mapping.get(dt, default))
+
+
+def dtype_c2r(d, default=np.float32):
+    """complex64->float32, complex128->float64 (librosa/util/utils.py:2420-2476)."""
+    mapping = {np.dtype(np.complex64): np.float32, np.dtype(np.complex128): np.float64}
+    dt = np.dtype(d)
+    if dt.kind == "f":
+        return dt
+    return np.dtype(mapping.get(dt, default))
+
+
+def pad_center(data, size, axis=-1):
+    """Zero-pad symmetrically, extra sample on the right (librosa/util/utils.py:436-458)."""
+    n = data.shape[axis]
+    left = int((size - n) // 2)
+    if left < 0:
+        raise ParameterError(f"Target size ({size}) must be at least input size ({n})")
+    widths = [(0, 0)] * data.ndim
+    widths[axis] = (left, int(size - n - left))
+    return np.pad(data, widths, mode="constant")
+
+
+def fix_length(data, size, axis=-1):
+    """Trim or zero-pad on the right to ``size`` (librosa/util/utils.py:570-588)."""
+    n = data.shape[axis]
+    if n > size:
+        sl = [slice(None)] * data.ndim
+        sl[axis] = slice(0, size)
+        return data[tuple(sl)]
+    if n < size:
+        widths = [(0, 0)] * data.ndim
+        widths[axis] = (0, size - n)
+        return np.pad(data, widths, mode="constant")
+    return data
+
+
+def frame(x, frame_length, hop_length):
+    """Strided view ``xf[..., k, j] = x[..., j*hop + k]`` (librosa/util/utils.py:210-242, axis=-1)."""
+    x = np.asarray(x)
+    if x.shape[-1] < frame_length:
+        raise ParameterError(f"Input is too short (n={x.shape[-1]}) for frame_length={frame_length}")
+    if hop_length < 1:
+        raise ParameterError(f"Invalid hop_length: {hop_length}")
+    n_frames = 1 + (x.shape[-1] - frame_length) // hop_length
+    s = x.strides[-1]
+    return np.lib.stride_tricks.as_strided(
+        x,
+        shape=x.shape[:-1] + (frame_length, n_frames),
+        strides=x.strides[:-1] + (s, s * hop_length),
+        writeable=False,
+    )
+
+
+def valid_audio(y):
+    """librosa/util/utils.py:294-308."""
+    if not isinstance(y, np.ndarray):
+        raise ParameterError("Audio data must be of type numpy.ndarray")
+    if not np.issubdtype(y.dtype, np.floating):
+        raise ParameterError("Audio data must be floating-point")
+    if y.ndim == 0:
+        raise ParameterError("Audio data must be at least one-dimensional")
+    if not np.isfinite(y).all():
+        raise ParameterError("Audio buffer is not finite everywhere")
+    return True
+
+
+def normalize(S, norm=np.inf, axis=0):
+    """Row/column normalisation, default threshold/fill (librosa/util/utils.py:797-1026)."""
+    S = np.asarray(S)
+    mag = np.abs(S).astype(float)
+    thresh = tiny(S)
+    if norm is None:
+        return S
+    if norm == np.inf:
+        length = mag.max(axis=axis, keepdims=True)
+    elif norm == -np.inf:
+        length = mag.min(axis=axis, keepdims=True)
+    elif norm == 0:
+        length = (mag > 0).sum(axis=axis, keepdims=True).astype(mag.dtype)
+    elif np.issubdtype(type(norm), np.number) and norm > 0:
+        length = (mag ** norm).sum(axis=axis, keepdims=True) ** (1.0 / norm)
+    else:
+        raise ParameterError(f"Unsupported norm: {norm!r}")
+    small = length < thresh
+    out = np.empty_like(S)
+    length = np.where(small, 1.0, length)
+    out[:] = S / length
+    return out
+
+
+# --------------------------------------------------------------------------- filters
+def get_window(window, Nx, fftbins=True):
+    """librosa/filters.py:961-977."""
+    if callable(window):
+        return window(Nx)
+    if isinstance(window, (str, tuple)) or np.isscalar(window):
+        return scipy.signal.get_window(window, Nx, fftbins=fftbins)
+    if isinstance(window, (np.ndarray, list)):
+        if len(window) == Nx:
+            return np.asarray(window)
+        raise ParameterError(f"Window size mismatch: {len(window)} != {Nx}")
+    raise ParameterError(f"Invalid window specification: {window!r}")
+
+
+def hz_to_mel(f, htk=False):
+    """librosa/core/convert.py:1032-1058 (Slaney: linear below 1 kHz, log above)."""
+    f = np.asanyarray(f, dtype=float)
+    if htk:
+        return 2595.0 * np.log10(1.0 + f / 700.0)
+    f_sp = 200.0 / 3
+    brk_hz = 1000.0
+    brk_mel = brk_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    lin = f / f_sp
+    with np.errstate(divide="ignore", invalid="ignore"):
+        log = brk_mel + np.log(np.maximum(f, 1e-300) / brk_hz) / logstep
+    return np.where(f >= brk_hz, log, lin)[()]
+
+
+def mel_to_hz(m, htk=False):
+    """librosa/core/convert.py:1098-1121."""
+    m = np.asanyarray(m, dtype=float)
+    if htk:
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    f_sp = 200.0 / 3
+    brk_hz = 1000.0
+    brk_mel = brk_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= brk_mel, brk_hz * np.exp(logstep * (m - brk_mel)), f_sp * m)[()]
+
+
+def mel_frequencies(n_mels=128, fmin=0.0, fmax=11025.0, htk=False):
+    """librosa/core/convert.py:1500-1508."""
+    lo = hz_to_mel(fmin, htk=htk)
+    hi = hz_to_mel(fmax, htk=htk)
+    return mel_to_hz(np.linspace(lo, hi, n_mels), htk=htk)
+
+
+def fft_frequencies(sr=22050, n_fft=2048):
+    """librosa/core/convert.py:1369 (np.fft.rfftfreq)."""
+    return np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+
+
+def mel(sr, n_fft, n_mels=128, fmin=0.0, fmax=None, htk=False, norm="slaney", dtype=np.float32):
+    """Triangular mel filterbank (librosa/filters.py:206-251)."""
+    if fmax is None:
+        fmax = float(sr) / 2
+    n_mels = int(n_mels)
+    W = np.zeros((n_mels, 1 + n_fft // 2), dtype=dtype)
+    bins = fft_frequencies(sr=sr, n_fft=n_fft)
+    edges = mel_frequencies(n_mels + 2, fmin=fmin, fmax=fmax, htk=htk)
+    width = np.diff(edges)
+    ramps = np.subtract.outer(edges, bins)
+    for i in range(n_mels):
+        rising = -ramps[i] / width[i]
+        falling = ramps[i + 2] / width[i + 1]
+        W[i] = np.maximum(0, np.minimum(rising, falling))  # stored in `dtype` before scaling
+    if isinstance(norm, str):
+        if norm != "slaney":
+            raise ParameterError(f"Unsupported norm={norm}")
+        W *= (2.0 / (edges[2 : n_mels + 2] - edges[:n_mels]))[:, np.newaxis]
+    else:
+        W = normalize(W, norm=norm, axis=-1)
+    if not np.all((edges[:-2] == 0) | (W.max(axis=1) > 0)):
+        warnings.warn("Empty filters detected in mel frequency basis.", stacklevel=2)
+    return W
+
+
+def window_sumsquare(window, n_frames, hop_length=512, win_length=None, n_fft=2048,
+                     dtype=np.float32, norm=None):
+    """librosa/filters.py:1325-1339 with the numba fill loop of :1258-1265 restated."""
+    if win_length is None:
+        win_length = n_fft
+    n = n_fft + hop_length * (n_frames - 1)
+    x = np.zeros(n, dtype=dtype)
+    wsq = get_window(window, win_length)
+    wsq = normalize(wsq, norm=norm) ** 2
+    wsq = pad_center(wsq, n_fft)
+    for i in range(n_frames):
+        s = i * hop_length
+        x[s : min(n, s + n_fft)] += wsq[: max(0, min(n_fft, n - s))]
+    return x
+
+
+# --------------------------------------------------------------------------- stft / istft
+_BAD_PAD = ("wrap", "maximum", "mean", "median", "minimum")
+
+
+def stft(y, n_fft=2048, hop_length=None, win_length=None, window="hann", center=True,
+         dtype=None, pad_mode="constant"):
+    """Short-time Fourier transform, restating librosa/core/spectrum.py:231-391.
+
+    The reference pads only the head and tail chunks (:273-328); SURVEY Appendix A.2 verified
+    that this equals framing ``np.pad(y, n_fft//2, mode)`` — which is what is done here.  The
+    float64 window product, the double-precision rfft, the rounding to ``dtype`` on store, the
+    Fortran-ordered output and the MAX_MEM_BLOCK column blocking (:380-390) are kept because they
+    determine both the numerics and the CPU cost.
+    """
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    elif not (isinstance(hop_length, (int, np.integer)) and hop_length > 0):
+        raise ParameterError(f"hop_length={hop_length} must be a positive integer")
+    valid_audio(y)
+    win = pad_center(get_window(window, win_length, fftbins=True), n_fft)
+    win = win.reshape((1,) * (y.ndim - 1) + (n_fft, 1))
+    if center:
+        if pad_mode in _BAD_PAD:
+            raise ParameterError(f"pad_mode='{pad_mode}' is not supported by librosa.stft")
+        if n_fft > y.shape[-1]:
+            warnings.warn(f"n_fft={n_fft} is too large for input signal of length={y.shape[-1]}",
+                          stacklevel=2)
+        widths = [(0, 0)] * (y.ndim - 1) + [(n_fft // 2, n_fft // 2)]
+        y = np.pad(y, widths, mode=pad_mode)
+    elif n_fft > y.shape[-1]:
+        raise ParameterError(f"n_fft={n_fft} is too large for uncentered analysis of input "
+                             f"signal of length={y.shape[-1]}")
+    if dtype is None:
+        dtype = dtype_r2c(y.dtype)
+    frames = frame(y, n_fft, hop_length)
+    shape = list(frames.shape)
+    shape[-2] = 1 + n_fft // 2
+    D = np.zeros(shape, dtype=dtype, order="F")
+    cols = max(int(MAX_MEM_BLOCK // (np.prod(frames.shape[:-1]) * frames.itemsize)), 1)
+    for s in range(0, frames.shape[-1], cols):
+        t = min(s + cols, frames.shape[-1])
+        D[..., s:t] = scipy.fft.rfft(win * frames[..., s:t], axis=-2)
+    return D
+
+
+def istft(D, hop_length=None, win_length=None, n_fft=None, window="hann", center=True,
+          dtype=None, length=None):
+    """Inverse STFT with least-squares WOLA normalisation, restating
+    librosa/core/spectrum.py:506-626 and the overlap-add loop of :629-643.
+
+    The head-block special case (:557-582) only avoids a padded copy; overlap-adding every frame
+    into a buffer of the untrimmed length and slicing ``n_fft//2`` off the front gives the same
+    sums in the same order per sample (frames are added in increasing frame index in both).
+    """
+    if n_fft is None:
+        n_fft = 2 * (D.shape[-2] - 1)
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    win = pad_center(get_window(window, win_length, fftbins=True), n_fft)
+    win = win.reshape((1,) * (D.ndim - 2) + (n_fft, 1))
+    if length:
+        padded = length + 2 * (n_fft // 2) if center else length
+        n_frames = min(D.shape[-1], int(np.ceil(padded / hop_length)))
+    else:
+        n_frames = D.shape[-1]
+    if dtype is None:
+        dtype = dtype_c2r(D.dtype)
+    full_len = n_fft + hop_length * (n_frames - 1)
+    if length:
+        out_len = length
+    elif center:
+        out_len = full_len - 2 * (n_fft // 2)
+    else:
+        out_len = full_len
+    lead = list(D.shape[:-2])
+    start = n_fft // 2 if center else 0
+    buf = np.zeros(lead + [max(full_len, start + out_len)], dtype=dtype)
+    cols = max(int(MAX_MEM_BLOCK // (np.prod(D.shape[:-1]) * D.itemsize)), 1)
+    limit = start + out_len  # samples at or beyond this are never kept (:639-641 clipping)
+    for s in range(0, n_frames, cols):
+        t = min(s + cols, n_frames)
+        ytmp = win * scipy.fft.irfft(D[..., s:t], n=n_fft, axis=-2)
+        for j in range(t - s):
+            a = (s + j) * hop_length
+            n = min(n_fft, limit - a)
+            if n > 0:
+                buf[..., a : a + n] += ytmp[..., :n, j]
+    y = np.ascontiguousarray(buf[..., start : start + out_len])
+    wss = window_sumsquare(window, n_frames, hop_length=hop_length, win_length=win_length,
+                           n_fft=n_fft, dtype=dtype)
+    wss = fix_length(wss[start:], out_len)
+    nz = wss > tiny(wss)
+    y[..., nz] /= wss[nz]
+    return y
+
+
+# --------------------------------------------------------------------------- features
+def spectrogram(y, n_fft=2048, hop_length=512, power=1.0, win_length=None, window="hann",
+                center=True, pad_mode="constant"):
+    """``|stft|**power`` (librosa/core/spectrum.py:3000-3013)."""
+    return np.abs(stft(y, n_fft=n_fft, hop_length=hop_length, win_length=win_length,
+                       window=window, center=center, pad_mode=pad_mode)) ** power
+
+
+def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0):
+    """librosa/core/spectrum.py:1839-1883 for real input, scalar or callable ``ref``,
+    ``axes='auto'`` (reduce over the last two axes, per leading index)."""
+    S = np.asarray(S)
+    if amin <= 0:
+        raise ParameterError("amin must be strictly positive")
+    mag = np.abs(S) if np.iscomplexobj(S) else S
+    axes = (-2, -1) if mag.ndim >= 2 else ((-1,) if mag.ndim == 1 else None)
+    ref_value = ref(mag, axis=axes, keepdims=True) if callable(ref) else np.abs(ref)
+    out = 10.0 * np.log10(np.maximum(amin, mag))
+    out -= 10.0 * np.log10(np.maximum(amin, ref_value))
+    if top_db is not None:
+        if top_db < 0:
+            raise ParameterError("top_db must be non-negative")
+        out = np.maximum(out, out.max(axis=axes, keepdims=True) - top_db)
+    return out[()]
+
+
+def melspectrogram(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None,
+                   window="hann", center=True, pad_mode="constant", power=2.0, **mel_kwargs):
+    """librosa/feature/spectral.py:2145-2161."""
+    if S is None:
+        S = spectrogram(y, n_fft=n_fft, hop_length=hop_length, power=power,
+                        win_length=win_length, window=window, center=center, pad_mode=pad_mode)
+    else:
+        if n_fft is None or n_fft // 2 + 1 != S.shape[-2]:
+            n_fft = 2 * (S.shape[-2] - 1)
+    basis = mel(sr=sr, n_fft=n_fft, **mel_kwargs)
+    return np.einsum("...ft,mf->...mt", S, basis, optimize=True)
+
+
+def mfcc(y=None, sr=22050, S=None, n_mfcc=20, dct_type=2, norm="ortho", lifter=0,
+         mel_norm="slaney", **kwargs):
+    """librosa/feature/spectral.py:1999-2019."""
+    if S is None:
+        S = power_to_db(melspectrogram(y=y, sr=sr, norm=mel_norm, **kwargs))
+    M = scipy.fft.dct(S, axis=-2, type=dct_type, norm=norm)[..., :n_mfcc, :]
+    if lifter > 0:
+        li = np.sin(np.pi * np.arange(1, 1 + n_mfcc, dtype=M.dtype) / lifter)
+        li = li.reshape((1,) * (S.ndim - 2) + (n_mfcc, 1))
+        M *= 1 + (lifter / 2) * li
+        return M
+    if lifter == 0:
+        return M
+    raise ParameterError(f"MFCC lifter={lifter} must be a non-negative number")
