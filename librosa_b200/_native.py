@@ -159,17 +159,22 @@ class Context:
         self.device = int(device)
         self._plans = {}
         self._wss = {}
-        self._finalizer = weakref.finalize(self, Context._destroy, self._h, self._plans, self._wss)
+        self._pool = {}
+        self._sizes = {}
+        self._pooled_bytes = 0
+        self.pool_limit_bytes = int(os.environ.get("B2L_POOL_LIMIT_MB", "65536")) << 20
+        self._finalizer = weakref.finalize(self, Context._destroy, self._h, self._plans, self._wss, self._sizes)
 
     @staticmethod
-    def _destroy(h, plans, wss):
+    def _destroy(h, plans, wss, sizes):
         try:
             L = lib()
             for p in plans.values():
                 L.b2l_plan_destroy(p.handle)
             plans.clear()
-            for arr in wss.values():
-                L.b2l_free(h, arr)
+            for ptr in list(sizes):
+                L.b2l_free(h, _vp(ptr))
+            sizes.clear()
             wss.clear()
             L.b2l_ctx_destroy(h)
         except Exception:  # pragma: no cover - interpreter shutdown
@@ -199,15 +204,47 @@ class Context:
         check(lib().b2l_mem_info(self._h, C.byref(f), C.byref(t)))
         return int(f.value), int(t.value)
 
-    # ---- memory
+    # ---- memory: a size-keyed free list in front of cudaMalloc / cudaFree.  All work of a context is
+    # ordered on one stream, so handing a released block to the next request is safe without a sync;
+    # it keeps multi-GB cudaMalloc / cudaFree calls (milliseconds each) out of steady-state loops.
+    _POOL_QUANTUM = 512
+
     def alloc(self, nbytes: int) -> int:
+        size = (max(int(nbytes), 1) + self._POOL_QUANTUM - 1) // self._POOL_QUANTUM * self._POOL_QUANTUM
+        bucket = self._pool.get(size)
+        if bucket:
+            self._pooled_bytes -= size
+            return bucket.pop()
         p = _vp()
-        check(lib().b2l_alloc(self._h, int(nbytes), C.byref(p)))
+        status = lib().b2l_alloc(self._h, size, C.byref(p))
+        if status == B2L_ERR_OOM and self._pooled_bytes:
+            self.empty_cache()
+            status = lib().b2l_alloc(self._h, size, C.byref(p))
+        check(status)
+        self._sizes[p.value] = size
         return p.value
 
     def free(self, ptr: int):
-        if ptr:
+        if not ptr:
+            return
+        size = self._sizes.get(ptr)
+        if size is None:   # not ours (or already trimmed): release for real
             check(lib().b2l_free(self._h, _vp(ptr)))
+            return
+        self._pool.setdefault(size, []).append(ptr)
+        self._pooled_bytes += size
+        if self._pooled_bytes > self.pool_limit_bytes:
+            self.empty_cache()
+
+    def empty_cache(self):
+        """Return every pooled block to the driver."""
+        L = lib()
+        for size, bucket in self._pool.items():
+            for ptr in bucket:
+                self._sizes.pop(ptr, None)
+                L.b2l_free(self._h, _vp(ptr))
+        self._pool.clear()
+        self._pooled_bytes = 0
 
     def empty(self, shape, dtype, layout: str = "c") -> "DeviceArray":
         return DeviceArray.empty(self, shape, dtype, layout=layout)
@@ -283,7 +320,7 @@ class DeviceArray:
     @staticmethod
     def _release(ctx, ptr):
         try:
-            lib().b2l_free(ctx.handle, _vp(ptr))
+            ctx.free(ptr)
         except Exception:  # pragma: no cover
             pass
 

@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
 
   int fr0 = fh;
   for (; fr0 < fe; fr0 += G) {
-    const int frame = fr0 + grp;
-    if (frame < fe) {
+    // Every group transforms a frame in every round (groups past the end redo the last frame and are
+    // ignored by the gather): sub-warp groups share a warp, so skipping would diverge at __syncwarp.
+    const int frame = min(fr0 + grp, fe - 1);
+    {
       // ---- bin pairs -> packed spectrum Z (re/im swapped for the inverse transform)
       const float2* Drow = Dclip + (long long)frame * (M + 1);
       static_for<0, NPAIR>([&](auto C) {
