@@ -109,24 +109,50 @@ def check_stft_geometry(n: int, n_fft: int, center: bool, pad_mode):
     return pad_mode if (center and isinstance(pad_mode, str)) else "constant"
 
 
+def precheck_signal(y):
+    """Host-side validation of an input signal, done before any GPU resource is touched so that
+    argument errors surface exactly as in the reference (util.valid_audio, core/spectrum.py:240).
+    Returns ``(length, requested dtype)``."""
+    if isinstance(y, nat.DeviceArray):
+        if y.dtype != np.float32 or y.layout != "c":
+            raise ParameterError("device input must be a C-ordered float32 DeviceArray")
+        if y.ndim == 0:
+            raise ParameterError("Audio data must be at least one-dimensional")
+        return y.shape[-1], np.dtype(np.float32)
+    valid_audio(y)
+    return y.shape[-1], check_real_dtype(y.dtype, "input signal")
+
+
+MIN_N_FFT, MAX_N_FFT = 8, 4096   # kMinLog2M / kMaxLog2M in csrc/internal.h
+
+
+def require_supported_n_fft(n_fft: int):
+    """The sm_100a kernels are built for power-of-two n_fft in [8, 4096]; anything else librosa accepts
+    (e.g. the reference tests' 501 / 1023 / 1025) is refused loudly — there is no CPU fallback."""
+    n_fft = int(n_fft)
+    if n_fft < MIN_N_FFT or n_fft > MAX_N_FFT or (n_fft & (n_fft - 1)):
+        raise nat.UnsupportedOnGPU(
+            f"n_fft={n_fft}: the sm_100a kernels are built for powers of two from {MIN_N_FFT} to {MAX_N_FFT} "
+            "(no CPU fallback)")
+
+
+def context_for(x):
+    return x.ctx if isinstance(x, nat.DeviceArray) else nat.default_context()
+
+
 class StagedInput:
-    """A batch of clips resident on the device as ``[n_clips][n]`` float32."""
+    """A batch of clips resident on the device as ``[n_clips][n]`` float32 (call precheck_signal first)."""
 
     def __init__(self, ctx, y):
         self.ctx = ctx
         if isinstance(y, nat.DeviceArray):
-            if y.dtype != np.float32 or y.layout != "c":
-                raise ParameterError("device input must be a C-ordered float32 DeviceArray")
-            if y.ndim == 0:
-                raise ParameterError("Audio data must be at least one-dimensional")
             if y.ctx is not ctx:
                 raise ParameterError("DeviceArray belongs to a different context")
             self.dev = y
             self.on_device = True
             self.req_dtype = np.dtype(np.float32)
         else:
-            valid_audio(y)
-            self.req_dtype = check_real_dtype(y.dtype, "input signal")
+            self.req_dtype = np.dtype(y.dtype)
             host = np.ascontiguousarray(y, dtype=np.float32)
             self.dev = nat.DeviceArray.empty(ctx, host.shape, np.float32)
             if host.nbytes:

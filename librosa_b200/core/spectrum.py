@@ -22,13 +22,6 @@ from ..util.utils import dtype_c2r, dtype_r2c, fix_length, tiny
 _vp = C.c_void_p
 
 
-def _stft_plan(ctx, n_fft, hop_length, center, pad_mode, window, win_length):
-    win, wkey = pl.resolve_window(window, win_length, n_fft)
-    key = ("stft", n_fft, hop_length, bool(center), pad_mode, wkey)
-    return nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=pad_mode,
-                         window=win)
-
-
 def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: Optional[int] = None,
          window="hann", center: bool = True, dtype=None, pad_mode="constant", out=None):
     """Short-time Fourier transform; same contract as ``librosa.stft`` (core/spectrum.py:58-391).
@@ -37,22 +30,19 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
     memory is ``[..., frame, bin]`` — for a 1-D signal that is the Fortran order librosa returns.
     """
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
-    staged = pl.StagedInput(ctx, y)
-    # window first (its errors precede the padding checks in the reference)
+    # host-side validation in the reference's order (valid_audio, window, padding), before any GPU work
+    n, req_dtype = pl.precheck_signal(y)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
-    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     if dtype is None:
-        dtype = dtype_r2c(staged.req_dtype)
+        dtype = dtype_r2c(req_dtype)
     dtype = np.dtype(dtype)
     if dtype != np.complex64 and not (dtype.kind == "c" and pl.float64_policy() == "downcast"):
         raise nat.UnsupportedOnGPU(f"stft dtype={dtype}: only complex64 is computed on the GPU "
                                    "(set B2L_FLOAT64=downcast to get float32 results in a wider dtype)")
-    key = ("stft", n_fft, hop_length, bool(center), mode, wkey)
-    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win)
-    T = plan.n_frames(staged.n)
     F = 1 + n_fft // 2
-    shape = staged.lead + (F, T)
+    T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length   # Appendix A.1 frame count
+    shape = tuple(y.shape[:-1]) + (F, T)
     if out is not None:
         if isinstance(out, nat.DeviceArray):
             raise ParameterError("out= must be a NumPy array")
@@ -61,6 +51,12 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
                                  f"target shape={list(shape)}")
         if not np.iscomplexobj(out):
             raise ParameterError(f"output with dtype={out.dtype} is not of complex type")
+    pl.require_supported_n_fft(n_fft)
+    ctx = pl.context_for(y)
+    staged = pl.StagedInput(ctx, y)
+    key = ("stft", n_fft, hop_length, bool(center), mode, wkey)
+    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win)
+    assert plan.n_frames(staged.n) == T
     D = nat.DeviceArray.empty(ctx, shape, np.complex64, layout="ft")
     nat.check(nat.lib().b2l_stft(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n, staged.n,
                                  _vp(D.ptr)))
@@ -145,6 +141,7 @@ def istft(stft_matrix, *, hop_length: Optional[int] = None, win_length: Optional
             raise ParameterError("out= must be a NumPy array")
         if tuple(out.shape) != shape:
             raise ParameterError(f"Shape mismatch for provided output array out.shape={out.shape} != {list(shape)}")
+    pl.require_supported_n_fft(n_fft)
     ctx = stft_matrix.ctx if on_device else nat.default_context()
     n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
     key = ("stft", n_fft, hop_length, bool(center), "constant", wkey)
@@ -208,10 +205,12 @@ def _spectrogram(*, y=None, S=None, n_fft: Optional[int] = 2048, hop_length: Opt
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
-    staged = pl.StagedInput(ctx, y)
+    n, _ = pl.precheck_signal(y)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
-    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
+    pl.require_supported_n_fft(n_fft)
+    ctx = pl.context_for(y)
+    staged = pl.StagedInput(ctx, y)
     key = ("spec", n_fft, hop_length, bool(center), mode, wkey, float(power))
     plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
                          power=float(power))

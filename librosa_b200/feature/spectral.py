@@ -69,11 +69,13 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
-    staged = pl.StagedInput(ctx, y)
+    n, _ = pl.precheck_signal(y)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
-    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     basis, bkey = pl.mel_basis(sr, n_fft, kwargs)
+    pl.require_supported_n_fft(n_fft)
+    ctx = pl.context_for(y)
+    staged = pl.StagedInput(ctx, y)
     key = ("mel", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power))
     plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
                          mel_basis=basis, power=float(power))
@@ -130,15 +132,17 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    ctx = y.ctx if isinstance(y, nat.DeviceArray) else nat.default_context()
-    staged = pl.StagedInput(ctx, y)
+    n, _ = pl.precheck_signal(y)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
-    mode = pl.check_stft_geometry(staged.n, n_fft, center, pad_mode)
+    mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     mel_kwargs = dict(kwargs)
     mel_kwargs["norm"] = mel_norm
     basis, bkey = pl.mel_basis(sr, n_fft, mel_kwargs)
     n_mels = basis.shape[0]
     dct = _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter)
+    pl.require_supported_n_fft(n_fft)
+    ctx = pl.context_for(y)
+    staged = pl.StagedInput(ctx, y)
     key = ("mfcc", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power), pl.digest(dct))
     # power_to_db defaults used by mfcc: ref=1.0, amin=1e-10, top_db=80 (feature/spectral.py:2001)
     plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,

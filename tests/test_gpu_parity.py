@@ -1,0 +1,316 @@
+"""GPU (-m gpu): the CUDA path, called through the public drop-in API (ctypes -> C ABI -> sm_100a
+kernels), against the oracle on identical inputs and against the fixtures produced by the unmodified
+reference.  Nothing here reads /root/reference.
+
+Stated tolerances (north_star: float32, rtol 1e-4; SURVEY §8d for the atol terms — the reference runs its
+forward FFT in float64, the GPU in float32, so near-zero bins need an absolute term relative to max|ref|):
+    stft            rtol 1e-4, atol 1e-5 * max|ref|
+    melspectrogram  rtol 1e-4, atol 1e-6 * max|ref|
+    mfcc            rtol 1e-4, atol 1e-3 (dB-domain values up to ~1e2)
+    istft           atol 1e-5 * max|ref| on the un-normalised overlap-add (see _istft_close), SNR >= 60 dB
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from cases import BY_NAME, CASES
+from conftest import case_input
+
+pytestmark = pytest.mark.gpu
+
+TOL = {
+    "stft": dict(rtol=1e-4, atol_rel=1e-5),
+    "mel": dict(rtol=1e-4, atol_rel=1e-6),
+    "mfcc": dict(rtol=1e-4, atol_abs=1e-3),
+    "istft": dict(rtol=1e-4, atol_rel=1e-5),
+}
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import librosa_b200
+
+    librosa_b200.default_context()   # fails loudly if the library or the GPU is missing
+    return librosa_b200
+
+
+def close(got, ref, rtol, atol_rel=None, atol_abs=None):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert got.dtype == ref.dtype, (got.dtype, ref.dtype)
+    atol = atol_abs if atol_abs is not None else atol_rel * float(np.abs(ref).max() if ref.size else 0.0)
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+
+
+def _istft_close(O, got, ref, case_kw, n_fft, T):
+    """istft divides by the window-sum-square, which tends to 0 at the ends when center=False; there the
+    quotient of two roundings is ill-conditioned in the reference itself.  Compare the un-normalised
+    overlap-add (y * wss) — identical to comparing y wherever wss is O(1)."""
+    kw = dict(case_kw)
+    center = kw.get("center", True)
+    hop = kw.get("hop_length") or int((kw.get("win_length") or n_fft) // 4)
+    wss = O.window_sumsquare(kw.get("window", "hann"), T, hop_length=hop, win_length=kw.get("win_length"), n_fft=n_fft)
+    start = n_fft // 2 if center else 0
+    wss = O.fix_length(wss[start:], ref.shape[-1])
+    w = np.where(wss > O.tiny(wss), wss, 1.0)
+    close(got * w, ref * w, **TOL["istft"])
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+
+
+def run_gpu(lb, case, golden):
+    kw = dict(case["kw"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if case["op"] == "istft":
+            return lb.istft(golden[case["src"]], **kw)
+        y = case_input(case)
+        if case["op"] == "stft":
+            return lb.stft(y, **kw)
+        if case["op"] == "mel":
+            return lb.feature.melspectrogram(y=y, **kw)
+        if case["op"] == "mfcc":
+            return lb.feature.mfcc(y=y, **kw)
+    raise ValueError(case["op"])
+
+
+def run_oracle(O, case, golden):
+    kw = dict(case["kw"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if case["op"] == "istft":
+            return O.istft(golden[case["src"]], **kw)
+        y = case_input(case)
+        return {"stft": lambda: O.stft(y, **kw), "mel": lambda: O.melspectrogram(y=y, **kw),
+                "mfcc": lambda: O.mfcc(y=y, **kw)}[case["op"]]()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_case_against_oracle_and_reference_fixture(case, lb, oracle, golden):
+    if case.get("gpu") == "unsupported":
+        with pytest.raises(lb.UnsupportedOnGPU):
+            run_gpu(lb, case, golden)
+        return
+    got = run_gpu(lb, case, golden)
+    want = run_oracle(oracle, case, golden)
+    fixture = golden[case["name"]]
+    if case["op"] == "istft":
+        D = golden[case["src"]]
+        n_fft = 2 * (D.shape[-2] - 1)
+        T = D.shape[-1]
+        length = case["kw"].get("length")
+        if length:
+            center = case["kw"].get("center", True)
+            hop = case["kw"].get("hop_length") or n_fft // 4
+            T = min(T, int(np.ceil((length + (2 * (n_fft // 2) if center else 0)) / hop)))
+        _istft_close(oracle, got, want, case["kw"], n_fft, T)
+        _istft_close(oracle, got, fixture, case["kw"], n_fft, T)
+    else:
+        close(got, want, **TOL[case["op"]])
+        close(got, fixture, **TOL[case["op"]])
+
+
+# ------------------------------------------------------------------ API behaviour on the device path
+def test_stft_layout_and_out(lb, oracle):
+    import signals
+
+    y = signals.make("A", (9000,), seed=1)
+    D = lb.stft(y)
+    assert D.shape == (1025, 18) and D.dtype == np.complex64
+    assert D.flags.f_contiguous                      # same memory order as the reference (spectrum.py:356)
+    out = np.zeros((1025, 30), dtype=np.complex64)   # oversize out -> prefix slice, returned by identity of base
+    res = lb.stft(y, out=out)
+    assert res.base is out or res is out
+    np.testing.assert_array_equal(res, D)
+    np.testing.assert_array_equal(out[:, 18:], 0)
+    exact = np.zeros((1025, 18), dtype=np.complex64, order="F")
+    assert lb.stft(y, out=exact) is exact
+    yo = np.zeros(512 * (D.shape[1] - 1), dtype=np.float32)   # default istft length: hop * (T - 1)
+    assert lb.istft(D, out=yo) is yo
+    close(yo, oracle.istft(D), **TOL["istft"])
+
+
+def test_multichannel_equals_per_channel(lb):
+    import signals
+
+    y = signals.make("C", (2, 3, 9000), seed=21)
+    for fn, kw in [(lb.stft, {}), (lambda y, **k: lb.feature.melspectrogram(y=y, **k), dict(sr=22050)),
+                   (lambda y, **k: lb.feature.mfcc(y=y, **k), dict(sr=22050, n_mfcc=13))]:
+        full = fn(y, **kw)
+        for i in range(2):
+            for j in range(3):
+                np.testing.assert_array_equal(full[i, j], fn(y[i, j], **kw))   # bit-identical: same kernel, same data
+
+
+def test_device_resident_chain(lb, oracle):
+    import signals
+
+    y = signals.make("A", (4, 30000), seed=5)
+    d = lb.to_device(y)
+    D = lb.stft(d, n_fft=1024, hop_length=256)
+    assert isinstance(D, lb.DeviceArray) and D.shape == (4, 513, 118) and D.layout == "ft"
+    yr = lb.istft(D, hop_length=256, length=30000)
+    assert isinstance(yr, lb.DeviceArray)
+    back = yr.get()
+    snr = 10 * np.log10((y.astype(np.float64) ** 2).sum() / ((y - back).astype(np.float64) ** 2).sum())
+    assert snr >= 60.0, snr
+    close(D.get(), oracle.stft(y, n_fft=1024, hop_length=256), **TOL["stft"])
+    M = lb.feature.melspectrogram(y=d, sr=22050, n_fft=1024, hop_length=256)
+    close(M.get(), oracle.melspectrogram(y=y, sr=22050, n_fft=1024, hop_length=256), **TOL["mel"])
+
+
+def test_s_inputs_and_power_to_db(lb, oracle, golden):
+    rng = np.random.default_rng(3)
+    S = (np.abs(rng.standard_normal((2, 1025, 40))) ** 2).astype(np.float32)
+    close(lb.feature.melspectrogram(S=S, sr=22050), oracle.melspectrogram(S=S, sr=22050), **TOL["mel"])
+    Sp = golden["const/power_to_db_in"]
+    close(lb.power_to_db(Sp), golden["const/power_to_db_out"], rtol=1e-5, atol_abs=1e-4)
+    close(lb.power_to_db(Sp, ref=np.max), golden["const/power_to_db_out_refmax"], rtol=1e-5, atol_abs=1e-4)
+    close(lb.power_to_db(Sp, top_db=40.0), golden["const/power_to_db_out_top40"], rtol=1e-5, atol_abs=1e-4)
+    assert abs(float(lb.power_to_db(np.float32(2.0))) - 3.0103) < 1e-3
+    L = oracle.power_to_db((np.abs(rng.standard_normal((2, 128, 50))) ** 2).astype(np.float32))
+    close(lb.feature.mfcc(S=L, n_mfcc=20), oracle.mfcc(S=L, n_mfcc=20), **TOL["mfcc"])
+    Sg, n_fft = lb._spectrogram(y=(0.1 * rng.standard_normal(8000)).astype(np.float32), n_fft=1024, hop_length=256, power=2.0)
+    assert n_fft == 1024 and Sg.shape == (513, 32)
+
+
+def test_ragged_and_edge_shapes(lb, oracle):
+    import signals
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for n, n_fft, hop in [(1, 8, 2), (7, 16, 1), (2048, 2048, 2048), (2049, 2048, 4096), (100, 2048, 512), (33333, 2048, 511)]:
+            y = signals.make("A", (n,), seed=n)
+            close(lb.stft(y, n_fft=n_fft, hop_length=hop), oracle.stft(y, n_fft=n_fft, hop_length=hop), **TOL["stft"])
+    y0 = np.zeros((0, 4096), dtype=np.float32)                       # empty batch
+    assert lb.stft(y0).shape == (0, 1025, 9)
+    assert lb.feature.melspectrogram(y=y0).shape == (0, 128, 9)
+    z = np.zeros(4096, dtype=np.float32)                             # all-zero clip: amin floor and top_db clamp
+    close(lb.feature.mfcc(y=z), oracle.mfcc(y=z), **TOL["mfcc"])
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes: size-independent properties
+def _block(n_clips, n, seed=0):
+    import signals
+
+    base = signals.make("A", (64, n), seed=seed)
+    reps = -(-n_clips // 64)
+    scale = (1.0 + 0.01 * np.arange(reps, dtype=np.float32))[:, None, None]
+    return (base[None] * scale).reshape(-1, n)[:n_clips]
+
+
+def test_cfg2_full_size_mel_properties(lb, oracle):
+    """cfg 2: 1024 clips x 10 s @ 22050 -> melspectrogram 2048/512/128."""
+    Y = _block(1024, 220500)
+    d = lb.to_device(Y)
+    M = lb.feature.melspectrogram(y=d, sr=22050, n_fft=2048, hop_length=512)
+    assert M.shape == (1024, 128, 431)
+    Mh = M.get()
+    assert np.isfinite(Mh).all() and (Mh >= 0).all()
+    # power-2 homogeneity: clip 64*r + i is clip i scaled by (1 + 0.01 r) -> mel scales by its square
+    for r in (1, 7, 15):
+        s = np.float64(1.0 + 0.01 * r) ** 2
+        np.testing.assert_allclose(Mh[64 * r : 64 * r + 64], Mh[:64] * s, rtol=2e-5)
+    # sampled clips against the oracle
+    for i in (0, 63, 517, 1023):
+        close(Mh[i], oracle.melspectrogram(y=Y[i], sr=22050, n_fft=2048, hop_length=512), **TOL["mel"])
+    # checksum of checksums: the batch result equals per-clip results
+    for i in (5, 1000):
+        np.testing.assert_array_equal(Mh[i], lb.feature.melspectrogram(y=Y[i], sr=22050, n_fft=2048, hop_length=512))
+
+
+def test_cfg5_round_trip_snr(lb):
+    """cfg 5: stft -> istft on 2048 clips x 10 s, 2048/512, reconstruction SNR >= 60 dB (per clip)."""
+    Y = _block(2048, 220500, seed=9)
+    d = lb.to_device(Y)
+    D = lb.stft(d, n_fft=2048, hop_length=512)
+    assert D.shape == (2048, 1025, 431)
+    yr = lb.istft(D, hop_length=512, length=220500).get()
+    D.free()
+    err = ((Y - yr).astype(np.float64) ** 2).sum(axis=1)
+    sig = (Y.astype(np.float64) ** 2).sum(axis=1)
+    snr = 10 * np.log10(sig / np.maximum(err, 1e-300))
+    assert snr.min() >= 60.0, snr.min()
+
+
+def test_cfg3_cfg4_sampled(lb, oracle):
+    """cfg 3 (stereo 44.1 kHz stft 4096/1024) and cfg 4 (mfcc 16 kHz 1024/256) on a shard-sized sample,
+    with linearity of the stft as the size-independent property."""
+    Y = _block(64, 441000, seed=3).reshape(32, 2, 441000)
+    d = lb.to_device(Y)
+    D = lb.stft(d, n_fft=4096, hop_length=1024)
+    assert D.shape == (32, 2, 2049, 431)
+    Dh = D.get()
+    close(Dh[3, 1], oracle.stft(Y[3, 1], n_fft=4096, hop_length=1024), **TOL["stft"])
+    both = lb.stft(Y[0, 0] + Y[5, 1], n_fft=4096, hop_length=1024)
+    scale = float(np.abs(both).max())
+    np.testing.assert_allclose(both, Dh[0, 0] + Dh[5, 1], rtol=1e-4, atol=2e-6 * scale)
+    Z = _block(32, 480000, seed=4)
+    C = lb.feature.mfcc(y=lb.to_device(Z), sr=16000, n_mfcc=40, n_fft=1024, hop_length=256).get()
+    assert C.shape == (32, 40, 1876)
+    for i in (0, 31):
+        close(C[i], oracle.mfcc(y=Z[i], sr=16000, n_mfcc=40, n_fft=1024, hop_length=256), **TOL["mfcc"])
+
+
+def test_pinned_host_end_to_end(lb, oracle):
+    import signals
+
+    y = lb.pinned_empty((8, 50000), np.float32)
+    y[...] = signals.make("B", (8, 50000), seed=2)
+    M = lb.feature.melspectrogram(y=y, sr=22050)
+    close(M, oracle.melspectrogram(y=np.array(y), sr=22050), **TOL["mel"])
+
+
+def test_launch_counter_and_no_fallback(lb):
+    ctx = lb.default_context()
+    before = ctx.launch_count
+    lb.stft(np.zeros(4096, dtype=np.float32))
+    assert ctx.launch_count == before + 1
+    lb.feature.mfcc(y=np.zeros(4096, dtype=np.float32))
+    assert ctx.launch_count == before + 3   # fused mel kernel + clamp/DCT kernel
+
+
+@pytest.mark.skipif("__import__('librosa_b200').device_count() < 2")
+def test_two_rank_split_join_on_gpu(lb, oracle):
+    """Two GPUs of one box: scatter a device-resident batch from rank 0 over NCCL, compute per rank,
+    gather back (run under pytest on a >= 2 GPU box; each rank is a thread with its own context)."""
+    import threading
+
+    import signals
+    from librosa_b200 import distributed as D
+
+    Y = signals.make("A", (8, 40000), seed=77)
+    box, results, errors = {}, {}, []
+    ready = threading.Barrier(2)
+
+    def bcast(payload):
+        if payload is not None:
+            box["uid"] = payload
+        ready.wait()
+        return box["uid"]
+
+    def rank_fn(rank):
+        try:
+            ctx = lb.Context(rank)
+            comm = D.Communicator(ctx, rank, 2, bcast)
+            full = ctx.to_device(Y) if rank == 0 else None
+            shard = ctx.empty((4, 40000), np.float32)
+            comm.scatter(full, shard)
+            M = lb.feature.melspectrogram(y=shard, sr=22050)
+            out = ctx.empty((8,) + M.shape[1:], np.float32) if rank == 0 else None
+            comm.gather(M, out)
+            ctx.synchronize()
+            comm.barrier()
+            if rank == 0:
+                results["mel"] = out.get()
+            comm.close()
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=rank_fn, args=(r,)) for r in range(2)]
+    [t.start() for t in threads]
+    [t.join(timeout=120) for t in threads]
+    assert not errors, errors
+    close(results["mel"], oracle.melspectrogram(y=Y, sr=22050), **TOL["mel"])

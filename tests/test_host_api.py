@@ -1,0 +1,194 @@
+"""CPU: host-side logic of the drop-in layer — array helpers, constant builders and the argument
+validation that must raise exactly like the reference *before* any GPU work
+(reference tests: tests/test_util.py:23-170, tests/test_filters.py:120-210, 486-514,
+tests/test_core.py:295-314, tests/test_failures.py:76-127, tests/test_features.py:890-894)."""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.signal
+
+import librosa_b200 as lb
+from librosa_b200 import ParameterError, UnsupportedOnGPU
+
+
+# ------------------------------------------------------------------ util.frame
+@pytest.mark.parametrize("frame_length,hop_length", [(4, 1), (4, 3), (16, 7), (50, 50)])
+def test_frame_1d(frame_length, hop_length):
+    y = np.arange(103.0)
+    f = lb.util.frame(y, frame_length=frame_length, hop_length=hop_length)
+    assert f.shape == (frame_length, 1 + (len(y) - frame_length) // hop_length)
+    for j in range(f.shape[1]):
+        np.testing.assert_array_equal(f[:, j], y[j * hop_length : j * hop_length + frame_length])
+    assert not f.flags.writeable
+    assert np.shares_memory(f, y)
+
+
+def test_frame_axes():
+    x = np.arange(2 * 3 * 40.0).reshape(2, 3, 40)
+    f = lb.util.frame(x, frame_length=8, hop_length=4)            # axis=-1 -> (..., frame_length, n_frames)
+    assert f.shape == (2, 3, 8, 9)
+    np.testing.assert_array_equal(f[1, 2, :, 3], x[1, 2, 12:20])
+    g = lb.util.frame(x, frame_length=2, hop_length=1, axis=0)    # axis=0 -> (n_frames, frame_length, ...)
+    assert g.shape == (1, 2, 3, 40)
+    np.testing.assert_array_equal(g[0], x)
+
+
+def test_frame_errors():
+    with pytest.raises(ParameterError):
+        lb.util.frame(np.zeros(10), frame_length=11, hop_length=1)
+    with pytest.raises(ParameterError):
+        lb.util.frame(np.zeros(10), frame_length=4, hop_length=0)
+
+
+# ------------------------------------------------------------------ small helpers
+def test_pad_center_fix_length_tiny_dtypes():
+    w = lb.util.pad_center(np.ones(5), size=12)
+    np.testing.assert_array_equal(w, [0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0])
+    with pytest.raises(ParameterError):
+        lb.util.pad_center(np.ones(5), size=4)
+    np.testing.assert_array_equal(lb.util.fix_length(np.arange(5), size=3), [0, 1, 2])
+    np.testing.assert_array_equal(lb.util.fix_length(np.arange(3), size=5), [0, 1, 2, 0, 0])
+    assert lb.util.tiny(np.float32(1.0)) == np.finfo(np.float32).tiny
+    assert lb.util.tiny(3) == np.finfo(np.float32).tiny
+    assert lb.util.dtype_r2c(np.float32) == np.complex64 and lb.util.dtype_r2c(np.float64) == np.complex128
+    assert lb.util.dtype_c2r(np.complex64) == np.float32 and lb.util.dtype_c2r(np.complex128) == np.float64
+    assert lb.util.dtype_r2c(np.int16) == np.complex64 and lb.util.dtype_c2r(np.float32) == np.float32
+    assert lb.util.expand_to(np.arange(3), ndim=3, axes=-2).shape == (1, 3, 1)
+    assert lb.util.is_positive_int(3) and not lb.util.is_positive_int(0) and not lb.util.is_positive_int(2.0)
+    x = np.array([3 + 4j, 1 - 1j])
+    np.testing.assert_allclose(lb.util.abs2(x), np.abs(x) ** 2)
+
+
+def test_valid_audio():
+    assert lb.util.valid_audio(np.zeros(4, dtype=np.float32))
+    for bad in ([0.0, 1.0], np.zeros(4, dtype=np.int16), np.float32(1.0) * np.ones(()), np.array([0.0, np.nan])):
+        with pytest.raises(ParameterError):
+            lb.util.valid_audio(bad)
+
+
+# ------------------------------------------------------------------ filters
+def test_get_window():
+    for w in ["hann", "hamming", ("kaiser", 4.0), 4.0]:
+        np.testing.assert_array_equal(lb.filters.get_window(w, 32), scipy.signal.get_window(w, 32, fftbins=True))
+    np.testing.assert_array_equal(lb.filters.get_window(np.ones(8), 8), np.ones(8))
+    assert np.allclose(lb.filters.get_window(lambda n: np.arange(n), 4), [0, 1, 2, 3])
+    with pytest.raises(ParameterError):
+        lb.filters.get_window(np.ones(7), 8)
+    with pytest.raises(ParameterError):
+        lb.filters.get_window(None, 8)
+
+
+@pytest.mark.parametrize("n_fft,n_mels,htk", [(2048, 128, False), (2048, 40, True), (1024, 128, False)])
+def test_mel_properties(n_fft, n_mels, htk):
+    sr = 22050
+    W = lb.filters.mel(sr=sr, n_fft=n_fft, n_mels=n_mels, htk=htk)
+    assert W.shape == (n_mels, 1 + n_fft // 2) and W.dtype == np.float32
+    assert (W >= 0).all()
+    # every filter peaks within one bin of its mel centre (reference tests/test_filters.py:120-165)
+    centres = lb.mel_frequencies(n_mels + 2, fmin=0, fmax=sr / 2, htk=htk)[1:-1]
+    bins = lb.fft_frequencies(sr=sr, n_fft=n_fft)
+    peak = bins[W.argmax(axis=1)]
+    assert np.all(np.abs(peak - centres) <= sr / n_fft)
+    # band structure the CUDA kernel relies on: contiguous support, <= 2 filters per bin
+    assert ((W > 0).sum(axis=0) <= 2).all()
+    for row in W:
+        nz = np.flatnonzero(row)
+        assert nz.size == 0 or nz[-1] - nz[0] + 1 == nz.size
+
+
+def test_mel_golden_and_norms(golden):
+    np.testing.assert_array_equal(lb.filters.mel(sr=22050, n_fft=2048), golden["const/mel_22050_2048"])
+    np.testing.assert_array_equal(lb.filters.mel(sr=44100, n_fft=4096), golden["const/mel_44100_4096"])
+    np.testing.assert_array_equal(lb.filters.mel(sr=16000, n_fft=1024, n_mels=40, htk=True), golden["const/mel_16000_1024_htk40"])
+    np.testing.assert_allclose(lb.filters.mel(sr=22050, n_fft=2048, norm=1, fmin=300.0, fmax=8000.0, n_mels=64),
+                               golden["const/mel_22050_2048_norm1"], rtol=1e-6)
+    W1 = lb.filters.mel(sr=22050, n_fft=2048, norm=1)
+    np.testing.assert_allclose(W1.sum(axis=1), 1.0, rtol=1e-5)
+    with pytest.raises(ParameterError):
+        lb.filters.mel(sr=22050, n_fft=2048, norm="bogus")
+    with pytest.warns(UserWarning, match="Empty filters"):
+        lb.filters.mel(sr=22050, n_fft=64, n_mels=128)
+
+
+def test_window_sumsquare_and_scales(golden):
+    np.testing.assert_allclose(lb.filters.window_sumsquare(window="hann", n_frames=50, hop_length=512, n_fft=2048),
+                               golden["const/wss_hann_2048_512_50"], rtol=1e-6)
+    np.testing.assert_allclose(
+        lb.filters.window_sumsquare(window="hamming", n_frames=20, hop_length=300, win_length=600, n_fft=1024),
+        golden["const/wss_hamming_600_1024_300_20"], rtol=1e-6)
+    f = np.array([0.0, 60.0, 440.0, 999.0, 1000.0, 5000.0, 11025.0])
+    np.testing.assert_allclose(lb.hz_to_mel(f), golden["const/hz_to_mel"], rtol=1e-12)
+    np.testing.assert_allclose(lb.hz_to_mel(f, htk=True), golden["const/hz_to_mel_htk"], rtol=1e-12)
+    np.testing.assert_allclose(lb.mel_to_hz(np.array([0.0, 3.0, 14.9, 15.0, 25.0, 40.0])), golden["const/mel_to_hz"], rtol=1e-12)
+    np.testing.assert_allclose(lb.mel_to_hz(np.array([0.0, 300.0, 1000.0, 2000.0, 3000.0]), htk=True),
+                               golden["const/mel_to_hz_htk"], rtol=1e-12)
+    np.testing.assert_allclose(lb.mel_frequencies(40), golden["const/mel_frequencies_40"], rtol=1e-12)
+    assert np.allclose(lb.hz_to_mel(60), 0.9) and np.allclose(lb.mel_to_hz(3), 200.0)
+
+
+# ------------------------------------------------------------------ argument errors raised before any GPU work
+Y = np.zeros(4096, dtype=np.float32)
+
+
+@pytest.mark.parametrize("call", [
+    lambda: lb.stft(Y, hop_length=0),
+    lambda: lb.stft(Y, hop_length=2.5),
+    lambda: lb.stft(Y, pad_mode="wrap"),
+    lambda: lb.stft(Y, pad_mode="mean"),
+    lambda: lb.stft(Y, window=np.ones(7)),
+    lambda: lb.stft(Y, win_length=4096),                       # window longer than n_fft
+    lambda: lb.stft(np.zeros(100, dtype=np.float32), center=False),
+    lambda: lb.stft(np.array([0.0, np.inf], dtype=np.float32)),
+    lambda: lb.stft(np.zeros(4096, dtype=np.int32)),
+    lambda: lb.stft([0.0] * 4096),
+    lambda: lb.stft(Y, out=np.zeros((1025, 3), dtype=np.complex64)),      # too few frames
+    lambda: lb.stft(Y, out=np.zeros((1025, 9), dtype=np.float32)),        # not complex
+    lambda: lb.istft(np.zeros((1025, 9), dtype=np.complex64), out=np.zeros(5, dtype=np.float32)),
+    lambda: lb.feature.melspectrogram(y=None),
+    lambda: lb.feature.melspectrogram(y=Y, n_fft=None),
+    lambda: lb.feature.mfcc(y=Y, lifter=-1),
+    lambda: lb.feature.mfcc(y=Y, lifter=np.nan),
+    lambda: lb.power_to_db(np.ones((4, 4), dtype=np.float32), amin=0),
+    lambda: lb.power_to_db(np.ones((4, 4), dtype=np.float32), top_db=-1),
+    lambda: lb.feature.melspectrogram(y=Y, norm="bogus"),
+])
+def test_parameter_errors(call):
+    with pytest.raises(ParameterError):
+        call()
+
+
+@pytest.mark.parametrize("call", [
+    lambda: lb.stft(Y, n_fft=501),          # non power of two (reference tests use 501 / 1023 / 1025)
+    lambda: lb.stft(Y, n_fft=8192),
+    lambda: lb.stft(Y.astype(np.float64)),  # float64 needs an explicit opt-in to be computed in float32
+    lambda: lb.stft(Y, dtype=np.complex128),
+    lambda: lb.stft(Y, pad_mode=lambda *a, **k: None),
+    lambda: lb.istft(np.zeros((1025, 9), dtype=np.complex128)),
+])
+def test_unsupported_is_loud(call):
+    with pytest.raises(UnsupportedOnGPU):
+        call()
+
+
+def test_warnings_match_reference():
+    with pytest.warns(UserWarning, match="is too large for input signal"):
+        try:
+            lb.stft(np.zeros(100, dtype=np.float32), n_fft=2048)
+        except lb.NativeLibraryError:
+            pass   # no GPU here: the warning is issued before the device is touched
+
+
+def test_shard_ranges():
+    from librosa_b200.distributed import join_batches, shard_range, split_batch
+
+    for n in (0, 1, 7, 8, 1024, 1031):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                assert 0 <= lo <= hi <= n
+                cover.extend(range(lo, hi))
+            assert cover == list(range(n))
+    y = np.arange(7 * 3).reshape(7, 3)
+    np.testing.assert_array_equal(join_batches([split_batch(y, r, 4) for r in range(4)]), y)
