@@ -80,6 +80,16 @@ int b2l_ctx_sm_count(const b2l_ctx* ctx, int* sms);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 int b2l_ctx_launch_count(const b2l_ctx* ctx, uint64_t* launches);
 
+/* ---- util.valid_audio on the device (librosa/util/utils.py:246-308) ----------------------------
+ * The forward kernels set bit 0 of a per-context status word when a non-finite sample reaches a frame;
+ * b2l_scan_finite covers samples [begin, n) that no frame reads (tail / hop > n_fft gaps).  The Python
+ * layer resets the word before a call on host data, reads it with the results and raises
+ * ParameterError("Audio buffer is not finite everywhere") exactly as the reference does. */
+int b2l_status_reset(b2l_ctx* ctx);
+int b2l_status_read(b2l_ctx* ctx, int* status); /* synchronises the ctx stream */
+int b2l_scan_finite(b2l_ctx* ctx, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
+                    int64_t begin);
+
 /* ---- memory --------------------------------------------------------------------------------- */
 int b2l_alloc(b2l_ctx* ctx, size_t bytes, void** d_ptr);
 int b2l_free(b2l_ctx* ctx, void* d_ptr);

@@ -71,6 +71,9 @@ def _declare(lib):
         "b2l_ctx_device": (C.c_int, [_vp, P(C.c_int)]),
         "b2l_ctx_sm_count": (C.c_int, [_vp, P(C.c_int)]),
         "b2l_ctx_launch_count": (C.c_int, [_vp, P(C.c_uint64)]),
+        "b2l_status_reset": (C.c_int, [_vp]),
+        "b2l_status_read": (C.c_int, [_vp, P(C.c_int)]),
+        "b2l_scan_finite": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64]),
         "b2l_alloc": (C.c_int, [_vp, C.c_size_t, P(_vp)]),
         "b2l_free": (C.c_int, [_vp, _vp]),
         "b2l_memset": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t]),
@@ -356,7 +359,7 @@ class DeviceArray:
         """Copy to the host; returns an array of the logical shape (a transposed view for "ft")."""
         mem_shape = self._mem_shape()
         if out is None:
-            host = np.empty(mem_shape, dtype=self.dtype)
+            host = pinned_empty(mem_shape, self.dtype) if self.nbytes >= (1 << 20) else np.empty(mem_shape, dtype=self.dtype)
         else:
             host = out
             if host.shape != mem_shape or host.dtype != self.dtype or not host.flags.c_contiguous:
@@ -380,17 +383,67 @@ class DeviceArray:
         return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, layout={self.layout!r}, device={self.ctx.device})"
 
 
+class _PinnedPool:
+    """Size-keyed free list of page-locked host blocks.  cudaHostAlloc costs milliseconds and fresh
+    pageable pages fault on first touch, so result arrays are carved from recycled pinned blocks: D2H runs
+    at full PCIe speed and a block returns to the pool when the NumPy array that wraps it is collected."""
+
+    QUANTUM = 1 << 16
+
+    def __init__(self):
+        self.free = {}
+        self.pooled = 0
+        self.limit = int(os.environ.get("B2L_PINNED_POOL_MB", "16384")) << 20
+        self.lock = threading.Lock()
+
+    def take(self, nbytes: int):
+        size = (max(int(nbytes), 1) + self.QUANTUM - 1) // self.QUANTUM * self.QUANTUM
+        with self.lock:
+            bucket = self.free.get(size)
+            if bucket:
+                self.pooled -= size
+                return bucket.pop(), size
+        p = _vp()
+        check(lib().b2l_host_alloc(size, C.byref(p)))
+        return p.value, size
+
+    def give(self, addr: int, size: int):
+        with self.lock:
+            if self.pooled + size <= self.limit:
+                self.free.setdefault(size, []).append(addr)
+                self.pooled += size
+                return
+        try:
+            lib().b2l_host_free(_vp(addr))
+        except Exception:  # pragma: no cover
+            pass
+
+    def empty(self):
+        with self.lock:
+            blocks = [(a, s) for s, b in self.free.items() for a in b]
+            self.free.clear()
+            self.pooled = 0
+        for a, _ in blocks:
+            lib().b2l_host_free(_vp(a))
+
+
+_pinned_pool = _PinnedPool()
+
+
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     """NumPy array backed by page-locked host memory (fast, truly asynchronous H2D / D2H)."""
-    shape = tuple(int(s) for s in np.atleast_1d(shape)) if not isinstance(shape, tuple) else shape
+    if not isinstance(shape, tuple):
+        shape = tuple(int(s) for s in np.atleast_1d(shape))
     dtype = np.dtype(dtype)
-    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-    p = _vp()
-    check(lib().b2l_host_alloc(max(nbytes, 16), C.byref(p)))
-    buf = (C.c_char * max(nbytes, 16)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
-    weakref.finalize(buf, lambda addr: lib().b2l_host_free(_vp(addr)), p.value)
-    return arr
+    count = int(np.prod(shape, dtype=np.int64))
+    addr, size = _pinned_pool.take(count * dtype.itemsize)
+    buf = (C.c_char * size).from_address(addr)
+    weakref.finalize(buf, _pinned_pool.give, addr, size)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+def empty_pinned_cache():
+    _pinned_pool.empty()
 
 
 # --------------------------------------------------------------------------------------------- plans

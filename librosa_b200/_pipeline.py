@@ -119,7 +119,14 @@ def precheck_signal(y):
         if y.ndim == 0:
             raise ParameterError("Audio data must be at least one-dimensional")
         return y.shape[-1], np.dtype(np.float32)
-    valid_audio(y)
+    # util.valid_audio's type / dtype / ndim checks on the host; its O(n) np.isfinite(y).all() pass runs on
+    # the GPU instead (status word set by the kernels, see StagedInput.scan_uncovered and finish()).
+    if not isinstance(y, np.ndarray):
+        raise ParameterError("Audio data must be of type numpy.ndarray")
+    if not np.issubdtype(y.dtype, np.floating):
+        raise ParameterError("Audio data must be floating-point")
+    if y.ndim == 0:
+        raise ParameterError(f"Audio data must be at least one-dimensional, given y.shape={y.shape}")
     return y.shape[-1], check_real_dtype(y.dtype, "input signal")
 
 
@@ -153,6 +160,7 @@ class StagedInput:
             self.req_dtype = np.dtype(np.float32)
         else:
             self.req_dtype = np.dtype(y.dtype)
+            nat.check(nat.lib().b2l_status_reset(ctx.handle))
             host = np.ascontiguousarray(y, dtype=np.float32)
             self.dev = nat.DeviceArray.empty(ctx, host.shape, np.float32)
             if host.nbytes:
@@ -165,12 +173,30 @@ class StagedInput:
         self.n_clips = int(np.prod(self.lead, dtype=np.int64)) if self.lead else 1
 
 
-def finish(ctx, dev_out: nat.DeviceArray, to_host: bool, host_dtype=None):
-    """Return the device array itself (device-resident pipelines) or copy it to a fresh NumPy array."""
+    def scan_uncovered(self, n_fft: int, hop: int, center: bool, n_frames: int):
+        """Host inputs only: samples that no frame reads (the tail after the last frame, or everything
+        when hop > n_fft leaves gaps) still have to be finite for util.valid_audio — scan just those."""
+        if self.on_device or self.n_clips == 0:
+            return
+        pad = n_fft // 2 if center else 0
+        begin = 0 if hop > n_fft else max(0, (n_frames - 1) * hop + n_fft - pad)
+        if begin < self.n:
+            nat.check(nat.lib().b2l_scan_finite(self.ctx.handle, C.c_void_p(self.dev.ptr), self.n_clips, self.n,
+                                                self.n, begin))
+
+
+def finish(ctx, dev_out: nat.DeviceArray, to_host: bool, host_dtype=None, validate: bool = False):
+    """Return the device array itself (device-resident pipelines) or copy it to a NumPy array; with
+    ``validate`` also fetch the device-side valid_audio verdict and raise like the reference."""
     if not to_host:
         return dev_out
     arr = dev_out.get()
     dev_out.free()
+    if validate:
+        flag = C.c_int(0)
+        nat.check(nat.lib().b2l_status_read(ctx.handle, C.byref(flag)))
+        if flag.value & 1:
+            raise ParameterError("Audio buffer is not finite everywhere")
     if host_dtype is not None and arr.dtype != host_dtype:
         arr = arr.astype(host_dtype)
     return arr

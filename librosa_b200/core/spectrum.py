@@ -60,9 +60,10 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
     D = nat.DeviceArray.empty(ctx, shape, np.complex64, layout="ft")
     nat.check(nat.lib().b2l_stft(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n, staged.n,
                                  _vp(D.ptr)))
+    staged.scan_uncovered(n_fft, hop_length, center, T)
     if staged.on_device and out is None:
         return D
-    res = pl.finish(ctx, D, True, dtype)
+    res = pl.finish(ctx, D, True, dtype, validate=not staged.on_device)
     if out is None:
         return res
     target = out if out.shape[-1] == shape[-1] else out[..., : shape[-1]]
@@ -218,7 +219,8 @@ def _spectrogram(*, y=None, S=None, n_fft: Optional[int] = 2048, hop_length: Opt
     Sd = nat.DeviceArray.empty(ctx, staged.lead + (1 + n_fft // 2, T), np.float32, layout="ft")
     nat.check(nat.lib().b2l_spectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
                                         staged.n, _vp(Sd.ptr)))
-    return pl.finish(ctx, Sd, not staged.on_device, staged.req_dtype), n_fft
+    staged.scan_uncovered(n_fft, hop_length, center, T)
+    return pl.finish(ctx, Sd, not staged.on_device, staged.req_dtype, validate=not staged.on_device), n_fft
 
 
 def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80.0, axes="auto"):

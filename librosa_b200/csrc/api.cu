@@ -104,6 +104,7 @@ struct b2l_ctx {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   unsigned int* d_clip_max = nullptr;   // scratch for per-clip maxima
+  int* d_status = nullptr;              // bit 0: a non-finite input sample was seen since the last reset
   size_t clip_max_cap = 0;
 };
 
@@ -172,9 +173,12 @@ extern "C" int b2l_ctx_create(int device, b2l_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_status, 256);
+  if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, 256);
   if (e != cudaSuccess) {
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
-    return fail(B2L_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    return fail(B2L_ERR_CUDA, "context setup: %s", cudaGetErrorString(e));
   }
   *out = c;
   return B2L_OK;
@@ -185,6 +189,7 @@ extern "C" int b2l_ctx_destroy(b2l_ctx* c) {
   DeviceGuard g(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   if (c->d_clip_max) cudaFree(c->d_clip_max);
+  if (c->d_status) cudaFree(c->d_status);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return B2L_OK;
@@ -209,6 +214,35 @@ extern "C" int b2l_ctx_sm_count(const b2l_ctx* c, int* sms) {
 extern "C" int b2l_ctx_launch_count(const b2l_ctx* c, uint64_t* launches) {
   if (!c || !launches) return fail(B2L_ERR_INVALID, "NULL argument");
   *launches = c->launches;
+  return B2L_OK;
+}
+
+// ------------------------------------------------------------------ device-side input validation
+extern "C" int b2l_status_reset(b2l_ctx* c) {
+  if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_status_read(b2l_ctx* c, int* status) {
+  if (!c || !status) return fail(B2L_ERR_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemcpyAsync(status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_scan_finite(b2l_ctx* c, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
+                               int64_t begin) {
+  if (!c || !d_y) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (n_clips <= 0 || begin >= n) return B2L_OK;
+  if (n_clips > 65535 || n > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "scan_finite: batch too large");
+  DeviceGuard g(c->device);
+  long long bx = ((n - begin) + 1023) / 1024;
+  if (bx > 64) bx = 64;
+  dim3 grid((unsigned)bx, (unsigned)n_clips);
+  finite_scan_kernel<<<grid, 256, 0, c->stream>>>(d_y, y_stride, (int)n, (int)(begin < 0 ? 0 : begin), c->d_status);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
   return B2L_OK;
 }
 
@@ -528,7 +562,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     a.off_in = (int)(off = align_up(off, 128)); off += (size_t)align_up((size_t)span * 4, 16);
     a.off_xbuf = (int)(off = align_up(off, 128));
     size_t xbytes = (size_t)ft * cfg.xbuf_f2() * 8;
-    size_t pbytes = mode == MODE_MEL ? (size_t)(M + 1) * ft * 4 : 0;
+    size_t pbytes = mode == MODE_MEL ? (size_t)(M + 1) * (ft + 1) * 4 : 0;   // P[k][FT+1] (fwd_kernel.cuh)
     off += xbytes > pbytes ? xbytes : pbytes;
     if (span > 0x3fffffff) continue;
     a.in_floats = (int)span;
@@ -570,6 +604,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   a.amin = p->amin;
   a.db_sub = 10.0f * log10f(fmaxf(p->amin, fabsf(p->ref_value)));
   a.clip_max = c->d_clip_max;
+  a.status = c->d_status;
 
   CUDA_TRY(op(OP_SET_SMEM, nw, mode, &a, 0, smem, c->stream, nullptr));
   int occ = 0;

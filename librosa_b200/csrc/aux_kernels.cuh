@@ -123,6 +123,18 @@ __global__ void db_clamp_kernel(float* __restrict__ x, long long per_clip, const
     xc[i] = fmaxf(xc[i], floor_v);
 }
 
+// ------------------------------------------------------------------ finite scan of samples no frame reads
+// y [n_clips][stride]; checks samples [begin, n) of every clip (the uncovered tail when the last frame
+// ends before the clip does, or the whole clip when hop > n_fft leaves gaps).
+__global__ void finite_scan_kernel(const float* __restrict__ y, long long stride, int n, int begin, int* status) {
+  const float* yc = y + (long long)blockIdx.y * stride;
+  bool bad = false;
+  for (long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    bad |= !(fabsf(yc[i]) <= 3.0e38f);
+  if (bad) *status = 1;
+}
+
 // ------------------------------------------------------------------ batched transpose
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ in, int rows, int cols, T* __restrict__ out) {

@@ -47,6 +47,7 @@ struct FwdArgs {
   int log_mode;              // 1: write 10*log10(max(amin, S)) - db_sub and track the per-clip max
   float amin, db_sub;
   unsigned int* clip_max;    // order-preserving uint keys of the per-clip max (log_mode)
+  int* status;               // bit 0 is set when a non-finite sample reached a frame (util.valid_audio)
   // dynamic shared-memory layout (byte offsets)
   int off_win, off_tw, off_twn, off_in, off_xbuf, off_melw, off_melband, off_bar;
   int in_floats;             // staged span length (floats)

@@ -90,12 +90,30 @@ __device__ __forceinline__ float load_padded(const float* __restrict__ y, int n,
   }
 }
 
-__device__ __forceinline__ float apply_power(float2 x, int power_mode, float power) {
-  float p2 = fmaf(x.x, x.x, x.y * x.y);
-  if (power_mode == 2) return p2;
+// |X|^power from |X|^2 for power != 2 (kept out of line: the default power-2 path never executes it)
+static __device__ __noinline__ float power_from_sq(float p2, int power_mode, float power) {
   float mag = sqrtf(p2);
-  if (power_mode == 1) return mag;
-  return powf(mag, power);
+  return power_mode == 1 ? mag : powf(mag, power);
+}
+__device__ __forceinline__ float sqmag(float2 x) { return fmaf(x.x, x.x, x.y * x.y); }
+
+// Exchange-buffer slot of Z[M - k] for k = t + TPF*c (the partner of bin k in the real-FFT un-mix).
+// For warp-multiple groups the padded index is affine in the lane with a compile-time offset.
+template <int M, int TPF, int C>
+__device__ __forceinline__ int partner_slot(int t) {
+  if constexpr (TPF % 32 == 0) {
+    constexpr int WPG = TPF / 32;                 // warps per group
+    const int tl = t & 31, tw = t >> 5;
+    const int row = tw + WPG * C;                 // k = tl + 32*row
+    const int rows = M / 32;
+    // tl != 0: M-k = 32*(rows-1-row) + (32-tl);  tl == 0: M-k = 32*((rows-row) mod rows)
+    const int a = 33 * (rows - 1 - row) + 32 - tl;
+    const int b = 33 * ((rows - row) & (rows - 1));
+    return tl == 0 ? b : a;
+  } else {
+    const int k = t + TPF * C;
+    return xphys((M - k) & (M - 1));
+  }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -214,13 +232,17 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
 
     const int frame = t0 + grp;
     const bool frame_ok = frame < a.n_frames;
+    // util.valid_audio (librosa/util/utils.py:303-306) on the device: one NaN / Inf sample makes every
+    // bin of every frame that reads it non-finite, so testing one spectrum value per thread and frame
+    // catches it without a separate pass over the input.
+    if (frame_ok && !(fabsf(v[0].x) + fabsf(v[0].y) <= 3.0e38f)) *a.status = 1;
 
     if constexpr (MODE == MODE_STFT) {
       float2* orow = a.out_c + ((long long)clip * a.n_frames + frame) * (M + 1);
       static_for<0, NPAIR>([&](auto C) {
         const int k = t + TPF * decltype(C)::value;
         float2 xa, xb;
-        r2c_pair(xbuf[xphys(k)], xbuf[xphys((M - k) & (M - 1))], s_twn[k], xa, xb);
+        r2c_pair(xbuf[xphys(k)], xbuf[partner_slot<M, TPF, decltype(C)::value>(t)], s_twn[k], xa, xb);
         if (frame_ok) {
           orow[k] = xa;
           orow[M - k] = xb;
@@ -239,16 +261,21 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         constexpr int c = decltype(C)::value;
         const int k = t + TPF * c;
         float2 xa, xb;
-        r2c_pair(xbuf[xphys(k)], xbuf[xphys((M - k) & (M - 1))], s_twn[k], xa, xb);
-        pw[2 * c] = apply_power(xa, a.power_mode, a.power);
-        pw[2 * c + 1] = apply_power(xb, a.power_mode, a.power);
+        r2c_pair(xbuf[xphys(k)], xbuf[partner_slot<M, TPF, decltype(C)::value>(t)], s_twn[k], xa, xb);
+        pw[2 * c] = sqmag(xa);
+        pw[2 * c + 1] = sqmag(xb);
       });
       pw[PPT] = 0.0f;
       if (t == 0) {
         float2 xa, xb;
         float2 zc = xbuf[xphys(M / 2)];
         r2c_pair(zc, zc, s_twn[M / 2], xa, xb);
-        pw[PPT] = apply_power(xa, a.power_mode, a.power);
+        pw[PPT] = sqmag(xa);
+      }
+      if (a.power_mode != 2) {   // warp-uniform, cold for the default power = 2
+        static_for<0, PPT + 1>([&](auto S) {
+          pw[decltype(S)::value] = power_from_sq(pw[decltype(S)::value], a.power_mode, a.power);
+        });
       }
       if constexpr (MODE == MODE_SPEC) {
         float* orow = a.out_r + ((long long)clip * a.n_frames + frame) * (M + 1);
@@ -265,7 +292,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       } else {
         // ---------------- band-sparse mel projection over the tile
         __syncthreads();   // B1: every group finished reading its Z
-        auto paddr = [&](int k, int f) { return k * FT + (f ^ ((k / H) & (FT - 1))); };
+        // P[k][f] with rows padded to PS = FT+1 words: the transposing writes (lanes = consecutive bins
+        // of one frame) are conflict-free, the mel reads (lanes = (frame, bin parity)) see one 2-way
+        // conflict per wavefront, and every address is base + immediate (no per-access swizzle math).
+        constexpr int PS = FT + 1;
+        auto paddr = [&](int k, int f) { return k * PS + f; };
         static_for<0, NPAIR>([&](auto C) {
           constexpr int c = decltype(C)::value;
           const int k = t + TPF * c;
@@ -281,12 +312,28 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
           float wmax = -INFINITY;
           for (int m = warp; m < a.n_mels; m += NW) {
             const MelBand band = s_band[m];
-            const float* wrow = s_melw + band.off;
-            float acc = 0.0f;
-            for (int kx = h; kx < band.len; kx += H) {
-              const int k = band.lo + kx;
-              acc = fmaf(wrow[kx], s_p[paddr(k, f)], acc);
+            // lane (f, h) takes bins lo + h, lo + h + H, ...; the trip count is warp-uniform (bands are
+            // split into a multiple-of-H body and a predicated tail) so the loop never diverges
+            const float* wp = s_melw + band.off + h;
+            const float* pp = s_p + (band.lo + h) * PS + f;
+            const int body = band.len / H;
+            float acc = 0.0f, acc2 = 0.0f;
+            int i = 0;
+            for (; i + 4 <= body; i += 4) {
+              acc = fmaf(wp[0], pp[0], acc);
+              acc2 = fmaf(wp[H], pp[H * PS], acc2);
+              acc = fmaf(wp[2 * H], pp[2 * H * PS], acc);
+              acc2 = fmaf(wp[3 * H], pp[3 * H * PS], acc2);
+              wp += 4 * H;
+              pp += 4 * H * PS;
             }
+            for (; i < body; ++i) {
+              acc = fmaf(wp[0], pp[0], acc);
+              wp += H;
+              pp += H * PS;
+            }
+            if (h < band.len - body * H) acc2 = fmaf(wp[0], pp[0], acc2);
+            acc += acc2;
 #pragma unroll
             for (int o = FT; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (a.log_mode) {

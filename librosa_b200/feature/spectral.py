@@ -83,7 +83,9 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
     out = nat.DeviceArray.empty(ctx, staged.lead + (basis.shape[0], T), np.float32)
     nat.check(nat.lib().b2l_melspectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
                                            staged.n, _vp(out.ptr)))
-    return pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype))
+    staged.scan_uncovered(n_fft, hop_length, center, T)
+    return pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype),
+                     validate=not staged.on_device)
 
 
 def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float) -> np.ndarray:
@@ -152,8 +154,10 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
     scratch = nat.DeviceArray.empty(ctx, (staged.n_clips, n_mels, T), np.float32)
     nat.check(nat.lib().b2l_mfcc(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n, staged.n,
                                  _vp(out.ptr), _vp(scratch.ptr)))
-    res = pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype))
-    if staged.on_device:
-        ctx.synchronize()
-    scratch.free()
+    staged.scan_uncovered(n_fft, hop_length, center, T)
+    try:
+        res = pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype),
+                        validate=not staged.on_device)
+    finally:
+        scratch.free()   # stream-ordered pool: safe to hand out again without a sync
     return res

@@ -191,6 +191,22 @@ def test_ragged_and_edge_shapes(lb, oracle):
     close(lb.feature.mfcc(y=z), oracle.mfcc(y=z), **TOL["mfcc"])
 
 
+def test_nonfinite_input_raises_like_valid_audio(lb):
+    """util.valid_audio's finite check (librosa/util/utils.py:303-306) runs on the device: same exception,
+    same message, for a bad sample anywhere — inside a frame, in the uncovered tail, or in a hop gap."""
+    y = np.zeros((3, 20000), dtype=np.float32)
+    for bad_pos, kw in [(12345, {}), (19999, dict(center=False, hop_length=1500)), (3000, dict(n_fft=256, hop_length=1024)),
+                        (0, {}), (19999, {})]:
+        for bad in (np.nan, np.inf, -np.inf):
+            z = y.copy()
+            z[1, bad_pos] = bad
+            for fn in (lambda a: lb.stft(a, **kw), lambda a: lb.feature.melspectrogram(y=a, **kw),
+                       lambda a: lb.feature.mfcc(y=a, **kw)):
+                with pytest.raises(lb.ParameterError, match="not finite everywhere"):
+                    fn(z)
+    assert np.isfinite(lb.stft(y)).all()          # and the flag does not stick
+
+
 # ------------------------------------------------------------------ BASELINE.json sizes: size-independent properties
 def _block(n_clips, n, seed=0):
     import signals
