@@ -562,7 +562,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     a.off_in = (int)(off = align_up(off, 128)); off += (size_t)align_up((size_t)span * 4, 16);
     a.off_xbuf = (int)(off = align_up(off, 128));
     size_t xbytes = (size_t)ft * cfg.xbuf_f2() * 8;
-    size_t pbytes = mode == MODE_MEL ? (size_t)(M + 1) * (ft + 1) * 4 : 0;   // P[k][FT+1] (fwd_kernel.cuh)
+    size_t pbytes = mode == MODE_MEL ? (size_t)(M + 1) * (M <= 1024 ? 33 : ft + 1) * 4 : 0;   // MelLayout (common.cuh)
     off += xbytes > pbytes ? xbytes : pbytes;
     if (span > 0x3fffffff) continue;
     a.in_floats = (int)span;

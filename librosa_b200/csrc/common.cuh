@@ -22,6 +22,18 @@ enum FwdMode : int {
 
 struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at mel_w[off ..]
 
+// Shared-memory layout of the power tile P[bin][frame] used by the mel phase (FT frames per tile,
+// H = 32/FT bin residues per warp step).  Wide: rows of 33 words, frame f at word H*f — bank = k + h + H*f
+// is distinct over the 32 lanes of both the transposing store and the (frame, residue) load.  For
+// M > 1024 the wide tile would not fit beside the exchange area, so rows shrink to FT+1 words.
+template <int M, int FT>
+struct MelLayout {
+  static constexpr bool WIDE = M <= 1024;
+  static constexpr int PS = WIDE ? 33 : FT + 1;
+  static constexpr int CS = WIDE ? (32 / FT) : 1;
+  static constexpr size_t bytes() { return (size_t)(M + 1) * PS * 4; }
+};
+
 struct FwdArgs {
   // input
   const float* y;            // [n_clips][clip_stride] (first n samples of each row are valid)

@@ -225,6 +225,21 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int gr
   });
 }
 
+// Offset (index minus t) of the spectrum element held in v[slot] after fft_forward, and the inverse map
+// for bin pairs: the slot that holds Z[t + TPF*c].  Both are compile-time functions of the schedule.
+template <class Cfg>
+__host__ __device__ constexpr int spectrum_offset(int slot) {
+  constexpr int RL = Cfg::radix(Cfg::NPASS - 1);
+  constexpr int pL = Cfg::sublen(Cfg::NPASS - 1);
+  return Cfg::TPF * (slot / RL) + (slot % RL) * pL;
+}
+template <class Cfg>
+__host__ __device__ constexpr int slot_of_pair(int c) {
+  for (int s = 0; s < Cfg::PPT; ++s)
+    if (spectrum_offset<Cfg>(s) == Cfg::TPF * c) return s;
+  return -1;
+}
+
 // Index of the spectrum element held in v[slot] after fft_forward.
 template <class Cfg>
 __device__ __forceinline__ int spectrum_index(int t, int slot) {

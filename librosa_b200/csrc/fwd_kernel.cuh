@@ -224,11 +224,23 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     // ---------------- M-point complex FFT, then publish Z for the pair un-mix
     fft_forward<Cfg>(v, t, grp, xbuf, s_tw);
     if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp);
+    // Bin pair (k, M-k), k = t + TPF*c < M/2: Z[k] is already in one of this thread's registers; only the
+    // upper half of the spectrum (indices >= M/2) goes through shared memory to reach its partner.
     static_for<0, PPT>([&](auto S) {
       constexpr int slot = decltype(S)::value;
-      xbuf[xphys(spectrum_index<Cfg>(t, slot))] = v[slot];
+      if constexpr (spectrum_offset<Cfg>(slot) >= M / 2) xbuf[xphys(t + spectrum_offset<Cfg>(slot))] = v[slot];
     });
     group_sync<TPF>(grp);
+    auto pair_operands = [&](auto C, float2& A, float2& B) {
+      constexpr int c = decltype(C)::value;
+      constexpr int sa = slot_of_pair<Cfg>(c);
+      static_assert(sa >= 0, "pair operand must be register resident");
+      A = v[sa];
+      B = xbuf[partner_slot<M, TPF, c>(t)];
+      if constexpr (c == 0) {
+        if (t == 0) B = A;   // k = 0 pairs with itself (Z[M] == Z[0])
+      }
+    };
 
     const int frame = t0 + grp;
     const bool frame_ok = frame < a.n_frames;
@@ -241,8 +253,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       float2* orow = a.out_c + ((long long)clip * a.n_frames + frame) * (M + 1);
       static_for<0, NPAIR>([&](auto C) {
         const int k = t + TPF * decltype(C)::value;
-        float2 xa, xb;
-        r2c_pair(xbuf[xphys(k)], xbuf[partner_slot<M, TPF, decltype(C)::value>(t)], s_twn[k], xa, xb);
+        float2 A, B, xa, xb;
+        pair_operands(C, A, B);
+        r2c_pair(A, B, s_twn[k], xa, xb);
         if (frame_ok) {
           orow[k] = xa;
           orow[M - k] = xb;
@@ -260,8 +273,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       static_for<0, NPAIR>([&](auto C) {
         constexpr int c = decltype(C)::value;
         const int k = t + TPF * c;
-        float2 xa, xb;
-        r2c_pair(xbuf[xphys(k)], xbuf[partner_slot<M, TPF, decltype(C)::value>(t)], s_twn[k], xa, xb);
+        float2 A, B, xa, xb;
+        pair_operands(C, A, B);
+        r2c_pair(A, B, s_twn[k], xa, xb);
         pw[2 * c] = sqmag(xa);
         pw[2 * c + 1] = sqmag(xb);
       });
@@ -292,11 +306,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       } else {
         // ---------------- band-sparse mel projection over the tile
         __syncthreads();   // B1: every group finished reading its Z
-        // P[k][f] with rows padded to PS = FT+1 words: the transposing writes (lanes = consecutive bins
-        // of one frame) are conflict-free, the mel reads (lanes = (frame, bin parity)) see one 2-way
-        // conflict per wavefront, and every address is base + immediate (no per-access swizzle math).
-        constexpr int PS = FT + 1;
-        auto paddr = [&](int k, int f) { return k * PS + f; };
+        // P[k][f] at word k*PS + CS*f (MelLayout, common.cuh): the transposing writes (lanes = consecutive
+        // bins of one frame) and the mel reads (lanes = (frame, bin residue)) are both conflict-free in
+        // the wide layout, and every address is base + immediate (no per-access swizzle math).
+        constexpr int PS = MelLayout<M, FT>::PS, CS = MelLayout<M, FT>::CS;
+        auto paddr = [&](int k, int f) { return k * PS + CS * f; };
         static_for<0, NPAIR>([&](auto C) {
           constexpr int c = decltype(C)::value;
           const int k = t + TPF * c;
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
             // lane (f, h) takes bins lo + h, lo + h + H, ...; the trip count is warp-uniform (bands are
             // split into a multiple-of-H body and a predicated tail) so the loop never diverges
             const float* wp = s_melw + band.off + h;
-            const float* pp = s_p + (band.lo + h) * PS + f;
+            const float* pp = s_p + (band.lo + h) * PS + CS * f;
             const int body = band.len / H;
             float acc = 0.0f, acc2 = 0.0f;
             int i = 0;
