@@ -5,8 +5,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -121,10 +124,15 @@ struct b2l_plan {
   float2* d_tw = nullptr;
   float2* d_twn = nullptr;
   int tw_count = 0;
-  // mel
+  // mel: band-sparse rows (bins [lo, lo+len) of each mel row); d_mel_w / d_band feed mel_project, the
+  // fused kernel uses a MelRow table built per tile geometry (H rows per warp step), cached here
   int n_mels = 0, mel_w_count = 0;
   float* d_mel_w = nullptr;
   MelBand* d_band = nullptr;
+  std::vector<MelBand> h_band;
+  std::vector<float> h_mel_w;
+  struct RowTable { MelRow* d_rows = nullptr; float* d_w = nullptr; int n_rows = 0, w_count = 0; };
+  mutable std::map<int, RowTable> row_tables;
   int power_mode = 2;
   float power = 2.0f;
   // mfcc
@@ -366,6 +374,10 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   cudaFree(p->d_twn);
   cudaFree(p->d_mel_w);
   cudaFree(p->d_band);
+  for (auto& kv : p->row_tables) {
+    cudaFree(kv.second.d_rows);
+    cudaFree(kv.second.d_w);
+  }
   cudaFree(p->d_dct);
   delete p;
   return B2L_OK;
@@ -461,6 +473,8 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     }
     p->n_mels = d->n_mels;
     p->mel_w_count = (int)w.size();
+    p->h_band = bands;
+    p->h_mel_w = w;
     if ((rc = upload(c, w, &p->d_mel_w)) || (rc = upload(c, bands, &p->d_band))) goto bad;
   }
   if (d->n_mfcc > 0) {
@@ -522,6 +536,74 @@ static int ensure_clip_max(b2l_ctx* c, size_t n_clips) {
   return B2L_OK;
 }
 
+// MelRow table for warps that process H mel rows at a time (see MelRow in common.cuh).
+static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, const b2l_plan::RowTable** out) {
+  auto it = p->row_tables.find(H);
+  if (it != p->row_tables.end()) {
+    *out = &it->second;
+    return B2L_OK;
+  }
+  const int n_rows = (p->n_mels + H - 1) / H * H;
+  std::vector<MelRow> rows(n_rows);
+  std::vector<float> w;
+  for (int item = 0; item < n_rows / H; ++item) {
+    std::vector<int> start(H), lenp(H);
+    int quads = 0;
+    for (int j = 0; j < H; ++j) {
+      const int m = item * H + j;
+      if (m < p->n_mels && p->h_band[m].len > 0) {
+        const MelBand& b = p->h_band[m];
+        int st = b.lo - (((b.lo - j) % H) + H) % H;   // largest row <= lo congruent to j mod H
+        if (st < 0) st = b.lo;
+        start[j] = st;
+        lenp[j] = b.lo + b.len - st;
+      } else {
+        start[j] = j;
+        lenp[j] = 0;
+      }
+      quads = std::max(quads, (lenp[j] + 3) / 4);
+    }
+    for (int j = 0; j < H; ++j) {
+      const int m = item * H + j;
+      MelRow r;
+      r.lo = (unsigned short)start[j];
+      r.quads = (unsigned short)quads;
+      r.off = (unsigned int)w.size();
+      size_t base = w.size();
+      w.resize(base + (size_t)4 * quads, 0.0f);
+      if (lenp[j] > 0) {
+        const MelBand& b = p->h_band[m];
+        for (int i = 0; i < b.len; ++i) w[base + (b.lo - start[j]) + i] = p->h_mel_w[b.off + i];
+      }
+      rows[m] = r;
+    }
+  }
+  b2l_plan::RowTable t;
+  t.n_rows = n_rows;
+  t.w_count = (int)w.size();
+  int rc;
+  if ((rc = upload(c, rows, &t.d_rows)) || (rc = upload(c, w, &t.d_w))) return rc;
+  auto ins = p->row_tables.emplace(H, t);
+  *out = &ins.first->second;
+  return B2L_OK;
+}
+
+// Kernel variants tried in order (first that fits shared memory wins): 116 = 16 warps as two independent
+// 8-warp halves, 16 / 8 = plain CTAs.  B2L_FWD_VARIANT forces one (A/B measurements).
+static int fwd_variants(const HostFftCfg& cfg, int out[3]) {
+  int n = 0;
+  const char* force = getenv("B2L_FWD_VARIANT");
+  if (force && *force) {
+    out[n++] = atoi(force);
+    return n;
+  }
+  if (cfg.log2m == 9 || cfg.log2m == 10) out[n++] = 116;
+  int nws[2];
+  const int k = cfg.nw_options(nws);
+  for (int i = 0; i < k; ++i) out[n++] = nws[i];
+  return n;
+}
+
 static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const float* d_y, int64_t n_clips,
                        int64_t n, int64_t y_stride, float2* out_c, float* out_r) {
   if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
@@ -540,42 +622,59 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   HostFftCfg cfg(p->log2m);
   const int N = p->n_fft, M = N / 2;
   fwd_op_fn op = fwd_table(p->log2m);
-  int nws[2];
-  const int n_opt = cfg.nw_options(nws);
+  int variants[3];
+  const int n_opt = fwd_variants(cfg, variants);
   FwdArgs a;
   memset(&a, 0, sizeof(a));
-  int nw = 0;
+  int variant = 0, ft = 0, halves = 1;
   size_t smem = 0;
-  for (int i = 0; i < n_opt; ++i) {
-    const int w = nws[i];
-    const int ft = w * 32 / cfg.tpf;
+  const b2l_plan::RowTable* rt = nullptr;
+  for (int i = 0; i < n_opt && !variant; ++i) {
+    const int v = variants[i];
+    const bool dual = v == 116;
+    const int nw = dual ? 16 : v;
+    const int nh = dual ? 2 : 1;
+    if (nw * 32 % (cfg.tpf * nh) != 0) continue;
+    const int f = nw * 32 / nh / cfg.tpf;
+    if (f < 1 || f > 32) continue;
+    const long long span = (long long)(f - 1) * p->hop + N;
+    if (span > 0x3fffffff) continue;
+    const b2l_plan::RowTable* t = nullptr;
+    if (mode == MODE_MEL) {
+      int rc = get_row_table(c, p, 32 / f, &t);
+      if (rc) return rc;
+    }
     size_t off = 0;
     a.off_win = (int)off; off = align_up(off + (size_t)N * 4, 16);
     a.off_tw = (int)off; off = align_up(off + (size_t)cfg.tw_count() * 8, 16);
-    a.off_twn = (int)off; off = align_up(off + (size_t)(M / 2 + 1) * 8, 16);
-    a.off_bar = (int)off; off = align_up(off + 8, 16);
-    if (mode == MODE_MEL) {
-      a.off_melw = (int)off; off = align_up(off + (size_t)p->mel_w_count * 4, 16);
-      a.off_melband = (int)off; off = align_up(off + (size_t)p->n_mels * sizeof(MelBand), 16);
+    a.off_bar = (int)off; off = align_up(off + 16, 16);
+    if (t) {
+      a.off_melw = (int)off; off = align_up(off + (size_t)t->w_count * 4, 16);
+      a.off_melband = (int)off; off = align_up(off + (size_t)t->n_rows * sizeof(MelRow), 16);
     }
-    const long long span = (long long)(ft - 1) * p->hop + N;
-    a.off_in = (int)(off = align_up(off, 128)); off += (size_t)align_up((size_t)span * 4, 16);
+    a.off_in = (int)(off = align_up(off, 128));
+    a.in_stride = (int)align_up((size_t)span * 4, 128);
+    off += (size_t)a.in_stride * nh;
     a.off_xbuf = (int)(off = align_up(off, 128));
-    size_t xbytes = (size_t)ft * cfg.xbuf_f2() * 8;
-    size_t pbytes = mode == MODE_MEL ? (size_t)(M + 1) * (M <= 1024 ? 33 : ft + 1) * 4 : 0;   // MelLayout (common.cuh)
-    off += xbytes > pbytes ? xbytes : pbytes;
-    if (span > 0x3fffffff) continue;
-    a.in_floats = (int)span;
-    if (off <= c->smem_optin) {
-      nw = w;
-      smem = off;
-      break;
+    size_t xbytes = (size_t)f * cfg.xbuf_f2() * 8;
+    if (mode == MODE_MEL) {
+      const bool wide = M <= 1024 && !dual;                       // MelLayout (common.cuh)
+      size_t pbytes = (size_t)(M + 4) * (wide ? 33 : f + 1) * 4;
+      if (pbytes > xbytes) xbytes = pbytes;
     }
+    a.xbuf_stride = (int)align_up(xbytes, 128);
+    off += (size_t)a.xbuf_stride * nh;
+    if (off > c->smem_optin) continue;
+    variant = v;
+    ft = f;
+    halves = nh;
+    smem = off;
+    rt = t;
+    a.in_floats = (int)span;
   }
-  if (nw == 0)
+  if (!variant)
     return fail(B2L_ERR_UNSUPPORTED, "hop_length=%d with n_fft=%d needs more shared memory than one SM has", p->hop,
                 p->n_fft);
-  const int ft = nw * 32 / cfg.tpf;
 
   a.y = d_y;
   a.clip_stride = y_stride;
@@ -597,22 +696,26 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   a.power_mode = p->power_mode;
   a.power = p->power;
   a.n_mels = p->n_mels;
-  a.mel_w_count = p->mel_w_count;
-  a.mel_w = p->d_mel_w;
-  a.mel_band = p->d_band;
+  if (rt) {
+    a.mel_w_count = rt->w_count;
+    a.mel_w = rt->d_w;
+    a.mel_rows = rt->d_rows;
+    a.n_mel_rows = rt->n_rows;
+  }
   a.log_mode = log_mode;
   a.amin = p->amin;
   a.db_sub = 10.0f * log10f(fmaxf(p->amin, fabsf(p->ref_value)));
   a.clip_max = c->d_clip_max;
   a.status = c->d_status;
 
-  CUDA_TRY(op(OP_SET_SMEM, nw, mode, &a, 0, smem, c->stream, nullptr));
+  CUDA_TRY(op(OP_SET_SMEM, variant, mode, &a, 0, smem, c->stream, nullptr));
   int occ = 0;
-  CUDA_TRY(op(OP_OCCUPANCY, nw, mode, &a, 0, smem, c->stream, &occ));
+  CUDA_TRY(op(OP_OCCUPANCY, variant, mode, &a, 0, smem, c->stream, &occ));
   if (occ < 1) return fail(B2L_ERR_CUDA, "forward kernel does not fit on an SM (smem %zu)", smem);
   long long grid = (long long)c->sm_count * occ;
-  if (grid > a.total_tiles) grid = a.total_tiles;
-  CUDA_TRY(op(OP_LAUNCH, nw, mode, &a, (int)grid, smem, c->stream, nullptr));
+  const long long ctas_needed = (a.total_tiles + halves - 1) / halves;
+  if (grid > ctas_needed) grid = ctas_needed;
+  CUDA_TRY(op(OP_LAUNCH, variant, mode, &a, (int)grid, smem, c->stream, nullptr));
   c->launches++;
   return B2L_OK;
 }

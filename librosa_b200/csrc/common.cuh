@@ -20,18 +20,23 @@ enum FwdMode : int {
   MODE_SPEC = 2,   // |X|^power -> float32 [clip][frame][bin]
 };
 
-struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at mel_w[off ..]
+struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at mel_w[off ..] (mel_project kernel)
+// Fused-kernel form of one mel row: `quads` groups of 4 consecutive bins starting at bin `lo`, weights at
+// mel_w[off ..] (zero padded to 4*quads, off % 4 == 0).  Rows are grouped H at a time (H = 32 / frames
+// per tile): the rows of a group share `quads` and their `lo` are congruent to their position mod H.
+struct MelRow { unsigned short lo, quads; unsigned int off; };
 
 // Shared-memory layout of the power tile P[bin][frame] used by the mel phase (FT frames per tile,
 // H = 32/FT bin residues per warp step).  Wide: rows of 33 words, frame f at word H*f — bank = k + h + H*f
-// is distinct over the 32 lanes of both the transposing store and the (frame, residue) load.  For
-// M > 1024 the wide tile would not fit beside the exchange area, so rows shrink to FT+1 words.
-template <int M, int FT>
+// is distinct over the 32 lanes of both the transposing store and the (frame, row) load.  For M > 1024,
+// or when two half-CTAs each need a tile (DUAL), the wide tile does not fit and rows shrink to FT+1 words.
+template <int M, int FT, bool DUAL>
 struct MelLayout {
-  static constexpr bool WIDE = M <= 1024;
+  static constexpr bool WIDE = M <= 1024 && !DUAL;
   static constexpr int PS = WIDE ? 33 : FT + 1;
   static constexpr int CS = WIDE ? (32 / FT) : 1;
-  static constexpr size_t bytes() { return (size_t)(M + 1) * PS * 4; }
+  static constexpr int ROWS = M + 4;   // bins 0 .. M plus three zero rows (see MelRow)
+  static constexpr size_t bytes() { return (size_t)ROWS * PS * 4; }
 };
 
 struct FwdArgs {
@@ -54,14 +59,16 @@ struct FwdArgs {
   int power_mode;            // 2: re^2+im^2, 1: sqrt, 0: powf(|X|, power)
   float power;
   int n_mels, mel_w_count;
-  const float* mel_w;
-  const MelBand* mel_band;
+  const float* mel_w;        // padded weights of the MelRow table built for this tile geometry
+  const MelRow* mel_rows;    // n_mel_rows = n_mels rounded up to a multiple of H
+  int n_mel_rows;
   int log_mode;              // 1: write 10*log10(max(amin, S)) - db_sub and track the per-clip max
   float amin, db_sub;
   unsigned int* clip_max;    // order-preserving uint keys of the per-clip max (log_mode)
   int* status;               // bit 0 is set when a non-finite sample reached a frame (util.valid_audio)
   // dynamic shared-memory layout (byte offsets)
-  int off_win, off_tw, off_twn, off_in, off_xbuf, off_melw, off_melband, off_bar;
+  int off_win, off_tw, off_in, off_xbuf, off_melw, off_melband, off_bar;
+  int in_stride, xbuf_stride; // per-half strides (bytes) of the staging / exchange areas (DUAL)
   int in_floats;             // staged span length (floats)
 };
 

@@ -117,41 +117,55 @@ __device__ __forceinline__ int partner_slot(int t) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int LOG2M, int TPF, int NW, int MODE>
+// NW warps per CTA.  With DUAL the CTA is two independent halves of NW/2 warps ("virtual CTAs"): each has
+// its own staging buffer, exchange area, mbarrier, named barrier and tile sequence, and only the constant
+// tables are shared.  The halves drift apart, so the shared-memory-bound phases of one (operand fetch,
+// exchange, mel gather) overlap the FP32-bound butterflies of the other instead of all warps of the SM
+// hitting the same pipe at once.
+template <int LOG2M, int TPF, int NW, int MODE, bool DUAL>
 __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   using Cfg = FftCfg<LOG2M, TPF>;
   constexpr int M = Cfg::M, N = 2 * M, PPT = Cfg::PPT;
   constexpr int NT = NW * 32;
-  constexpr int FT = NT / TPF;                 // frames per tile == frame groups per CTA
+  constexpr int NH = DUAL ? 2 : 1;             // halves
+  constexpr int HT = NT / NH;                  // threads per half
+  constexpr int HW = NW / NH;                  // warps per half
+  constexpr int FT = HT / TPF;                 // frames per tile == frame groups per half
+  static_assert(!DUAL || (TPF <= 32 && NW % 2 == 0), "DUAL needs warp-sized frame groups");
   static_assert(FT >= 1 && FT <= 32, "tile must hold 1..32 frames");
-  constexpr int H = 32 / FT;                   // bin interleave of the mel phase
+  constexpr int H = 32 / FT;                   // mel rows handled concurrently by one warp
   constexpr int NPAIR = PPT / 2;               // bin pairs (k, M-k) per thread
 
   extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int half = DUAL ? tid / HT : 0;
+  const int htid = tid - half * HT;
   float* s_win = reinterpret_cast<float*>(smem + a.off_win);
   float2* s_tw = reinterpret_cast<float2*>(smem + a.off_tw);
-  float2* s_twn = reinterpret_cast<float2*>(smem + a.off_twn);
-  float* s_in = reinterpret_cast<float*>(smem + a.off_in);
-  float2* s_xall = reinterpret_cast<float2*>(smem + a.off_xbuf);
-  float* s_p = reinterpret_cast<float*>(smem + a.off_xbuf);     // P[k][FT] aliases the exchange area
   float* s_melw = reinterpret_cast<float*>(smem + a.off_melw);
-  MelBand* s_band = reinterpret_cast<MelBand*>(smem + a.off_melband);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+  MelRow* s_row = reinterpret_cast<MelRow*>(smem + a.off_melband);
+  float* s_in = reinterpret_cast<float*>(smem + a.off_in + half * a.in_stride);
+  float2* s_xall = reinterpret_cast<float2*>(smem + a.off_xbuf + half * a.xbuf_stride);
+  float* s_p = reinterpret_cast<float*>(s_xall);               // P tile aliases the exchange area
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + half;
 
-  const int tid = threadIdx.x;
-  const int grp = tid / TPF;                   // frame group == local frame index
-  const int t = tid % TPF;
+  const int grp = htid / TPF;                  // frame group == local frame index
+  const int t = htid % TPF;
   float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
 
-  // ---- one-time table staging
+  auto half_sync = [&]() {
+    if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");
+    else __syncthreads();
+  };
+
+  // ---- one-time table staging (whole CTA)
   for (int i = tid; i < N; i += NT) s_win[i] = a.window[i];
   for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.tw[i];
-  for (int i = tid; i <= M / 2; i += NT) s_twn[i] = a.twn[i];
   if constexpr (MODE == MODE_MEL) {
     for (int i = tid; i < a.mel_w_count; i += NT) s_melw[i] = a.mel_w[i];
-    for (int i = tid; i < a.n_mels; i += NT) s_band[i] = a.mel_band[i];
+    for (int i = tid; i < a.n_mel_rows; i += NT) s_row[i] = a.mel_rows[i];
   }
-  if (tid == 0) {
+  if (htid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
   }
@@ -159,6 +173,13 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
 
   const int span = a.in_floats;
   const bool hop_even = (a.hop & 1) == 0;
+  // un-mix twiddle of bin k = t + TPF*c:  W_N^k = W_N^t * W_(2*PPT)^c  (register x compile-time constant)
+  const float2 wt = __ldg(a.twn + t);
+  auto unmix_tw = [&](auto C) -> float2 {
+    constexpr int c = decltype(C)::value;
+    if constexpr (c == 0) return wt;
+    else return cmul(wt, make_float2(TwC<c, 2 * PPT>::re, TwC<c, 2 * PPT>::im));
+  };
 
   auto tile_origin = [&](long long tile, int& clip, int& t0, long long& s0) {
     clip = (int)(tile / a.tiles_per_clip);
@@ -180,11 +201,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     tma_load_1d(s_in, a.y + (long long)clip * a.clip_stride + s0, (uint32_t)span * 4u, s_bar);
   };
 
-  long long tile = blockIdx.x;
+  const long long tile_step = (long long)gridDim.x * NH;
+  long long tile = (long long)blockIdx.x * NH + half;
   uint32_t phase = 0;
-  if (tile < a.total_tiles && tid == 0 && tile_is_tma(tile)) issue_tma(tile);
+  if (tile < a.total_tiles && htid == 0 && tile_is_tma(tile)) issue_tma(tile);
 
-  for (; tile < a.total_tiles; tile += gridDim.x) {
+  for (; tile < a.total_tiles; tile += tile_step) {
     int clip, t0;
     long long s0;
     tile_origin(tile, clip, t0, s0);
@@ -194,8 +216,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       phase ^= 1;
     } else {
       const float* yc = a.y + (long long)clip * a.clip_stride;
-      for (int i = tid; i < span; i += NT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
-      __syncthreads();
+      for (int i = htid; i < span; i += HT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
+      half_sync();
     }
 
     // ---------------- windowed frame -> registers (pass-0 operands)
@@ -215,13 +237,13 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         });
       }
     }
-    __syncthreads();   // B0: staging buffer consumed -> prefetch the next tile behind the math
+    half_sync();   // B0: staging buffer consumed -> prefetch the next tile behind the math
     {
-      long long nxt = tile + gridDim.x;
-      if (tid == 0 && nxt < a.total_tiles && tile_is_tma(nxt)) issue_tma(nxt);
+      long long nxt = tile + tile_step;
+      if (htid == 0 && nxt < a.total_tiles && tile_is_tma(nxt)) issue_tma(nxt);
     }
 
-    // ---------------- M-point complex FFT, then publish Z for the pair un-mix
+    // ---------------- M-point complex FFT
     fft_forward<Cfg>(v, t, grp, xbuf, s_tw);
     if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp);
     // Bin pair (k, M-k), k = t + TPF*c < M/2: Z[k] is already in one of this thread's registers; only the
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         const int k = t + TPF * decltype(C)::value;
         float2 A, B, xa, xb;
         pair_operands(C, A, B);
-        r2c_pair(A, B, s_twn[k], xa, xb);
+        r2c_pair(A, B, unmix_tw(C), xa, xb);
         if (frame_ok) {
           orow[k] = xa;
           orow[M - k] = xb;
@@ -264,7 +286,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       if (t == 0) {
         float2 xa, xb;
         float2 zc = xbuf[xphys(M / 2)];
-        r2c_pair(zc, zc, s_twn[M / 2], xa, xb);
+        r2c_pair(zc, zc, make_float2(0.0f, -1.0f), xa, xb);   // W_N^(M/2) = -i
         if (frame_ok) orow[M / 2] = xa;
       }
       group_sync<TPF>(grp);   // pair reads done before the next tile's exchange writes
@@ -272,10 +294,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       float pw[PPT + 1];
       static_for<0, NPAIR>([&](auto C) {
         constexpr int c = decltype(C)::value;
-        const int k = t + TPF * c;
         float2 A, B, xa, xb;
         pair_operands(C, A, B);
-        r2c_pair(A, B, s_twn[k], xa, xb);
+        r2c_pair(A, B, unmix_tw(C), xa, xb);
         pw[2 * c] = sqmag(xa);
         pw[2 * c + 1] = sqmag(xb);
       });
@@ -283,7 +304,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       if (t == 0) {
         float2 xa, xb;
         float2 zc = xbuf[xphys(M / 2)];
-        r2c_pair(zc, zc, s_twn[M / 2], xa, xb);
+        r2c_pair(zc, zc, make_float2(0.0f, -1.0f), xa, xb);
         pw[PPT] = sqmag(xa);
       }
       if (a.power_mode != 2) {   // warp-uniform, cold for the default power = 2
@@ -305,56 +326,51 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         group_sync<TPF>(grp);
       } else {
         // ---------------- band-sparse mel projection over the tile
-        __syncthreads();   // B1: every group finished reading its Z
-        // P[k][f] at word k*PS + CS*f (MelLayout, common.cuh): the transposing writes (lanes = consecutive
-        // bins of one frame) and the mel reads (lanes = (frame, bin residue)) are both conflict-free in
-        // the wide layout, and every address is base + immediate (no per-access swizzle math).
-        constexpr int PS = MelLayout<M, FT>::PS, CS = MelLayout<M, FT>::CS;
-        auto paddr = [&](int k, int f) { return k * PS + CS * f; };
+        half_sync();   // B1: every group finished reading its Z
+        // P[k][f] at word k*PS + CS*f (MelLayout, common.cuh); rows M+1 .. M+3 are kept at zero so the
+        // 4-bin groups of the mel loop may run past the Nyquist bin.
+        using ML = MelLayout<M, FT, DUAL>;
+        constexpr int PS = ML::PS, CS = ML::CS;
         static_for<0, NPAIR>([&](auto C) {
           constexpr int c = decltype(C)::value;
           const int k = t + TPF * c;
-          s_p[paddr(k, grp)] = pw[2 * c];
-          s_p[paddr(M - k, grp)] = pw[2 * c + 1];
+          s_p[k * PS + CS * grp] = pw[2 * c];
+          s_p[(M - k) * PS + CS * grp] = pw[2 * c + 1];
         });
-        if (t == 0) s_p[paddr(M / 2, grp)] = pw[PPT];
-        __syncthreads();   // B2
+        if (t == 0) s_p[(M / 2) * PS + CS * grp] = pw[PPT];
+        if (htid < 3 * PS) s_p[(M + 1) * PS + htid] = 0.0f;
+        half_sync();   // B2
         {
-          const int warp = tid >> 5, lane = tid & 31;
-          const int f = lane & (FT - 1), h = lane / FT;
+          // Work item = H adjacent mel rows; lane (f, j) accumulates row i*H + j for frame f over that
+          // row's padded band (host-built MelRow table: the rows of an item share one trip count, start
+          // rows are congruent to j mod H so the wide layout reads conflict-free, weights are zero
+          // padded and 16-byte aligned).  No cross-lane reduction, one short loop per item.
+          const int hwarp = htid >> 5, lane = htid & 31;
+          const int f = lane & (FT - 1), j = lane / FT;
           const bool ok = (t0 + f) < a.n_frames;
           float wmax = -INFINITY;
-          for (int m = warp; m < a.n_mels; m += NW) {
-            const MelBand band = s_band[m];
-            // lane (f, h) takes bins lo + h, lo + h + H, ...; the trip count is warp-uniform (bands are
-            // split into a multiple-of-H body and a predicated tail) so the loop never diverges
-            const float* wp = s_melw + band.off + h;
-            const float* pp = s_p + (band.lo + h) * PS + CS * f;
-            const int body = band.len / H;
-            float acc = 0.0f, acc2 = 0.0f;
-            int i = 0;
-            for (; i + 4 <= body; i += 4) {
-              acc = fmaf(wp[0], pp[0], acc);
-              acc2 = fmaf(wp[H], pp[H * PS], acc2);
-              acc = fmaf(wp[2 * H], pp[2 * H * PS], acc);
-              acc2 = fmaf(wp[3 * H], pp[3 * H * PS], acc2);
-              wp += 4 * H;
-              pp += 4 * H * PS;
+          const int n_items = a.n_mel_rows / H;
+          for (int item = hwarp; item < n_items; item += HW) {
+            const int m = item * H + j;
+            const MelRow row = s_row[m];
+            const float4* wp = reinterpret_cast<const float4*>(s_melw + row.off);
+            const float* pp = s_p + row.lo * PS + CS * f;
+            const float4* wend = wp + row.quads;
+            float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 1
+            for (; wp != wend; ++wp, pp += 4 * PS) {
+              const float4 w = *wp;
+              acc0 = fmaf(w.x, pp[0], acc0);
+              acc1 = fmaf(w.y, pp[PS], acc1);
+              acc0 = fmaf(w.z, pp[2 * PS], acc0);
+              acc1 = fmaf(w.w, pp[3 * PS], acc1);
             }
-            for (; i < body; ++i) {
-              acc = fmaf(wp[0], pp[0], acc);
-              wp += H;
-              pp += H * PS;
-            }
-            if (h < band.len - body * H) acc2 = fmaf(wp[0], pp[0], acc2);
-            acc += acc2;
-#pragma unroll
-            for (int o = FT; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            float acc = acc0 + acc1;
             if (a.log_mode) {
               acc = 10.0f * log10f(fmaxf(a.amin, acc)) - a.db_sub;
-              if (ok) wmax = fmaxf(wmax, acc);
+              if (ok && m < a.n_mels) wmax = fmaxf(wmax, acc);
             }
-            if (h == 0 && ok) a.out_r[((long long)clip * a.n_mels + m) * a.n_frames + t0 + f] = acc;
+            if (ok && m < a.n_mels) a.out_r[((long long)clip * a.n_mels + m) * a.n_frames + t0 + f] = acc;
           }
           if (a.log_mode) {
 #pragma unroll
@@ -362,7 +378,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
             if (lane == 0 && wmax > -INFINITY) atomicMax(a.clip_max + clip, float_to_key(wmax));
           }
         }
-        __syncthreads();   // B3: P reads done before the next tile's exchange writes
+        half_sync();   // B3: P reads done before the next tile's exchange writes
       }
     }
   }
