@@ -597,7 +597,7 @@ static int fwd_variants(const HostFftCfg& cfg, int out[3]) {
     out[n++] = atoi(force);
     return n;
   }
-  if (cfg.log2m == 9 || cfg.log2m == 10) out[n++] = 116;
+  if (cfg.log2m >= 9 && cfg.log2m <= 11) out[n++] = 116;
   int nws[2];
   const int k = cfg.nw_options(nws);
   for (int i = 0; i < k; ++i) out[n++] = nws[i];
@@ -658,8 +658,9 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     a.off_xbuf = (int)(off = align_up(off, 128));
     size_t xbytes = (size_t)f * cfg.xbuf_f2() * 8;
     if (mode == MODE_MEL) {
-      const bool wide = M <= 1024 && !dual;                       // MelLayout (common.cuh)
-      size_t pbytes = (size_t)(M + 4) * (wide ? 33 : f + 1) * 4;
+      const int Hh = 32 / f;                                      // MelLayout (common.cuh)
+      const int rs = ((M + 4 - Hh + 31) / 32) * 32 + Hh;
+      size_t pbytes = (size_t)f * rs * 4;
       if (pbytes > xbytes) xbytes = pbytes;
     }
     a.xbuf_stride = (int)align_up(xbytes, 128);

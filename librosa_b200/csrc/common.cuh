@@ -26,17 +26,17 @@ struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at me
 // per tile): the rows of a group share `quads` and their `lo` are congruent to their position mod H.
 struct MelRow { unsigned short lo, quads; unsigned int off; };
 
-// Shared-memory layout of the power tile P[bin][frame] used by the mel phase (FT frames per tile,
-// H = 32/FT bin residues per warp step).  Wide: rows of 33 words, frame f at word H*f — bank = k + h + H*f
-// is distinct over the 32 lanes of both the transposing store and the (frame, row) load.  For M > 1024,
-// or when two half-CTAs each need a tile (DUAL), the wide tile does not fit and rows shrink to FT+1 words.
-template <int M, int FT, bool DUAL>
+// Shared-memory layout of the power tile used by the mel phase: frame-major, P[f][k] at word f*RS + k with
+// the row stride RS = (M + 4 rounded up) congruent to H = 32/FT modulo 32.  The transposing store (lanes =
+// consecutive bins of one frame) is contiguous; the mel load (lane (f, j) reads bin k_j + i with
+// k_j = j mod H, see MelRow) hits bank f*H + j + const — 32 distinct banks.  Rows hold bins 0 .. M plus
+// three zero bins so that 4-bin groups may run past the Nyquist bin.
+template <int M, int FT>
 struct MelLayout {
-  static constexpr bool WIDE = M <= 1024 && !DUAL;
-  static constexpr int PS = WIDE ? 33 : FT + 1;
-  static constexpr int CS = WIDE ? (32 / FT) : 1;
-  static constexpr int ROWS = M + 4;   // bins 0 .. M plus three zero rows (see MelRow)
-  static constexpr size_t bytes() { return (size_t)ROWS * PS * 4; }
+  static constexpr int H = 32 / FT;
+  static constexpr int RS = ((M + 4 - H + 31) / 32) * 32 + H;
+  static_assert(RS >= M + 4 && RS % 32 == H % 32, "row stride");
+  static constexpr size_t bytes() { return (size_t)FT * RS * 4; }
 };
 
 struct FwdArgs {

@@ -148,13 +148,14 @@ struct FftCfg {
 
 __device__ __forceinline__ int xphys(int e) { return e + (e >> 5); }
 
-// Group barrier: warp-sized (or smaller) groups use __syncwarp, larger ones a named barrier.
+// Group barrier: warp-sized (or smaller) groups use __syncwarp, larger ones the named barrier whose id the
+// caller assigns to the group (unique within the CTA, 1..15).
 template <int TPF>
-__device__ __forceinline__ void group_sync(int group_in_cta) {
+__device__ __forceinline__ void group_sync(int barrier_id) {
   if constexpr (TPF <= 32) {
     __syncwarp();
   } else {
-    asm volatile("bar.sync %0, %1;" ::"r"(group_in_cta + 1), "n"(TPF) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "n"(TPF) : "memory");   // ids 1..15, caller-assigned
   }
 }
 
@@ -178,7 +179,7 @@ __device__ __forceinline__ void load_pass0(float2 (&v)[Cfg::PPT], int t, LoadIn&
 // v[] must hold the pass-0 operands (see load_pass0) and receives the spectrum:
 //   v[b*RL + q] = Z[t + TPF*b + q*pL]   (RL, pL = radix / sub-length of the last pass, b = 0 .. PPT/RL-1).
 template <class Cfg>
-__device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int group_in_cta,
+__device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int barrier_id,
                                             float2* __restrict__ xbuf, const float2* __restrict__ tw) {
   constexpr int M = Cfg::M, TPF = Cfg::TPF, PPT = Cfg::PPT;
   static_for<0, Cfg::NPASS>([&](auto S) {
@@ -209,7 +210,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int gr
     static_for<0, NB>([&](auto B) { dft_reg<R, decltype(B)::value * R>(v); });
     // ---- store for the next pass
     if constexpr (s + 1 < Cfg::NPASS) {
-      if constexpr (s > 0) group_sync<TPF>(group_in_cta);   // everyone finished reading pass s-1 data
+      if constexpr (s > 0) group_sync<TPF>(barrier_id);   // everyone finished reading pass s-1 data
       static_for<0, NB>([&](auto B) {
         constexpr int b = decltype(B)::value;
         const int i = t + TPF * b;
@@ -220,7 +221,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int gr
           xbuf[xphys(j + q * p)] = v[b * R + q];
         });
       });
-      group_sync<TPF>(group_in_cta);
+      group_sync<TPF>(barrier_id);
     }
   });
 }

@@ -41,9 +41,7 @@ cudaError_t fwd_dispatch(int op, int nw, int mode, const FwdArgs* a, int grid, s
   if constexpr (L >= 10) {
     if (nw == 16) return by_mode<L, TPF, 16, false>(op, mode, a, grid, smem, st, result);
     if (nw == 8) return by_mode<L, TPF, 8, false>(op, mode, a, grid, smem, st, result);
-    if constexpr (TPF <= 32) {
-      if (nw == 116) return by_mode<L, TPF, 16, true>(op, mode, a, grid, smem, st, result);
-    }
+    if (nw == 116) return by_mode<L, TPF, 16, true>(op, mode, a, grid, smem, st, result);
   } else {
     constexpr int NW = TPF > 16 ? 16 : TPF;
     if (nw == NW) return by_mode<L, TPF, NW, false>(op, mode, a, grid, smem, st, result);

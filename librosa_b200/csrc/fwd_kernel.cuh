@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   constexpr int HT = NT / NH;                  // threads per half
   constexpr int HW = NW / NH;                  // warps per half
   constexpr int FT = HT / TPF;                 // frames per tile == frame groups per half
-  static_assert(!DUAL || (TPF <= 32 && NW % 2 == 0), "DUAL needs warp-sized frame groups");
+  static_assert(!DUAL || NW % 2 == 0, "DUAL splits the warps in two");
+  static_assert(TPF <= 32 || NH + NT / TPF <= 15, "named barriers: 1..NH for the halves, then one per frame group");
   static_assert(FT >= 1 && FT <= 32, "tile must hold 1..32 frames");
   constexpr int H = 32 / FT;                   // mel rows handled concurrently by one warp
   constexpr int NPAIR = PPT / 2;               // bin pairs (k, M-k) per thread
@@ -151,10 +152,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
 
   const int grp = htid / TPF;                  // frame group == local frame index
   const int t = htid % TPF;
+  const int gbar = 1 + NH + half * FT + grp;   // named barrier of this frame group (used when TPF > 32)
   float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
 
   auto half_sync = [&]() {
-    if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");
+    if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");   // ids 1, 2
     else __syncthreads();
   };
 
@@ -244,15 +246,15 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     }
 
     // ---------------- M-point complex FFT
-    fft_forward<Cfg>(v, t, grp, xbuf, s_tw);
-    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp);
+    fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
+    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
     // Bin pair (k, M-k), k = t + TPF*c < M/2: Z[k] is already in one of this thread's registers; only the
     // upper half of the spectrum (indices >= M/2) goes through shared memory to reach its partner.
     static_for<0, PPT>([&](auto S) {
       constexpr int slot = decltype(S)::value;
       if constexpr (spectrum_offset<Cfg>(slot) >= M / 2) xbuf[xphys(t + spectrum_offset<Cfg>(slot))] = v[slot];
     });
-    group_sync<TPF>(grp);
+    group_sync<TPF>(gbar);
     auto pair_operands = [&](auto C, float2& A, float2& B) {
       constexpr int c = decltype(C)::value;
       constexpr int sa = slot_of_pair<Cfg>(c);
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         r2c_pair(zc, zc, make_float2(0.0f, -1.0f), xa, xb);   // W_N^(M/2) = -i
         if (frame_ok) orow[M / 2] = xa;
       }
-      group_sync<TPF>(grp);   // pair reads done before the next tile's exchange writes
+      group_sync<TPF>(gbar);   // pair reads done before the next tile's exchange writes
     } else {
       float pw[PPT + 1];
       static_for<0, NPAIR>([&](auto C) {
@@ -323,27 +325,27 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
           });
           if (t == 0) orow[M / 2] = pw[PPT];
         }
-        group_sync<TPF>(grp);
+        group_sync<TPF>(gbar);
       } else {
         // ---------------- band-sparse mel projection over the tile
         half_sync();   // B1: every group finished reading its Z
-        // P[k][f] at word k*PS + CS*f (MelLayout, common.cuh); rows M+1 .. M+3 are kept at zero so the
-        // 4-bin groups of the mel loop may run past the Nyquist bin.
-        using ML = MelLayout<M, FT, DUAL>;
-        constexpr int PS = ML::PS, CS = ML::CS;
+        // P[f][k] frame-major with a bank-skewed row stride (MelLayout, common.cuh); bins M+1 .. M+3 of
+        // every row are kept at zero so the 4-bin groups of the mel loop may run past the Nyquist bin.
+        constexpr int RS = MelLayout<M, FT>::RS;
+        float* prow = s_p + grp * RS;
         static_for<0, NPAIR>([&](auto C) {
           constexpr int c = decltype(C)::value;
           const int k = t + TPF * c;
-          s_p[k * PS + CS * grp] = pw[2 * c];
-          s_p[(M - k) * PS + CS * grp] = pw[2 * c + 1];
+          prow[k] = pw[2 * c];
+          prow[M - k] = pw[2 * c + 1];
         });
-        if (t == 0) s_p[(M / 2) * PS + CS * grp] = pw[PPT];
-        if (htid < 3 * PS) s_p[(M + 1) * PS + htid] = 0.0f;
+        if (t == 0) prow[M / 2] = pw[PPT];
+        if (htid < 3 * FT) s_p[(htid / 3) * RS + M + 1 + (htid % 3)] = 0.0f;
         half_sync();   // B2
         {
           // Work item = H adjacent mel rows; lane (f, j) accumulates row i*H + j for frame f over that
           // row's padded band (host-built MelRow table: the rows of an item share one trip count, start
-          // rows are congruent to j mod H so the wide layout reads conflict-free, weights are zero
+          // bins are congruent to j mod H so the skewed tile reads conflict-free, weights are zero
           // padded and 16-byte aligned).  No cross-lane reduction, one short loop per item.
           const int hwarp = htid >> 5, lane = htid & 31;
           const int f = lane & (FT - 1), j = lane / FT;
@@ -354,16 +356,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
             const int m = item * H + j;
             const MelRow row = s_row[m];
             const float4* wp = reinterpret_cast<const float4*>(s_melw + row.off);
-            const float* pp = s_p + row.lo * PS + CS * f;
+            const float* pp = s_p + f * RS + row.lo;
             const float4* wend = wp + row.quads;
             float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll 1
-            for (; wp != wend; ++wp, pp += 4 * PS) {
+            for (; wp != wend; ++wp, pp += 4) {
               const float4 w = *wp;
               acc0 = fmaf(w.x, pp[0], acc0);
-              acc1 = fmaf(w.y, pp[PS], acc1);
-              acc0 = fmaf(w.z, pp[2 * PS], acc0);
-              acc1 = fmaf(w.w, pp[3 * PS], acc1);
+              acc1 = fmaf(w.y, pp[1], acc1);
+              acc0 = fmaf(w.z, pp[2], acc0);
+              acc1 = fmaf(w.w, pp[3], acc1);
             }
             float acc = acc0 + acc1;
             if (a.log_mode) {

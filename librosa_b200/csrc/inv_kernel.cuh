@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
         c2r_pair(xc, xc, s_twn[M / 2], A, B);
         xbuf[xphys(M / 2)] = make_float2(A.y, A.x);
       }
-      group_sync<TPF>(grp);
+      group_sync<TPF>(grp + 1);
       float2 v[PPT];
       load_pass0<Cfg>(v, t, [&](int e) { return xbuf[xphys(e)]; });
-      group_sync<TPF>(grp);           // operands fetched before the exchange area is overwritten
-      fft_forward<Cfg>(v, t, grp, xbuf, s_tw);
-      if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp);
+      group_sync<TPF>(grp + 1);           // operands fetched before the exchange area is overwritten
+      fft_forward<Cfg>(v, t, grp + 1, xbuf, s_tw);
+      if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp + 1);
       // ---- un-swap, window (carries 1/n_fft), park the frame: ybuf[j], j = 0 .. n_fft-1
       float2* ybuf = xbuf;
       static_for<0, PPT>([&](auto S) {
