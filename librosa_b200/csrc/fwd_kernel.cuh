@@ -188,38 +188,66 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     t0 = (int)(tile % a.tiles_per_clip) * FT;
     s0 = (long long)t0 * a.hop - a.pad;
   };
-  auto tile_is_tma = [&](long long tile) -> bool {
+  // How a tile's span gets into shared memory:
+  //   TILE_TMA      entirely inside the clip and 16-byte aligned -> one bulk copy
+  //   TILE_TMA_ZERO zero ("constant") padding, aligned: bulk-copy the in-range part, threads zero the rest
+  //   TILE_GATHER   anything else (reflect / edge / ... padding, unaligned clips): per-sample gather
+  enum { TILE_GATHER = 0, TILE_TMA = 1, TILE_TMA_ZERO = 2 };
+  auto tile_kind = [&](long long tile, int& lead, int& valid) -> int {
     int clip, t0;
     long long s0;
     tile_origin(tile, clip, t0, s0);
-    return a.tma_ok && s0 >= 0 && s0 + span <= a.n && (s0 & 3) == 0;
+    lead = s0 < 0 ? (int)(-s0) : 0;                                   // floats before the clip starts
+    long long end = s0 + span;
+    valid = (int)((end > a.n ? (long long)a.n : end) - (s0 + lead));  // in-range floats
+    if (!a.tma_ok || ((s0 + lead) & 3) != 0) return TILE_GATHER;
+    if (lead == 0 && valid == span) return TILE_TMA;
+    if (a.pad_mode == PAD_CONSTANT && valid > 0 && (lead & 3) == 0 && (valid & 3) == 0) return TILE_TMA_ZERO;
+    return TILE_GATHER;
   };
-  auto issue_tma = [&](long long tile) {
+  auto issue_tma = [&](long long tile, int lead, int valid) {
     int clip, t0;
     long long s0;
     tile_origin(tile, clip, t0, s0);
     fence_proxy_async();
-    mbar_expect_tx(s_bar, (uint32_t)span * 4u);
-    tma_load_1d(s_in, a.y + (long long)clip * a.clip_stride + s0, (uint32_t)span * 4u, s_bar);
+    mbar_expect_tx(s_bar, (uint32_t)valid * 4u);
+    tma_load_1d(s_in + lead, a.y + (long long)clip * a.clip_stride + s0 + lead, (uint32_t)valid * 4u, s_bar);
+  };
+  // Called by the whole half after the staging buffer has been released (B0): start the copy of `tile`.
+  auto prefetch = [&](long long tile) {
+    if (tile >= a.total_tiles) return;
+    int lead, valid;
+    const int kind = tile_kind(tile, lead, valid);
+    if (kind == TILE_GATHER) return;
+    if (htid == 0) issue_tma(tile, lead, valid);
+    if (kind == TILE_TMA_ZERO) {
+      for (int i = htid; i < lead; i += HT) s_in[i] = 0.0f;
+      for (int i = lead + valid + htid; i < span; i += HT) s_in[i] = 0.0f;
+    }
   };
 
   const long long tile_step = (long long)gridDim.x * NH;
   long long tile = (long long)blockIdx.x * NH + half;
   uint32_t phase = 0;
-  if (tile < a.total_tiles && htid == 0 && tile_is_tma(tile)) issue_tma(tile);
+  prefetch(tile);
 
   for (; tile < a.total_tiles; tile += tile_step) {
     int clip, t0;
     long long s0;
     tile_origin(tile, clip, t0, s0);
     // ---------------- stage the tile's sample span
-    if (tile_is_tma(tile)) {
-      mbar_wait(s_bar, phase);
-      phase ^= 1;
-    } else {
-      const float* yc = a.y + (long long)clip * a.clip_stride;
-      for (int i = htid; i < span; i += HT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
-      half_sync();
+    {
+      int lead, valid;
+      const int kind = tile_kind(tile, lead, valid);
+      if (kind == TILE_GATHER) {
+        const float* yc = a.y + (long long)clip * a.clip_stride;
+        for (int i = htid; i < span; i += HT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
+        half_sync();
+      } else {
+        mbar_wait(s_bar, phase);
+        phase ^= 1;
+        if (kind == TILE_TMA_ZERO) half_sync();   // zeros written by other threads
+      }
     }
 
     // ---------------- windowed frame -> registers (pass-0 operands)
@@ -240,10 +268,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       }
     }
     half_sync();   // B0: staging buffer consumed -> prefetch the next tile behind the math
-    {
-      long long nxt = tile + tile_step;
-      if (htid == 0 && nxt < a.total_tiles && tile_is_tma(nxt)) issue_tma(nxt);
-    }
+    prefetch(tile + tile_step);
 
     // ---------------- M-point complex FFT
     fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
@@ -359,13 +384,24 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
             const float* pp = s_p + f * RS + row.lo;
             const float4* wend = wp + row.quads;
             float acc0 = 0.0f, acc1 = 0.0f;
+            if (wp != wend) {
+              // software pipeline: the next group's weights and powers are in flight while this one is summed
+              float4 w = *wp;
+              float p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
 #pragma unroll 1
-            for (; wp != wend; ++wp, pp += 4) {
-              const float4 w = *wp;
-              acc0 = fmaf(w.x, pp[0], acc0);
-              acc1 = fmaf(w.y, pp[1], acc1);
-              acc0 = fmaf(w.z, pp[2], acc0);
-              acc1 = fmaf(w.w, pp[3], acc1);
+              for (++wp, pp += 4; wp != wend; ++wp, pp += 4) {
+                const float4 wn = *wp;
+                const float n0 = pp[0], n1 = pp[1], n2 = pp[2], n3 = pp[3];
+                acc0 = fmaf(w.x, p0, acc0);
+                acc1 = fmaf(w.y, p1, acc1);
+                acc0 = fmaf(w.z, p2, acc0);
+                acc1 = fmaf(w.w, p3, acc1);
+                w = wn; p0 = n0; p1 = n1; p2 = n2; p3 = n3;
+              }
+              acc0 = fmaf(w.x, p0, acc0);
+              acc1 = fmaf(w.y, p1, acc1);
+              acc0 = fmaf(w.z, p2, acc0);
+              acc1 = fmaf(w.w, p3, acc1);
             }
             float acc = acc0 + acc1;
             if (a.log_mode) {
