@@ -478,7 +478,11 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     if ((rc = upload(c, w, &p->d_mel_w)) || (rc = upload(c, bands, &p->d_band))) goto bad;
   }
   if (d->n_mfcc > 0) {
-    std::vector<float> dct(d->h_dct_basis, d->h_dct_basis + (size_t)d->n_mfcc * d->n_mels);
+    // transposed and zero padded to 8-coefficient groups: dctT[m][8*KG] (dct_clamp_kernel)
+    const int KP = (d->n_mfcc + 7) / 8 * 8;
+    std::vector<float> dct((size_t)d->n_mels * KP, 0.0f);
+    for (int k = 0; k < d->n_mfcc; ++k)
+      for (int m = 0; m < d->n_mels; ++m) dct[(size_t)m * KP + k] = d->h_dct_basis[(size_t)k * d->n_mels + m];
     p->n_mfcc = d->n_mfcc;
     if ((rc = upload(c, dct, &p->d_dct))) goto bad;
   }
@@ -738,15 +742,19 @@ static int launch_dct(b2l_ctx* c, const b2l_plan* p, const float* d_L, int64_t n
                       float* d_out) {
   const int KG = (p->n_mfcc + 7) / 8;
   if (KG > 32) return fail(B2L_ERR_UNSUPPORTED, "n_mfcc=%d > 256 is not supported", p->n_mfcc);
-  size_t smem = ((size_t)p->n_mels * DCT_TILE + (size_t)p->n_mels * 8 * KG) * 4;
+  size_t smem = ((size_t)p->n_mels * 8 * KG + 2 * (size_t)p->n_mels * DCT_TILE) * 4;
   if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_mels=%d is too large for the DCT kernel", p->n_mels);
   CUDA_TRY(cudaFuncSetAttribute(dct_clamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (int)((T + DCT_TILE - 1) / DCT_TILE);
-  const long long grid = (long long)tiles * n_clips;
-  if (grid > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many DCT tiles");
+  const long long total = (long long)tiles * n_clips;
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dct_clamp_kernel, KG * 32, smem));
+  if (occ < 1) return fail(B2L_ERR_CUDA, "DCT kernel does not fit on an SM");
+  long long grid = (long long)c->sm_count * occ;
+  if (grid > total) grid = total;
   dct_clamp_kernel<<<(int)grid, KG * 32, smem, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
                                                             clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, (int)T,
-                                                            tiles, d_out);
+                                                            tiles, total, d_out);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return B2L_OK;
@@ -790,31 +798,48 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
   HostFftCfg cfg(p->log2m);
   const int N = p->n_fft, M = N / 2;
   inv_op_fn op = inv_table(p->log2m);
-  int nws[2];
-  const int n_opt = cfg.nw_options(nws);
+  int variants[3];
+  int n_opt = 0;
+  {
+    const char* force = getenv("B2L_INV_VARIANT");
+    if (force && *force) {
+      variants[n_opt++] = atoi(force);
+    } else {
+      if (cfg.log2m >= 9 && cfg.log2m <= 11) variants[n_opt++] = 116;
+      int nws[2];
+      const int k = cfg.nw_options(nws);
+      for (int i = 0; i < k; ++i) variants[n_opt++] = nws[i];
+    }
+  }
   InvArgs a;
   memset(&a, 0, sizeof(a));
-  int nw = 0;
+  int variant = 0, G = 0, halves = 1;
   size_t smem = 0;
   const int clen = N > p->hop ? N - p->hop : 0;
-  for (int i = 0; i < n_opt; ++i) {
-    const int w = nws[i];
-    const int G = w * 32 / cfg.tpf;
+  for (int i = 0; i < n_opt && !variant; ++i) {
+    const int v = variants[i];
+    const bool dual = v == 116;
+    const int nw = dual ? 16 : v;
+    const int nh = dual ? 2 : 1;
+    if (nw * 32 % (cfg.tpf * nh) != 0) continue;
+    const int gg = nw * 32 / nh / cfg.tpf;
+    if (gg < 1) continue;
     size_t off = 0;
     a.off_win = (int)off; off = align_up(off + (size_t)N * 4, 16);
     a.off_tw = (int)off; off = align_up(off + (size_t)cfg.tw_count() * 8, 16);
-    a.off_twn = (int)off; off = align_up(off + (size_t)(M / 2 + 1) * 8, 16);
-    a.off_acc = (int)off; off = align_up(off + (size_t)2 * clen * 4, 16);
+    a.off_acc = (int)off;
+    a.acc_stride = (int)align_up((size_t)2 * clen * 4, 16);
+    off += (size_t)a.acc_stride * nh;
     a.off_xbuf = (int)(off = align_up(off, 128));
-    off += (size_t)G * cfg.xbuf_f2() * 8;
-    if (off <= c->smem_optin) {
-      nw = w;
-      smem = off;
-      break;
-    }
+    a.xbuf_stride = (int)align_up((size_t)gg * cfg.xbuf_f2() * 8, 128);
+    off += (size_t)a.xbuf_stride * nh;
+    if (off > c->smem_optin) continue;
+    variant = v;
+    G = gg;
+    halves = nh;
+    smem = off;
   }
-  if (nw == 0) return fail(B2L_ERR_UNSUPPORTED, "istft configuration does not fit in shared memory");
-  const int G = nw * 32 / cfg.tpf;
+  if (!variant) return fail(B2L_ERR_UNSUPPORTED, "istft configuration does not fit in shared memory");
   a.acc_floats = 2 * clen;
   a.D = (const float2*)d_D;
   a.d_clip_stride = (long long)n_frames_stored * (M + 1);
@@ -830,10 +855,10 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
   a.inv_wss = d_inv_wss;
   a.tw = p->d_tw;
   a.twn = p->d_twn;
-  // segments: enough CTAs to fill the machine twice; each at least 4 rounds long so the halo frames
+  // segments: enough half-CTAs to fill the machine twice; each at least 4 rounds long so the halo frames
   // (recomputed at every segment start) stay a small fraction
   {
-    const long long want = 2LL * c->sm_count;
+    const long long want = 2LL * c->sm_count * halves;
     long long segs = (want + n_clips - 1) / n_clips;
     const long long max_segs = (n_frames_used + 4LL * G - 1) / (4LL * G);
     if (segs > max_segs) segs = max_segs;
@@ -844,10 +869,11 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
     a.segs_per_clip = (int)segs;
     a.frames_per_seg = (int)fps;
   }
-  const long long grid = (long long)a.segs_per_clip * n_clips;
+  const long long items = (long long)a.segs_per_clip * n_clips;
+  const long long grid = (items + halves - 1) / halves;
   if (grid > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many istft segments");
-  CUDA_TRY(op(OP_SET_SMEM, nw, &a, 0, smem, c->stream, nullptr));
-  CUDA_TRY(op(OP_LAUNCH, nw, &a, (int)grid, smem, c->stream, nullptr));
+  CUDA_TRY(op(OP_SET_SMEM, variant, &a, 0, smem, c->stream, nullptr));
+  CUDA_TRY(op(OP_LAUNCH, variant, &a, (int)grid, smem, c->stream, nullptr));
   c->launches++;
   return B2L_OK;
 }

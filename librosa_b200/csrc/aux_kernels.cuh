@@ -10,64 +10,101 @@ namespace b2l {
 // out C   [n_clips][n_mfcc][T]   C[k][t] = sum_m dct[k][m] * max(L[m][t], clipmax - top_db)
 // Reference: np.maximum(log_spec, log_spec.max(...) - top_db) (librosa/core/spectrum.py:1881) followed by
 // scipy.fft.dct(S, axis=-2, type, norm)[..., :n_mfcc, :] (* lifter) (librosa/feature/spectral.py:2005-2015);
-// the DCT (any type / norm, lifter folded in) arrives as an explicit [n_mfcc][n_mels] matrix.
-// Block: KG warps; warp w owns coefficients 8w .. 8w+7, lane owns frames lane + 32 i (i = 0..3) of a
-// 128-frame tile that is staged (clamped) in shared memory; DCT rows are read as warp-uniform float4.
-constexpr int DCT_TILE = 128;
+// the DCT (any type / norm, lifter folded in) arrives transposed and zero padded: dctT[m][8*KG].
+//
+// Persistent blocks of KG warps walk (clip, 64-frame tile) pairs.  Warp w owns coefficients 8w..8w+7,
+// lane owns frames lane and lane+32 of the tile; DCT rows are warp-uniform float4 loads.  Tiles are
+// double buffered with cp.async (LDGSTS) so the next tile streams in while this one is multiplied; the
+// top_db clamp is applied as the values are read.
+constexpr int DCT_TILE = 64;
 
-__global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __restrict__ dct,
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __restrict__ dctT,
                                  const unsigned int* __restrict__ clip_max, float top_db, int n_mels,
-                                 int n_mfcc, int T, int tiles_per_clip, float* __restrict__ C) {
+                                 int n_mfcc, int T, int tiles_per_clip, long long total_tiles,
+                                 float* __restrict__ C) {
   extern __shared__ __align__(16) float s_dyn[];
-  const int KG = blockDim.x >> 5;
-  float* s_tile = s_dyn;                       // [n_mels][DCT_TILE]
-  float* s_dct = s_dyn + n_mels * DCT_TILE;    // [n_mels][8*KG]  (transposed, zero padded)
+  const int KG = blockDim.x >> 5, KP = 8 * KG;
+  float* s_dct = s_dyn;                                     // [n_mels][KP]
+  float* s_tile0 = s_dyn + n_mels * KP;                     // 2 x [n_mels][DCT_TILE]
+  const int tile_words = n_mels * DCT_TILE;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KP = 8 * KG;
-  for (int i = tid; i < n_mels * KP; i += blockDim.x) {
-    int m = i / KP, k = i % KP;
-    s_dct[i] = k < n_mfcc ? dct[k * n_mels + m] : 0.0f;
-  }
-  const int clip = blockIdx.x / tiles_per_clip;
-  const int t0 = (blockIdx.x % tiles_per_clip) * DCT_TILE;
-  float floor_v = -INFINITY;
-  if (clip_max != nullptr && top_db >= 0.0f) floor_v = key_to_float(clip_max[clip]) - top_db;
-  const float* Lc = L + (long long)clip * n_mels * T;
-  for (int i = tid; i < n_mels * DCT_TILE; i += blockDim.x) {
-    int m = i / DCT_TILE, x = i % DCT_TILE;
-    float val = 0.0f;
-    if (t0 + x < T) val = fmaxf(Lc[(long long)m * T + t0 + x], floor_v);
-    s_tile[i] = val;
-  }
-  __syncthreads();
-  float acc[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
-  for (int m = 0; m < n_mels; ++m) {
-    const float4 d0 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp);
-    const float4 d1 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp + 4);
-    const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    float xv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) xv[i] = s_tile[m * DCT_TILE + lane + 32 * i];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(dv[j], xv[i], acc[j][i]);
-  }
-  float* Cc = C + (long long)clip * n_mfcc * T;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = 8 * warp + j;
-    if (k < n_mfcc) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int tt = t0 + lane + 32 * i;
-        if (tt < T) Cc[(long long)k * T + tt] = acc[j][i];
+  for (int i = tid; i < n_mels * KP; i += blockDim.x) s_dct[i] = dctT[i];
+  const bool vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(L) & 15) == 0);
+
+  auto stage = [&](long long tile, float* buf) {
+    const int clip = (int)(tile / tiles_per_clip);
+    const int t0 = (int)(tile % tiles_per_clip) * DCT_TILE;
+    const float* Lc = L + (long long)clip * n_mels * T + t0;
+    if (vec_ok && t0 + DCT_TILE <= T) {
+      for (int i = tid; i < n_mels * (DCT_TILE / 4); i += blockDim.x) {
+        const int m = i / (DCT_TILE / 4), q = i % (DCT_TILE / 4);
+        cp_async16(buf + m * DCT_TILE + 4 * q, Lc + (long long)m * T + 4 * q);
+      }
+    } else {
+      for (int i = tid; i < tile_words; i += blockDim.x) {
+        const int m = i / DCT_TILE, x = i % DCT_TILE;
+        if (t0 + x < T) cp_async4(buf + i, Lc + (long long)m * T + x);
+        else buf[i] = 0.0f;
       }
     }
+    cp_async_commit();
+  };
+
+  long long tile = blockIdx.x;
+  if (tile < total_tiles) stage(tile, s_tile0);
+  int cur = 0;
+  for (; tile < total_tiles; tile += gridDim.x, cur ^= 1) {
+    const long long nxt = tile + gridDim.x;
+    if (nxt < total_tiles) {
+      stage(nxt, s_tile0 + (cur ^ 1) * tile_words);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* tile_s = s_tile0 + cur * tile_words;
+    const int clip = (int)(tile / tiles_per_clip);
+    const int t0 = (int)(tile % tiles_per_clip) * DCT_TILE;
+    float floor_v = -INFINITY;
+    if (clip_max != nullptr && top_db >= 0.0f) floor_v = key_to_float(clip_max[clip]) - top_db;
+    float acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0f;
+#pragma unroll 4
+    for (int m = 0; m < n_mels; ++m) {
+      const float4 d0 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp);
+      const float4 d1 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp + 4);
+      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const float x0 = fmaxf(tile_s[m * DCT_TILE + lane], floor_v);
+      const float x1 = fmaxf(tile_s[m * DCT_TILE + lane + 32], floor_v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j][0] = fmaf(dv[j], x0, acc[j][0]);
+        acc[j][1] = fmaf(dv[j], x1, acc[j][1]);
+      }
+    }
+    float* Cc = C + (long long)clip * n_mfcc * T;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = 8 * warp + j;
+      if (k < n_mfcc) {
+        if (t0 + lane < T) Cc[(long long)k * T + t0 + lane] = acc[j][0];
+        if (t0 + lane + 32 < T) Cc[(long long)k * T + t0 + lane + 32] = acc[j][1];
+      }
+    }
+    __syncthreads();   // tile consumed before the buffer is refilled two iterations later
   }
 }
 

@@ -176,6 +176,20 @@ __device__ __forceinline__ void load_pass0(float2 (&v)[Cfg::PPT], int t, LoadIn&
   });
 }
 
+// Element offset (index minus t) that load_pass0 puts in v[slot], and the slot that receives element
+// t + TPF*c — used by the inverse path, whose rebuilt spectrum values are born in registers.
+template <class Cfg>
+__host__ __device__ constexpr int pass0_offset(int slot) {
+  constexpr int R = Cfg::radix(0), LOGR = Cfg::log_radix(0), T = Cfg::M / R;
+  return Cfg::TPF * (slot / R) + bitrevc(slot % R, LOGR) * T;   // bitrevc is an involution
+}
+template <class Cfg>
+__host__ __device__ constexpr int pass0_slot_of_pair(int c) {
+  for (int s = 0; s < Cfg::PPT; ++s)
+    if (pass0_offset<Cfg>(s) == Cfg::TPF * c) return s;
+  return -1;
+}
+
 // v[] must hold the pass-0 operands (see load_pass0) and receives the spectrum:
 //   v[b*RL + q] = Z[t + TPF*b + q*pL]   (RL, pL = radix / sub-length of the last pass, b = 0 .. PPT/RL-1).
 template <class Cfg>

@@ -384,24 +384,13 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
             const float* pp = s_p + f * RS + row.lo;
             const float4* wend = wp + row.quads;
             float acc0 = 0.0f, acc1 = 0.0f;
-            if (wp != wend) {
-              // software pipeline: the next group's weights and powers are in flight while this one is summed
-              float4 w = *wp;
-              float p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
-#pragma unroll 1
-              for (++wp, pp += 4; wp != wend; ++wp, pp += 4) {
-                const float4 wn = *wp;
-                const float n0 = pp[0], n1 = pp[1], n2 = pp[2], n3 = pp[3];
-                acc0 = fmaf(w.x, p0, acc0);
-                acc1 = fmaf(w.y, p1, acc1);
-                acc0 = fmaf(w.z, p2, acc0);
-                acc1 = fmaf(w.w, p3, acc1);
-                w = wn; p0 = n0; p1 = n1; p2 = n2; p3 = n3;
-              }
-              acc0 = fmaf(w.x, p0, acc0);
-              acc1 = fmaf(w.y, p1, acc1);
-              acc0 = fmaf(w.z, p2, acc0);
-              acc1 = fmaf(w.w, p3, acc1);
+#pragma unroll 2
+            for (; wp != wend; ++wp, pp += 4) {
+              const float4 w = *wp;
+              acc0 = fmaf(w.x, pp[0], acc0);
+              acc1 = fmaf(w.y, pp[1], acc1);
+              acc0 = fmaf(w.z, pp[2], acc0);
+              acc1 = fmaf(w.w, pp[3], acc1);
             }
             float acc = acc0 + acc1;
             if (a.log_mode) {

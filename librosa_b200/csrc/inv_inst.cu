@@ -20,16 +20,21 @@ cudaError_t run_op(K kern, int op, int nt, const InvArgs* a, int grid, size_t sm
 #define B2L_CAT2(a, b) a##b
 #define B2L_CAT(a, b) B2L_CAT2(a, b)
 
+// `nw`: 16 or 8 warps; 116 = 16 warps as two independent 8-warp halves (DUAL).
 template <int L>
 cudaError_t inv_dispatch(int op, int nw, const InvArgs* a, int grid, size_t smem, cudaStream_t st, int* result) {
   constexpr int M = 1 << L;
   constexpr int TPF = M >= 32 ? M / 32 : 1;
   if constexpr (L >= 10) {
-    if (nw == 16) return run_op(inv_kernel<L, TPF, 16>, op, 16 * 32, a, grid, smem, st, result);
-    if (nw == 8) return run_op(inv_kernel<L, TPF, 8>, op, 8 * 32, a, grid, smem, st, result);
+    if (nw == 16) return run_op(inv_kernel<L, TPF, 16, false>, op, 16 * 32, a, grid, smem, st, result);
+    if (nw == 8) return run_op(inv_kernel<L, TPF, 8, false>, op, 8 * 32, a, grid, smem, st, result);
+    if (nw == 116) return run_op(inv_kernel<L, TPF, 16, true>, op, 16 * 32, a, grid, smem, st, result);
   } else {
     constexpr int NW = TPF > 16 ? 16 : TPF;
-    if (nw == NW) return run_op(inv_kernel<L, TPF, NW>, op, NW * 32, a, grid, smem, st, result);
+    if (nw == NW) return run_op(inv_kernel<L, TPF, NW, false>, op, NW * 32, a, grid, smem, st, result);
+    if constexpr (L == 9) {
+      if (nw == 116) return run_op(inv_kernel<L, TPF, 16, true>, op, 16 * 32, a, grid, smem, st, result);
+    }
   }
   return cudaErrorInvalidValue;
 }

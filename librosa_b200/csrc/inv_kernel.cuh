@@ -3,48 +3,60 @@
 // Replaces librosa.istft's per-block  win * scipy.fft.irfft(D)  (librosa/core/spectrum.py:566, :598),
 // the numba __overlap_add loop (:629-643) and the window-sum-square division (:606-624).
 //
-// A CTA owns one (clip, segment of frames).  It walks its frames G at a time (one frame per thread
-// group): each group rebuilds the packed half-length spectrum from bin pairs (c2r_pair), runs the
-// same register FFT as the forward path with re/im swapped (== inverse transform), multiplies by
-// the window (which carries 1/n_fft) and parks the frame in its exchange region.  The CTA then
-// *gathers*: every output sample sums the frames that cover it in increasing frame order — the
-// order the reference adds them — plus the carry of the previous rounds, and is written exactly once,
-// already divided by the window-sum-square.  No atomics, bit-reproducible.
+// A half-CTA (see DUAL in fwd_kernel.cuh) owns one (clip, segment of frames).  It walks its frames G at
+// a time (one frame per thread group): each group rebuilds the packed half-length spectrum from bin
+// pairs (c2r_pair) — the lower half lands directly in the registers that feed the first FFT pass, the
+// upper half crosses shared memory to its partner thread — runs the same register FFT as the forward
+// path with re/im swapped (== inverse transform), multiplies by the window (which carries 1/n_fft) and
+// parks the frame in its exchange region.  The half then *gathers*: every output sample sums the frames
+// that cover it in increasing frame order — the order the reference adds them — plus the carry of the
+// previous rounds, and is written exactly once, already divided by the window-sum-square.  No atomics,
+// bit-reproducible.
 #pragma once
 #include "common.cuh"
 #include "fft_engine.cuh"
 
 namespace b2l {
 
-template <int LOG2M, int TPF, int NW>
+template <int LOG2M, int TPF, int NW, bool DUAL>
 __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
   using Cfg = FftCfg<LOG2M, TPF>;
   constexpr int M = Cfg::M, N = 2 * M, PPT = Cfg::PPT;
   constexpr int NT = NW * 32;
-  constexpr int G = NT / TPF;
+  constexpr int NH = DUAL ? 2 : 1;
+  constexpr int HT = NT / NH;
+  constexpr int G = HT / TPF;                  // frames per round of one half
   constexpr int NPAIR = PPT / 2;
+  static_assert(TPF <= 32 || NH + NT / TPF <= 15, "named barriers: 1..NH for the halves, then one per frame group");
 
   extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int half = DUAL ? tid / HT : 0;
+  const int htid = tid - half * HT;
   float* s_win = reinterpret_cast<float*>(smem + a.off_win);
   float2* s_tw = reinterpret_cast<float2*>(smem + a.off_tw);
-  float2* s_twn = reinterpret_cast<float2*>(smem + a.off_twn);
-  float2* s_xall = reinterpret_cast<float2*>(smem + a.off_xbuf);
-  float* s_carry = reinterpret_cast<float*>(smem + a.off_acc);   // two buffers of clen floats
+  float2* s_xall = reinterpret_cast<float2*>(smem + a.off_xbuf + half * a.xbuf_stride);
+  float* s_carry = reinterpret_cast<float*>(smem + a.off_acc + half * a.acc_stride);   // 2 x clen floats
 
-  const int tid = threadIdx.x;
-  const int grp = tid / TPF;
-  const int t = tid % TPF;
+  const int grp = htid / TPF;
+  const int t = htid % TPF;
+  const int gbar = 1 + NH + half * G + grp;
   float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
+  auto half_sync = [&]() {
+    if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");
+    else __syncthreads();
+  };
 
   for (int i = tid; i < N; i += NT) s_win[i] = a.window[i];
   for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.tw[i];
-  for (int i = tid; i <= M / 2; i += NT) s_twn[i] = a.twn[i];
   const int clen = a.n_fft > a.hop ? a.n_fft - a.hop : 0;
-  for (int i = tid; i < 2 * clen; i += NT) s_carry[i] = 0.0f;
+  for (int i = htid; i < 2 * clen; i += HT) s_carry[i] = 0.0f;
   __syncthreads();
 
-  const int clip = blockIdx.x / a.segs_per_clip;
-  const int seg = blockIdx.x % a.segs_per_clip;
+  const long long item = (long long)blockIdx.x * NH + half;     // (clip, segment)
+  if (item >= (long long)a.n_clips * a.segs_per_clip) return;
+  const int clip = (int)(item / a.segs_per_clip);
+  const int seg = (int)(item % a.segs_per_clip);
   const int fs = seg * a.frames_per_seg;
   const int fe = min(a.n_frames, fs + a.frames_per_seg);
   if (fs >= fe) return;
@@ -58,6 +70,7 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
   float* yclip = a.y + (long long)clip * a.y_clip_stride;
   float* carry_cur = s_carry;
   float* carry_nxt = s_carry + clen;
+  const float2 wt = __ldg(a.twn + t);                         // W_N^t, see unmix twiddle in fwd_kernel.cuh
 
   int fr0 = fh;
   for (; fr0 < fe; fr0 += G) {
@@ -67,26 +80,35 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
     {
       // ---- bin pairs -> packed spectrum Z (re/im swapped for the inverse transform)
       const float2* Drow = Dclip + (long long)frame * (M + 1);
+      float2 v[PPT];
       static_for<0, NPAIR>([&](auto C) {
-        const int k = t + TPF * decltype(C)::value;
+        constexpr int c = decltype(C)::value;
+        const int k = t + TPF * c;
         float2 xa = __ldg(Drow + k), xb = __ldg(Drow + M - k);
         if (k == 0) { xa.y = 0.0f; xb.y = 0.0f; }    // irfft ignores Im of DC and Nyquist
+        float2 w;
+        if constexpr (c == 0) w = wt;
+        else w = cmul(wt, make_float2(TwC<c, 2 * PPT>::re, TwC<c, 2 * PPT>::im));
         float2 A, B;
-        c2r_pair(xa, xb, s_twn[k], A, B);
-        xbuf[xphys(k)] = make_float2(A.y, A.x);
-        if (k != 0) xbuf[xphys(M - k)] = make_float2(B.y, B.x);
+        c2r_pair(xa, xb, w, A, B);
+        constexpr int sa = pass0_slot_of_pair<Cfg>(c);
+        static_assert(sa >= 0, "lower-half element must be a pass-0 operand of the same thread");
+        v[sa] = make_float2(A.y, A.x);                                 // Z[k] stays in registers
+        if (k != 0) xbuf[xphys(M - k)] = make_float2(B.y, B.x);        // Z[M-k] goes to its owner
       });
       if (t == 0) {
         float2 xc = __ldg(Drow + M / 2), A, B;
-        c2r_pair(xc, xc, s_twn[M / 2], A, B);
+        c2r_pair(xc, xc, make_float2(0.0f, -1.0f), A, B);
         xbuf[xphys(M / 2)] = make_float2(A.y, A.x);
       }
-      group_sync<TPF>(grp + 1);
-      float2 v[PPT];
-      load_pass0<Cfg>(v, t, [&](int e) { return xbuf[xphys(e)]; });
-      group_sync<TPF>(grp + 1);           // operands fetched before the exchange area is overwritten
-      fft_forward<Cfg>(v, t, grp + 1, xbuf, s_tw);
-      if constexpr (Cfg::NPASS > 1) group_sync<TPF>(grp + 1);
+      group_sync<TPF>(gbar);
+      static_for<0, PPT>([&](auto S) {
+        constexpr int slot = decltype(S)::value;
+        if constexpr (pass0_offset<Cfg>(slot) >= M / 2) v[slot] = xbuf[xphys(t + pass0_offset<Cfg>(slot))];
+      });
+      group_sync<TPF>(gbar);          // operands fetched before the exchange area is overwritten
+      fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
+      if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
       // ---- un-swap, window (carries 1/n_fft), park the frame: ybuf[j], j = 0 .. n_fft-1
       float2* ybuf = xbuf;
       static_for<0, PPT>([&](auto S) {
@@ -96,13 +118,13 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
         ybuf[e] = make_float2(v[slot].y * w.x, v[slot].x * w.y);
       });
     }
-    __syncthreads();
+    half_sync();
 
     // ---- gather: emit positions [fr0*hop, (fr0+G)*hop), then rebuild the carry
     const int ng = min(G, fe - fr0);                 // valid frames in this round
     const long long u0 = (long long)fr0 * a.hop;
     const int emit_n = G * a.hop;
-    for (int x = tid; x < emit_n + clen; x += NT) {
+    for (int x = htid; x < emit_n + clen; x += HT) {
       float val = (x < clen) ? carry_cur[x] : 0.0f;
       int g_hi = x / a.hop;
       if (g_hi > ng - 1) g_hi = ng - 1;
@@ -120,17 +142,17 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
         carry_nxt[x - emit_n] = val;
       }
     }
-    __syncthreads();
+    half_sync();
     float* tmp = carry_cur; carry_cur = carry_nxt; carry_nxt = tmp;
   }
   // ---- flush: samples past the last round that only the carry reaches, then zero-fill the rest
   if (last_seg) {
     const long long u0 = (long long)fr0 * a.hop;     // fr0 == first frame index past the last round
-    for (int x = tid; x < clen; x += NT) {
+    for (int x = htid; x < clen; x += HT) {
       const long long o = u0 + x - a.start;
       if (o >= 0 && o < a.out_len) yclip[o] = carry_cur[x] * __ldg(a.inv_wss + o);
     }
-    for (long long o = u0 + clen - a.start + tid; o < a.out_len; o += NT)
+    for (long long o = u0 + clen - a.start + htid; o < a.out_len; o += HT)
       if (o >= 0) yclip[o] = 0.0f;
   }
 }
