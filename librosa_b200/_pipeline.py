@@ -200,3 +200,94 @@ def finish(ctx, dev_out: nat.DeviceArray, to_host: bool, host_dtype=None, valida
     if host_dtype is not None and arr.dtype != host_dtype:
         arr = arr.astype(host_dtype)
     return arr
+
+
+# --------------------------------------------------------------------------------------------- host batches
+_secondary = {}
+
+
+def _second_context(primary):
+    """A second stream (Context) on the same device, so that the H2D copy of one chunk overlaps the kernel
+    and the D2H copy of the previous one (PCIe is full duplex; one stream would serialise them)."""
+    ctx = _secondary.get(primary.device)
+    if ctx is None:
+        ctx = nat.Context(primary.device)
+        _secondary[primary.device] = ctx
+    return ctx
+
+
+def host_chunks(n_clips: int, nbytes: int) -> int:
+    """How many chunks a host batch is cut into (B2L_HOST_CHUNKS overrides; 1 disables the pipeline)."""
+    env = os.environ.get("B2L_HOST_CHUNKS")
+    if env:
+        return max(1, min(int(env), n_clips))
+    if n_clips < 8 or nbytes < (32 << 20):
+        return 1
+    return int(min(8, n_clips // 4))
+
+
+def run_host_forward(y: np.ndarray, *, n_fft: int, hop_length: int, center: bool, n_frames: int,
+                     out_mem_tail, out_dtype, make_plan, launch, scratch_per_clip: int = 0):
+    """Run one forward op over a host batch ``y`` (..., n), float32-convertible, already validated.
+
+    ``make_plan(ctx)`` returns the Plan; ``launch(ctx, plan, d_in, n_clips, n, d_out, d_scratch)`` enqueues
+    the kernels; ``out_mem_tail`` is the per-clip memory shape of the result.  Large batches are cut into
+    chunks that alternate between two streams: chunk i+1 uploads while chunk i computes and downloads.
+    Returns the result as an array of memory shape ``lead + out_mem_tail`` (pinned when large).
+    """
+    L = nat.lib()
+    host = np.ascontiguousarray(y, dtype=np.float32)
+    lead = host.shape[:-1]
+    n = host.shape[-1]
+    n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    flat = host.reshape(n_clips, n)
+    per_clip_out = int(np.prod(out_mem_tail, dtype=np.int64))
+    out_dtype = np.dtype(out_dtype)
+    total_out = n_clips * per_clip_out * out_dtype.itemsize
+    out = nat.pinned_empty((n_clips,) + tuple(out_mem_tail), out_dtype) if total_out >= (1 << 20) else \
+        np.empty((n_clips,) + tuple(out_mem_tail), out_dtype)
+    primary = nat.default_context()
+    k = host_chunks(n_clips, host.nbytes)
+    ctxs = [primary] if k == 1 else [primary, _second_context(primary)]
+    pad = n_fft // 2 if center else 0
+    tail_begin = 0 if hop_length > n_fft else max(0, (n_frames - 1) * hop_length + n_fft - pad)
+    bounds = [(i * n_clips) // k for i in range(k + 1)]
+    held = []
+    used = []
+    try:
+        for i in range(k):
+            lo, hi = bounds[i], bounds[i + 1]
+            if hi <= lo:
+                continue
+            ctx = ctxs[i % len(ctxs)]
+            if ctx not in used:
+                nat.check(L.b2l_status_reset(ctx.handle))
+                used.append(ctx)
+            plan = make_plan(ctx)
+            m = hi - lo
+            d_in = ctx.alloc(m * n * 4)
+            d_out = ctx.alloc(max(m * per_clip_out * out_dtype.itemsize, 16))
+            d_scr = ctx.alloc(m * scratch_per_clip * 4) if scratch_per_clip else 0
+            held.append((ctx, d_in, d_out, d_scr))
+            src = flat[lo:hi]
+            nat.check(L.b2l_h2d(ctx.handle, C.c_void_p(d_in), src.ctypes.data_as(C.c_void_p), src.nbytes))
+            if tail_begin < n:
+                nat.check(L.b2l_scan_finite(ctx.handle, C.c_void_p(d_in), m, n, n, tail_begin))
+            launch(ctx, plan, d_in, m, n, d_out, d_scr)
+            dst = out[lo:hi]
+            if dst.nbytes:
+                nat.check(L.b2l_d2h(ctx.handle, dst.ctypes.data_as(C.c_void_p), C.c_void_p(d_out), dst.nbytes))
+        bad = False
+        for ctx in used:
+            flag = C.c_int(0)
+            nat.check(L.b2l_status_read(ctx.handle, C.byref(flag)))   # synchronises that stream
+            bad |= bool(flag.value & 1)
+    finally:
+        for ctx, d_in, d_out, d_scr in held:
+            ctx.free(d_in)
+            ctx.free(d_out)
+            if d_scr:
+                ctx.free(d_scr)
+    if bad:
+        raise ParameterError("Audio buffer is not finite everywhere")
+    return out.reshape(tuple(lead) + tuple(out_mem_tail))

@@ -52,18 +52,31 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
         if not np.iscomplexobj(out):
             raise ParameterError(f"output with dtype={out.dtype} is not of complex type")
     pl.require_supported_n_fft(n_fft)
-    ctx = pl.context_for(y)
-    staged = pl.StagedInput(ctx, y)
     key = ("stft", n_fft, hop_length, bool(center), mode, wkey)
-    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win)
-    assert plan.n_frames(staged.n) == T
-    D = nat.DeviceArray.empty(ctx, shape, np.complex64, layout="ft")
-    nat.check(nat.lib().b2l_stft(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n, staged.n,
-                                 _vp(D.ptr)))
-    staged.scan_uncovered(n_fft, hop_length, center, T)
-    if staged.on_device and out is None:
-        return D
-    res = pl.finish(ctx, D, True, dtype, validate=not staged.on_device)
+
+    def make_plan(ctx):
+        return nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win)
+
+    if isinstance(y, nat.DeviceArray):
+        ctx = y.ctx
+        staged = pl.StagedInput(ctx, y)
+        plan = make_plan(ctx)
+        assert plan.n_frames(staged.n) == T
+        D = nat.DeviceArray.empty(ctx, shape, np.complex64, layout="ft")
+        nat.check(nat.lib().b2l_stft(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
+                                     staged.n, _vp(D.ptr)))
+        if out is None:
+            return D
+        res = pl.finish(ctx, D, True, dtype)
+    else:
+        def launch(ctx, plan, d_in, m, n_, d_out, d_scr):
+            nat.check(nat.lib().b2l_stft(ctx.handle, plan.handle, _vp(d_in), m, n_, n_, _vp(d_out)))
+
+        mem = pl.run_host_forward(y, n_fft=n_fft, hop_length=hop_length, center=center, n_frames=T,
+                                  out_mem_tail=(T, F), out_dtype=np.complex64, make_plan=make_plan, launch=launch)
+        res = np.swapaxes(mem, -1, -2)
+        if res.dtype != dtype:
+            res = res.astype(dtype)
     if out is None:
         return res
     target = out if out.shape[-1] == shape[-1] else out[..., : shape[-1]]
@@ -206,21 +219,36 @@ def _spectrogram(*, y=None, S=None, n_fft: Optional[int] = 2048, hop_length: Opt
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    n, _ = pl.precheck_signal(y)
+    n, req_dtype = pl.precheck_signal(y)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     pl.require_supported_n_fft(n_fft)
-    ctx = pl.context_for(y)
-    staged = pl.StagedInput(ctx, y)
     key = ("spec", n_fft, hop_length, bool(center), mode, wkey, float(power))
-    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
-                         power=float(power))
-    T = plan.n_frames(staged.n)
-    Sd = nat.DeviceArray.empty(ctx, staged.lead + (1 + n_fft // 2, T), np.float32, layout="ft")
-    nat.check(nat.lib().b2l_spectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
-                                        staged.n, _vp(Sd.ptr)))
-    staged.scan_uncovered(n_fft, hop_length, center, T)
-    return pl.finish(ctx, Sd, not staged.on_device, staged.req_dtype, validate=not staged.on_device), n_fft
+    F = 1 + n_fft // 2
+    T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length
+
+    def make_plan(ctx):
+        return nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
+                             power=float(power))
+
+    if isinstance(y, nat.DeviceArray):
+        ctx = y.ctx
+        staged = pl.StagedInput(ctx, y)
+        plan = make_plan(ctx)
+        Sd = nat.DeviceArray.empty(ctx, staged.lead + (F, T), np.float32, layout="ft")
+        nat.check(nat.lib().b2l_spectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
+                                            staged.n, _vp(Sd.ptr)))
+        return Sd, n_fft
+
+    def launch(ctx, plan, d_in, m, n_, d_out, d_scr):
+        nat.check(nat.lib().b2l_spectrogram(ctx.handle, plan.handle, _vp(d_in), m, n_, n_, _vp(d_out)))
+
+    mem = pl.run_host_forward(y, n_fft=n_fft, hop_length=hop_length, center=center, n_frames=T,
+                              out_mem_tail=(T, F), out_dtype=np.float32, make_plan=make_plan, launch=launch)
+    res = np.swapaxes(mem, -1, -2)
+    if res.dtype != req_dtype:
+        res = res.astype(req_dtype)
+    return res, n_fft
 
 
 def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80.0, axes="auto"):

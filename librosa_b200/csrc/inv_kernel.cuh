@@ -120,26 +120,34 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
     }
     half_sync();
 
-    // ---- gather: emit positions [fr0*hop, (fr0+G)*hop), then rebuild the carry
+    // ---- gather: emit positions [fr0*hop, (fr0+G)*hop), then rebuild the carry.
+    // Position x = c*hop + i is covered by the round's frames g = c-q .. c (clipped to [0, ng)), where
+    // q = (n_fft-1-i)/hop depends only on the offset i inside the hop.  A thread keeps i fixed and walks
+    // the chunks c, so the inner loop has no division; frames are added in increasing g, the order in
+    // which the reference accumulates them (librosa/core/spectrum.py:629-643).
     const int ng = min(G, fe - fr0);                 // valid frames in this round
     const long long u0 = (long long)fr0 * a.hop;
     const int emit_n = G * a.hop;
-    for (int x = htid; x < emit_n + clen; x += HT) {
-      float val = (x < clen) ? carry_cur[x] : 0.0f;
-      int g_hi = x / a.hop;
-      if (g_hi > ng - 1) g_hi = ng - 1;
-      int g_lo = x - a.n_fft + 1;
-      g_lo = g_lo <= 0 ? 0 : (g_lo + a.hop - 1) / a.hop;
-      for (int g = g_lo; g <= g_hi; ++g) {
-        const float* yb = reinterpret_cast<const float*>(s_xall + g * Cfg::XBUF_F2);
-        val += yb[x - g * a.hop];
-      }
-      if (x < emit_n) {
-        const long long u = u0 + x;
-        const long long o = u - a.start;
-        if (u >= emit_lo && u < emit_hi && o >= 0 && o < a.out_len) yclip[o] = val * __ldg(a.inv_wss + o);
-      } else {
-        carry_nxt[x - emit_n] = val;
+    const int n_chunks = G + (clen + a.hop - 1) / a.hop;      // chunks of hop positions incl. the carry zone
+    for (int i = htid; i < a.hop; i += HT) {
+      const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;   // hop > n_fft: gap positions see no frame
+      for (int c = 0; c < n_chunks; ++c) {
+        const int x = c * a.hop + i;
+        if (x >= emit_n + clen) break;
+        float val = (x < clen) ? carry_cur[x] : 0.0f;
+        const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
+        const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
+        for (int g = g_lo; g <= g_hi; ++g) {
+          val += *yb;
+          yb += 2 * Cfg::XBUF_F2 - a.hop;            // next frame's buffer, one hop earlier inside it
+        }
+        if (x < emit_n) {
+          const long long u = u0 + x;
+          const long long o = u - a.start;
+          if (u >= emit_lo && u < emit_hi && o >= 0 && o < a.out_len) yclip[o] = val * __ldg(a.inv_wss + o);
+        } else {
+          carry_nxt[x - emit_n] = val;
+        }
       }
     }
     half_sync();

@@ -69,23 +69,35 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    n, _ = pl.precheck_signal(y)
+    n, req_dtype = pl.precheck_signal(y)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     basis, bkey = pl.mel_basis(sr, n_fft, kwargs)
     pl.require_supported_n_fft(n_fft)
-    ctx = pl.context_for(y)
-    staged = pl.StagedInput(ctx, y)
     key = ("mel", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power))
-    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
-                         mel_basis=basis, power=float(power))
-    T = plan.n_frames(staged.n)
-    out = nat.DeviceArray.empty(ctx, staged.lead + (basis.shape[0], T), np.float32)
-    nat.check(nat.lib().b2l_melspectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
-                                           staged.n, _vp(out.ptr)))
-    staged.scan_uncovered(n_fft, hop_length, center, T)
-    return pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype),
-                     validate=not staged.on_device)
+    n_mels = basis.shape[0]
+    T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length
+    res_dtype = np.result_type(req_dtype, basis.dtype)
+
+    def make_plan(ctx):
+        return nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
+                             mel_basis=basis, power=float(power))
+
+    if isinstance(y, nat.DeviceArray):
+        ctx = y.ctx
+        staged = pl.StagedInput(ctx, y)
+        plan = make_plan(ctx)
+        out = nat.DeviceArray.empty(ctx, staged.lead + (n_mels, T), np.float32)
+        nat.check(nat.lib().b2l_melspectrogram(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips,
+                                               staged.n, staged.n, _vp(out.ptr)))
+        return out
+
+    def launch(ctx, plan, d_in, m, n_, d_out, d_scr):
+        nat.check(nat.lib().b2l_melspectrogram(ctx.handle, plan.handle, _vp(d_in), m, n_, n_, _vp(d_out)))
+
+    res = pl.run_host_forward(y, n_fft=n_fft, hop_length=hop_length, center=center, n_frames=T,
+                              out_mem_tail=(n_mels, T), out_dtype=np.float32, make_plan=make_plan, launch=launch)
+    return res if res.dtype == res_dtype else res.astype(res_dtype)
 
 
 def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float) -> np.ndarray:
@@ -134,7 +146,7 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    n, _ = pl.precheck_signal(y)
+    n, req_dtype = pl.precheck_signal(y)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     mel_kwargs = dict(kwargs)
@@ -143,21 +155,31 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
     n_mels = basis.shape[0]
     dct = _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter)
     pl.require_supported_n_fft(n_fft)
-    ctx = pl.context_for(y)
-    staged = pl.StagedInput(ctx, y)
     key = ("mfcc", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power), pl.digest(dct))
-    # power_to_db defaults used by mfcc: ref=1.0, amin=1e-10, top_db=80 (feature/spectral.py:2001)
-    plan = nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
-                         mel_basis=basis, power=float(power), dct_basis=dct, amin=1e-10, ref_value=1.0, top_db=80.0)
-    T = plan.n_frames(staged.n)
-    out = nat.DeviceArray.empty(ctx, staged.lead + (dct.shape[0], T), np.float32)
-    scratch = nat.DeviceArray.empty(ctx, (staged.n_clips, n_mels, T), np.float32)
-    nat.check(nat.lib().b2l_mfcc(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n, staged.n,
-                                 _vp(out.ptr), _vp(scratch.ptr)))
-    staged.scan_uncovered(n_fft, hop_length, center, T)
-    try:
-        res = pl.finish(ctx, out, not staged.on_device, np.result_type(staged.req_dtype, basis.dtype),
-                        validate=not staged.on_device)
-    finally:
-        scratch.free()   # stream-ordered pool: safe to hand out again without a sync
-    return res
+    T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length
+    res_dtype = np.result_type(req_dtype, basis.dtype)
+
+    def make_plan(ctx):
+        # power_to_db defaults used by mfcc: ref=1.0, amin=1e-10, top_db=80 (feature/spectral.py:2001)
+        return nat.make_plan(ctx, key, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=mode, window=win,
+                             mel_basis=basis, power=float(power), dct_basis=dct, amin=1e-10, ref_value=1.0,
+                             top_db=80.0)
+
+    if isinstance(y, nat.DeviceArray):
+        ctx = y.ctx
+        staged = pl.StagedInput(ctx, y)
+        plan = make_plan(ctx)
+        out = nat.DeviceArray.empty(ctx, staged.lead + (dct.shape[0], T), np.float32)
+        scratch = nat.DeviceArray.empty(ctx, (staged.n_clips, n_mels, T), np.float32)
+        nat.check(nat.lib().b2l_mfcc(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
+                                     staged.n, _vp(out.ptr), _vp(scratch.ptr)))
+        scratch.free()   # stream-ordered pool: the block can be handed out again without a sync
+        return out
+
+    def launch(ctx, plan, d_in, m, n_, d_out, d_scr):
+        nat.check(nat.lib().b2l_mfcc(ctx.handle, plan.handle, _vp(d_in), m, n_, n_, _vp(d_out), _vp(d_scr)))
+
+    res = pl.run_host_forward(y, n_fft=n_fft, hop_length=hop_length, center=center, n_frames=T,
+                              out_mem_tail=(dct.shape[0], T), out_dtype=np.float32, make_plan=make_plan,
+                              launch=launch, scratch_per_clip=n_mels * T)
+    return res if res.dtype == res_dtype else res.astype(res_dtype)

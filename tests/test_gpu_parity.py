@@ -217,6 +217,40 @@ def _block(n_clips, n, seed=0):
     return (base[None] * scale).reshape(-1, n)[:n_clips]
 
 
+def test_cfg1_single_60s_clip(lb, oracle):
+    """cfg 1: one 60 s mono clip @ 22050, stft 2048/512 center=True, and its inverse — a single clip is split
+    into many frame segments per CTA half (halo frames recomputed at every segment start)."""
+    import signals
+
+    y = signals.make("B", (1323000,), seed=0)
+    D = lb.stft(y, n_fft=2048, hop_length=512)
+    Do = oracle.stft(y, n_fft=2048, hop_length=512)
+    assert D.shape == (1025, 2584)
+    close(D, Do, **TOL["stft"])
+    yr = lb.istft(Do, hop_length=512, length=len(y))
+    yo = oracle.istft(Do, hop_length=512, length=len(y))
+    close(yr, yo, **TOL["istft"])
+    snr = 10 * np.log10((y.astype(np.float64) ** 2).sum() / ((y - yr).astype(np.float64) ** 2).sum())
+    assert snr >= 60.0, snr
+
+
+@pytest.mark.parametrize("n_fft,hop,window", [(256, 300, "hann"), (256, 256, "hann"), (512, 128, "blackmanharris"),
+                                              (1024, 512, "hann"), (64, 100, "hamming"), (2048, 2048, "hann")])
+def test_istft_hop_geometries(lb, oracle, n_fft, hop, window):
+    """hop > n_fft leaves gaps (window-sum-square is 0 there and the output stays 0), hop == n_fft has no
+    overlap, small hops have deep overlap; several clips so that segment boundaries are exercised."""
+    import signals
+
+    y = signals.make("A", (3, 20000), seed=n_fft + hop)
+    D = oracle.stft(y, n_fft=n_fft, hop_length=hop, window=window)
+    for length in (None, 20000):
+        got = lb.istft(D, hop_length=hop, window=window, length=length)
+        want = oracle.istft(D, hop_length=hop, window=window, length=length)
+        assert got.shape == want.shape
+        T = D.shape[-1] if not length else min(D.shape[-1], int(np.ceil((length + 2 * (n_fft // 2)) / hop)))
+        _istft_close(oracle, got, want, dict(hop_length=hop, window=window), n_fft, T)
+
+
 def test_cfg2_full_size_mel_properties(lb, oracle):
     """cfg 2: 1024 clips x 10 s @ 22050 -> melspectrogram 2048/512/128."""
     Y = _block(1024, 220500)
