@@ -85,6 +85,7 @@ struct InvArgs {
   const float2* tw;
   const float2* twn;
   int segs_per_clip, frames_per_seg;
+  int vec4;                  // gather 4 samples per thread (alignment conditions checked on the host)
   int off_win, off_tw, off_xbuf, off_acc;
   int xbuf_stride, acc_stride;   // per-half strides in bytes (DUAL)
   int acc_floats;

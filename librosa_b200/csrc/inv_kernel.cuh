@@ -72,6 +72,16 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
   float* carry_nxt = s_carry + clen;
   const float2 wt = __ldg(a.twn + t);                         // W_N^t, see unmix twiddle in fwd_kernel.cuh
 
+  // The spectrum row of the next round's frame is pulled into L2 while this round is gathered, so the
+  // operand loads at the top of the next round see L2 latency instead of HBM latency (the registers
+  // are all taken by the FFT, so a register prefetch would spill).
+  auto prefetch_row = [&](int first_frame) {
+    const int frame = min(first_frame + grp, fe - 1);
+    const char* row = reinterpret_cast<const char*>(Dclip + (long long)frame * (M + 1));
+    for (int off = t * 128; off < (M + 1) * 8; off += TPF * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+  };
+
   int fr0 = fh;
   for (; fr0 < fe; fr0 += G) {
     // Every group transforms a frame in every round (groups past the end redo the last frame and are
@@ -118,6 +128,7 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
         ybuf[e] = make_float2(v[slot].y * w.x, v[slot].x * w.y);
       });
     }
+    if (fr0 + G < fe) prefetch_row(fr0 + G);        // next round's rows -> L2 while this round is gathered
     half_sync();
 
     // ---- gather: emit positions [fr0*hop, (fr0+G)*hop), then rebuild the carry.
@@ -126,27 +137,65 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
     // the chunks c, so the inner loop has no division; frames are added in increasing g, the order in
     // which the reference accumulates them (librosa/core/spectrum.py:629-643).
     const int ng = min(G, fe - fr0);                 // valid frames in this round
-    const long long u0 = (long long)fr0 * a.hop;
     const int emit_n = G * a.hop;
     const int n_chunks = G + (clen + a.hop - 1) / a.hop;      // chunks of hop positions incl. the carry zone
-    for (int i = htid; i < a.hop; i += HT) {
-      const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;   // hop > n_fft: gap positions see no frame
-      for (int c = 0; c < n_chunks; ++c) {
-        const int x = c * a.hop + i;
-        if (x >= emit_n + clen) break;
-        float val = (x < clen) ? carry_cur[x] : 0.0f;
-        const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
-        const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
-        for (int g = g_lo; g <= g_hi; ++g) {
-          val += *yb;
-          yb += 2 * Cfg::XBUF_F2 - a.hop;            // next frame's buffer, one hop earlier inside it
+    const int o0 = (int)((long long)fr0 * a.hop - a.start);   // output index of x = 0 (fits: out_len < 2^31)
+    // chunks whose positions this segment owns: emit_lo <= u < emit_hi
+    const int c_lo = (int)max(0LL, (emit_lo - (long long)fr0 * a.hop + a.hop - 1) / a.hop);
+    const int c_hi = (int)min((long long)G, (emit_hi - (long long)fr0 * a.hop) / a.hop);
+    if (a.vec4) {
+      // 4 consecutive samples per thread: 16-byte shared loads, one 16-byte store (hop, n_fft - hop,
+      // start and the row strides are multiples of 4 and the buffers 16-byte aligned; host-checked)
+      for (int i = 4 * htid; i < a.hop; i += 4 * HT) {
+        const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;
+        for (int c = 0; c < n_chunks; ++c) {
+          const int x = c * a.hop + i;
+          if (x >= emit_n + clen) break;
+          float4 val = (x < clen) ? *reinterpret_cast<const float4*>(carry_cur + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
+          const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
+          for (int g = g_lo; g <= g_hi; ++g) {
+            const float4 f = *reinterpret_cast<const float4*>(yb);
+            val.x += f.x; val.y += f.y; val.z += f.z; val.w += f.w;
+            yb += 2 * Cfg::XBUF_F2 - a.hop;          // next frame's buffer, one hop earlier inside it
+          }
+          if (x < emit_n) {
+            const int o = o0 + x;
+            if (c >= c_lo && c < c_hi && o + 3 >= 0 && o < a.out_len) {
+              if (o >= 0 && o + 3 < a.out_len) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.inv_wss + o));
+                *reinterpret_cast<float4*>(yclip + o) = make_float4(val.x * s4.x, val.y * s4.y, val.z * s4.z, val.w * s4.w);
+              } else {
+                const float vv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (o + e >= 0 && o + e < a.out_len) yclip[o + e] = vv[e] * __ldg(a.inv_wss + o + e);
+              }
+            }
+          } else {
+            *reinterpret_cast<float4*>(carry_nxt + (x - emit_n)) = val;
+          }
         }
-        if (x < emit_n) {
-          const long long u = u0 + x;
-          const long long o = u - a.start;
-          if (u >= emit_lo && u < emit_hi && o >= 0 && o < a.out_len) yclip[o] = val * __ldg(a.inv_wss + o);
-        } else {
-          carry_nxt[x - emit_n] = val;
+      }
+    } else {
+      for (int i = htid; i < a.hop; i += HT) {
+        const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;   // hop > n_fft: gap positions see no frame
+        for (int c = 0; c < n_chunks; ++c) {
+          const int x = c * a.hop + i;
+          if (x >= emit_n + clen) break;
+          float val = (x < clen) ? carry_cur[x] : 0.0f;
+          const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
+          const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
+          for (int g = g_lo; g <= g_hi; ++g) {
+            val += *yb;
+            yb += 2 * Cfg::XBUF_F2 - a.hop;
+          }
+          if (x < emit_n) {
+            const int o = o0 + x;
+            if (c >= c_lo && c < c_hi && o >= 0 && o < a.out_len) yclip[o] = val * __ldg(a.inv_wss + o);
+          } else {
+            carry_nxt[x - emit_n] = val;
+          }
         }
       }
     }
