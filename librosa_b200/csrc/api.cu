@@ -635,9 +635,8 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   const b2l_plan::RowTable* rt = nullptr;
   for (int i = 0; i < n_opt && !variant; ++i) {
     const int v = variants[i];
-    const bool dual = v == 116;
-    const int nw = dual ? 16 : v;
-    const int nh = dual ? 2 : 1;
+    const int nh = v == 216 ? 4 : (v == 116 ? 2 : 1);
+    const int nw = nh > 1 ? 16 : v;
     if (nw * 32 % (cfg.tpf * nh) != 0) continue;
     const int f = nw * 32 / nh / cfg.tpf;
     if (f < 1 || f > 32) continue;

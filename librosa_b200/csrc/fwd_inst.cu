@@ -17,7 +17,7 @@ cudaError_t run_op(K kern, int op, int nt, const FwdArgs* a, int grid, size_t sm
   return cudaGetLastError();
 }
 
-template <int L, int TPF, int NW, bool DUAL>
+template <int L, int TPF, int NW, int DUAL>
 cudaError_t by_mode(int op, int mode, const FwdArgs* a, int grid, size_t smem, cudaStream_t st, int* result) {
   switch (mode) {
     case MODE_STFT: return run_op(fwd_kernel<L, TPF, NW, MODE_STFT, DUAL>, op, NW * 32, a, grid, smem, st, result);
@@ -32,21 +32,24 @@ cudaError_t by_mode(int op, int mode, const FwdArgs* a, int grid, size_t smem, c
 #define B2L_CAT2(a, b) a##b
 #define B2L_CAT(a, b) B2L_CAT2(a, b)
 
-// `nw` selects the variant: 16 or 8 warps; 116 = 16 warps as two independent 8-warp halves (DUAL).
+// `nw` selects the variant: 16 or 8 warps; 116 / 216 = 16 warps as two / four independent parts.
 template <int L>
 cudaError_t fwd_dispatch(int op, int nw, int mode, const FwdArgs* a, int grid, size_t smem, cudaStream_t st,
                          int* result) {
   constexpr int M = 1 << L;
   constexpr int TPF = M >= 32 ? M / 32 : 1;
   if constexpr (L >= 10) {
-    if (nw == 16) return by_mode<L, TPF, 16, false>(op, mode, a, grid, smem, st, result);
-    if (nw == 8) return by_mode<L, TPF, 8, false>(op, mode, a, grid, smem, st, result);
-    if (nw == 116) return by_mode<L, TPF, 16, true>(op, mode, a, grid, smem, st, result);
+    if (nw == 16) return by_mode<L, TPF, 16, 1>(op, mode, a, grid, smem, st, result);
+    if (nw == 8) return by_mode<L, TPF, 8, 1>(op, mode, a, grid, smem, st, result);
+    if (nw == 116) return by_mode<L, TPF, 16, 2>(op, mode, a, grid, smem, st, result);
+    if constexpr (L == 10) {
+      if (nw == 216) return by_mode<L, TPF, 16, 4>(op, mode, a, grid, smem, st, result);
+    }
   } else {
     constexpr int NW = TPF > 16 ? 16 : TPF;
-    if (nw == NW) return by_mode<L, TPF, NW, false>(op, mode, a, grid, smem, st, result);
+    if (nw == NW) return by_mode<L, TPF, NW, 1>(op, mode, a, grid, smem, st, result);
     if constexpr (L == 9) {
-      if (nw == 116) return by_mode<L, TPF, 16, true>(op, mode, a, grid, smem, st, result);
+      if (nw == 116) return by_mode<L, TPF, 16, 2>(op, mode, a, grid, smem, st, result);
     }
   }
   return cudaErrorInvalidValue;

@@ -117,21 +117,23 @@ __device__ __forceinline__ int partner_slot(int t) {
 }
 
 // ------------------------------------------------------------------ the kernel
-// NW warps per CTA.  With DUAL the CTA is two independent halves of NW/2 warps ("virtual CTAs"): each has
+// NW warps per CTA.  With NSPLIT > 1 the CTA is NSPLIT independent parts of NW/NSPLIT warps ("virtual CTAs",
+// called halves below): each has
 // its own staging buffer, exchange area, mbarrier, named barrier and tile sequence, and only the constant
 // tables are shared.  The halves drift apart, so the shared-memory-bound phases of one (operand fetch,
 // exchange, mel gather) overlap the FP32-bound butterflies of the other instead of all warps of the SM
 // hitting the same pipe at once.
-template <int LOG2M, int TPF, int NW, int MODE, bool DUAL>
+template <int LOG2M, int TPF, int NW, int MODE, int NSPLIT>
 __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   using Cfg = FftCfg<LOG2M, TPF>;
   constexpr int M = Cfg::M, N = 2 * M, PPT = Cfg::PPT;
   constexpr int NT = NW * 32;
-  constexpr int NH = DUAL ? 2 : 1;             // halves
+  constexpr int NH = NSPLIT;                   // independent parts ("halves" when 2)
+  constexpr bool DUAL = NSPLIT > 1;
   constexpr int HT = NT / NH;                  // threads per half
   constexpr int HW = NW / NH;                  // warps per half
   constexpr int FT = HT / TPF;                 // frames per tile == frame groups per half
-  static_assert(!DUAL || NW % 2 == 0, "DUAL splits the warps in two");
+  static_assert(NW % NSPLIT == 0, "the warps are split evenly");
   static_assert(TPF <= 32 || NH + NT / TPF <= 15, "named barriers: 1..NH for the halves, then one per frame group");
   static_assert(FT >= 1 && FT <= 32, "tile must hold 1..32 frames");
   constexpr int H = 32 / FT;                   // mel rows handled concurrently by one warp
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
 
   auto half_sync = [&]() {
-    if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");   // ids 1, 2
+    if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");   // ids 1 .. NH
     else __syncthreads();
   };
 
