@@ -540,47 +540,46 @@ static int ensure_clip_max(b2l_ctx* c, size_t n_clips) {
   return B2L_OK;
 }
 
-// MelRow table for warps that process 2H mel rows at a time (see MelRow in common.cuh, fwd_kernel.cuh).
+// MelRow table for warps that process H mel rows at a time (see MelRow in common.cuh).
 static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, const b2l_plan::RowTable** out) {
   auto it = p->row_tables.find(H);
   if (it != p->row_tables.end()) {
     *out = &it->second;
     return B2L_OK;
   }
-  const int IR = 2 * H;                                   // rows per work item (two per lane group)
-  const int n_rows = (p->n_mels + IR - 1) / IR * IR;
+  const int n_rows = (p->n_mels + H - 1) / H * H;
   std::vector<MelRow> rows(n_rows);
   std::vector<float> w;
-  for (int item = 0; item < n_rows / IR; ++item) {
-    std::vector<int> start(IR), lenp(IR);
+  for (int item = 0; item < n_rows / H; ++item) {
+    std::vector<int> start(H), lenp(H);
     int quads = 0;
-    for (int r = 0; r < IR; ++r) {
-      const int m = item * IR + r, j = r % H;
+    for (int j = 0; j < H; ++j) {
+      const int m = item * H + j;
       if (m < p->n_mels && p->h_band[m].len > 0) {
         const MelBand& b = p->h_band[m];
-        int st = b.lo - (((b.lo - j) % H) + H) % H;   // largest bin <= lo congruent to j mod H
+        int st = b.lo - (((b.lo - j) % H) + H) % H;   // largest row <= lo congruent to j mod H
         if (st < 0) st = b.lo;
-        start[r] = st;
-        lenp[r] = b.lo + b.len - st;
+        start[j] = st;
+        lenp[j] = b.lo + b.len - st;
       } else {
-        start[r] = j;
-        lenp[r] = 0;
+        start[j] = j;
+        lenp[j] = 0;
       }
-      quads = std::max(quads, (lenp[r] + 3) / 4);
+      quads = std::max(quads, (lenp[j] + 3) / 4);
     }
-    for (int r = 0; r < IR; ++r) {
-      const int m = item * IR + r;
-      MelRow row;
-      row.lo = (unsigned short)start[r];
-      row.quads = (unsigned short)quads;
-      row.off = (unsigned int)w.size();
+    for (int j = 0; j < H; ++j) {
+      const int m = item * H + j;
+      MelRow r;
+      r.lo = (unsigned short)start[j];
+      r.quads = (unsigned short)quads;
+      r.off = (unsigned int)w.size();
       size_t base = w.size();
       w.resize(base + (size_t)4 * quads, 0.0f);
-      if (lenp[r] > 0) {
+      if (lenp[j] > 0) {
         const MelBand& b = p->h_band[m];
-        for (int i = 0; i < b.len; ++i) w[base + (b.lo - start[r]) + i] = p->h_mel_w[b.off + i];
+        for (int i = 0; i < b.len; ++i) w[base + (b.lo - start[j]) + i] = p->h_mel_w[b.off + i];
       }
-      rows[m] = row;
+      rows[m] = r;
     }
   }
   b2l_plan::RowTable t;

@@ -22,9 +22,8 @@ enum FwdMode : int {
 
 struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at mel_w[off ..] (mel_project kernel)
 // Fused-kernel form of one mel row: `quads` groups of 4 consecutive bins starting at bin `lo`, weights at
-// mel_w[off ..] (zero padded to 4*quads, off % 4 == 0).  Rows are grouped 2H at a time (H = 32 / frames
-// per tile, two rows per lane group): the rows of a group share `quads` and `lo` is congruent to the
-// row's position mod H.
+// mel_w[off ..] (zero padded to 4*quads, off % 4 == 0).  Rows are grouped H at a time (H = 32 / frames
+// per tile): the rows of a group share `quads` and their `lo` are congruent to their position mod H.
 struct MelRow { unsigned short lo, quads; unsigned int off; };
 
 // Shared-memory layout of the power tile used by the mel phase: frame-major, P[f][k] at word f*RS + k with

@@ -370,48 +370,36 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         if (htid < 3 * FT) s_p[(htid / 3) * RS + M + 1 + (htid % 3)] = 0.0f;
         half_sync();   // B2
         {
-          // Work item = 2H adjacent mel rows; lane (f, j) accumulates rows i*2H + j and i*2H + H + j for
-          // frame f over their padded bands (host-built MelRow table: the rows of an item share one trip
-          // count, start bins are congruent to j mod H so the skewed tile reads conflict-free, weights
-          // are zero padded and 16-byte aligned).  Two independent sums per lane hide the LDS latency;
-          // no cross-lane reduction, one short loop per item.
+          // Work item = H adjacent mel rows; lane (f, j) accumulates row i*H + j for frame f over that
+          // row's padded band (host-built MelRow table: the rows of an item share one trip count, start
+          // bins are congruent to j mod H so the skewed tile reads conflict-free, weights are zero
+          // padded and 16-byte aligned).  No cross-lane reduction, one short loop per item.
           const int hwarp = htid >> 5, lane = htid & 31;
           const int f = lane & (FT - 1), j = lane / FT;
           const bool ok = (t0 + f) < a.n_frames;
           float wmax = -INFINITY;
-          const int n_items = a.n_mel_rows / (2 * H);
-          const float* pbase = s_p + f * RS;
-          float* obase = a.out_r + (long long)clip * a.n_mels * a.n_frames + t0 + f;
+          const int n_items = a.n_mel_rows / H;
           for (int item = hwarp; item < n_items; item += HW) {
-            const int m0 = item * 2 * H + j, m1 = m0 + H;
-            const MelRow r0 = s_row[m0], r1 = s_row[m1];
-            const float4* w0 = reinterpret_cast<const float4*>(s_melw + r0.off);
-            const float4* w1 = reinterpret_cast<const float4*>(s_melw + r1.off);
-            const float* p0 = pbase + r0.lo;
-            const float* p1 = pbase + r1.lo;
-            const float4* wend = w0 + r0.quads;     // r1.quads == r0.quads
-            float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
-#pragma unroll 1
-            for (; w0 != wend; ++w0, ++w1, p0 += 4, p1 += 4) {
-              const float4 u = *w0, v4 = *w1;
-              a0 = fmaf(u.x, p0[0], a0);
-              b0 = fmaf(v4.x, p1[0], b0);
-              a1 = fmaf(u.y, p0[1], a1);
-              b1 = fmaf(v4.y, p1[1], b1);
-              a0 = fmaf(u.z, p0[2], a0);
-              b0 = fmaf(v4.z, p1[2], b0);
-              a1 = fmaf(u.w, p0[3], a1);
-              b1 = fmaf(v4.w, p1[3], b1);
+            const int m = item * H + j;
+            const MelRow row = s_row[m];
+            const float4* wp = reinterpret_cast<const float4*>(s_melw + row.off);
+            const float* pp = s_p + f * RS + row.lo;
+            const float4* wend = wp + row.quads;
+            float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 2
+            for (; wp != wend; ++wp, pp += 4) {
+              const float4 w = *wp;
+              acc0 = fmaf(w.x, pp[0], acc0);
+              acc1 = fmaf(w.y, pp[1], acc1);
+              acc0 = fmaf(w.z, pp[2], acc0);
+              acc1 = fmaf(w.w, pp[3], acc1);
             }
-            float acc0 = a0 + a1, acc1 = b0 + b1;
+            float acc = acc0 + acc1;
             if (a.log_mode) {
-              acc0 = 10.0f * log10f(fmaxf(a.amin, acc0)) - a.db_sub;
-              acc1 = 10.0f * log10f(fmaxf(a.amin, acc1)) - a.db_sub;
-              if (ok && m0 < a.n_mels) wmax = fmaxf(wmax, acc0);
-              if (ok && m1 < a.n_mels) wmax = fmaxf(wmax, acc1);
+              acc = 10.0f * log10f(fmaxf(a.amin, acc)) - a.db_sub;
+              if (ok && m < a.n_mels) wmax = fmaxf(wmax, acc);
             }
-            if (ok && m0 < a.n_mels) obase[(long long)m0 * a.n_frames] = acc0;
-            if (ok && m1 < a.n_mels) obase[(long long)m1 * a.n_frames] = acc1;
+            if (ok && m < a.n_mels) a.out_r[((long long)clip * a.n_mels + m) * a.n_frames + t0 + f] = acc;
           }
           if (a.log_mode) {
 #pragma unroll
