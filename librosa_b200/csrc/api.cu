@@ -635,7 +635,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   const b2l_plan::RowTable* rt = nullptr;
   for (int i = 0; i < n_opt && !variant; ++i) {
     const int v = variants[i];
-    const int nh = v == 216 ? 4 : (v == 116 ? 2 : 1);
+    const int nh = v == 116 ? 2 : 1;
     const int nw = nh > 1 ? 16 : v;
     if (nw * 32 % (cfg.tpf * nh) != 0) continue;
     const int f = nw * 32 / nh / cfg.tpf;

@@ -32,7 +32,7 @@ cudaError_t by_mode(int op, int mode, const FwdArgs* a, int grid, size_t smem, c
 #define B2L_CAT2(a, b) a##b
 #define B2L_CAT(a, b) B2L_CAT2(a, b)
 
-// `nw` selects the variant: 16 or 8 warps; 116 / 216 = 16 warps as two / four independent parts.
+// `nw` selects the variant: 16 or 8 warps; 116 = 16 warps as two independent 8-warp halves (NSPLIT = 2).
 template <int L>
 cudaError_t fwd_dispatch(int op, int nw, int mode, const FwdArgs* a, int grid, size_t smem, cudaStream_t st,
                          int* result) {
@@ -42,9 +42,6 @@ cudaError_t fwd_dispatch(int op, int nw, int mode, const FwdArgs* a, int grid, s
     if (nw == 16) return by_mode<L, TPF, 16, 1>(op, mode, a, grid, smem, st, result);
     if (nw == 8) return by_mode<L, TPF, 8, 1>(op, mode, a, grid, smem, st, result);
     if (nw == 116) return by_mode<L, TPF, 16, 2>(op, mode, a, grid, smem, st, result);
-    if constexpr (L == 10) {
-      if (nw == 216) return by_mode<L, TPF, 16, 4>(op, mode, a, grid, smem, st, result);
-    }
   } else {
     constexpr int NW = TPF > 16 ? 16 : TPF;
     if (nw == NW) return by_mode<L, TPF, NW, 1>(op, mode, a, grid, smem, st, result);
