@@ -130,11 +130,11 @@ def precheck_signal(y):
     return y.shape[-1], check_real_dtype(y.dtype, "input signal")
 
 
-MIN_N_FFT, MAX_N_FFT = 8, 4096   # kMinLog2M / kMaxLog2M in csrc/internal.h
+MIN_N_FFT, MAX_N_FFT = 8, 8192   # kMinLog2M / kMaxLog2M in csrc/internal.h
 
 
 def require_supported_n_fft(n_fft: int):
-    """The sm_100a kernels are built for power-of-two n_fft in [8, 4096]; anything else librosa accepts
+    """The sm_100a kernels are built for power-of-two n_fft in [8, 8192]; anything else librosa accepts
     (e.g. the reference tests' 501 / 1023 / 1025) is refused loudly — there is no CPU fallback."""
     n_fft = int(n_fft)
     if n_fft < MIN_N_FFT or n_fft > MAX_N_FFT or (n_fft & (n_fft - 1)):

@@ -512,7 +512,7 @@ static fwd_op_fn fwd_table(int log2m) {
   switch (log2m) {
     case 2: return fwd_op_2; case 3: return fwd_op_3; case 4: return fwd_op_4; case 5: return fwd_op_5;
     case 6: return fwd_op_6; case 7: return fwd_op_7; case 8: return fwd_op_8; case 9: return fwd_op_9;
-    case 10: return fwd_op_10; case 11: return fwd_op_11;
+    case 10: return fwd_op_10; case 11: return fwd_op_11; case 12: return fwd_op_12;
   }
   return nullptr;
 }
@@ -520,7 +520,7 @@ static inv_op_fn inv_table(int log2m) {
   switch (log2m) {
     case 2: return inv_op_2; case 3: return inv_op_3; case 4: return inv_op_4; case 5: return inv_op_5;
     case 6: return inv_op_6; case 7: return inv_op_7; case 8: return inv_op_8; case 9: return inv_op_9;
-    case 10: return inv_op_10; case 11: return inv_op_11;
+    case 10: return inv_op_10; case 11: return inv_op_11; case 12: return inv_op_12;
   }
   return nullptr;
 }

@@ -14,11 +14,11 @@ enum KernelOp : int { OP_LAUNCH = 0, OP_SET_SMEM = 1, OP_OCCUPANCY = 2 };
   cudaError_t inv_op_##L(int op, int nw, const InvArgs* a, int grid, size_t smem, cudaStream_t st, int* result);
 
 B2L_DECL_FWD(2) B2L_DECL_FWD(3) B2L_DECL_FWD(4) B2L_DECL_FWD(5) B2L_DECL_FWD(6) B2L_DECL_FWD(7)
-B2L_DECL_FWD(8) B2L_DECL_FWD(9) B2L_DECL_FWD(10) B2L_DECL_FWD(11)
+B2L_DECL_FWD(8) B2L_DECL_FWD(9) B2L_DECL_FWD(10) B2L_DECL_FWD(11) B2L_DECL_FWD(12)
 B2L_DECL_INV(2) B2L_DECL_INV(3) B2L_DECL_INV(4) B2L_DECL_INV(5) B2L_DECL_INV(6) B2L_DECL_INV(7)
-B2L_DECL_INV(8) B2L_DECL_INV(9) B2L_DECL_INV(10) B2L_DECL_INV(11)
+B2L_DECL_INV(8) B2L_DECL_INV(9) B2L_DECL_INV(10) B2L_DECL_INV(11) B2L_DECL_INV(12)
 
-constexpr int kMinLog2M = 2, kMaxLog2M = 11;   // n_fft = 2^(LOG2M+1): 8 .. 4096
+constexpr int kMinLog2M = 2, kMaxLog2M = 12;   // n_fft = 2^(LOG2M+1): 8 .. 8192
 
 // Host mirror of FftCfg<LOG2M, TPF> (fft_engine.cuh): same schedule, evaluated at run time.
 struct HostFftCfg {

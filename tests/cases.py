@@ -18,6 +18,7 @@ CASES = [
     dict(name="stft_1024_symmetric_oddhop_A", op="stft", mix="A", shape=(7000,), kw=dict(n_fft=1024, hop_length=300, pad_mode="symmetric")),
     dict(name="stft_256_linear_ramp_A", op="stft", mix="A", shape=(6000,), kw=dict(n_fft=256, hop_length=64, pad_mode="linear_ramp")),
     dict(name="stft_4096_1024_A", op="stft", mix="A", shape=(12000,), kw=dict(n_fft=4096, hop_length=1024)),
+    dict(name="stft_8192_2048_A", op="stft", mix="A", shape=(30000,), kw=dict(n_fft=8192, hop_length=2048)),
     dict(name="stft_64_16_B", op="stft", mix="B", shape=(2000,), kw=dict(n_fft=64, hop_length=16)),
     dict(name="stft_16_4_A", op="stft", mix="A", shape=(500,), kw=dict(n_fft=16, hop_length=4)),
     dict(name="stft_8_2_A", op="stft", mix="A", shape=(200,), kw=dict(n_fft=8, hop_length=2, center=False)),
@@ -36,6 +37,7 @@ CASES = [
     dict(name="istft_1024_winlen600", op="istft", src="stft_1024_winlen600_hamming_A", kw=dict(win_length=600, window="hamming")),
     dict(name="istft_512_stereo", op="istft", src="stft_512_stereo_A", kw=dict(hop_length=128)),
     dict(name="istft_64_16", op="istft", src="stft_64_16_B", kw=dict(hop_length=16, length=2000)),
+    dict(name="istft_8192_2048", op="istft", src="stft_8192_2048_A", kw=dict(hop_length=2048, length=30000)),
     dict(name="istft_4096_1024_short_length", op="istft", src="stft_4096_1024_A", kw=dict(hop_length=1024, length=7000)),
     # ---- melspectrogram
     dict(name="mel_22050_2048_A", op="mel", mix="A", shape=(9000,), kw=dict(sr=22050, n_fft=2048, hop_length=512)),
@@ -43,6 +45,7 @@ CASES = [
     dict(name="mel_22050_2048_C", op="mel", mix="C", shape=(9000,), kw=dict(sr=22050, n_fft=2048, hop_length=512)),
     dict(name="mel_16000_1024_stereo_A", op="mel", mix="A", shape=(2, 6000), kw=dict(sr=16000, n_fft=1024, hop_length=256)),
     dict(name="mel_44100_4096_A", op="mel", mix="A", shape=(14000,), kw=dict(sr=44100, n_fft=4096, hop_length=1024)),
+    dict(name="mel_48000_8192_A", op="mel", mix="A", shape=(40000,), kw=dict(sr=48000, n_fft=8192, hop_length=2048)),
     dict(name="mel_htk_40_power1_A", op="mel", mix="A", shape=(6000,), kw=dict(sr=22050, n_fft=1024, hop_length=256, n_mels=40, htk=True, power=1.0)),
     dict(name="mel_norm1_fminfmax_B", op="mel", mix="B", shape=(6000,), kw=dict(sr=22050, n_fft=2048, hop_length=512, n_mels=64, fmin=300.0, fmax=8000.0, norm=1)),
     dict(name="mel_power3_A", op="mel", mix="A", shape=(4000,), kw=dict(sr=22050, n_fft=512, hop_length=128, n_mels=32, power=3.0)),
