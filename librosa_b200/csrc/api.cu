@@ -108,6 +108,7 @@ struct b2l_ctx {
   int rank = 0, world = 1;
   unsigned int* d_clip_max = nullptr;   // scratch for per-clip maxima
   int* d_status = nullptr;              // bit 0: a non-finite input sample was seen since the last reset
+  std::map<unsigned long long, int> launch_cache;   // (kernel variant, smem) -> blocks/SM, attribute already set
   size_t clip_max_cap = 0;
 };
 
@@ -712,9 +713,18 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   a.clip_max = c->d_clip_max;
   a.status = c->d_status;
 
-  CUDA_TRY(op(OP_SET_SMEM, variant, mode, &a, 0, smem, c->stream, nullptr));
+  // cudaFuncSetAttribute + the occupancy query cost tens of microseconds; do them once per configuration
+  const unsigned long long ckey = ((unsigned long long)p->log2m << 56) | ((unsigned long long)variant << 44) |
+                                  ((unsigned long long)mode << 40) | (unsigned long long)smem;
   int occ = 0;
-  CUDA_TRY(op(OP_OCCUPANCY, variant, mode, &a, 0, smem, c->stream, &occ));
+  auto hit = c->launch_cache.find(ckey);
+  if (hit != c->launch_cache.end()) {
+    occ = hit->second;
+  } else {
+    CUDA_TRY(op(OP_SET_SMEM, variant, mode, &a, 0, smem, c->stream, nullptr));
+    CUDA_TRY(op(OP_OCCUPANCY, variant, mode, &a, 0, smem, c->stream, &occ));
+    c->launch_cache[ckey] = occ;
+  }
   if (occ < 1) return fail(B2L_ERR_CUDA, "forward kernel does not fit on an SM (smem %zu)", smem);
   long long grid = (long long)c->sm_count * occ;
   const long long ctas_needed = (a.total_tiles + halves - 1) / halves;
