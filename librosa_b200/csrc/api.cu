@@ -867,10 +867,10 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
   a.vec4 = (p->hop % 4 == 0) && (clen % 4 == 0) && (a.start % 4 == 0) && (y_stride % 4 == 0) &&
            (cfg.xbuf_f2() % 2 == 0) &&   // frame buffers 16-byte aligned inside the exchange area
            (((uintptr_t)d_y & 15) == 0) && (((uintptr_t)d_inv_wss & 15) == 0);
-  // segments: enough half-CTAs to fill the machine twice; each at least 4 rounds long so the halo frames
-  // (recomputed at every segment start) stay a small fraction
+  // segments: about six work items per resident half-CTA so the last wave is short; each at least 4 rounds
+  // long so the halo frames (recomputed at every segment start) stay a small fraction
   {
-    const long long want = 2LL * c->sm_count * halves;
+    const long long want = 6LL * c->sm_count * halves;
     long long segs = (want + n_clips - 1) / n_clips;
     const long long max_segs = (n_frames_used + 4LL * G - 1) / (4LL * G);
     if (segs > max_segs) segs = max_segs;

@@ -133,9 +133,8 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
 
     // ---- gather: emit positions [fr0*hop, (fr0+G)*hop), then rebuild the carry.
     // Position x = c*hop + i is covered by the round's frames g = c-q .. c (clipped to [0, ng)), where
-    // q = (n_fft-1-i)/hop depends only on the offset i inside the hop.  A thread keeps i fixed and walks
-    // the chunks c, so the inner loop has no division; frames are added in increasing g, the order in
-    // which the reference accumulates them (librosa/core/spectrum.py:629-643).
+    // q = (n_fft-1-i)/hop depends only on the offset i inside the hop; frames are added in increasing g,
+    // the order in which the reference accumulates them (librosa/core/spectrum.py:629-643).
     const int ng = min(G, fe - fr0);                 // valid frames in this round
     const int emit_n = G * a.hop;
     const int n_chunks = G + (clen + a.hop - 1) / a.hop;      // chunks of hop positions incl. the carry zone
@@ -143,59 +142,61 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
     // chunks whose positions this segment owns: emit_lo <= u < emit_hi
     const int c_lo = (int)max(0LL, (emit_lo - (long long)fr0 * a.hop + a.hop - 1) / a.hop);
     const int c_hi = (int)min((long long)G, (emit_hi - (long long)fr0 * a.hop) / a.hop);
+    // Work items are (chunk c, offset i) pairs spread over every thread of the half.
     if (a.vec4) {
-      // 4 consecutive samples per thread: 16-byte shared loads, one 16-byte store (hop, n_fft - hop,
+      // 4 consecutive samples per item: 16-byte shared loads, one 16-byte store (hop, n_fft - hop,
       // start and the row strides are multiples of 4 and the buffers 16-byte aligned; host-checked)
-      for (int i = 4 * htid; i < a.hop; i += 4 * HT) {
+      const int per = a.hop >> 2;
+      for (int item = htid; item < per * n_chunks; item += HT) {
+        const int c = item / per;
+        const int i = (item - c * per) << 2;
+        const int x = c * a.hop + i;
+        if (x >= emit_n + clen) continue;
         const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;
-        for (int c = 0; c < n_chunks; ++c) {
-          const int x = c * a.hop + i;
-          if (x >= emit_n + clen) break;
-          float4 val = (x < clen) ? *reinterpret_cast<const float4*>(carry_cur + x) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
-          const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
-          for (int g = g_lo; g <= g_hi; ++g) {
-            const float4 f = *reinterpret_cast<const float4*>(yb);
-            val.x += f.x; val.y += f.y; val.z += f.z; val.w += f.w;
-            yb += 2 * Cfg::XBUF_F2 - a.hop;          // next frame's buffer, one hop earlier inside it
-          }
-          if (x < emit_n) {
-            const int o = o0 + x;
-            if (c >= c_lo && c < c_hi && o + 3 >= 0 && o < a.out_len) {
-              if (o >= 0 && o + 3 < a.out_len) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.inv_wss + o));
-                *reinterpret_cast<float4*>(yclip + o) = make_float4(val.x * s4.x, val.y * s4.y, val.z * s4.z, val.w * s4.w);
-              } else {
-                const float vv[4] = {val.x, val.y, val.z, val.w};
+        float4 val = (x < clen) ? *reinterpret_cast<const float4*>(carry_cur + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
+        const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
+        for (int g = g_lo; g <= g_hi; ++g) {
+          const float4 f = *reinterpret_cast<const float4*>(yb);
+          val.x += f.x; val.y += f.y; val.z += f.z; val.w += f.w;
+          yb += 2 * Cfg::XBUF_F2 - a.hop;          // next frame's buffer, one hop earlier inside it
+        }
+        if (x < emit_n) {
+          const int o = o0 + x;
+          if (c >= c_lo && c < c_hi && o + 3 >= 0 && o < a.out_len) {
+            if (o >= 0 && o + 3 < a.out_len) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.inv_wss + o));
+              *reinterpret_cast<float4*>(yclip + o) = make_float4(val.x * s4.x, val.y * s4.y, val.z * s4.z, val.w * s4.w);
+            } else {
+              const float vv[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (o + e >= 0 && o + e < a.out_len) yclip[o + e] = vv[e] * __ldg(a.inv_wss + o + e);
-              }
+              for (int e = 0; e < 4; ++e)
+                if (o + e >= 0 && o + e < a.out_len) yclip[o + e] = vv[e] * __ldg(a.inv_wss + o + e);
             }
-          } else {
-            *reinterpret_cast<float4*>(carry_nxt + (x - emit_n)) = val;
           }
+        } else {
+          *reinterpret_cast<float4*>(carry_nxt + (x - emit_n)) = val;
         }
       }
     } else {
-      for (int i = htid; i < a.hop; i += HT) {
+      for (int item = htid; item < a.hop * n_chunks; item += HT) {
+        const int c = item / a.hop;
+        const int i = item - c * a.hop;
+        const int x = c * a.hop + i;
+        if (x >= emit_n + clen) continue;
         const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;   // hop > n_fft: gap positions see no frame
-        for (int c = 0; c < n_chunks; ++c) {
-          const int x = c * a.hop + i;
-          if (x >= emit_n + clen) break;
-          float val = (x < clen) ? carry_cur[x] : 0.0f;
-          const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
-          const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
-          for (int g = g_lo; g <= g_hi; ++g) {
-            val += *yb;
-            yb += 2 * Cfg::XBUF_F2 - a.hop;
-          }
-          if (x < emit_n) {
-            const int o = o0 + x;
-            if (c >= c_lo && c < c_hi && o >= 0 && o < a.out_len) yclip[o] = val * __ldg(a.inv_wss + o);
-          } else {
-            carry_nxt[x - emit_n] = val;
-          }
+        float val = (x < clen) ? carry_cur[x] : 0.0f;
+        const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
+        const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
+        for (int g = g_lo; g <= g_hi; ++g) {
+          val += *yb;
+          yb += 2 * Cfg::XBUF_F2 - a.hop;
+        }
+        if (x < emit_n) {
+          const int o = o0 + x;
+          if (c >= c_lo && c < c_hi && o >= 0 && o < a.out_len) yclip[o] = val * __ldg(a.inv_wss + o);
+        } else {
+          carry_nxt[x - emit_n] = val;
         }
       }
     }
