@@ -164,6 +164,13 @@ int b2l_dct_project(b2l_ctx* ctx, const b2l_plan* plan, const float* d_S, int64_
 int b2l_transpose(b2l_ctx* ctx, const void* d_in, int64_t n_clips, int64_t rows, int64_t cols,
                   int32_t elem_bytes, void* d_out);
 
+/* ---- first "next" row of SURVEY 8f: Griffin-Lim (core/spectrum.py:2669-2917) -----------------------
+ * Phase update between the istft and stft of one iteration, elementwise over n complex values:
+ *   angles = rebuilt - scale * tprev (tprev may be NULL);  angles = angles / (|angles| + eps) * S
+ * (core/spectrum.py:2898-2903; scale = momentum / (1 + momentum)).  All arrays in the D / S layouts. */
+int b2l_gl_update(b2l_ctx* ctx, const void* d_rebuilt, const void* d_tprev, const float* d_S, float scale, float eps,
+                  void* d_angles, int64_t n);
+
 /* ---- multi-GPU split / join (one process per GPU; NCCL over NVLink) --------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and handed to the other ranks by the launcher. */
 int b2l_comm_unique_id(void* id128);

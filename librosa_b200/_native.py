@@ -99,6 +99,7 @@ def _declare(lib):
         "b2l_power_to_db": (C.c_int, [_vp, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),
+        "b2l_gl_update": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _i64]),
         "b2l_comm_unique_id": (C.c_int, [_vp]),
         "b2l_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
         "b2l_comm_destroy": (C.c_int, [_vp]),

@@ -1,6 +1,6 @@
 """``librosa.core`` names of the FFT time-frequency path."""
 from .convert import fft_frequencies, hz_to_mel, mel_frequencies, mel_to_hz
-from .spectrum import _spectrogram, istft, power_to_db, stft
+from .spectrum import _spectrogram, griffinlim, istft, power_to_db, stft
 
-__all__ = ["stft", "istft", "_spectrogram", "power_to_db", "hz_to_mel", "mel_to_hz", "mel_frequencies",
+__all__ = ["stft", "istft", "griffinlim", "_spectrogram", "power_to_db", "hz_to_mel", "mel_to_hz", "mel_frequencies",
            "fft_frequencies"]

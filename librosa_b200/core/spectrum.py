@@ -311,3 +311,78 @@ def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80
         return out
     res = pl.finish(ctx, out, True, req)
     return res[()]
+
+
+def griffinlim(S, *, n_iter: int = 32, hop_length: Optional[int] = None, win_length: Optional[int] = None,
+               n_fft: Optional[int] = None, window="hann", center: bool = True, dtype=None,
+               length: Optional[int] = None, pad_mode="constant", momentum: float = 0.99, init="random",
+               rng=None):
+    """Approximate magnitude-spectrogram inversion with the fast Griffin-Lim algorithm; same contract as
+    ``librosa.griffinlim`` (core/spectrum.py:2669-2917).  The whole iteration — istft, stft and the phase
+    update — stays on the device; only ``S`` goes up and the final signal comes down."""
+    on_device = isinstance(S, nat.DeviceArray)
+    if not isinstance(rng, np.random.RandomState):
+        rng = np.random.default_rng(rng)
+    if momentum > 1:
+        warnings.warn(f"Griffin-Lim with momentum={momentum} > 1 can be unstable. Proceed with caution!",
+                      stacklevel=2)
+    elif momentum < 0:
+        raise ParameterError(f"griffinlim() called with momentum={momentum} < 0")
+    if not on_device:
+        S = np.asarray(S)
+    if n_fft is None:
+        n_fft = 2 * (S.shape[-2] - 1)
+    if init not in ("random", None):
+        raise ParameterError(f"init={init} must either None or 'random'")
+    s_dtype = pl.check_real_dtype(S.dtype, "griffinlim S")
+    cdtype = dtype_r2c(np.float32)
+    eps = float(tiny(np.zeros(1, dtype=cdtype)))
+    F, T = S.shape[-2], S.shape[-1]
+    lead = tuple(S.shape[:-2])
+    n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    pl.require_supported_n_fft(n_fft)
+    ctx = S.ctx if on_device else nat.default_context()
+    L = nat.lib()
+
+    def to_ft(dev_c, itemsize, np_dtype):
+        out = nat.DeviceArray.empty(ctx, dev_c.shape, np_dtype, layout="ft")
+        nat.check(L.b2l_transpose(ctx.handle, _vp(dev_c.ptr), n_clips, F, T, itemsize, _vp(out.ptr)))
+        return out
+
+    if on_device:
+        S_ft = S if S.layout == "ft" else to_ft(S, 4, np.float32)
+        S_host_shape = S.shape
+    else:
+        S_c = ctx.to_device(np.ascontiguousarray(S, dtype=np.float32))
+        S_ft = to_ft(S_c, 4, np.float32)
+        S_host_shape = S.shape
+    if init == "random":
+        # same generator calls as the reference, so a given seed gives the same starting phases
+        ph = 2 * np.pi * rng.random(size=S_host_shape)
+        a0 = (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64)
+        a0 = a0 * (np.asarray(S.get()) if on_device else S.astype(np.float32))
+        angles = to_ft(ctx.to_device(np.ascontiguousarray(a0, dtype=np.complex64)), 8, np.complex64)
+    else:
+        angles = nat.DeviceArray.empty(ctx, S_host_shape, np.complex64, layout="ft")
+        ones = to_ft(ctx.to_device(np.ones(S_host_shape, dtype=np.complex64)), 8, np.complex64)
+        nat.check(L.b2l_gl_update(ctx.handle, _vp(ones.ptr), None, _vp(S_ft.ptr), 0.0, 0.0, _vp(angles.ptr),
+                                  n_clips * F * T))
+    kw_i = dict(hop_length=hop_length, win_length=win_length, n_fft=n_fft, window=window, center=center, length=length)
+    kw_f = dict(n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window, center=center,
+                pad_mode=pad_mode)
+    scale = float(momentum / (1 + momentum))
+    tprev = None
+    for _ in range(int(n_iter)):
+        inverse = istft(angles, **kw_i)
+        rebuilt = stft(inverse, **kw_f)
+        inverse.free()
+        nat.check(L.b2l_gl_update(ctx.handle, _vp(rebuilt.ptr), _vp(tprev.ptr) if tprev is not None else None,
+                                  _vp(S_ft.ptr), scale, eps, _vp(angles.ptr), n_clips * F * T))
+        if tprev is not None:
+            tprev.free()
+        tprev = rebuilt
+    y = istft(angles, **kw_i)
+    if on_device:
+        return y
+    out_dtype = np.dtype(dtype) if dtype is not None else s_dtype
+    return pl.finish(ctx, y, True, out_dtype)

@@ -947,6 +947,21 @@ extern "C" int b2l_dct_project(b2l_ctx* c, const b2l_plan* p, const float* d_S, 
   return launch_dct(c, p, d_S, n_clips, n_frames, 0, d_mfcc);
 }
 
+extern "C" int b2l_gl_update(b2l_ctx* c, const void* d_rebuilt, const void* d_tprev, const float* d_S, float scale,
+                             float eps, void* d_angles, int64_t n) {
+  if (!c || !d_rebuilt || !d_S || !d_angles) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (n <= 0) return B2L_OK;
+  DeviceGuard g(c->device);
+  long long blocks = (n + 255) / 256;
+  const long long cap = 8LL * c->sm_count;
+  if (blocks > cap) blocks = cap;
+  gl_update_kernel<<<(int)blocks, 256, 0, c->stream>>>((const float2*)d_rebuilt, (const float2*)d_tprev, d_S, scale, eps,
+                                                     (float2*)d_angles, n);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_transpose(b2l_ctx* c, const void* d_in, int64_t n_clips, int64_t rows, int64_t cols,
                              int32_t elem_bytes, void* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");

@@ -172,6 +172,25 @@ __global__ void finite_scan_kernel(const float* __restrict__ y, long long stride
   if (bad) *status = 1;
 }
 
+// ------------------------------------------------------------------ Griffin-Lim phase update
+// angles <- rebuilt - scale * tprev ;  angles <- angles / (|angles| + eps) * S      (elementwise)
+// librosa/core/spectrum.py:2898-2903 (scale = momentum / (1 + momentum), eps = tiny(complex64)).
+__global__ void gl_update_kernel(const float2* __restrict__ rebuilt, const float2* __restrict__ tprev,
+                                 const float* __restrict__ S, float scale, float eps, float2* __restrict__ out,
+                                 long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float2 a = rebuilt[i];
+    if (tprev != nullptr) {
+      const float2 p = tprev[i];
+      a.x = fmaf(-scale, p.x, a.x);
+      a.y = fmaf(-scale, p.y, a.y);
+    }
+    const float mag = hypotf(a.x, a.y) + eps;
+    const float s = S[i];
+    out[i] = make_float2(a.x / mag * s, a.y / mag * s);
+  }
+}
+
 // ------------------------------------------------------------------ batched transpose
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ in, int rows, int cols, T* __restrict__ out) {

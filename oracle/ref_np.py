@@ -389,3 +389,38 @@ def mfcc(y=None, sr=22050, S=None, n_mfcc=20, dct_type=2, norm="ortho", lifter=0
     if lifter == 0:
         return M
     raise ParameterError(f"MFCC lifter={lifter} must be a non-negative number")
+
+
+def griffinlim(S, n_iter=32, hop_length=None, win_length=None, n_fft=None, window="hann", center=True,
+               dtype=None, length=None, pad_mode="constant", momentum=0.99, init="random", rng=None):
+    """Fast Griffin-Lim, restating librosa/core/spectrum.py:2819-2917 (first "next" row of SURVEY 8f)."""
+    if not isinstance(rng, np.random.RandomState):
+        rng = np.random.default_rng(rng)
+    if momentum < 0:
+        raise ParameterError(f"griffinlim() called with momentum={momentum} < 0")
+    if n_fft is None:
+        n_fft = 2 * (S.shape[-2] - 1)
+    angles = np.empty(S.shape, dtype=dtype_r2c(S.dtype))
+    eps = tiny(angles)
+    if init == "random":
+        ph = 2 * np.pi * rng.random(size=S.shape)
+        angles[:] = np.cos(ph) + 1j * np.sin(ph)
+    elif init is None:
+        angles[:] = 1.0
+    else:
+        raise ParameterError(f"init={init} must either None or 'random'")
+    angles *= S
+    tprev = None
+    kw_i = dict(hop_length=hop_length, win_length=win_length, n_fft=n_fft, window=window, center=center,
+                dtype=dtype, length=length)
+    for _ in range(n_iter):
+        inverse = istft(angles, **kw_i)
+        rebuilt = stft(inverse, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window,
+                       center=center, pad_mode=pad_mode)
+        angles[:] = rebuilt
+        if tprev is not None:
+            angles -= (momentum / (1 + momentum)) * tprev
+        angles /= np.abs(angles) + eps
+        angles *= S
+        tprev = rebuilt
+    return istft(angles, **kw_i)

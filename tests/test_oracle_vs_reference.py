@@ -44,6 +44,13 @@ def test_features_bit_exact(ref, oracle):
                                   oracle.mfcc(y=y, sr=16000, n_mfcc=13, lifter=22, dct_type=3))
 
 
+def test_griffinlim_bit_exact(ref, oracle):
+    y = (0.1 * np.random.default_rng(2).standard_normal(6000)).astype(np.float32)
+    S = np.abs(ref.stft(y, n_fft=512, hop_length=128))
+    for kw in [dict(n_iter=4, rng=0), dict(n_iter=3, init=None, momentum=0.5), dict(n_iter=2, rng=7, length=6000)]:
+        np.testing.assert_array_equal(ref.griffinlim(S, hop_length=128, **kw), oracle.griffinlim(S, hop_length=128, **kw))
+
+
 def test_product_host_constants_match_reference(ref):
     """The product's own host-side constant builders (librosa_b200.filters / convert / util) against the
     reference — these feed the GPU plans, so they are pinned as tightly as the oracle."""
