@@ -713,17 +713,21 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   a.clip_max = c->d_clip_max;
   a.status = c->d_status;
 
-  // cudaFuncSetAttribute + the occupancy query cost tens of microseconds; do them once per configuration
-  const unsigned long long ckey = ((unsigned long long)p->log2m << 56) | ((unsigned long long)variant << 44) |
-                                  ((unsigned long long)mode << 40) | (unsigned long long)smem;
+  // cudaFuncSetAttribute + the occupancy query cost tens of microseconds: raise the kernel's dynamic
+  // shared-memory limit to the device maximum once per kernel, cache blocks/SM per (kernel, smem)
+  const unsigned long long kkey = ((unsigned long long)p->log2m << 56) | ((unsigned long long)variant << 44) |
+                                  ((unsigned long long)mode << 40);
+  if (c->launch_cache.find(kkey) == c->launch_cache.end()) {
+    CUDA_TRY(op(OP_SET_SMEM, variant, mode, &a, 0, c->smem_optin, c->stream, nullptr));
+    c->launch_cache[kkey] = 1;
+  }
   int occ = 0;
-  auto hit = c->launch_cache.find(ckey);
+  auto hit = c->launch_cache.find(kkey | (unsigned long long)smem);
   if (hit != c->launch_cache.end()) {
     occ = hit->second;
   } else {
-    CUDA_TRY(op(OP_SET_SMEM, variant, mode, &a, 0, smem, c->stream, nullptr));
     CUDA_TRY(op(OP_OCCUPANCY, variant, mode, &a, 0, smem, c->stream, &occ));
-    c->launch_cache[ckey] = occ;
+    c->launch_cache[kkey | (unsigned long long)smem] = occ;
   }
   if (occ < 1) return fail(B2L_ERR_CUDA, "forward kernel does not fit on an SM (smem %zu)", smem);
   long long grid = (long long)c->sm_count * occ;
