@@ -130,17 +130,31 @@ def precheck_signal(y):
     return y.shape[-1], check_real_dtype(y.dtype, "input signal")
 
 
-MIN_N_FFT, MAX_N_FFT = 8, 8192   # kMinLog2M / kMaxLog2M in csrc/internal.h
+MIN_N_FFT, MAX_N_FFT = 8, 8192   # powers of two: kMinLog2M / kMaxLog2M in csrc/internal.h
+MAX_CZT_N_FFT = 2047               # other sizes: Bluestein with P = 2^ceil(log2(2 n_fft - 1)) <= 4096
 
 
-def require_supported_n_fft(n_fft: int):
-    """The sm_100a kernels are built for power-of-two n_fft in [8, 8192]; anything else librosa accepts
-    (e.g. the reference tests' 501 / 1023 / 1025) is refused loudly — there is no CPU fallback."""
+def is_pow2(n: int) -> bool:
+    return n > 0 and (n & (n - 1)) == 0
+
+
+def require_supported_n_fft(n_fft: int, inverse: bool = False):
+    """Power-of-two n_fft in [8, 8192] runs on the packed real-FFT kernels; any other n_fft in [3, 2047]
+    (the reference tests' 501 / 1023 / 1025, the 400 of speech front ends, ...) on the chirp-z forward
+    kernel.  Everything else librosa accepts is refused loudly — there is no CPU fallback."""
     n_fft = int(n_fft)
-    if n_fft < MIN_N_FFT or n_fft > MAX_N_FFT or (n_fft & (n_fft - 1)):
+    if is_pow2(n_fft):
+        if MIN_N_FFT <= n_fft <= MAX_N_FFT:
+            return
         raise nat.UnsupportedOnGPU(
             f"n_fft={n_fft}: the sm_100a kernels are built for powers of two from {MIN_N_FFT} to {MAX_N_FFT} "
             "(no CPU fallback)")
+    if inverse:
+        raise nat.UnsupportedOnGPU(f"n_fft={n_fft}: the inverse transform is built for powers of two only "
+                                   "(no CPU fallback)")
+    if not (3 <= n_fft <= MAX_CZT_N_FFT):
+        raise nat.UnsupportedOnGPU(f"n_fft={n_fft}: non-power-of-two sizes are supported from 3 to {MAX_CZT_N_FFT} "
+                                   "(no CPU fallback)")
 
 
 def context_for(x):

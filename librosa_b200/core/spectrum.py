@@ -155,7 +155,7 @@ def istft(stft_matrix, *, hop_length: Optional[int] = None, win_length: Optional
             raise ParameterError("out= must be a NumPy array")
         if tuple(out.shape) != shape:
             raise ParameterError(f"Shape mismatch for provided output array out.shape={out.shape} != {list(shape)}")
-    pl.require_supported_n_fft(n_fft)
+    pl.require_supported_n_fft(n_fft, inverse=True)
     ctx = stft_matrix.ctx if on_device else nat.default_context()
     n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
     key = ("stft", n_fft, hop_length, bool(center), "constant", wkey)
@@ -340,7 +340,7 @@ def griffinlim(S, *, n_iter: int = 32, hop_length: Optional[int] = None, win_len
     F, T = S.shape[-2], S.shape[-1]
     lead = tuple(S.shape[:-2])
     n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
-    pl.require_supported_n_fft(n_fft)
+    pl.require_supported_n_fft(n_fft, inverse=True)
     ctx = S.ctx if on_device else nat.default_context()
     L = nat.lib()
 

@@ -16,7 +16,9 @@
 #include "../../include/b2l.h"
 #include "aux_kernels.cuh"
 #include "common.cuh"
+#include "czt_kernel.cuh"
 #include "internal.h"
+#include <complex>
 
 using namespace b2l;
 
@@ -136,6 +138,11 @@ struct b2l_plan {
   mutable std::map<int, RowTable> row_tables;
   int power_mode = 2;
   float power = 2.0f;
+  // chirp-z path for n_fft that is not a power of two (czt_kernel.cuh): transform size P = 2^log2p
+  int czt = 0, log2p = 0;
+  float2* d_czt_wb = nullptr;   // [n_fft] window * b
+  float2* d_czt_bk = nullptr;   // [1 + n_fft/2] b
+  float2* d_czt_hf = nullptr;   // [P] FFT_P(h)/P followed by the engine's inter-pass twiddles
   // mfcc
   int n_mfcc = 0;
   float* d_dct = nullptr;
@@ -365,6 +372,45 @@ static int upload(b2l_ctx* c, const std::vector<T>& h, T** d) {
   return B2L_OK;
 }
 
+// inter-pass twiddles of the register FFT for a complex size 2^log2m (FftCfg::tw_offset layout)
+static std::vector<float2> engine_twiddles(const HostFftCfg& cfg) {
+  const double two_pi = 6.283185307179586476925286766559;
+  std::vector<float2> tw((size_t)cfg.tw_count());
+  for (int s = 1; s < cfg.npass; ++s) {
+    const int R = cfg.radix(s), pl = cfg.sublen(s), off = cfg.tw_offset(s);
+    for (int r = 1; r < R; ++r)
+      for (int k = 0; k < pl; ++k) {
+        // exp(-2*pi*i * r*k / (p*R)); reduce the integer phase first to keep the argument small
+        long long num = ((long long)r * k) % ((long long)pl * R);
+        double ang = -two_pi * (double)num / (double)((long long)pl * R);
+        tw[(size_t)off + (size_t)(r - 1) * pl + k] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+  }
+  return tw;
+}
+
+// in-place radix-2 FFT in double precision (host, plan construction only)
+static void host_fft(std::vector<std::complex<double>>& x) {
+  const size_t n = x.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(x[i], x[j]);
+  }
+  const double pi = 3.14159265358979323846264338327950288;
+  for (size_t len = 2; len <= n; len <<= 1) {
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; ++k) {
+        const double ang = -2.0 * pi * (double)k / (double)len;
+        const std::complex<double> w(cos(ang), sin(ang));
+        const std::complex<double> u = x[i + k], v = x[i + k + len / 2] * w;
+        x[i + k] = u + v;
+        x[i + k + len / 2] = u - v;
+      }
+  }
+}
+
 extern "C" int b2l_plan_destroy(b2l_plan* p) {
   if (!p) return B2L_OK;
   DeviceGuard g(p->ctx->device);
@@ -374,6 +420,9 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   cudaFree(p->d_tw);
   cudaFree(p->d_twn);
   cudaFree(p->d_mel_w);
+  cudaFree(p->d_czt_wb);
+  cudaFree(p->d_czt_bk);
+  cudaFree(p->d_czt_hf);
   cudaFree(p->d_band);
   for (auto& kv : p->row_tables) {
     cudaFree(kv.second.d_rows);
@@ -389,10 +438,19 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
   if (d->n_fft < 1) return fail(B2L_ERR_INVALID, "n_fft=%d must be positive", d->n_fft);
   if (d->hop_length < 1) return fail(B2L_ERR_INVALID, "hop_length=%d must be a positive integer", d->hop_length);
   int l2n = ilog2_exact(d->n_fft);
-  if (l2n < 0 || l2n - 1 < kMinLog2M || l2n - 1 > kMaxLog2M)
+  int czt_log2p = 0;
+  if (l2n < 0) {
+    // not a power of two: Bluestein with P = next power of two >= 2*n_fft - 1 (czt_kernel.cuh)
+    while ((1 << czt_log2p) < 2 * d->n_fft - 1) ++czt_log2p;
+    if (czt_log2p < 5) czt_log2p = 5;
+    if (d->n_fft < 3 || czt_log2p > 12)
+      return fail(B2L_ERR_UNSUPPORTED,
+                  "n_fft=%d: non-power-of-two sizes are supported from 3 to 2047 (no CPU fallback)", d->n_fft);
+  } else if (l2n - 1 < kMinLog2M || l2n - 1 > kMaxLog2M) {
     return fail(B2L_ERR_UNSUPPORTED,
                 "n_fft=%d: the sm_100a kernels are built for powers of two from %d to %d (no CPU fallback)",
                 d->n_fft, 2 << kMinLog2M, 2 << kMaxLog2M);
+  }
   if (!d->h_window) return fail(B2L_ERR_INVALID, "window is NULL");
   if (d->pad_mode < 0 || d->pad_mode > B2L_PAD_EMPTY) return fail(B2L_ERR_INVALID, "bad pad_mode %d", d->pad_mode);
   if (d->n_mels < 0 || d->n_mfcc < 0) return fail(B2L_ERR_INVALID, "negative n_mels / n_mfcc");
@@ -415,37 +473,58 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
   p->ref_value = d->ref_value;
   p->top_db = d->top_db;
   const int N = d->n_fft, M = N / 2;
-  HostFftCfg cfg(p->log2m);
-
   int rc = B2L_OK;
-  {
-    std::vector<float> wf(N), wi(N);
-    for (int i = 0; i < N; ++i) {
-      wf[i] = (float)(d->h_window[i] * 0.5);
-      wi[i] = (float)(d->h_window[i] / (double)N);
+  if (l2n < 0) {
+    // ---- chirp-z tables (double precision on the host)
+    p->czt = 1;
+    p->log2p = czt_log2p;
+    p->log2m = -1;
+    const int L = N, P = 1 << czt_log2p;
+    const double pi = 3.14159265358979323846264338327950288;
+    std::vector<std::complex<double>> b(L);
+    for (int n = 0; n < L; ++n) {
+      const long long q = ((long long)n * n) % (2LL * L);          // n^2 mod 2L keeps the phase exact
+      const double ang = -pi * (double)q / (double)L;
+      b[n] = std::complex<double>(cos(ang), sin(ang));
     }
-    if ((rc = upload(c, wf, &p->d_win_fwd)) || (rc = upload(c, wi, &p->d_win_inv))) goto bad;
-  }
-  {
-    const double two_pi = 6.283185307179586476925286766559;
-    std::vector<float2> tw((size_t)cfg.tw_count());
-    for (int s = 1; s < cfg.npass; ++s) {
-      const int R = cfg.radix(s), pl = cfg.sublen(s), off = cfg.tw_offset(s);
-      for (int r = 1; r < R; ++r)
-        for (int k = 0; k < pl; ++k) {
-          // exp(-2*pi*i * r*k / (p*R)); reduce the integer phase first to keep the argument small
-          long long num = ((long long)r * k) % ((long long)pl * R);
-          double ang = -two_pi * (double)num / (double)((long long)pl * R);
-          tw[(size_t)off + (size_t)(r - 1) * pl + k] = make_float2((float)cos(ang), (float)sin(ang));
-        }
+    std::vector<float2> wb(L), bk(L / 2 + 1);
+    for (int n = 0; n < L; ++n) {
+      const std::complex<double> z = d->h_window[n] * b[n];
+      wb[n] = make_float2((float)z.real(), (float)z.imag());
     }
-    p->tw_count = cfg.tw_count();
-    std::vector<float2> twn((size_t)M / 2 + 1);
-    for (int k = 0; k <= M / 2; ++k) {
-      double ang = -two_pi * (double)k / (double)N;
-      twn[k] = make_float2((float)cos(ang), (float)sin(ang));
+    for (int k = 0; k <= L / 2; ++k) bk[k] = make_float2((float)b[k].real(), (float)b[k].imag());
+    std::vector<std::complex<double>> h(P, std::complex<double>(0.0, 0.0));
+    h[0] = std::conj(b[0]);
+    for (int m = 1; m < L; ++m) h[m] = h[P - m] = std::conj(b[m]);
+    host_fft(h);
+    HostFftCfg ccfg(czt_log2p);
+    std::vector<float2> hf((size_t)P);
+    for (int i = 0; i < P; ++i) hf[i] = make_float2((float)(h[i].real() / P), (float)(h[i].imag() / P));
+    std::vector<float2> tw = engine_twiddles(ccfg);
+    hf.insert(hf.end(), tw.begin(), tw.end());
+    if ((rc = upload(c, wb, &p->d_czt_wb)) || (rc = upload(c, bk, &p->d_czt_bk)) || (rc = upload(c, hf, &p->d_czt_hf)))
+      goto bad;
+  } else {
+    HostFftCfg cfg(p->log2m);
+    {
+      std::vector<float> wf(N), wi(N);
+      for (int i = 0; i < N; ++i) {
+        wf[i] = (float)(d->h_window[i] * 0.5);
+        wi[i] = (float)(d->h_window[i] / (double)N);
+      }
+      if ((rc = upload(c, wf, &p->d_win_fwd)) || (rc = upload(c, wi, &p->d_win_inv))) goto bad;
     }
-    if ((rc = upload(c, tw, &p->d_tw)) || (rc = upload(c, twn, &p->d_twn))) goto bad;
+    {
+      const double two_pi = 6.283185307179586476925286766559;
+      std::vector<float2> tw = engine_twiddles(cfg);
+      p->tw_count = cfg.tw_count();
+      std::vector<float2> twn((size_t)M / 2 + 1);
+      for (int k = 0; k <= M / 2; ++k) {
+        double ang = -two_pi * (double)k / (double)N;
+        twn[k] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+      if ((rc = upload(c, tw, &p->d_tw)) || (rc = upload(c, twn, &p->d_twn))) goto bad;
+    }
   }
   if (d->n_mels > 0) {
     const int F = M + 1;
@@ -738,16 +817,87 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   return B2L_OK;
 }
 
+// ------------------------------------------------------------------ chirp-z launch (n_fft not a power of two)
+typedef cudaError_t (*czt_op_fn)(int, const CztArgs*, int, size_t, cudaStream_t, int*);
+static czt_op_fn czt_table(int log2p) {
+  switch (log2p) {
+    case 5: return czt_op_5; case 6: return czt_op_6; case 7: return czt_op_7; case 8: return czt_op_8;
+    case 9: return czt_op_9; case 10: return czt_op_10; case 11: return czt_op_11; case 12: return czt_op_12;
+  }
+  return nullptr;
+}
+
+static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, int64_t n_clips, int64_t n,
+                   int64_t y_stride, float2* out_c, float* out_r) {
+  if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
+  if (n_clips < 0 || n < 0 || y_stride < n) return fail(B2L_ERR_INVALID, "bad clip geometry");
+  if (n > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "clips longer than 2^31-1 samples are not supported");
+  const long long T = plan_frames(p, n);
+  if (T <= 0)
+    return fail(B2L_ERR_INVALID, "n_fft=%d is too large for input signal of length=%lld", p->n_fft, (long long)n);
+  if (n_clips == 0) return B2L_OK;
+  if (!d_y || (mode == 0 ? (void*)out_c : (void*)out_r) == nullptr) return fail(B2L_ERR_INVALID, "NULL device pointer");
+  DeviceGuard g(c->device);
+  HostFftCfg cfg(p->log2p);
+  const int nw = cfg.czt_nw();
+  const int G = nw * 32 / cfg.tpf;
+  CztArgs a;
+  memset(&a, 0, sizeof(a));
+  a.y = d_y;
+  a.clip_stride = y_stride;
+  a.n = (int)n;
+  a.n_clips = (int)n_clips;
+  a.L = p->n_fft;
+  a.hop = p->hop;
+  a.pad = p->center ? p->n_fft / 2 : 0;
+  a.pad_mode = p->pad_mode;
+  a.n_frames = (int)T;
+  a.n_bins = 1 + p->n_fft / 2;
+  a.wb = p->d_czt_wb;
+  a.bk = p->d_czt_bk;
+  a.hf = p->d_czt_hf;
+  a.out_c = out_c;
+  a.out_r = out_r;
+  a.mode = mode;
+  a.power_mode = p->power_mode;
+  a.power = p->power;
+  a.status = c->d_status;
+  const size_t smem = (size_t)((cfg.tw_count() + 15) & ~15) * 8 + (size_t)G * cfg.xbuf_f2() * 8;
+  czt_op_fn op = czt_table(p->log2p);
+  const unsigned long long kkey = (1ULL << 63) | ((unsigned long long)p->log2p << 40);
+  int occ = 0;
+  auto hit = c->launch_cache.find(kkey);
+  if (hit != c->launch_cache.end()) {
+    occ = hit->second;
+  } else {
+    CUDA_TRY(op(OP_SET_SMEM, &a, 0, smem, c->stream, nullptr));
+    CUDA_TRY(op(OP_OCCUPANCY, &a, 0, smem, c->stream, &occ));
+    c->launch_cache[kkey] = occ;
+  }
+  if (occ < 1) return fail(B2L_ERR_CUDA, "chirp-z kernel does not fit on an SM (smem %zu)", smem);
+  const long long steps = ((long long)n_clips * T + G - 1) / G;
+  long long grid = (long long)c->sm_count * occ;
+  if (grid > steps) grid = steps;
+  CUDA_TRY(op(OP_LAUNCH, &a, (int)grid, smem, c->stream, nullptr));
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_stft(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
                         void* d_D) {
+  if (c && p && p->czt) return run_czt(c, p, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
   return run_forward(c, p, MODE_STFT, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
 }
 extern "C" int b2l_spectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
                                int64_t y_stride, float* d_S) {
+  if (c && p && p->czt) return run_czt(c, p, 1, d_y, n_clips, n, y_stride, nullptr, d_S);
   return run_forward(c, p, MODE_SPEC, 0, d_y, n_clips, n, y_stride, nullptr, d_S);
 }
 extern "C" int b2l_melspectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
                                   int64_t y_stride, float* d_mel) {
+  if (p && p->czt)
+    return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d: compose b2l_spectrogram + b2l_mel_project for non-power-of-two sizes",
+                p->n_fft);
   return run_forward(c, p, MODE_MEL, 0, d_y, n_clips, n, y_stride, nullptr, d_mel);
 }
 
@@ -777,6 +927,9 @@ extern "C" int b2l_mfcc(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t
                         float* d_mfcc, float* d_logmel) {
   if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
   if (p->n_mfcc == 0) return fail(B2L_ERR_INVALID, "plan has no mfcc stage");
+  if (p->czt)
+    return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d: compose spectrogram, mel_project, power_to_db and dct_project for "
+                "non-power-of-two sizes", p->n_fft);
   if (n_clips <= 0) return n_clips == 0 ? B2L_OK : fail(B2L_ERR_INVALID, "negative n_clips");
   DeviceGuard g(c->device);
   const long long T = plan_frames(p, n);
@@ -803,6 +956,7 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
   if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
   if (n_clips < 0 || n_frames_used < 1 || n_frames_used > n_frames_stored || out_len < 0 || y_stride < out_len)
     return fail(B2L_ERR_INVALID, "bad istft geometry");
+  if (p->czt) return fail(B2L_ERR_UNSUPPORTED, "istft with n_fft=%d (not a power of two) is not built", p->n_fft);
   if (n_clips == 0 || out_len == 0) return B2L_OK;
   if (!d_D || !d_inv_wss || !d_y) return fail(B2L_ERR_INVALID, "NULL device pointer");
   if (out_len > 0x7fffffffLL || n_frames_stored > 0x7fffffffLL)

@@ -1,0 +1,102 @@
+// czt_kernel.cuh — STFT frames of arbitrary length L (not a power of two) by Bluestein's chirp-z
+// transform on top of the register FFT engine.
+//
+// librosa.stft accepts any n_fft (the reference's own tests use 501 / 1023 / 1025, speech front ends use
+// 400); scipy.fft.rfft handles them with mixed-radix / Bluestein plans (librosa/core/spectrum.py:388).
+// With b[n] = exp(-i*pi*n^2/L):
+//     X[k] = b[k] * sum_n (x[n] w[n] b[n]) * conj(b[k-n])  =  b[k] * IFFT_P( FFT_P(a) . FFT_P(h) )[k]
+// a[n] = x[n] w[n] b[n] zero-padded to P >= 2L-1 (a power of two), h[m] = conj(b[|m|]) wrapped to length P.
+// FFT_P(h)/P, w*b and b are precomputed on the host in double precision.
+//
+// One group of TPF = P/32 threads per frame (same engine configuration as an n_fft = 2P real frame);
+// frames are read straight from global memory through the np.pad index map (the 2-4x frame overlap is
+// served by L2), the product with FFT_P(h) is applied in registers, and the inverse transform reuses the
+// forward one with re/im swapped.
+#pragma once
+#include "common.cuh"
+#include "fft_engine.cuh"
+#include "fwd_kernel.cuh"   // load_padded, power_from_sq, sqmag
+
+namespace b2l {
+
+struct CztArgs {
+  const float* y;
+  long long clip_stride;
+  int n, n_clips;
+  int L, hop, pad, pad_mode, n_frames, n_bins;   // n_bins = 1 + L/2
+  const float2* wb;      // [L]  window[n] * b[n]
+  const float2* bk;      // [n_bins] b[k]
+  const float2* hf;      // [P]  FFT_P(h) / P
+  float2* out_c;         // complex64 [clip][frame][bin]   (mode 0)
+  float* out_r;          // |X|^power [clip][frame][bin]   (mode 1)
+  int mode, power_mode;
+  float power;
+  int* status;
+};
+
+template <int LOG2P, int TPF, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
+  using Cfg = FftCfg<LOG2P, TPF>;
+  constexpr int P = Cfg::M, PPT = Cfg::PPT;
+  constexpr int NT = NW * 32;
+  constexpr int G = NT / TPF;                  // frames per CTA step
+  static_assert(TPF <= 32 || 1 + NT / TPF <= 15, "named barriers");
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* s_tw = reinterpret_cast<float2*>(smem);
+  float2* s_xall = s_tw + ((Cfg::TW_COUNT + 15) & ~15);
+  const int tid = threadIdx.x, grp = tid / TPF, t = tid % TPF;
+  const int gbar = 2 + grp;
+  float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
+  // inter-pass twiddles of the engine (the host appends them to the FFT_P(h)/P table)
+  for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.hf[P + i];   // appended after FFT_P(h)/P
+  __syncthreads();
+
+  const long long total = (long long)a.n_clips * a.n_frames;
+  for (long long f0 = (long long)blockIdx.x * G; f0 < total; f0 += (long long)gridDim.x * G) {
+    // groups past the end redo the last frame (their stores are masked): sub-warp groups share a warp
+    const long long fidx = min(f0 + grp, total - 1);
+    const bool live = f0 + grp < total;
+    const int clip = (int)(fidx / a.n_frames), frame = (int)(fidx % a.n_frames);
+    const float* yc = a.y + (long long)clip * a.clip_stride;
+    const long long s0 = (long long)frame * a.hop - a.pad;
+    float2 v[PPT];
+    load_pass0<Cfg>(v, t, [&](int e) {
+      if (e >= a.L) return make_float2(0.0f, 0.0f);
+      const float x = load_padded(yc, a.n, s0 + e, a.pad_mode, a.pad);
+      const float2 w = __ldg(a.wb + e);
+      return make_float2(x * w.x, x * w.y);
+    });
+    fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
+    if (live && !(fabsf(v[0].x) + fabsf(v[0].y) <= 3.0e38f)) *a.status = 1;   // util.valid_audio
+    // C = A . FFT(h)/P in registers, published (re/im swapped) for the inverse transform's first pass
+    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
+    static_for<0, PPT>([&](auto S) {
+      constexpr int slot = decltype(S)::value;
+      const int idx = t + spectrum_offset<Cfg>(slot);
+      const float2 c = cmul(v[slot], __ldg(a.hf + idx));
+      xbuf[xphys(idx)] = make_float2(c.y, c.x);
+    });
+    group_sync<TPF>(gbar);
+    load_pass0<Cfg>(v, t, [&](int e) { return xbuf[xphys(e)]; });
+    group_sync<TPF>(gbar);
+    fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
+    // X[k] = b[k] * c[k]  (un-swap), k <= L/2
+    static_for<0, PPT>([&](auto S) {
+      constexpr int slot = decltype(S)::value;
+      const int k = t + spectrum_offset<Cfg>(slot);
+      if (k < a.n_bins && live) {
+        const float2 X = cmul(make_float2(v[slot].y, v[slot].x), __ldg(a.bk + k));
+        const long long o = ((long long)clip * a.n_frames + frame) * a.n_bins + k;
+        if (a.mode == 0) {
+          a.out_c[o] = X;
+        } else {
+          float p2 = sqmag(X);
+          a.out_r[o] = a.power_mode == 2 ? p2 : power_from_sq(p2, a.power_mode, a.power);
+        }
+      }
+    });
+    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);   // exchange area reused by the next frame
+  }
+}
+
+}  // namespace b2l

@@ -18,6 +18,11 @@ B2L_DECL_FWD(8) B2L_DECL_FWD(9) B2L_DECL_FWD(10) B2L_DECL_FWD(11) B2L_DECL_FWD(1
 B2L_DECL_INV(2) B2L_DECL_INV(3) B2L_DECL_INV(4) B2L_DECL_INV(5) B2L_DECL_INV(6) B2L_DECL_INV(7)
 B2L_DECL_INV(8) B2L_DECL_INV(9) B2L_DECL_INV(10) B2L_DECL_INV(11) B2L_DECL_INV(12)
 
+struct CztArgs;
+#define B2L_DECL_CZT(L) \
+  cudaError_t czt_op_##L(int op, const CztArgs* a, int grid, size_t smem, cudaStream_t st, int* result);
+B2L_DECL_CZT(5) B2L_DECL_CZT(6) B2L_DECL_CZT(7) B2L_DECL_CZT(8) B2L_DECL_CZT(9) B2L_DECL_CZT(10) B2L_DECL_CZT(11) B2L_DECL_CZT(12)
+
 constexpr int kMinLog2M = 2, kMaxLog2M = 12;   // n_fft = 2^(LOG2M+1): 8 .. 8192
 
 // Host mirror of FftCfg<LOG2M, TPF> (fft_engine.cuh): same schedule, evaluated at run time.
@@ -42,6 +47,8 @@ struct HostFftCfg {
   }
   int tw_count() const { return tw_offset(npass); }
   int xbuf_f2() const { return M + M / 32; }
+  // warps per CTA of czt_kernel for P = 2^log2p (mirror of czt_inst.cu)
+  int czt_nw() const { return log2m >= 10 ? 16 : (tpf > 16 ? 16 : tpf); }
   // warps per CTA tried in order (first that fits shared memory wins)
   int nw_options(int out[2]) const {
     if (log2m >= 10) { out[0] = 16; out[1] = 8; return 2; }

@@ -74,6 +74,12 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     basis, bkey = pl.mel_basis(sr, n_fft, kwargs)
     pl.require_supported_n_fft(n_fft)
+    if not pl.is_pow2(n_fft):
+        # chirp-z frames: |STFT|**power on the device, then the band-sparse projection (two kernels)
+        res_dtype = np.result_type(req_dtype, basis.dtype)
+        return _compose_nonpow2(y, lambda Sd: melspectrogram(S=Sd, sr=sr, n_fft=n_fft, **kwargs), res_dtype,
+                                n_fft=n_fft, hop_length=hop_length, power=power, win_length=win_length,
+                                window=window, center=center, pad_mode=pad_mode)
     key = ("mel", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power))
     n_mels = basis.shape[0]
     T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length
@@ -98,6 +104,31 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
     res = pl.run_host_forward(y, n_fft=n_fft, hop_length=hop_length, center=center, n_frames=T,
                               out_mem_tail=(n_mels, T), out_dtype=np.float32, make_plan=make_plan, launch=launch)
     return res if res.dtype == res_dtype else res.astype(res_dtype)
+
+
+def _compose_nonpow2(y, tail, res_dtype, **spec_kw):
+    """melspectrogram / mfcc for n_fft that is not a power of two: the chirp-z spectrogram kernel followed by
+    the S= kernels, all on the device; host inputs get the device-side valid_audio verdict at the end."""
+    from ..core.spectrum import _spectrogram
+
+    if isinstance(y, nat.DeviceArray):
+        Sd, _ = _spectrogram(y=y, **spec_kw)
+        return tail(Sd)
+    ctx = nat.default_context()
+    L = nat.lib()
+    host = np.ascontiguousarray(y, dtype=np.float32)
+    nat.check(L.b2l_status_reset(ctx.handle))
+    yd = ctx.to_device(host)
+    n_fft, hop, center = spec_kw["n_fft"], spec_kw["hop_length"], spec_kw["center"]
+    n = host.shape[-1]
+    T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop
+    staged = pl.StagedInput(ctx, yd)
+    begin = 0 if hop > n_fft else max(0, (T - 1) * hop + n_fft - (n_fft // 2 if center else 0))
+    if begin < n and staged.n_clips:
+        nat.check(L.b2l_scan_finite(ctx.handle, _vp(yd.ptr), staged.n_clips, n, n, begin))
+    Sd, _ = _spectrogram(y=yd, **spec_kw)
+    out = tail(Sd)
+    return pl.finish(ctx, out, True, res_dtype, validate=True)
 
 
 def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float) -> np.ndarray:
@@ -155,6 +186,15 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
     n_mels = basis.shape[0]
     dct = _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter)
     pl.require_supported_n_fft(n_fft)
+    if not pl.is_pow2(n_fft):
+        res_dtype = np.result_type(req_dtype, basis.dtype)
+
+        def tail(Sd):
+            mel_d = melspectrogram(S=Sd, sr=sr, n_fft=n_fft, norm=mel_norm, **kwargs)
+            return mfcc(S=power_to_db(mel_d), n_mfcc=n_mfcc, dct_type=dct_type, norm=norm, lifter=lifter)
+
+        return _compose_nonpow2(y, tail, res_dtype, n_fft=n_fft, hop_length=hop_length, power=power,
+                                win_length=win_length, window=window, center=center, pad_mode=pad_mode)
     key = ("mfcc", n_fft, hop_length, bool(center), mode, wkey, bkey, float(power), pl.digest(dct))
     T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length
     res_dtype = np.result_type(req_dtype, basis.dtype)

@@ -25,9 +25,18 @@ CASES = [
     dict(name="stft_1024_winlen600_hamming_A", op="stft", mix="A", shape=(5000,), kw=dict(n_fft=1024, win_length=600, window="hamming")),
     dict(name="stft_512_stereo_A", op="stft", mix="A", shape=(2, 3000), kw=dict(n_fft=512, hop_length=128)),
     dict(name="stft_2048_C_burst", op="stft", mix="C", shape=(9000,), kw=dict(n_fft=2048, hop_length=512)),
+    # n_fft that is not a power of two (chirp-z kernel): the sizes the reference's own tests use, the 400/160
+    # of speech front ends, tiny and near-maximal sizes
+    dict(name="stft_501_nonpow2", op="stft", mix="A", shape=(3000,), kw=dict(n_fft=501, hop_length=128)),
+    dict(name="stft_1025_nonpow2", op="stft", mix="A", shape=(5000,), kw=dict(n_fft=1025, hop_length=300)),
+    dict(name="stft_1023_reflect_B", op="stft", mix="B", shape=(6000,), kw=dict(n_fft=1023, hop_length=256, pad_mode="reflect")),
+    dict(name="stft_400_160_stereo_A", op="stft", mix="A", shape=(2, 8000), kw=dict(n_fft=400, hop_length=160)),
+    dict(name="stft_2000_500_nocenter_A", op="stft", mix="A", shape=(9000,), kw=dict(n_fft=2000, hop_length=500, center=False)),
+    dict(name="stft_6_2_A", op="stft", mix="A", shape=(100,), kw=dict(n_fft=6, hop_length=2)),
+    dict(name="stft_12_5_edge_A", op="stft", mix="A", shape=(300,), kw=dict(n_fft=12, hop_length=5, pad_mode="edge")),
+    dict(name="stft_600_winlen400_hamming_A", op="stft", mix="A", shape=(4000,), kw=dict(n_fft=600, win_length=400, window="hamming")),
     # reference-supported, GPU kernels not built: the CUDA path must refuse loudly (oracle still pinned)
-    dict(name="stft_501_nonpow2", op="stft", mix="A", shape=(3000,), kw=dict(n_fft=501, hop_length=128), gpu="unsupported"),
-    dict(name="stft_1025_nonpow2", op="stft", mix="A", shape=(5000,), kw=dict(n_fft=1025, hop_length=300), gpu="unsupported"),
+    dict(name="stft_3001_toolarge", op="stft", mix="A", shape=(9000,), kw=dict(n_fft=3001, hop_length=700), gpu="unsupported"),
     # ---- istft: input is the golden stft of the named case
     dict(name="istft_2048_512", op="istft", src="stft_2048_512_A", kw=dict(hop_length=512)),
     dict(name="istft_2048_512_length", op="istft", src="stft_2048_512_A", kw=dict(hop_length=512, length=9000)),
@@ -48,12 +57,15 @@ CASES = [
     dict(name="mel_48000_8192_A", op="mel", mix="A", shape=(40000,), kw=dict(sr=48000, n_fft=8192, hop_length=2048)),
     dict(name="mel_htk_40_power1_A", op="mel", mix="A", shape=(6000,), kw=dict(sr=22050, n_fft=1024, hop_length=256, n_mels=40, htk=True, power=1.0)),
     dict(name="mel_norm1_fminfmax_B", op="mel", mix="B", shape=(6000,), kw=dict(sr=22050, n_fft=2048, hop_length=512, n_mels=64, fmin=300.0, fmax=8000.0, norm=1)),
+    dict(name="mel_16000_400_80_B", op="mel", mix="B", shape=(2, 8000), kw=dict(sr=16000, n_fft=400, hop_length=160, n_mels=80)),
+    dict(name="mel_22050_1025_A", op="mel", mix="A", shape=(6000,), kw=dict(sr=22050, n_fft=1025, hop_length=256, n_mels=40)),
     dict(name="mel_power3_A", op="mel", mix="A", shape=(4000,), kw=dict(sr=22050, n_fft=512, hop_length=128, n_mels=32, power=3.0)),
     # ---- mfcc
     dict(name="mfcc_16000_1024_A", op="mfcc", mix="A", shape=(8000,), kw=dict(sr=16000, n_mfcc=40, n_fft=1024, hop_length=256)),
     dict(name="mfcc_16000_1024_B", op="mfcc", mix="B", shape=(8000,), kw=dict(sr=16000, n_mfcc=40, n_fft=1024, hop_length=256)),
     dict(name="mfcc_22050_2048_C_clamped", op="mfcc", mix="C", shape=(9000,), kw=dict(sr=22050, n_mfcc=20)),
     dict(name="mfcc_stereo_perchannel_max", op="mfcc", mix="C", shape=(2, 9000), kw=dict(sr=22050, n_mfcc=13)),
+    dict(name="mfcc_16000_400_C", op="mfcc", mix="C", shape=(2, 8000), kw=dict(sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=40)),
     dict(name="mfcc_lifter22_dct3", op="mfcc", mix="A", shape=(6000,), kw=dict(sr=22050, n_mfcc=13, lifter=22, dct_type=3)),
     dict(name="mfcc_dct1_nonorm", op="mfcc", mix="A", shape=(6000,), kw=dict(sr=22050, n_mfcc=13, dct_type=1, norm=None)),
 ]
