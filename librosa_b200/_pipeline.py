@@ -20,27 +20,44 @@ _UNSUPPORTED_PAD = ("wrap", "maximum", "mean", "median", "minimum")   # librosa/
 
 
 def float64_policy() -> str:
-    """``B2L_FLOAT64``: "error" (default) refuses float64 / complex128 requests — the kernels compute in
-    float32 and silently lowering precision would not be a drop-in; "downcast" computes in float32 and
-    returns arrays of the requested dtype."""
-    return os.environ.get("B2L_FLOAT64", "error").lower()
+    """``B2L_FLOAT64``: the kernels compute in float32.  "downcast" (default) accepts float64 / complex128
+    data, computes in float32, returns arrays of the dtype librosa would return and warns once;
+    "error" refuses such requests (``UnsupportedOnGPU``); "quiet" is "downcast" without the warning."""
+    return os.environ.get("B2L_FLOAT64", "downcast").lower()
+
+
+_warned_float64 = False
+
+
+def _note_float64(what: str):
+    global _warned_float64
+    if float64_policy() == "downcast" and not _warned_float64:
+        _warned_float64 = True
+        warnings.warn(f"{what}: float64 data is computed in float32 on the GPU (results agree with librosa to "
+                      "about 1e-6 relative, not to float64 precision); set B2L_FLOAT64=error to refuse instead, "
+                      "or B2L_FLOAT64=quiet to silence this warning", stacklevel=4)
 
 
 def check_real_dtype(dtype, what: str) -> np.dtype:
     dtype = np.dtype(dtype)
     if dtype == np.float32:
         return dtype
-    if dtype == np.float64 and float64_policy() == "downcast":
-        return dtype
-    if dtype == np.float64:
-        raise nat.UnsupportedOnGPU(
-            f"{what}: float64 data is not supported by the float32 sm_100a kernels; cast to float32 or set "
-            "B2L_FLOAT64=downcast to compute in float32 (there is no CPU fallback)")
     if np.issubdtype(dtype, np.floating):
-        if float64_policy() == "downcast":
-            return dtype
-        raise nat.UnsupportedOnGPU(f"{what}: dtype {dtype} is not supported (float32 only)")
+        if float64_policy() == "error":
+            raise nat.UnsupportedOnGPU(
+                f"{what}: dtype {dtype} is not supported by the float32 sm_100a kernels and B2L_FLOAT64=error "
+                "(there is no CPU fallback)")
+        _note_float64(what)
+        return dtype
     raise ParameterError(f"{what}: data must be floating-point, got {dtype}")
+
+
+def wide_complex_ok(what: str) -> bool:
+    """complex128 requests (stft dtype=, istft input) under the float64 policy."""
+    if float64_policy() == "error":
+        return False
+    _note_float64(what)
+    return True
 
 
 def digest(arr: np.ndarray) -> str:

@@ -37,9 +37,9 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
     if dtype is None:
         dtype = dtype_r2c(req_dtype)
     dtype = np.dtype(dtype)
-    if dtype != np.complex64 and not (dtype.kind == "c" and pl.float64_policy() == "downcast"):
+    if dtype != np.complex64 and not (dtype.kind == "c" and pl.wide_complex_ok("stft dtype")):
         raise nat.UnsupportedOnGPU(f"stft dtype={dtype}: only complex64 is computed on the GPU "
-                                   "(set B2L_FLOAT64=downcast to get float32 results in a wider dtype)")
+                                   "(B2L_FLOAT64=error forbids returning float32 results in a wider dtype)")
     F = 1 + n_fft // 2
     T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length   # Appendix A.1 frame count
     shape = tuple(y.shape[:-1]) + (F, T)
@@ -131,11 +131,11 @@ def istft(stft_matrix, *, hop_length: Optional[int] = None, win_length: Optional
         n_frames = T_stored
     in_dtype = np.dtype(stft_matrix.dtype)
     if in_dtype != np.complex64:
-        if in_dtype.kind == "c" and pl.float64_policy() == "downcast":
+        if in_dtype.kind == "c" and pl.wide_complex_ok("istft input"):
             pass
         elif in_dtype.kind == "c":
             raise nat.UnsupportedOnGPU("istft: only complex64 input is computed on the GPU "
-                                       "(set B2L_FLOAT64=downcast to compute in float32)")
+                                       "(B2L_FLOAT64=error forbids computing complex128 data in float32)")
         else:
             raise ParameterError(f"stft_matrix must be complex, got {in_dtype}")
     if dtype is None:
@@ -277,7 +277,7 @@ def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80
         req = np.dtype(np.float32)
     else:
         if not np.issubdtype(S.dtype, np.floating):
-            S = S.astype(np.float32) if pl.float64_policy() != "downcast" else S.astype(np.float64)
+            S = S.astype(np.float32)
         req = pl.check_real_dtype(S.dtype, "power_to_db input")
         dev = ctx.to_device(np.ascontiguousarray(S, dtype=np.float32))
     ndim = len(dev.shape)

@@ -191,6 +191,27 @@ def test_ragged_and_edge_shapes(lb, oracle):
     close(lb.feature.mfcc(y=z), oracle.mfcc(y=z), **TOL["mfcc"])
 
 
+def test_float64_inputs_follow_librosa_dtypes(lb, oracle):
+    """float64 / complex128 data is computed in float32 (default policy, one warning) and comes back in the
+    dtype librosa returns; values agree with the float64 reference to float32 accuracy."""
+    import signals
+
+    y = signals.make("A", (9000,), seed=8).astype(np.float64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        D = lb.stft(y)
+        Do = oracle.stft(y)
+        assert D.dtype == np.complex128 and D.shape == Do.shape
+        np.testing.assert_allclose(D, Do, rtol=1e-4, atol=1e-5 * float(np.abs(Do).max()))
+        M = lb.feature.melspectrogram(y=y, sr=22050)
+        Mo = oracle.melspectrogram(y=y, sr=22050)
+        assert M.dtype == Mo.dtype == np.float64
+        np.testing.assert_allclose(M, Mo, rtol=1e-4, atol=1e-6 * float(Mo.max()))
+        yr = lb.istft(Do, length=9000)
+        assert yr.dtype == np.float64
+        np.testing.assert_allclose(yr, y, atol=1e-5)
+
+
 def test_griffinlim(lb, oracle):
     """istft -> stft -> phase update iterated on the device.  With identical starting
     phases the first iterations track the oracle; after many iterations the phase of near-zero bins is

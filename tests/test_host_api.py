@@ -157,6 +157,11 @@ def test_parameter_errors(call):
         call()
 
 
+@pytest.fixture
+def strict_float64(monkeypatch):
+    monkeypatch.setenv("B2L_FLOAT64", "error")
+
+
 @pytest.mark.parametrize("call", [
     lambda: lb.stft(Y, n_fft=3001),         # non power of two beyond the chirp-z range (<= 2047)
     lambda: lb.istft(np.zeros((251, 9), dtype=np.complex64), n_fft=501),   # inverse: powers of two only
@@ -166,9 +171,21 @@ def test_parameter_errors(call):
     lambda: lb.stft(Y, pad_mode=lambda *a, **k: None),
     lambda: lb.istft(np.zeros((1025, 9), dtype=np.complex128)),
 ])
-def test_unsupported_is_loud(call):
+def test_unsupported_is_loud(call, strict_float64):
     with pytest.raises(UnsupportedOnGPU):
         call()
+
+
+def test_float64_policy_warns_by_default(monkeypatch):
+    import librosa_b200._pipeline as pl
+
+    monkeypatch.delenv("B2L_FLOAT64", raising=False)
+    monkeypatch.setattr(pl, "_warned_float64", False)
+    with pytest.warns(UserWarning, match="computed in float32"):
+        try:
+            lb.stft(Y.astype(np.float64))
+        except lb.NativeLibraryError:
+            pass   # no GPU here: the policy is applied before the device is touched
 
 
 def test_warnings_match_reference():
