@@ -791,10 +791,6 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   a.db_sub = 10.0f * log10f(fmaxf(p->amin, fabsf(p->ref_value)));
   a.clip_max = c->d_clip_max;
   a.status = c->d_status;
-  {
-    const char* sg = getenv("B2L_STAGGER_NS");
-    a.stagger_ns = sg ? atoi(sg) : 0;
-  }
 
   // cudaFuncSetAttribute + the occupancy query cost tens of microseconds: raise the kernel's dynamic
   // shared-memory limit to the device maximum once per kernel, cache blocks/SM per (kernel, smem)

@@ -70,7 +70,6 @@ struct FwdArgs {
   int off_win, off_tw, off_in, off_xbuf, off_melw, off_melband, off_bar;
   int in_stride, xbuf_stride; // per-half strides (bytes) of the staging / exchange areas (DUAL)
   int in_floats;             // staged span length (floats)
-  int stagger_ns;            // experiment: delay the second half's first tile by this long
 };
 
 struct InvArgs {

@@ -231,7 +231,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   const long long tile_step = (long long)gridDim.x * NH;
   long long tile = (long long)blockIdx.x * NH + half;
   uint32_t phase = 0;
-  if (DUAL && half > 0 && a.stagger_ns > 0) __nanosleep((unsigned)a.stagger_ns * half);
   prefetch(tile);
 
   for (; tile < a.total_tiles; tile += tile_step) {
