@@ -157,8 +157,8 @@ def is_pow2(n: int) -> bool:
 
 def require_supported_n_fft(n_fft: int, inverse: bool = False):
     """Power-of-two n_fft in [8, 8192] runs on the packed real-FFT kernels; any other n_fft in [3, 2047]
-    (the reference tests' 501 / 1023 / 1025, the 400 of speech front ends, ...) on the chirp-z forward
-    kernel.  Everything else librosa accepts is refused loudly — there is no CPU fallback."""
+    (the reference tests' 501 / 1023 / 1025, the 400 of speech front ends, ...) on the chirp-z kernels
+    (forward and inverse).  Everything else librosa accepts is refused loudly — there is no CPU fallback."""
     n_fft = int(n_fft)
     if is_pow2(n_fft):
         if MIN_N_FFT <= n_fft <= MAX_N_FFT:
@@ -166,9 +166,6 @@ def require_supported_n_fft(n_fft: int, inverse: bool = False):
         raise nat.UnsupportedOnGPU(
             f"n_fft={n_fft}: the sm_100a kernels are built for powers of two from {MIN_N_FFT} to {MAX_N_FFT} "
             "(no CPU fallback)")
-    if inverse:
-        raise nat.UnsupportedOnGPU(f"n_fft={n_fft}: the inverse transform is built for powers of two only "
-                                   "(no CPU fallback)")
     if not (3 <= n_fft <= MAX_CZT_N_FFT):
         raise nat.UnsupportedOnGPU(f"n_fft={n_fft}: non-power-of-two sizes are supported from 3 to {MAX_CZT_N_FFT} "
                                    "(no CPU fallback)")

@@ -110,6 +110,8 @@ struct b2l_ctx {
   int rank = 0, world = 1;
   unsigned int* d_clip_max = nullptr;   // scratch for per-clip maxima
   int* d_status = nullptr;              // bit 0: a non-finite input sample was seen since the last reset
+  float* d_scratch = nullptr;           // grow-only scratch (chirp-z istft frames)
+  size_t scratch_bytes = 0;
   std::map<unsigned long long, int> launch_cache;   // (kernel variant, smem) -> blocks/SM, attribute already set
   size_t clip_max_cap = 0;
 };
@@ -143,6 +145,8 @@ struct b2l_plan {
   float2* d_czt_wb = nullptr;   // [n_fft] window * b
   float2* d_czt_bk = nullptr;   // [1 + n_fft/2] b
   float2* d_czt_hf = nullptr;   // [P] FFT_P(h)/P followed by the engine's inter-pass twiddles
+  float2* d_czt_bfull = nullptr;   // [n_fft] b (inverse)
+  float2* d_czt_wbi = nullptr;     // [n_fft] conj(b) * window / n_fft (inverse)
   // mfcc
   int n_mfcc = 0;
   float* d_dct = nullptr;
@@ -206,6 +210,7 @@ extern "C" int b2l_ctx_destroy(b2l_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   if (c->d_clip_max) cudaFree(c->d_clip_max);
   if (c->d_status) cudaFree(c->d_status);
+  if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return B2L_OK;
@@ -423,6 +428,8 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   cudaFree(p->d_czt_wb);
   cudaFree(p->d_czt_bk);
   cudaFree(p->d_czt_hf);
+  cudaFree(p->d_czt_bfull);
+  cudaFree(p->d_czt_wbi);
   cudaFree(p->d_band);
   for (auto& kv : p->row_tables) {
     cudaFree(kv.second.d_rows);
@@ -502,7 +509,14 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     for (int i = 0; i < P; ++i) hf[i] = make_float2((float)(h[i].real() / P), (float)(h[i].imag() / P));
     std::vector<float2> tw = engine_twiddles(ccfg);
     hf.insert(hf.end(), tw.begin(), tw.end());
-    if ((rc = upload(c, wb, &p->d_czt_wb)) || (rc = upload(c, bk, &p->d_czt_bk)) || (rc = upload(c, hf, &p->d_czt_hf)))
+    std::vector<float2> bfull(L), wbi(L);
+    for (int n = 0; n < L; ++n) {
+      bfull[n] = make_float2((float)b[n].real(), (float)b[n].imag());
+      const std::complex<double> z = std::conj(b[n]) * (d->h_window[n] / (double)L);
+      wbi[n] = make_float2((float)z.real(), (float)z.imag());
+    }
+    if ((rc = upload(c, wb, &p->d_czt_wb)) || (rc = upload(c, bk, &p->d_czt_bk)) || (rc = upload(c, hf, &p->d_czt_hf)) ||
+        (rc = upload(c, bfull, &p->d_czt_bfull)) || (rc = upload(c, wbi, &p->d_czt_wbi)))
       goto bad;
   } else {
     HostFftCfg cfg(p->log2m);
@@ -827,6 +841,15 @@ static czt_op_fn czt_table(int log2p) {
   return nullptr;
 }
 
+typedef cudaError_t (*czt_inv_op_fn)(int, const CztInvArgs*, int, size_t, cudaStream_t, int*);
+static czt_inv_op_fn czt_inv_table(int log2p) {
+  switch (log2p) {
+    case 5: return czt_inv_op_5; case 6: return czt_inv_op_6; case 7: return czt_inv_op_7; case 8: return czt_inv_op_8;
+    case 9: return czt_inv_op_9; case 10: return czt_inv_op_10; case 11: return czt_inv_op_11; case 12: return czt_inv_op_12;
+  }
+  return nullptr;
+}
+
 static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, int64_t n_clips, int64_t n,
                    int64_t y_stride, float2* out_c, float* out_r) {
   if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
@@ -956,9 +979,66 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
   if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
   if (n_clips < 0 || n_frames_used < 1 || n_frames_used > n_frames_stored || out_len < 0 || y_stride < out_len)
     return fail(B2L_ERR_INVALID, "bad istft geometry");
-  if (p->czt) return fail(B2L_ERR_UNSUPPORTED, "istft with n_fft=%d (not a power of two) is not built", p->n_fft);
   if (n_clips == 0 || out_len == 0) return B2L_OK;
   if (!d_D || !d_inv_wss || !d_y) return fail(B2L_ERR_INVALID, "NULL device pointer");
+  if (p->czt) {
+    // chirp-z inverse frames into scratch, then a gather overlap-add (czt_kernel.cuh)
+    if (out_len > 0x7fffffffLL || n_clips > 65535) return fail(B2L_ERR_UNSUPPORTED, "istft batch too large");
+    DeviceGuard g(c->device);
+    const int L = p->n_fft;
+    const size_t need = (size_t)n_clips * (size_t)n_frames_used * L * sizeof(float);
+    if (c->scratch_bytes < need) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (c->d_scratch) CUDA_TRY(cudaFree(c->d_scratch));
+      c->d_scratch = nullptr;
+      c->scratch_bytes = 0;
+      CUDA_TRY(cudaMalloc((void**)&c->d_scratch, need));
+      c->scratch_bytes = need;
+    }
+    HostFftCfg cfg(p->log2p);
+    const int nw = cfg.czt_nw();
+    const int G = nw * 32 / cfg.tpf;
+    CztInvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.D = (const float2*)d_D;
+    a.d_clip_stride = (long long)n_frames_stored * (L / 2 + 1);
+    a.n_clips = (int)n_clips;
+    a.n_frames = (int)n_frames_used;
+    a.L = L;
+    a.n_bins = L / 2 + 1;
+    a.bfull = p->d_czt_bfull;
+    a.wbi = p->d_czt_wbi;
+    a.hf = p->d_czt_hf;
+    a.ytmp = c->d_scratch;
+    const size_t smem = (size_t)((cfg.tw_count() + 15) & ~15) * 8 + (size_t)G * cfg.xbuf_f2() * 8;
+    czt_inv_op_fn op = czt_inv_table(p->log2p);
+    const unsigned long long kkey = (3ULL << 62) | ((unsigned long long)p->log2p << 40);
+    int occ = 0;
+    auto hit = c->launch_cache.find(kkey);
+    if (hit != c->launch_cache.end()) {
+      occ = hit->second;
+    } else {
+      CUDA_TRY(op(OP_SET_SMEM, &a, 0, smem, c->stream, nullptr));
+      CUDA_TRY(op(OP_OCCUPANCY, &a, 0, smem, c->stream, &occ));
+      c->launch_cache[kkey] = occ;
+    }
+    if (occ < 1) return fail(B2L_ERR_CUDA, "chirp-z inverse kernel does not fit on an SM");
+    const long long steps = ((long long)n_clips * n_frames_used + G - 1) / G;
+    long long grid = (long long)c->sm_count * occ;
+    if (grid > steps) grid = steps;
+    CUDA_TRY(op(OP_LAUNCH, &a, (int)grid, smem, c->stream, nullptr));
+    c->launches++;
+    long long bx = (out_len + 255) / 256;
+    const long long cap = (8LL * c->sm_count + n_clips - 1) / n_clips;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 og((unsigned)bx, (unsigned)n_clips);
+    ola_kernel<<<og, 256, 0, c->stream>>>(c->d_scratch, (int)n_frames_used, L, p->hop, p->center ? L / 2 : 0, (int)out_len,
+                                          y_stride, d_inv_wss, d_y);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return B2L_OK;
+  }
   if (out_len > 0x7fffffffLL || n_frames_stored > 0x7fffffffLL)
     return fail(B2L_ERR_UNSUPPORTED, "istft output longer than 2^31-1 samples is not supported");
   DeviceGuard g(c->device);

@@ -191,6 +191,27 @@ __global__ void gl_update_kernel(const float2* __restrict__ rebuilt, const float
   }
 }
 
+// ------------------------------------------------------------------ overlap-add of chirp-z inverse frames
+// Gather-form overlap-add of scratch frames [clip][n_frames][L] into y [clip][out_len], frames added in
+// increasing index (the reference's order), then the WOLA normalisation.
+__global__ void ola_kernel(const float* __restrict__ ytmp, int n_frames, int L, int hop, int start, int out_len,
+                           long long y_stride, const float* __restrict__ inv_wss, float* __restrict__ y) {
+  const int clip = blockIdx.y;
+  const float* yt = ytmp + (long long)clip * n_frames * L;
+  float* yc = y + (long long)clip * y_stride;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < out_len;
+       o += (long long)gridDim.x * blockDim.x) {
+    const long long u = o + start;
+    long long t_hi = u / hop;
+    if (t_hi > n_frames - 1) t_hi = n_frames - 1;
+    long long t_lo = u - L + 1;
+    t_lo = t_lo <= 0 ? 0 : (t_lo + hop - 1) / hop;
+    float val = 0.0f;
+    for (long long tt = t_lo; tt <= t_hi; ++tt) val += yt[tt * L + (u - tt * hop)];
+    yc[o] = val * __ldg(inv_wss + o);
+  }
+}
+
 // ------------------------------------------------------------------ batched transpose
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ in, int rows, int cols, T* __restrict__ out) {

@@ -99,4 +99,81 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------ inverse: irfft of length L per frame
+// y[n] = (1/L) sum_k Xfull[k] e^{+2 pi i k n / L} with Xfull the Hermitian extension of the L/2+1 stored bins
+// (scipy.fft.irfft(D, n=L): Im of DC — and of the Nyquist bin for even L — is ignored).  Same chirp-z
+// structure with conjugated chirps:  y[n] = Re( conj(b[n]) * IFFT_P( FFT_P(Xfull conj(b)) . conj(FFT_P(h)) )[n] ) / L.
+// The windowed frames (window * 1/L folded into `wbi`) go to a scratch array [clip][frame][L]; ola_kernel
+// overlap-adds and normalises them (librosa/core/spectrum.py:598-624).
+struct CztInvArgs {
+  const float2* D;       // [clip][frames_stored][n_bins]
+  long long d_clip_stride;
+  int n_clips, n_frames, L, n_bins;
+  const float2* bfull;   // [L] b[k]
+  const float2* wbi;     // [L] conj(b[n]) * window[n] / L
+  const float2* hf;      // [P] FFT_P(h)/P, then the engine twiddles
+  float* ytmp;           // [clip][n_frames][L]
+};
+
+template <int LOG2P, int TPF, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a) {
+  using Cfg = FftCfg<LOG2P, TPF>;
+  constexpr int P = Cfg::M, PPT = Cfg::PPT;
+  constexpr int NT = NW * 32;
+  constexpr int G = NT / TPF;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* s_tw = reinterpret_cast<float2*>(smem);
+  float2* s_xall = s_tw + ((Cfg::TW_COUNT + 15) & ~15);
+  const int tid = threadIdx.x, grp = tid / TPF, t = tid % TPF;
+  const int gbar = 2 + grp;
+  float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
+  for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.hf[P + i];
+  __syncthreads();
+  const long long total = (long long)a.n_clips * a.n_frames;
+  for (long long f0 = (long long)blockIdx.x * G; f0 < total; f0 += (long long)gridDim.x * G) {
+    const long long fidx = min(f0 + grp, total - 1);
+    const bool live = f0 + grp < total;
+    const int clip = (int)(fidx / a.n_frames), frame = (int)(fidx % a.n_frames);
+    const float2* Drow = a.D + (long long)clip * a.d_clip_stride + (long long)frame * a.n_bins;
+    float2 v[PPT];
+    load_pass0<Cfg>(v, t, [&](int e) {
+      if (e >= a.L) return make_float2(0.0f, 0.0f);
+      float2 x;
+      if (e < a.n_bins) {
+        x = __ldg(Drow + e);
+        if (e == 0 || 2 * e == a.L) x.y = 0.0f;          // DC, and Nyquist when L is even
+      } else {
+        x = __ldg(Drow + (a.L - e));
+        x.y = -x.y;                                      // Hermitian extension
+      }
+      const float2 b = __ldg(a.bfull + e);
+      return cmul(x, make_float2(b.x, -b.y));            // Xfull[e] * conj(b[e])
+    });
+    fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
+    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
+    static_for<0, PPT>([&](auto S) {
+      constexpr int slot = decltype(S)::value;
+      const int idx = t + spectrum_offset<Cfg>(slot);
+      const float2 h = __ldg(a.hf + idx);
+      const float2 c = cmul(v[slot], make_float2(h.x, -h.y));     // conj(FFT_P(h)) = FFT_P(conj h), h symmetric
+      xbuf[xphys(idx)] = make_float2(c.y, c.x);
+    });
+    group_sync<TPF>(gbar);
+    load_pass0<Cfg>(v, t, [&](int e) { return xbuf[xphys(e)]; });
+    group_sync<TPF>(gbar);
+    fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
+    static_for<0, PPT>([&](auto S) {
+      constexpr int slot = decltype(S)::value;
+      const int nn = t + spectrum_offset<Cfg>(slot);
+      if (nn < a.L && live) {
+        const float2 w = __ldg(a.wbi + nn);
+        // Re( (c.re + i c.im) * w ) with c un-swapped: c.re = v.y, c.im = v.x
+        a.ytmp[((long long)clip * a.n_frames + frame) * a.L + nn] = fmaf(v[slot].y, w.x, -v[slot].x * w.y);
+      }
+    });
+    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
+  }
+}
+
 }  // namespace b2l

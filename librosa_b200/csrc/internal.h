@@ -19,8 +19,10 @@ B2L_DECL_INV(2) B2L_DECL_INV(3) B2L_DECL_INV(4) B2L_DECL_INV(5) B2L_DECL_INV(6) 
 B2L_DECL_INV(8) B2L_DECL_INV(9) B2L_DECL_INV(10) B2L_DECL_INV(11) B2L_DECL_INV(12)
 
 struct CztArgs;
-#define B2L_DECL_CZT(L) \
-  cudaError_t czt_op_##L(int op, const CztArgs* a, int grid, size_t smem, cudaStream_t st, int* result);
+struct CztInvArgs;
+#define B2L_DECL_CZT(L)                                                                                    \
+  cudaError_t czt_op_##L(int op, const CztArgs* a, int grid, size_t smem, cudaStream_t st, int* result); \
+  cudaError_t czt_inv_op_##L(int op, const CztInvArgs* a, int grid, size_t smem, cudaStream_t st, int* result);
 B2L_DECL_CZT(5) B2L_DECL_CZT(6) B2L_DECL_CZT(7) B2L_DECL_CZT(8) B2L_DECL_CZT(9) B2L_DECL_CZT(10) B2L_DECL_CZT(11) B2L_DECL_CZT(12)
 
 constexpr int kMinLog2M = 2, kMaxLog2M = 12;   // n_fft = 2^(LOG2M+1): 8 .. 8192

@@ -46,6 +46,11 @@ CASES = [
     dict(name="istft_1024_winlen600", op="istft", src="stft_1024_winlen600_hamming_A", kw=dict(win_length=600, window="hamming")),
     dict(name="istft_512_stereo", op="istft", src="stft_512_stereo_A", kw=dict(hop_length=128)),
     dict(name="istft_64_16", op="istft", src="stft_64_16_B", kw=dict(hop_length=16, length=2000)),
+    dict(name="istft_1025_nonpow2", op="istft", src="stft_1025_nonpow2", kw=dict(hop_length=300, n_fft=1025)),
+    dict(name="istft_501_length", op="istft", src="stft_501_nonpow2", kw=dict(hop_length=128, n_fft=501, length=3000)),
+    dict(name="istft_400_160_stereo", op="istft", src="stft_400_160_stereo_A", kw=dict(hop_length=160, length=8000)),
+    dict(name="istft_2000_nocenter", op="istft", src="stft_2000_500_nocenter_A", kw=dict(hop_length=500, center=False)),
+    dict(name="istft_6_2", op="istft", src="stft_6_2_A", kw=dict(hop_length=2)),
     dict(name="istft_8192_2048", op="istft", src="stft_8192_2048_A", kw=dict(hop_length=2048, length=30000)),
     dict(name="istft_4096_1024_short_length", op="istft", src="stft_4096_1024_A", kw=dict(hop_length=1024, length=7000)),
     # ---- melspectrogram

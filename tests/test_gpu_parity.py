@@ -98,7 +98,7 @@ def test_case_against_oracle_and_reference_fixture(case, lb, oracle, golden):
     fixture = golden[case["name"]]
     if case["op"] == "istft":
         D = golden[case["src"]]
-        n_fft = 2 * (D.shape[-2] - 1)
+        n_fft = case["kw"].get("n_fft") or 2 * (D.shape[-2] - 1)
         T = D.shape[-1]
         length = case["kw"].get("length")
         if length:
