@@ -40,6 +40,9 @@ WORKLOADS = {
                  desc="1024 channel-clips (512 stereo) x10s sr=44100 -> stft n_fft=4096 hop=1024 per GPU"),
     "cfg4": dict(clips=512, n=480000, sr=16000, op="mfcc", kw=dict(n_mfcc=40, n_mels=128, n_fft=1024, hop_length=256),
                  desc="512 clips x30s mono sr=16000 -> mfcc n_mfcc=40 n_mels=128 n_fft=1024 hop=256 per GPU"),
+    # frame-wise statistics fused with the stft (cfg-2 shapes); one launch yields all six rows
+    "stats": dict(clips=1024, n=220500, sr=22050, op="centroid", kw=dict(n_fft=2048, hop_length=512),
+                  desc="batch=1024 clips x10s mono sr=22050 -> spectral_centroid n_fft=2048 hop=512 (fused statistics kernel)"),
     "cfg5": dict(clips=256, n=220500, sr=22050, op="roundtrip", kw=dict(n_fft=2048, hop_length=512),
                  desc="256 clips x10s -> stft -> istft n_fft=2048 hop=512 per GPU"),
 }
@@ -63,6 +66,8 @@ def algorithmic_bytes_per_step(w):
         return clips * (4 * n + 4 * w["kw"]["n_mfcc"] * T)
     if w["op"] == "roundtrip":
         return clips * (4 * n + 8 * F * T) + clips * (8 * F * T + 4 * n)
+    if w["op"] == "centroid":
+        return clips * (4 * n + 4 * 6 * T)      # six statistics rows per frame
     raise ValueError(w["op"])
 
 
@@ -157,6 +162,8 @@ def _cpu_clip_job(args):
         return O.stft(y, **kw).shape[-1]
     if op == "mfcc":
         return O.mfcc(y=y, sr=sr, **kw).shape[-1]
+    if op == "centroid":
+        return O.spectral_centroid(y=y, sr=sr, **kw).shape[-1]
     D = O.stft(y, **kw)
     O.istft(D, hop_length=kw["hop_length"], length=len(y))
     return D.shape[-1]
@@ -201,7 +208,7 @@ class CpuPort:
 
 def cpu_sample_clips(w):
     # sized for roughly 10-30 s of CPU work in total over warm-up + timed steps
-    return {"mel": 128, "stft": 128, "mfcc": 64, "roundtrip": 64}[w["op"]]
+    return {"mel": 128, "stft": 128, "mfcc": 64, "roundtrip": 64, "centroid": 128}[w["op"]]
 
 
 def run_reference(args, w, rank, world):
@@ -265,6 +272,8 @@ def run_ours(args, w, rank, world, local_rank):
             lb.stft(dev, **kw).free()
         elif op == "mfcc":
             lb.feature.mfcc(y=dev, sr=sr, **kw).free()
+        elif op == "centroid":
+            lb.feature.spectral_centroid(y=dev, sr=sr, **kw).free()
         else:
             D = lb.stft(dev, **kw)
             lb.istft(D, hop_length=kw["hop_length"], length=w["n"]).free()
@@ -277,6 +286,8 @@ def run_ours(args, w, rank, world, local_rank):
             return lb.stft(host, **kw)
         if op == "mfcc":
             return lb.feature.mfcc(y=host, sr=sr, **kw)
+        if op == "centroid":
+            return lb.feature.spectral_centroid(y=host, sr=sr, **kw)
         return lb.istft(lb.stft(host, **kw), hop_length=kw["hop_length"], length=w["n"])
 
     def barrier():
@@ -344,7 +355,8 @@ def run_ours(args, w, rank, world, local_rank):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel": {"mel": "fwd_kernel<10,32,16,MODE_MEL>", "stft": "fwd_kernel<.,.,.,MODE_STFT>",
-                           "mfcc": "fwd_kernel<.,.,.,MODE_MEL>+dct_clamp_kernel", "roundtrip": "fwd_kernel+inv_kernel"}[op],
+                           "mfcc": "fwd_kernel<.,.,.,MODE_MEL>+dct_clamp_kernel", "roundtrip": "fwd_kernel+inv_kernel",
+                           "centroid": "fwd_kernel<10,32,16,MODE_STATS>"}[op],
                 "note": "kernel time == step time (one launch per step, CUDA events on the launching stream)"}
 
     # ---- CPU baseline on this box (bounded sample)

@@ -97,6 +97,9 @@ int b2l_memset(b2l_ctx* ctx, void* d_ptr, int value, size_t bytes);
 int b2l_h2d(b2l_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on the ctx stream */
 int b2l_d2h(b2l_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async on the ctx stream */
 int b2l_d2d(b2l_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+/* strided device-to-device copy of `rows` rows of `width_bytes` (cudaMemcpy2DAsync on the context stream) */
+int b2l_copy2d(b2l_ctx* ctx, void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t width_bytes,
+               size_t rows);
 int b2l_host_alloc(size_t bytes, void** h_ptr);                          /* pinned host memory */
 int b2l_host_free(void* h_ptr);
 int b2l_mem_info(b2l_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
@@ -170,6 +173,42 @@ int b2l_transpose(b2l_ctx* ctx, const void* d_in, int64_t n_clips, int64_t rows,
  * (core/spectrum.py:2898-2903; scale = momentum / (1 + momentum)).  All arrays in the D / S layouts. */
 int b2l_gl_update(b2l_ctx* ctx, const void* d_rebuilt, const void* d_tprev, const float* d_S, float scale, float eps,
                   void* d_angles, int64_t n);
+
+/* ---- second "next" row of SURVEY 8f: the frame-wise consumers of _spectrogram -----------------------
+ * Statistics of the magnitude spectrum |X| of every frame, out [n_clips][B2L_N_STATS][n_frames]:
+ *   row 0 spectral_centroid  (feature/spectral.py:46-191)   sum f S / sum S  (util.normalize, norm=1)
+ *   row 1 spectral_bandwidth (:194-352)  (sum S |f - centroid|^p)^(1/p), S normalised when bw_norm
+ *   row 2 spectral_rolloff   (:535-684)  lowest f whose running sum reaches roll_percent * total
+ *   row 3 spectral_flatness  (:687-803)  geometric / arithmetic mean of max(amin, S^power)
+ *   row 4 rms(S=...)         (:806-916)  with frame_length = n_fft
+ *   row 5 sum S
+ * d_freq: [bins] bin frequencies in Hz (core/convert.py:1369 fft_frequencies, or the caller's `freq`). */
+#define B2L_N_STATS 6
+typedef struct b2l_stats_desc {
+  float roll_percent;  /* (0, 1) */
+  float flat_amin;     /* > 0 */
+  float flat_power;
+  float bw_p;          /* > 0 */
+  int32_t bw_norm;
+  int32_t frame_length;
+} b2l_stats_desc;
+/* y= form: fused with the stft (no spectrogram is written); power-of-two n_fft plans. */
+int b2l_spectral_stats(b2l_ctx* ctx, const b2l_plan* plan, const b2l_stats_desc* desc, const float* d_y,
+                       int64_t n_clips, int64_t n, int64_t y_stride, const float* d_freq, float* d_out);
+/* S= form: d_S [n_clips][n_frames][n_bins] magnitudes.  Bit 1 of the status word (b2l_status_read) is set
+ * when S holds a negative entry (the reference raises ParameterError). */
+int b2l_spectral_stats_from_spec(b2l_ctx* ctx, const b2l_stats_desc* desc, const float* d_S, int64_t n_clips,
+                                 int64_t n_frames, int32_t n_bins, const float* d_freq, float* d_out);
+/* Time-domain framings, out [n_clips][n_frames] with n_frames = 1 + (n + 2*pad - frame_length) / hop:
+ *   B2L_FRAME_RMS            rms(y=...)          feature/spectral.py:881-890
+ *   B2L_FRAME_ZERO_CROSSINGS zero_crossing_rate  feature/spectral.py:1062-1133 + core/audio.py:1588-1728;
+ *                            writes count * out_scale per frame (out_scale = 1: the caller divides by
+ *                            frame_length in float64, like np.mean over booleans); threshold / zero_pos / pad_first as in
+ *                            zero_crossings(threshold=, zero_pos=, pad=). */
+enum { B2L_FRAME_RMS = 0, B2L_FRAME_ZERO_CROSSINGS = 1 };
+int b2l_frame_feature(b2l_ctx* ctx, int32_t what, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
+                      int32_t frame_length, int32_t hop_length, int32_t center, int32_t pad_mode, float threshold,
+                      int32_t zero_pos, int32_t pad_first, float out_scale, float* d_out);
 
 /* ---- multi-GPU split / join (one process per GPU; NCCL over NVLink) --------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and handed to the other ranks by the launcher. */

@@ -52,6 +52,22 @@ class PlanDesc(C.Structure):
     ]
 
 
+class StatsDesc(C.Structure):
+    """struct b2l_stats_desc (include/b2l.h)."""
+    _fields_ = [
+        ("roll_percent", C.c_float),
+        ("flat_amin", C.c_float),
+        ("flat_power", C.c_float),
+        ("bw_p", C.c_float),
+        ("bw_norm", C.c_int32),
+        ("frame_length", C.c_int32),
+    ]
+
+
+N_STATS = 6
+STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
+FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -80,6 +96,7 @@ def _declare(lib):
         "b2l_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
         "b2l_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
         "b2l_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+        "b2l_copy2d": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t]),
         "b2l_host_alloc": (C.c_int, [C.c_size_t, P(_vp)]),
         "b2l_host_free": (C.c_int, [_vp]),
         "b2l_mem_info": (C.c_int, [_vp, P(C.c_size_t), P(C.c_size_t)]),
@@ -100,6 +117,10 @@ def _declare(lib):
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),
         "b2l_gl_update": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _i64]),
+        "b2l_spectral_stats": (C.c_int, [_vp, _vp, P(StatsDesc), _vp, _i64, _i64, _i64, _vp, _vp]),
+        "b2l_spectral_stats_from_spec": (C.c_int, [_vp, P(StatsDesc), _vp, _i64, _i64, C.c_int32, _vp, _vp]),
+        "b2l_frame_feature": (C.c_int, [_vp, C.c_int32, _vp, _i64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_float, _vp]),
         "b2l_comm_unique_id": (C.c_int, [_vp]),
         "b2l_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
         "b2l_comm_destroy": (C.c_int, [_vp]),

@@ -17,6 +17,7 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "czt_kernel.cuh"
+#include "feat_kernels.cuh"
 #include "internal.h"
 #include <complex>
 
@@ -306,6 +307,15 @@ extern "C" int b2l_d2d(b2l_ctx* c, void* d_dst, const void* d_src, size_t bytes)
   if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(c->device);
   CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return B2L_OK;
+}
+extern "C" int b2l_copy2d(b2l_ctx* c, void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch,
+                          size_t width_bytes, size_t rows) {
+  if (!c || !d_dst || !d_src) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (width_bytes == 0 || rows == 0) return B2L_OK;
+  if (dst_pitch < width_bytes || src_pitch < width_bytes) return fail(B2L_ERR_INVALID, "pitch smaller than the row width");
+  DeviceGuard g(c->device);
+  CUDA_TRY(cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToDevice, c->stream));
   return B2L_OK;
 }
 extern "C" int b2l_host_alloc(size_t bytes, void** h_ptr) {
@@ -702,8 +712,10 @@ static int fwd_variants(const HostFftCfg& cfg, int out[3]) {
   return n;
 }
 
+struct StatsCall { StatsParams sp; const float* d_freq; };
+
 static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const float* d_y, int64_t n_clips,
-                       int64_t n, int64_t y_stride, float2* out_c, float* out_r) {
+                       int64_t n, int64_t y_stride, float2* out_c, float* out_r, const StatsCall* stats = nullptr) {
   if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
   if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
   if (n_clips < 0 || n < 0 || y_stride < n) return fail(B2L_ERR_INVALID, "bad clip geometry");
@@ -749,12 +761,15 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
       a.off_melw = (int)off; off = align_up(off + (size_t)t->w_count * 4, 16);
       a.off_melband = (int)off; off = align_up(off + (size_t)t->n_rows * sizeof(MelRow), 16);
     }
+    if (mode == MODE_STATS) {   // bin frequencies take the place of the mel weights
+      a.off_melw = (int)off; off = align_up(off + (size_t)(M + 1) * 4, 16);
+    }
     a.off_in = (int)(off = align_up(off, 128));
     a.in_stride = (int)align_up((size_t)span * 4, 128);
     off += (size_t)a.in_stride * nh;
     a.off_xbuf = (int)(off = align_up(off, 128));
     size_t xbytes = (size_t)f * cfg.xbuf_f2() * 8;
-    if (mode == MODE_MEL) {
+    if (mode == MODE_MEL || mode == MODE_STATS) {
       const int Hh = 32 / f;                                      // MelLayout (common.cuh)
       const int rs = ((M + 4 - Hh + 31) / 32) * 32 + Hh;
       size_t pbytes = (size_t)f * rs * 4;
@@ -794,6 +809,14 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   a.power_mode = p->power_mode;
   a.power = p->power;
   a.n_mels = p->n_mels;
+  if (mode == MODE_STATS) {
+    if (!stats || !stats->d_freq) return fail(B2L_ERR_INVALID, "NULL frequency table");
+    a.power_mode = 1;          // the statistics are defined on the magnitude |X|
+    a.power = 1.0f;
+    a.stats = stats->sp;
+    a.mel_w = stats->d_freq;
+    a.mel_w_count = M + 1;
+  }
   if (rt) {
     a.mel_w_count = rt->w_count;
     a.mel_w = rt->d_w;
@@ -916,6 +939,95 @@ extern "C" int b2l_spectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, 
   if (c && p && p->czt) return run_czt(c, p, 1, d_y, n_clips, n, y_stride, nullptr, d_S);
   return run_forward(c, p, MODE_SPEC, 0, d_y, n_clips, n, y_stride, nullptr, d_S);
 }
+// ------------------------------------------------------------------ frame-wise spectral statistics / framings
+static int check_stats_desc(const b2l_stats_desc* d, StatsParams* sp) {
+  if (!d) return fail(B2L_ERR_INVALID, "NULL stats descriptor");
+  if (!(d->roll_percent > 0.0f && d->roll_percent < 1.0f))
+    return fail(B2L_ERR_INVALID, "roll_percent must lie in the range (0, 1)");
+  if (!(d->flat_amin > 0.0f)) return fail(B2L_ERR_INVALID, "amin must be strictly positive");
+  if (!(d->bw_p > 0.0f)) return fail(B2L_ERR_INVALID, "p must be strictly positive");
+  if (d->frame_length < 1) return fail(B2L_ERR_INVALID, "frame_length must be positive");
+  sp->roll_percent = d->roll_percent;
+  sp->flat_amin = d->flat_amin;
+  sp->flat_power = d->flat_power;
+  sp->bw_p = d->bw_p;
+  sp->bw_norm = d->bw_norm ? 1 : 0;
+  sp->frame_length = d->frame_length;
+  return B2L_OK;
+}
+
+extern "C" int b2l_spectral_stats_from_spec(b2l_ctx* c, const b2l_stats_desc* d, const float* d_S, int64_t n_clips,
+                                            int64_t n_frames, int32_t n_bins, const float* d_freq, float* d_out) {
+  if (!c || !d_S || !d_freq || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  StatsCall sc;
+  int rc = check_stats_desc(d, &sc.sp);
+  if (rc) return rc;
+  if (n_bins < 2) return fail(B2L_ERR_INVALID, "a spectrum needs at least two bins");
+  if (n_clips <= 0 || n_frames <= 0) return B2L_OK;
+  if (n_frames > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many frames");
+  DeviceGuard g(c->device);
+  const int Fp = (n_bins + 3) & ~3;
+  int nw = 8;
+  while (nw > 1 && (size_t)(nw + 1) * Fp * 4 > c->smem_optin) nw >>= 1;
+  const size_t smem = (size_t)(nw + 1) * Fp * 4;
+  if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_bins=%d rows do not fit in shared memory", n_bins);
+  CUDA_TRY(cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  const long long rows = (long long)n_clips * n_frames;
+  long long grid = (rows + nw - 1) / nw;
+  const long long cap = (long long)c->sm_count * 8;
+  if (grid > cap) grid = cap;
+  stats_kernel<<<(int)grid, nw * 32, smem, c->stream>>>(d_S, rows, (int)n_frames, n_bins, d_freq, sc.sp, d_out,
+                                                        c->d_status);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
+extern "C" int b2l_spectral_stats(b2l_ctx* c, const b2l_plan* p, const b2l_stats_desc* d, const float* d_y,
+                                  int64_t n_clips, int64_t n, int64_t y_stride, const float* d_freq, float* d_out) {
+  if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
+  if (p->czt)
+    return fail(B2L_ERR_UNSUPPORTED,
+                "n_fft=%d: compose b2l_spectrogram + b2l_spectral_stats_from_spec for non-power-of-two sizes", p->n_fft);
+  StatsCall sc;
+  int rc = check_stats_desc(d, &sc.sp);
+  if (rc) return rc;
+  sc.d_freq = d_freq;
+  return run_forward(c, p, MODE_STATS, 0, d_y, n_clips, n, y_stride, nullptr, d_out, &sc);
+}
+
+extern "C" int b2l_frame_feature(b2l_ctx* c, int32_t what, const float* d_y, int64_t n_clips, int64_t n,
+                                 int64_t y_stride, int32_t frame_length, int32_t hop_length, int32_t center,
+                                 int32_t pad_mode, float threshold, int32_t zero_pos, int32_t pad_first, float out_scale,
+                                 float* d_out) {
+  if (!c) return fail(B2L_ERR_INVALID, "NULL ctx");
+  if (what != B2L_FRAME_RMS && what != B2L_FRAME_ZERO_CROSSINGS) return fail(B2L_ERR_INVALID, "bad feature id %d", what);
+  if (frame_length < 1) return fail(B2L_ERR_INVALID, "frame_length=%d must be positive", frame_length);
+  if (hop_length < 1) return fail(B2L_ERR_INVALID, "hop_length=%d must be a positive integer", hop_length);
+  if (pad_mode < 0 || pad_mode > B2L_PAD_EMPTY) return fail(B2L_ERR_INVALID, "bad pad_mode %d", pad_mode);
+  if (n_clips < 0 || n < 0 || y_stride < n) return fail(B2L_ERR_INVALID, "bad clip geometry");
+  if (n > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "clips longer than 2^31-1 samples are not supported");
+  const int pad = center ? frame_length / 2 : 0;
+  const long long padded = n + 2LL * pad;
+  if (padded < frame_length)
+    return fail(B2L_ERR_INVALID, "Input is too short (n=%lld) for frame_length=%d", (long long)padded, frame_length);
+  const long long T = 1 + (padded - frame_length) / hop_length;
+  if (n_clips == 0) return B2L_OK;
+  if (!d_y || !d_out) return fail(B2L_ERR_INVALID, "NULL device pointer");
+  if (T > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many frames");
+  DeviceGuard g(c->device);
+  const long long rows = (long long)n_clips * T;
+  long long grid = (rows + 7) / 8;
+  const long long cap = (long long)c->sm_count * 8;
+  if (grid > cap) grid = cap;
+  frame_td_kernel<<<(int)grid, 256, 0, c->stream>>>(d_y, y_stride, (int)n, n_clips, frame_length, hop_length, pad,
+                                                    pad_mode, (int)T, what, threshold, zero_pos, pad_first, out_scale,
+                                                    d_out,                                                    c->d_status);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_melspectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
                                   int64_t y_stride, float* d_mel) {
   if (p && p->czt)

@@ -18,6 +18,7 @@ enum FwdMode : int {
   MODE_STFT = 0,   // complex64 [clip][frame][bin]
   MODE_MEL = 1,    // |X|^power -> band-sparse mel projection -> float32 [clip][mel][frame]
   MODE_SPEC = 2,   // |X|^power -> float32 [clip][frame][bin]
+  MODE_STATS = 3,  // per-frame statistics of |X| (centroid, bandwidth, rolloff, flatness, rms) [clip][stat][frame]
 };
 
 struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at mel_w[off ..] (mel_project kernel)
@@ -37,6 +38,17 @@ struct MelLayout {
   static constexpr int RS = ((M + 4 - H + 31) / 32) * 32 + H;
   static_assert(RS >= M + 4 && RS % 32 == H % 32, "row stride");
   static constexpr size_t bytes() { return (size_t)FT * RS * 4; }
+};
+
+// Per-frame spectral statistics (stats.cuh): the rows of the [clip][N_STATS][frame] output.
+enum StatRow : int { STAT_CENTROID = 0, STAT_BANDWIDTH = 1, STAT_ROLLOFF = 2, STAT_FLATNESS = 3, STAT_RMS = 4, STAT_TOTAL = 5 };
+constexpr int N_STATS = 6;
+struct StatsParams {
+  float roll_percent;            // spectral_rolloff
+  float flat_amin, flat_power;   // spectral_flatness: max(amin, S^power)
+  float bw_p;                    // spectral_bandwidth: (sum S |f - centroid|^p)^(1/p)
+  int bw_norm;                   //   ... with S normalised to unit sum per frame
+  int frame_length;              // rms(S=...): DC (and Nyquist when even) count half
 };
 
 struct FwdArgs {
@@ -66,6 +78,7 @@ struct FwdArgs {
   float amin, db_sub;
   unsigned int* clip_max;    // order-preserving uint keys of the per-clip max (log_mode)
   int* status;               // bit 0 is set when a non-finite sample reached a frame (util.valid_audio)
+  StatsParams stats;         // MODE_STATS (the frequency table travels in mel_w / mel_w_count)
   // dynamic shared-memory layout (byte offsets)
   int off_win, off_tw, off_in, off_xbuf, off_melw, off_melband, off_bar;
   int in_stride, xbuf_stride; // per-half strides (bytes) of the staging / exchange areas (DUAL)

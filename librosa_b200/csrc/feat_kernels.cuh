@@ -1,0 +1,86 @@
+// feat_kernels.cuh — frame-wise features that sit next to the FFT path: spectral statistics of a stored
+// magnitude spectrogram (the S= form of librosa.feature.spectral_centroid / bandwidth / rolloff / flatness /
+// rms; the y= form is fused into fwd_kernel, MODE_STATS) and the two time-domain framings that need no FFT
+// (rms(y=...), zero_crossing_rate).
+#pragma once
+#include "common.cuh"
+#include "fwd_kernel.cuh"   // load_padded
+#include "stats.cuh"
+
+namespace b2l {
+
+// S [n_rows][F] (one row per (clip, frame), bins contiguous) -> out [clip][N_STATS][n_frames].
+// One warp per row: coalesced copy into shared memory, then frame_stats.  Sets bit 1 of *status when a
+// negative entry is seen (the reference raises "only defined with non-negative energies").
+__global__ void stats_kernel(const float* __restrict__ S, long long n_rows, int n_frames, int F,
+                             const float* __restrict__ freq, StatsParams sp, float* __restrict__ out, int* status) {
+  extern __shared__ __align__(16) float s_dyn[];
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Fp = (F + 3) & ~3;
+  float* s_freq = s_dyn;
+  float* s_row = s_dyn + Fp + (size_t)warp * Fp;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) s_freq[i] = freq[i];
+  __syncthreads();
+  for (long long r = (long long)blockIdx.x * nw + warp; r < n_rows; r += (long long)gridDim.x * nw) {
+    const float* src = S + r * F;
+    for (int i = lane; i < F; i += 32) s_row[i] = __ldg(src + i);
+    __syncwarp();
+    bool negative;
+    const float v = frame_stats(s_row, s_freq, F, lane, sp, &negative);
+    if (negative && lane == 0) atomicOr(status, 2);
+    const long long clip = r / n_frames, frame = r % n_frames;
+    if (lane < N_STATS) out[(clip * N_STATS + lane) * n_frames + frame] = v;
+    __syncwarp();
+  }
+}
+
+// Time-domain framing features.  Frame t of a clip covers padded samples [t*hop - pad, t*hop - pad + L).
+//   what == 0: rms       sqrt(mean(x^2))                      (librosa/feature/spectral.py:881-890)
+//   what == 1: the number of zero crossings inside the frame  (librosa/feature/spectral.py:1115-1133,
+//              librosa/core/audio.py:1588-1602): samples with |x| <= threshold count as +0, a crossing at
+//              position i >= 1 is signbit(x[i]) != signbit(x[i-1]) (zero_pos) or sign(x[i]) != sign(x[i-1]);
+//              position 0 contributes `pad_first`.  Written as count * out_scale: callers that need the
+//              float64 mean of the reference pass 1 and divide on the host.
+// One warp per frame; the 4x overlap between frames is served by L1 / L2.
+__global__ void frame_td_kernel(const float* __restrict__ y, long long clip_stride, int n, long long n_clips,
+                                int L, int hop, int pad, int pad_mode, int n_frames, int what, float threshold,
+                                int zero_pos, int pad_first, float out_scale, float* __restrict__ out, int* status) {
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = n_clips * n_frames;
+  for (long long r = (long long)blockIdx.x * nw + warp; r < total; r += (long long)gridDim.x * nw) {
+    const long long clip = r / n_frames;
+    const int frame = (int)(r % n_frames);
+    const float* yc = y + clip * clip_stride;
+    const long long s0 = (long long)frame * hop - pad;
+    if (what == 0) {
+      float acc = 0.0f;
+      for (int i = lane; i < L; i += 32) {
+        const float x = load_padded(yc, n, s0 + i, pad_mode, pad);
+        acc = fmaf(x, x, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[r] = sqrtf(acc / (float)L);
+    } else {
+      int count = 0;
+      bool bad = false;
+      // class of a sample: 0 = non-negative / zero, 1 = negative (zero_pos) or -1/0/+1 (sign form)
+      auto cls = [&](float x) -> int {
+        if (!(fabsf(x) <= 3.0e38f)) bad = true;
+        if (fabsf(x) <= threshold) x = 0.0f;
+        return zero_pos ? (int)(x < 0.0f) : (x > 0.0f) - (x < 0.0f);
+      };
+      for (int base = 0; base < L; base += 32) {
+        const int i = base + lane;
+        const int c = i < L ? cls(load_padded(yc, n, s0 + i, pad_mode, pad)) : 0;
+        int prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0 && i > 0 && i < L) prev = cls(load_padded(yc, n, s0 + i - 1, pad_mode, pad));
+        const bool cross = i < L && (i == 0 ? pad_first != 0 : c != prev);
+        count += __popc(__ballot_sync(0xffffffffu, cross));
+      }
+      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, 1);
+      if (lane == 0) out[r] = (float)count * out_scale;
+    }
+  }
+}
+
+}  // namespace b2l

@@ -23,6 +23,7 @@ cudaError_t by_mode(int op, int mode, const FwdArgs* a, int grid, size_t smem, c
     case MODE_STFT: return run_op(fwd_kernel<L, TPF, NW, MODE_STFT, DUAL>, op, NW * 32, a, grid, smem, st, result);
     case MODE_MEL: return run_op(fwd_kernel<L, TPF, NW, MODE_MEL, DUAL>, op, NW * 32, a, grid, smem, st, result);
     case MODE_SPEC: return run_op(fwd_kernel<L, TPF, NW, MODE_SPEC, DUAL>, op, NW * 32, a, grid, smem, st, result);
+    case MODE_STATS: return run_op(fwd_kernel<L, TPF, NW, MODE_STATS, DUAL>, op, NW * 32, a, grid, smem, st, result);
   }
   return cudaErrorInvalidValue;
 }

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "fft_engine.cuh"
+#include "stats.cuh"
 
 namespace b2l {
 
@@ -168,6 +169,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   if constexpr (MODE == MODE_MEL) {
     for (int i = tid; i < a.mel_w_count; i += NT) s_melw[i] = a.mel_w[i];
     for (int i = tid; i < a.n_mel_rows; i += NT) s_row[i] = a.mel_rows[i];
+  }
+  if constexpr (MODE == MODE_STATS) {
+    for (int i = tid; i < a.mel_w_count; i += NT) s_melw[i] = a.mel_w[i];   // bin frequencies
   }
   if (htid == 0) {
     mbar_init(s_bar, 1);
@@ -369,7 +373,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         if (t == 0) prow[M / 2] = pw[PPT];
         if (htid < 3 * FT) s_p[(htid / 3) * RS + M + 1 + (htid % 3)] = 0.0f;
         half_sync();   // B2
-        {
+        if constexpr (MODE == MODE_STATS) {
+          // one warp per frame of the tile: statistics of the magnitude row (stats.cuh)
+          const int hwarp = htid >> 5, lane = htid & 31;
+          for (int f = hwarp; f < FT; f += HW) {
+            bool negative;
+            const float r = frame_stats(s_p + f * RS, s_melw, M + 1, lane, a.stats, &negative);
+            if (lane < N_STATS && t0 + f < a.n_frames)
+              a.out_r[((long long)clip * N_STATS + lane) * a.n_frames + t0 + f] = r;
+          }
+        } else {
           // Work item = H adjacent mel rows; lane (f, j) accumulates row i*H + j for frame f over that
           // row's padded band (host-built MelRow table: the rows of an item share one trip count, start
           // bins are congruent to j mod H so the skewed tile reads conflict-free, weights are zero

@@ -1,4 +1,5 @@
-"""CPU oracle: NumPy/SciPy restatement of librosa's stft / istft / melspectrogram / mfcc path.
+"""CPU oracle: NumPy/SciPy restatement of librosa's stft / istft / melspectrogram / mfcc path and of the
+frame-wise features built on it (spectral centroid / bandwidth / rolloff / flatness, rms, zero-crossing rate).
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``librosa_b200/`` imports this module; it is used by
 ``tests/``, by ``__graft_entry__.smoke()`` and by ``bench.py``'s CPU-baseline / ``--impl reference``
@@ -389,6 +390,144 @@ def mfcc(y=None, sr=22050, S=None, n_mfcc=20, dct_type=2, norm="ortho", lifter=0
     if lifter == 0:
         return M
     raise ParameterError(f"MFCC lifter={lifter} must be a non-negative number")
+
+
+# --------------------------------------------------------------------------- frame-wise spectral statistics
+def _spec_or_S(y, S, n_fft, hop_length, power, win_length, window, center, pad_mode):
+    """``_spectrogram`` (librosa/core/spectrum.py:2988-3013): pass ``S`` through (re-inferring n_fft) or
+    compute ``|stft|**power``."""
+    if S is not None:
+        if n_fft is None or n_fft // 2 + 1 != S.shape[-2]:
+            n_fft = 2 * (S.shape[-2] - 1)
+        return S, n_fft
+    return spectrogram(y, n_fft=n_fft, hop_length=hop_length, power=power, win_length=win_length,
+                       window=window, center=center, pad_mode=pad_mode), n_fft
+
+
+def _check_energy(S, what):
+    if not np.isrealobj(S):
+        raise ParameterError(f"{what} is only defined with real-valued input")
+    if np.any(S < 0):
+        raise ParameterError(f"{what} is only defined with non-negative energies")
+
+
+def spectral_centroid(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, freq=None, win_length=None,
+                      window="hann", center=True, pad_mode="constant"):
+    """librosa/feature/spectral.py:158-191."""
+    S, n_fft = _spec_or_S(y, S, n_fft, hop_length, 1, win_length, window, center, pad_mode)
+    _check_energy(S, "Spectral centroid")
+    if freq is None:
+        freq = fft_frequencies(sr=sr, n_fft=n_fft)
+    if freq.ndim == 1:
+        freq = freq.reshape((1,) * (S.ndim - 2) + (-1, 1))
+    return np.sum(freq * normalize(S, norm=1, axis=-2), axis=-2, keepdims=True)
+
+
+def spectral_bandwidth(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                       center=True, pad_mode="constant", freq=None, centroid=None, norm=True, p=2):
+    """librosa/feature/spectral.py:309-352."""
+    S, n_fft = _spec_or_S(y, S, n_fft, hop_length, 1, win_length, window, center, pad_mode)
+    _check_energy(S, "Spectral bandwidth")
+    if centroid is None:
+        centroid = spectral_centroid(y=y, sr=sr, S=S, n_fft=n_fft, hop_length=hop_length, freq=freq)
+    if freq is None:
+        freq = fft_frequencies(sr=sr, n_fft=n_fft)
+    if freq.ndim == 1:
+        deviation = np.abs(np.subtract.outer(centroid[..., 0, :], freq).swapaxes(-2, -1))
+    else:
+        deviation = np.abs(freq - centroid)
+    if norm:
+        S = normalize(S, norm=1, axis=-2)
+    return np.sum(S * deviation ** p, axis=-2, keepdims=True) ** (1.0 / p)
+
+
+def spectral_rolloff(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                     center=True, pad_mode="constant", freq=None, roll_percent=0.85):
+    """librosa/feature/spectral.py:641-684."""
+    if not 0.0 < roll_percent < 1.0:
+        raise ParameterError("roll_percent must lie in the range (0, 1)")
+    S, n_fft = _spec_or_S(y, S, n_fft, hop_length, 1, win_length, window, center, pad_mode)
+    _check_energy(S, "Spectral rolloff")
+    if freq is None:
+        freq = fft_frequencies(sr=sr, n_fft=n_fft)
+    if freq.ndim == 1:
+        freq = freq.reshape((1,) * (S.ndim - 2) + (-1, 1))
+    total_energy = np.cumsum(S, axis=-2)
+    threshold = np.expand_dims(roll_percent * total_energy[..., -1, :], axis=-2)
+    ind = np.where(total_energy < threshold, np.nan, 1)
+    return np.nanmin(ind * freq, axis=-2, keepdims=True)
+
+
+def spectral_flatness(y=None, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann", center=True,
+                      pad_mode="constant", amin=1e-10, power=2.0):
+    """librosa/feature/spectral.py:772-803."""
+    if amin <= 0:
+        raise ParameterError("amin must be strictly positive")
+    S, n_fft = _spec_or_S(y, S, n_fft, hop_length, 1.0, win_length, window, center, pad_mode)
+    _check_energy(S, "Spectral flatness")
+    S_thresh = np.maximum(amin, S ** power)
+    gmean = np.exp(np.mean(np.log(S_thresh), axis=-2, keepdims=True))
+    amean = np.mean(S_thresh, axis=-2, keepdims=True)
+    return gmean / amean
+
+
+def rms(y=None, S=None, frame_length=2048, hop_length=512, center=True, pad_mode="constant", dtype=np.float32):
+    """librosa/feature/spectral.py:881-916 (``util.abs2`` = ``np.square`` for real input,
+    ``re^2 + im^2`` for complex, librosa/util/utils.py:2479-2530)."""
+    if y is not None:
+        if center:
+            padding = [(0, 0)] * y.ndim
+            padding[-1] = (int(frame_length // 2), int(frame_length // 2))
+            y = np.pad(y, padding, mode=pad_mode)
+        x = frame(y, frame_length=frame_length, hop_length=hop_length)
+        power = np.mean(np.square(x, dtype=dtype), axis=-2, keepdims=True)
+    elif S is not None:
+        if S.shape[-2] != frame_length // 2 + 1:
+            raise ParameterError(
+                f"Since S.shape[-2] is {S.shape[-2]}, frame_length is expected to be {S.shape[-2] * 2 - 2} or "
+                f"{S.shape[-2] * 2 - 1}; found {frame_length}")
+        if np.iscomplexobj(S):
+            x = (S.real ** 2 + S.imag ** 2).astype(dtype)
+        else:
+            x = np.square(S, dtype=dtype)
+        x[..., 0, :] *= 0.5
+        if frame_length % 2 == 0:
+            x[..., -1, :] *= 0.5
+        power = 2 * np.sum(x, axis=-2, keepdims=True) / frame_length ** 2
+    else:
+        raise ParameterError("Either `y` or `S` must be input.")
+    return np.sqrt(power)
+
+
+def zero_crossings(y, threshold=1e-10, ref_magnitude=None, pad=True, zero_pos=True, axis=-1):
+    """librosa/core/audio.py:1588-1602 (stencil) and :1711-1728: samples within ``threshold`` of zero count
+    as 0; position i is a crossing when the sign (bit) of y[i] differs from that of y[i-1]; position 0 is
+    ``pad``."""
+    if callable(ref_magnitude):
+        threshold = threshold * ref_magnitude(np.abs(y))
+    elif ref_magnitude is not None:
+        threshold = threshold * ref_magnitude
+    yi = np.moveaxis(np.asarray(y), axis, -1)
+    clipped = np.where((yi >= -threshold) & (yi <= threshold), 0, yi)
+    sgn = np.signbit(clipped) if zero_pos else np.sign(clipped)
+    z = np.empty(yi.shape, dtype=bool)
+    z[..., 1:] = sgn[..., 1:] != sgn[..., :-1]
+    z[..., 0] = pad
+    return np.moveaxis(z, -1, axis)
+
+
+def zero_crossing_rate(y, frame_length=2048, hop_length=512, center=True, **kwargs):
+    """librosa/feature/spectral.py:1115-1133."""
+    valid_audio(y)
+    if center:
+        padding = [(0, 0)] * y.ndim
+        padding[-1] = (int(frame_length // 2), int(frame_length // 2))
+        y = np.pad(y, padding, mode="edge")
+    y_framed = frame(y, frame_length=frame_length, hop_length=hop_length)
+    kwargs["axis"] = -2
+    kwargs.setdefault("pad", False)
+    crossings = zero_crossings(y_framed, **kwargs)
+    return np.mean(crossings, axis=-2, keepdims=True)
 
 
 def griffinlim(S, n_iter=32, hop_length=None, win_length=None, n_fft=None, window="hann", center=True,

@@ -32,9 +32,11 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def golden():
-    path = os.path.join(ROOT, "tests", "golden", "hotpath_v1.npz")
-    with np.load(path) as z:
-        return {k: z[k] for k in z.files}
+    out = {}
+    for name in ("hotpath_v1.npz", "features_v1.npz"):
+        with np.load(os.path.join(ROOT, "tests", "golden", name)) as z:
+            out.update({k: z[k] for k in z.files})
+    return out
 
 
 @pytest.fixture(scope="session")

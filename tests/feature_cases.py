@@ -1,0 +1,81 @@
+"""Parity cases for the frame-wise consumers of the spectrogram: spectral centroid /
+bandwidth / rolloff / flatness, rms, zero-crossing rate.  Same three uses as tests/cases.py:
+tools/make_golden.py -> tests/golden/features_v1.npz (unmodified reference), the CPU oracle test, the GPU
+parity test.
+
+Inputs: ``mix``/``shape`` -> tests/signals.py signal; ``src`` -> |golden stft| of the named hot-path case
+(the S= form); ``freq`` -> a synthetic 1-D frequency table of that many bins.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FEATURE_CASES = [
+    # ---- spectral_centroid
+    dict(name="centroid_2048_A", fn="spectral_centroid", mix="A", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="centroid_1024_stereo_B", fn="spectral_centroid", mix="B", shape=(2, 6000), kw=dict(sr=16000, n_fft=1024, hop_length=256)),
+    dict(name="centroid_C_silence", fn="spectral_centroid", mix="C", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="centroid_4096_reflect_B", fn="spectral_centroid", mix="B", shape=(14000,), kw=dict(sr=44100, n_fft=4096, hop_length=1024, pad_mode="reflect")),
+    dict(name="centroid_400_nonpow2_A", fn="spectral_centroid", mix="A", shape=(2, 8000), kw=dict(sr=16000, n_fft=400, hop_length=160)),
+    dict(name="centroid_fromS", fn="spectral_centroid", src="stft_2048_512_A", kw=dict(sr=22050)),
+    dict(name="centroid_fromS_stereo", fn="spectral_centroid", src="stft_512_stereo_A", kw=dict(sr=22050)),
+    dict(name="centroid_custom_freq", fn="spectral_centroid", mix="B", shape=(6000,), freq=513, kw=dict(sr=22050, n_fft=1024, hop_length=256)),
+    dict(name="centroid_64_16_B", fn="spectral_centroid", mix="B", shape=(2000,), kw=dict(sr=8000, n_fft=64, hop_length=16)),
+    # ---- spectral_bandwidth
+    dict(name="bandwidth_2048_A", fn="spectral_bandwidth", mix="A", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="bandwidth_2048_B", fn="spectral_bandwidth", mix="B", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="bandwidth_p3_nonorm_B", fn="spectral_bandwidth", mix="B", shape=(6000,), kw=dict(sr=22050, n_fft=1024, hop_length=256, p=3, norm=False)),
+    dict(name="bandwidth_C_silence", fn="spectral_bandwidth", mix="C", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="bandwidth_fromS", fn="spectral_bandwidth", src="stft_1024_256_reflect_B", kw=dict(sr=22050)),
+    dict(name="bandwidth_501_nonpow2_A", fn="spectral_bandwidth", mix="A", shape=(3000,), kw=dict(sr=22050, n_fft=501, hop_length=128)),
+    # ---- spectral_rolloff
+    dict(name="rolloff_2048_A", fn="spectral_rolloff", mix="A", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="rolloff_095_B", fn="spectral_rolloff", mix="B", shape=(9000,), kw=dict(sr=22050, roll_percent=0.95)),
+    dict(name="rolloff_010_stereo_A", fn="spectral_rolloff", mix="A", shape=(2, 6000), kw=dict(sr=16000, n_fft=1024, hop_length=256, roll_percent=0.1)),
+    dict(name="rolloff_C_silence", fn="spectral_rolloff", mix="C", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="rolloff_fromS", fn="spectral_rolloff", src="stft_2048_512_A", kw=dict(sr=22050, roll_percent=0.5)),
+    # ---- spectral_flatness
+    dict(name="flatness_2048_A", fn="spectral_flatness", mix="A", shape=(9000,), kw=dict()),
+    dict(name="flatness_2048_B", fn="spectral_flatness", mix="B", shape=(9000,), kw=dict()),
+    dict(name="flatness_power1_amin_B", fn="spectral_flatness", mix="B", shape=(6000,), kw=dict(n_fft=1024, hop_length=256, power=1.0, amin=1e-6)),
+    dict(name="flatness_power3_A", fn="spectral_flatness", mix="A", shape=(4000,), kw=dict(n_fft=512, hop_length=128, power=3.0)),
+    dict(name="flatness_C_silence", fn="spectral_flatness", mix="C", shape=(9000,), kw=dict()),
+    dict(name="flatness_fromS", fn="spectral_flatness", src="stft_4096_1024_A", kw=dict()),
+    # ---- rms
+    dict(name="rms_y_A", fn="rms", mix="A", shape=(9000,), ykw=True, kw=dict()),
+    dict(name="rms_y_reflect_stereo_B", fn="rms", mix="B", shape=(2, 6000), ykw=True, kw=dict(frame_length=1000, hop_length=250, pad_mode="reflect")),
+    dict(name="rms_y_nocenter_C", fn="rms", mix="C", shape=(9000,), ykw=True, kw=dict(frame_length=512, hop_length=100, center=False)),
+    dict(name="rms_y_edge_odd_A", fn="rms", mix="A", shape=(5000,), ykw=True, kw=dict(frame_length=1001, hop_length=333, pad_mode="edge")),
+    dict(name="rms_S_2048", fn="rms", src="stft_2048_512_A", kw=dict(frame_length=2048)),
+    dict(name="rms_S_odd_1025", fn="rms", src="stft_1025_nonpow2", kw=dict(frame_length=1025)),
+    # ---- zero_crossing_rate
+    dict(name="zcr_A", fn="zero_crossing_rate", mix="A", shape=(9000,), pos=True, kw=dict()),
+    dict(name="zcr_B_nocenter_stereo", fn="zero_crossing_rate", mix="B", shape=(2, 6000), pos=True, kw=dict(frame_length=1000, hop_length=300, center=False)),
+    dict(name="zcr_C_threshold", fn="zero_crossing_rate", mix="C", shape=(9000,), pos=True, kw=dict(threshold=1e-3)),
+    dict(name="zcr_sign_form_pad_C", fn="zero_crossing_rate", mix="C", shape=(9000,), pos=True, kw=dict(zero_pos=False, pad=True, frame_length=512, hop_length=128)),
+    dict(name="zcr_ref_magnitude_A", fn="zero_crossing_rate", mix="A", shape=(5000,), pos=True, kw=dict(threshold=0.5, ref_magnitude=0.1, frame_length=256, hop_length=64)),
+]
+
+FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
+
+
+def case_args(case, golden):
+    """(positional args, keyword args) for ``<namespace>.<fn>``."""
+    import signals
+
+    kw = dict(case["kw"])
+    if "src" in case:
+        kw["S"] = np.abs(golden[case["src"]])
+        return (), kw
+    y = signals.make(case["mix"], case["shape"], seed=len(case["name"]), sr=kw.get("sr", 22050))
+    if "freq" in case:
+        kw["freq"] = (np.linspace(0.0, 1.0, case["freq"]) ** 2 * 9000.0 + 20.0)
+    if case.get("pos"):
+        return (y,), kw
+    kw["y"] = y
+    return (), kw
+
+
+def call(namespace, case, golden):
+    args, kw = case_args(case, golden)
+    return getattr(namespace, case["fn"])(*args, **kw)

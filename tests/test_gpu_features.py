@@ -1,0 +1,181 @@
+"""GPU (-m gpu): the frame-wise consumers of the spectrogram (spectral centroid / bandwidth / rolloff /
+flatness, rms, zero-crossing rate) through the public drop-in API, against the oracle on identical inputs
+and against fixtures produced by the unmodified reference (tests/golden/features_v1.npz).
+
+Stated tolerances (float32 pipeline vs the reference's float64 FFT):
+    spectral_centroid / bandwidth   rtol 1e-4, atol 1e-6 * max|ref|  (Hz)
+    spectral_rolloff                equal to the reference bin frequency, except in frames where the
+                                    reference's own float32 running sum passes within 2e-5 * total of the
+                                    threshold at the deciding bin (there one bin either way is rounding)
+    spectral_flatness               rtol 1e-4, atol 1e-7
+    rms                             rtol 1e-4, atol 1e-7 * max|ref|
+    zero_crossing_rate              exact
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from feature_cases import FEATURE_CASES, call, case_args
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import librosa_b200
+
+    librosa_b200.default_context()
+    return librosa_b200
+
+
+def _close(got, ref, rtol, atol):
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert got.dtype == ref.dtype, (got.dtype, ref.dtype)
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+
+
+def _rolloff_close(O, case, golden, got, ref):
+    """Frames may differ only where the reference's running sum is within rounding of the threshold."""
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    args, kw = case_args(case, golden)
+    roll = kw.get("roll_percent", 0.85)
+    if "S" in kw:
+        S, n_fft = kw["S"], 2 * (kw["S"].shape[-2] - 1)
+    else:
+        n_fft = kw.get("n_fft", 2048)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            S = O.spectrogram(kw["y"], n_fft=n_fft, hop_length=kw.get("hop_length", 512), power=1,
+                              pad_mode=kw.get("pad_mode", "constant"))
+    freq = O.fft_frequencies(sr=kw.get("sr", 22050), n_fft=n_fft)
+    cum = np.cumsum(S, axis=-2)
+    total = cum[..., -1:, :]
+    thr = roll * total
+    bad = ~np.isclose(got, ref, rtol=1e-6, atol=1e-3)
+    if not bad.any():
+        return
+    # index of the bins chosen by each side; every bin between them must sit within rounding of the threshold
+    ig = np.abs(freq[:, None] - np.moveaxis(got, -2, -1)[..., None, :, 0].reshape(-1)[None, :]).argmin(axis=0)
+    ir = np.abs(freq[:, None] - np.moveaxis(ref, -2, -1)[..., None, :, 0].reshape(-1)[None, :]).argmin(axis=0)
+    cum2 = np.moveaxis(cum, -2, 0).reshape(cum.shape[-2], -1)
+    thr2, tot2 = thr.reshape(-1), total.reshape(-1)
+    for col in np.flatnonzero(bad.reshape(-1)):
+        lo, hi = sorted((ig[col], ir[col]))
+        assert hi - lo <= 2, (case["name"], col, lo, hi)
+        assert np.all(np.abs(cum2[lo:hi, col] - thr2[col]) <= 2e-5 * tot2[col]), (case["name"], col)
+    assert bad.mean() <= 0.05, (case["name"], bad.mean())
+
+
+@pytest.mark.parametrize("case", FEATURE_CASES, ids=[c["name"] for c in FEATURE_CASES])
+def test_feature_case_against_oracle_and_reference_fixture(case, lb, oracle, golden):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = call(lb.feature, case, golden)
+        want = call(oracle, case, golden)
+    fixture = golden[case["name"]]
+    fn = case["fn"]
+    for ref in (want, fixture):
+        scale = float(np.abs(ref).max()) if ref.size else 0.0
+        if fn in ("spectral_centroid", "spectral_bandwidth"):
+            _close(got, ref, 1e-4, 1e-6 * scale)
+        elif fn == "spectral_rolloff":
+            _rolloff_close(oracle, case, golden, got, ref)
+        elif fn == "spectral_flatness":
+            _close(got, ref, 1e-4, 1e-7)
+        elif fn == "rms":
+            _close(got, ref, 1e-4, 1e-7 * scale)
+        else:
+            assert got.shape == ref.shape and got.dtype == ref.dtype
+            np.testing.assert_array_equal(got, ref)
+
+
+def test_device_resident_inputs_and_S_path_agree(lb):
+    """DeviceArray in -> DeviceArray out; the fused y= kernel and the S= kernel on the stored spectrogram see
+    the same magnitudes, so their statistics agree to float32 rounding."""
+    import signals
+
+    y = signals.make("B", (3, 2, 20000), seed=11)
+    yd = lb.to_device(y)
+    Sd, _ = lb._spectrogram(y=yd, n_fft=2048, hop_length=512, power=1)
+    for fn, kw in [(lb.feature.spectral_centroid, dict(sr=22050)), (lb.feature.spectral_bandwidth, dict(sr=22050)),
+                   (lb.feature.spectral_rolloff, dict(sr=22050)), (lb.feature.spectral_flatness, {})]:
+        a = fn(y=yd, **kw)
+        b = fn(S=Sd, **kw)
+        h = fn(y=y, **kw)
+        assert isinstance(a, lb.DeviceArray) and isinstance(b, lb.DeviceArray)
+        assert a.shape == (3, 2, 1, 40) and h.shape == (3, 2, 1, 40)
+        np.testing.assert_allclose(a.get(), b.get(), rtol=2e-6, atol=1e-6 * float(np.abs(h).max()))
+        np.testing.assert_allclose(a.get(), h.astype(np.float32), rtol=1e-6)
+    r = lb.feature.rms(y=yd)
+    z = lb.feature.zero_crossing_rate(yd)
+    assert isinstance(r, lb.DeviceArray) and isinstance(z, lb.DeviceArray)
+    np.testing.assert_allclose(r.get(), lb.feature.rms(y=y), rtol=1e-6)
+    np.testing.assert_allclose(z.get(), lb.feature.zero_crossing_rate(y), rtol=1e-6)
+
+
+def test_rms_from_rectangular_stft_matches_rms_from_samples(lb):
+    """The reference's own docstring property (feature/spectral.py:872-879): with a constant window and no
+    centering, rms(S=|stft|) equals rms(y=...) frame by frame (Parseval)."""
+    import signals
+
+    y = signals.make("A", (4, 30000), seed=2)
+    S = np.abs(lb.stft(y, window=np.ones, center=False))
+    a = lb.feature.rms(S=S)
+    b = lb.feature.rms(y=y, center=False)
+    np.testing.assert_allclose(a, b, rtol=2e-5)
+
+
+def test_error_behaviour_on_device(lb):
+    import signals
+
+    y = signals.make("A", (6000,), seed=4)
+    S = np.abs(lb.stft(y, n_fft=512))
+    neg = S.copy()
+    neg[3, 2] = -1.0
+    for fn in (lb.feature.spectral_centroid, lb.feature.spectral_bandwidth, lb.feature.spectral_rolloff):
+        with pytest.raises(lb.ParameterError, match="non-negative"):
+            fn(S=neg, sr=22050)
+        with pytest.raises(lb.ParameterError, match="real-valued"):
+            fn(S=S.astype(np.complex64), sr=22050)
+    with pytest.raises(lb.ParameterError, match="non-negative"):
+        lb.feature.spectral_flatness(S=neg)
+    # a clean call right after a failing one must not see a stale flag
+    assert np.isfinite(lb.feature.spectral_centroid(S=S, sr=22050)).all()
+    bad = y.copy()
+    bad[1234] = np.nan
+    with pytest.raises(lb.ParameterError, match="not finite"):
+        lb.feature.zero_crossing_rate(bad)
+    with pytest.raises(lb.ParameterError, match="not finite"):
+        lb.feature.spectral_centroid(y=bad)
+    with pytest.raises(lb.UnsupportedOnGPU):
+        lb.feature.spectral_centroid(S=S, freq=np.ones_like(S))
+    with pytest.raises(lb.UnsupportedOnGPU):
+        lb.feature.spectral_bandwidth(S=S, centroid=np.ones((1, S.shape[-1])))
+
+
+def test_full_size_cfg2_statistics_properties(lb):
+    """BASELINE cfg-2 shapes (1024 x 10 s @ 22.05 kHz, 2048/512): one fused launch; properties that do not
+    need a CPU pass over 441 k frames."""
+    rng = np.random.default_rng(0)
+    y = (0.1 * rng.standard_normal((1024, 220500))).astype(np.float32)
+    yd = lb.to_device(y)
+    c = lb.feature.spectral_centroid(y=yd).get()
+    bw = lb.feature.spectral_bandwidth(y=yd).get()
+    ro = lb.feature.spectral_rolloff(y=yd).get()
+    fl = lb.feature.spectral_flatness(y=yd).get()
+    assert c.shape == (1024, 1, 431)
+    # white noise: centroid near sr/4, bandwidth near sr/(4*sqrt(3)), roll-off at 85 % of the band, flat spectrum
+    assert abs(float(c.mean()) - 22050 / 4) < 30 and c.min() > 4000 and c.max() < 7000
+    assert abs(float(bw.mean()) - 22050 / (4 * np.sqrt(3))) < 40
+    assert abs(float(ro.mean()) - 0.85 * 11025) < 60 and ro.max() <= 11025
+    assert 0.4 < fl.min() and fl.max() <= 1.0
+    # a sample of clips against the oracle-sized path (host input -> same kernels through the chunked pipeline)
+    idx = [0, 511, 1023]
+    np.testing.assert_allclose(lb.feature.spectral_centroid(y=y[idx]).astype(np.float32), c[idx], rtol=1e-6)
+    # time-domain framings at full size
+    r = lb.feature.rms(y=yd).get()
+    z = lb.feature.zero_crossing_rate(yd).get()
+    assert r.shape == (1024, 1, 431) and z.shape == (1024, 1, 431)
+    assert abs(float(r[:, :, 2:-2].mean()) - 0.1) < 1e-3
+    assert abs(float(z[:, :, 2:-2].mean()) - 0.5) < 5e-3

@@ -209,3 +209,35 @@ def test_shard_ranges():
             assert cover == list(range(n))
     y = np.arange(7 * 3).reshape(7, 3)
     np.testing.assert_array_equal(join_batches([split_batch(y, r, 4) for r in range(4)]), y)
+
+
+def test_frame_statistics_argument_errors_before_any_gpu_work():
+    """Argument errors of the frame-wise features are raised on the host exactly as in the reference
+    (feature/spectral.py:641, :772, :893-902; core/spectrum.py:237) — no GPU needed to see them."""
+    import librosa_b200 as lb
+
+    y = np.zeros(4000, dtype=np.float32)
+    with pytest.raises(lb.ParameterError, match="roll_percent"):
+        lb.feature.spectral_rolloff(y=y, roll_percent=1.0)
+    with pytest.raises(lb.ParameterError, match="amin"):
+        lb.feature.spectral_flatness(y=y, amin=0)
+    with pytest.raises(lb.ParameterError, match="frame_length is expected"):
+        lb.feature.rms(S=np.ones((100, 5), dtype=np.float32), frame_length=2048)
+    with pytest.raises(lb.ParameterError, match="Either"):
+        lb.feature.rms()
+    with pytest.raises(lb.ParameterError, match="hop_length"):
+        lb.feature.spectral_centroid(y=y, hop_length=0)
+    with pytest.raises(lb.ParameterError, match="Input signal must be provided"):
+        lb.feature.spectral_centroid()
+    with pytest.raises(lb.ParameterError, match="too short"):
+        lb.feature.rms(y=np.zeros(100, dtype=np.float32), frame_length=2048, center=False)
+    with pytest.raises(TypeError):
+        lb.feature.zero_crossing_rate(y, bogus=1)
+    with pytest.raises(lb.ParameterError, match="floating-point"):
+        lb.feature.zero_crossing_rate(np.zeros(4000, dtype=np.int16))
+    with pytest.raises(lb.UnsupportedOnGPU):
+        lb.feature.zero_crossing_rate(y, ref_magnitude=np.max)
+    with pytest.raises(lb.UnsupportedOnGPU):
+        lb.feature.rms(y=y, pad_mode="wrap")
+    with pytest.raises(ValueError):
+        lb.feature.rms(y=y, pad_mode="nonsense")

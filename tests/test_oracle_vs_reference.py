@@ -44,6 +44,17 @@ def test_features_bit_exact(ref, oracle):
                                   oracle.mfcc(y=y, sr=16000, n_mfcc=13, lifter=22, dct_type=3))
 
 
+def test_frame_statistics_bit_exact(ref, oracle, golden):
+    from feature_cases import FEATURE_CASES, call
+
+    for case in FEATURE_CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a, b = call(ref.feature, case, golden), call(oracle, case, golden)
+        assert a.dtype == b.dtype and a.shape == b.shape, case["name"]
+        np.testing.assert_array_equal(a, b, err_msg=case["name"])
+
+
 def test_griffinlim_bit_exact(ref, oracle):
     y = (0.1 * np.random.default_rng(2).standard_normal(6000)).astype(np.float32)
     S = np.abs(ref.stft(y, n_fft=512, hop_length=128))

@@ -1,4 +1,5 @@
-"""Generate tests/golden/hotpath_v1.npz by running tests/cases.py through the UNMODIFIED reference.
+"""Generate tests/golden/hotpath_v1.npz (tests/cases.py) and tests/golden/features_v1.npz
+(tests/feature_cases.py) by running the cases through the UNMODIFIED reference.
 
 Build-container only (needs /root/reference; see tools/ref_shim.py).  The fixtures travel to the GPU box,
 where /root/reference does not exist.  Also stores a handful of constant tables (mel bases, window
@@ -72,6 +73,19 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "hotpath_v1.npz")
     np.savez_compressed(path, **store)
     print("wrote", path, os.path.getsize(path), "bytes; reference", ref.__version__)
+    # ---- frame-wise consumers (tests/feature_cases.py)
+    from feature_cases import FEATURE_CASES, call
+
+    feats = {}
+    for case in FEATURE_CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = call(ref.feature, case, store)
+        feats[case["name"]] = np.ascontiguousarray(out)
+        print(f"{case['name']:40s} {out.shape} {out.dtype}")
+    path = os.path.join(ROOT, "tests", "golden", "features_v1.npz")
+    np.savez_compressed(path, **feats)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
