@@ -159,6 +159,13 @@ int b2l_mel_project(b2l_ctx* ctx, const b2l_plan* plan, const float* d_S, int64_
  * (core/spectrum.py:1839-1883); in place when d_out == d_in. */
 int b2l_power_to_db(b2l_ctx* ctx, const float* d_in, int64_t n_clips, int64_t per_clip, float amin,
                     float ref_value, float top_db, float* d_out);
+/* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
+ *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
+ *                                                        of the squared magnitudes with ref^2 / amin^2
+ *   B2L_UNARY_DB_TO_POWER      param * 10^(0.1 x)        db_to_power (core/spectrum.py:1899-1925), param = ref
+ *   B2L_UNARY_DB_TO_AMPLITUDE  sqrt(param * 10^(0.1 x))  db_to_amplitude (:2054-2081), param = ref^2 */
+enum { B2L_UNARY_SQUARE = 0, B2L_UNARY_DB_TO_POWER = 1, B2L_UNARY_DB_TO_AMPLITUDE = 2 };
+int b2l_unary(b2l_ctx* ctx, int32_t op, const float* d_in, int64_t n, float param, float* d_out);
 /* DCT rows applied along the mel axis of S [n_clips][n_mels][n_frames] (feature/spectral.py:2005). */
 int b2l_dct_project(b2l_ctx* ctx, const b2l_plan* plan, const float* d_S, int64_t n_clips,
                     int64_t n_frames, float* d_mfcc);
@@ -191,6 +198,7 @@ typedef struct b2l_stats_desc {
   float bw_p;          /* > 0 */
   int32_t bw_norm;
   int32_t frame_length;
+  int32_t want;        /* bit r set: row r is needed (0 = all rows); rows not asked for are unspecified */
 } b2l_stats_desc;
 /* y= form: fused with the stft (no spectrogram is written); power-of-two n_fft plans. */
 int b2l_spectral_stats(b2l_ctx* ctx, const b2l_plan* plan, const b2l_stats_desc* desc, const float* d_y,

@@ -61,12 +61,14 @@ class StatsDesc(C.Structure):
         ("bw_p", C.c_float),
         ("bw_norm", C.c_int32),
         ("frame_length", C.c_int32),
+        ("want", C.c_int32),
     ]
 
 
 N_STATS = 6
 STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
 FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
+UNARY_SQUARE, UNARY_DB_TO_POWER, UNARY_DB_TO_AMPLITUDE = 0, 1, 2
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -114,6 +116,7 @@ def _declare(lib):
         "b2l_istft": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64]),
         "b2l_mel_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_power_to_db": (C.c_int, [_vp, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp]),
+        "b2l_unary": (C.c_int, [_vp, C.c_int32, _vp, _i64, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),
         "b2l_gl_update": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _i64]),

@@ -256,17 +256,29 @@ def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80
 
     The reference maximum of ``top_db`` is taken per leading index over the last two axes
     (``axes="auto"``), which is what ``mfcc`` relies on for multichannel input."""
+    return _to_db(S, ref, amin, top_db, axes, amplitude=False)
+
+
+def amplitude_to_db(S, *, ref=1.0, amin: float = 1e-5, top_db: Optional[float] = 80.0, axes="auto"):
+    """``20*log10(|S|/ref)``: ``power_to_db(S**2, ref=ref**2, amin=amin**2)``; mirror of
+    core/spectrum.py:1946-2038."""
+    return _to_db(S, ref, amin, top_db, axes, amplitude=True)
+
+
+def _to_db(S, ref, amin, top_db, axes, amplitude: bool):
+    name = "amplitude_to_db" if amplitude else "power_to_db"
     on_device = isinstance(S, nat.DeviceArray)
     if not on_device:
         S = np.asarray(S)
     if amin <= 0:
         raise ParameterError("amin must be strictly positive")
     if not on_device and np.issubdtype(S.dtype, np.complexfloating):
-        warnings.warn("power_to_db was called on complex input so phase information will be discarded. "
-                      "To suppress this warning, call power_to_db(np.abs(D)**2) instead.", stacklevel=2)
+        hint = "amplitude_to_db(np.abs(S))" if amplitude else "power_to_db(np.abs(D)**2)"
+        warnings.warn(f"{name} was called on complex input so phase information will be discarded. "
+                      f"To suppress this warning, call {hint} instead.", stacklevel=3)
         S = np.abs(S)
     if axes != "auto":
-        raise nat.UnsupportedOnGPU("power_to_db: only axes='auto' is computed on the GPU")
+        raise nat.UnsupportedOnGPU(f"{name}: only axes='auto' is computed on the GPU")
     if top_db is not None and top_db < 0:
         raise ParameterError("top_db must be non-negative")
     ctx = S.ctx if on_device else nat.default_context()
@@ -278,7 +290,7 @@ def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80
     else:
         if not np.issubdtype(S.dtype, np.floating):
             S = S.astype(np.float32)
-        req = pl.check_real_dtype(S.dtype, "power_to_db input")
+        req = pl.check_real_dtype(S.dtype, f"{name} input")
         dev = ctx.to_device(np.ascontiguousarray(S, dtype=np.float32))
     ndim = len(dev.shape)
     if ndim >= 2:
@@ -291,26 +303,66 @@ def power_to_db(S, *, ref=1.0, amin: float = 1e-10, top_db: Optional[float] = 80
     out = nat.DeviceArray.empty(ctx, dev.shape, np.float32, layout=dev.layout)
     tdb = -1.0 if top_db is None else float(top_db)
     L = nat.lib()
+    src = dev
+    if amplitude:
+        # power = |S|**2 (written into the output buffer, converted in place), amin**2, ref**2
+        nat.check(L.b2l_unary(ctx.handle, nat.UNARY_SQUARE, _vp(dev.ptr), dev.size, 0.0, _vp(out.ptr)))
+        src = out
+        amin = float(amin) ** 2
     if callable(ref):
         if on_device:
             raise nat.UnsupportedOnGPU("callable ref needs a host array")
         ax = (-2, -1) if ndim >= 2 else ((-1,) if ndim == 1 else None)
         try:
-            ref_value = np.asarray(ref(S, axis=ax, keepdims=True), dtype=np.float64).reshape(-1)
+            ref_value = np.asarray(ref(np.abs(S) if amplitude else S, axis=ax, keepdims=True), dtype=np.float64).reshape(-1)
         except TypeError as exc:
             raise ParameterError("The provided reference function must support 'axis' and 'keepdims' "
                                  "arguments for proper multichannel processing.") from exc
+        if amplitude:
+            ref_value = ref_value ** 2
         for i in range(n_lead):   # one reference level per leading index
-            nat.check(L.b2l_power_to_db(ctx.handle, _vp(dev.ptr + 4 * i * per), 1, per, float(amin),
+            nat.check(L.b2l_power_to_db(ctx.handle, _vp(src.ptr + 4 * i * per), 1, per, float(amin),
                                         float(ref_value[i if ref_value.size > 1 else 0]), tdb,
                                         _vp(out.ptr + 4 * i * per)))
     else:
-        nat.check(L.b2l_power_to_db(ctx.handle, _vp(dev.ptr), n_lead, per, float(amin), float(np.abs(ref)), tdb,
+        ref_value = float(np.abs(ref)) ** 2 if amplitude else float(np.abs(ref))
+        nat.check(L.b2l_power_to_db(ctx.handle, _vp(src.ptr), n_lead, per, float(amin), ref_value, tdb,
                                     _vp(out.ptr)))
     if on_device:
         return out
     res = pl.finish(ctx, out, True, req)
     return res[()]
+
+
+def _db_inverse(S_db, op, param):
+    on_device = isinstance(S_db, nat.DeviceArray)
+    ctx = S_db.ctx if on_device else nat.default_context()
+    if on_device:
+        if S_db.dtype != np.float32:
+            raise ParameterError("device input must be float32")
+        dev, req = S_db, np.dtype(np.float32)
+    else:
+        S_db = np.asarray(S_db)
+        if np.iscomplexobj(S_db):
+            raise nat.UnsupportedOnGPU("complex dB values are not supported on the GPU")
+        req = np.dtype(np.float64) if not np.issubdtype(S_db.dtype, np.floating) else \
+            pl.check_real_dtype(S_db.dtype, "dB input")
+        dev = ctx.to_device(np.ascontiguousarray(S_db, dtype=np.float32))
+    out = nat.DeviceArray.empty(ctx, dev.shape, np.float32, layout=dev.layout)
+    nat.check(nat.lib().b2l_unary(ctx.handle, op, _vp(dev.ptr), dev.size, float(param), _vp(out.ptr)))
+    if on_device:
+        return out
+    return pl.finish(ctx, out, True, req)[()]
+
+
+def db_to_power(S_db, *, ref: float = 1.0):
+    """``ref * 10**(S_db / 10)``; mirror of core/spectrum.py:1899-1925."""
+    return _db_inverse(S_db, nat.UNARY_DB_TO_POWER, ref)
+
+
+def db_to_amplitude(S_db, *, ref: float = 1.0):
+    """``db_to_power(S_db, ref=ref**2) ** 0.5``; mirror of core/spectrum.py:2054-2081."""
+    return _db_inverse(S_db, nat.UNARY_DB_TO_AMPLITUDE, float(ref) ** 2)
 
 
 def griffinlim(S, *, n_iter: int = 32, hop_length: Optional[int] = None, win_length: Optional[int] = None,

@@ -953,6 +953,7 @@ static int check_stats_desc(const b2l_stats_desc* d, StatsParams* sp) {
   sp->bw_p = d->bw_p;
   sp->bw_norm = d->bw_norm ? 1 : 0;
   sp->frame_length = d->frame_length;
+  sp->want = d->want ? (d->want & ((1 << N_STATS) - 1)) : (1 << N_STATS) - 1;
   return B2L_OK;
 }
 
@@ -1285,6 +1286,19 @@ extern "C" int b2l_power_to_db(b2l_ctx* c, const float* d_in, int64_t n_clips, i
     CUDA_TRY(cudaGetLastError());
     c->launches++;
   }
+  return B2L_OK;
+}
+
+extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
+  if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);
+  if (n <= 0) return B2L_OK;
+  DeviceGuard g(c->device);
+  long long grid = (n + 256LL * 8 - 1) / (256LL * 8);
+  if (grid > 8LL * c->sm_count) grid = 8LL * c->sm_count;
+  unary_kernel<<<(int)grid, 256, 0, c->stream>>>(d_in, n, op, param, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
   return B2L_OK;
 }
 

@@ -49,6 +49,7 @@ struct StatsParams {
   float bw_p;                    // spectral_bandwidth: (sum S |f - centroid|^p)^(1/p)
   int bw_norm;                   //   ... with S normalised to unit sum per frame
   int frame_length;              // rms(S=...): DC (and Nyquist when even) count half
+  int want;                      // bit r set: row r is needed (the others may hold anything)
 };
 
 struct FwdArgs {

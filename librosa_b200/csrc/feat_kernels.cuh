@@ -83,4 +83,22 @@ __global__ void frame_td_kernel(const float* __restrict__ y, long long clip_stri
   }
 }
 
+// Elementwise helpers of the dB conversions (librosa/core/spectrum.py):
+//   UNARY_SQUARE           x*x                        amplitude_to_db squares |S| before power_to_db (:2032-2037)
+//   UNARY_DB_TO_POWER      ref * 10^(0.1 x)           db_to_power (:1899-1925)
+//   UNARY_DB_TO_AMPLITUDE  sqrt(ref^2 * 10^(0.1 x))   db_to_amplitude (:2054-2081), param = ref^2
+enum UnaryOp : int { UNARY_SQUARE = 0, UNARY_DB_TO_POWER = 1, UNARY_DB_TO_AMPLITUDE = 2 };
+__global__ void unary_kernel(const float* __restrict__ in, long long n, int op, float param, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = in[i];
+    float r;
+    if (op == UNARY_SQUARE) r = x * x;
+    else {
+      r = param * powf(10.0f, x * 0.1f);
+      if (op == UNARY_DB_TO_AMPLITUDE) r = sqrtf(r);
+    }
+    out[i] = r;
+  }
+}
+
 }  // namespace b2l

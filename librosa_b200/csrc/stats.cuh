@@ -34,17 +34,26 @@ __device__ inline float frame_stats(const float* row, const float* freq, int F, 
   float m0 = 0.0f, m1 = 0.0f, e2 = 0.0f, am = 0.0f, lg = 0.0f;
   bool neg = false;
   const int fmode = sp.flat_power == 2.0f ? 2 : (sp.flat_power == 1.0f ? 1 : 0);
+  // warp-uniform switches: a caller that wants one row does not pay for the others
+  const bool need_m1 = sp.want & ((1 << STAT_CENTROID) | (1 << STAT_BANDWIDTH));
+  const bool need_flat = sp.want & (1 << STAT_FLATNESS);
+  const bool need_e2 = sp.want & (1 << STAT_RMS);
+  const bool need_pass2 = sp.want & ((1 << STAT_BANDWIDTH) | (1 << STAT_ROLLOFF));
   for (int k = k0; k < k1; ++k) {
     const float s = row[k];
     neg |= s < 0.0f;
     m0 += s;
-    m1 = fmaf(freq[k], s, m1);
-    const float p2 = s * s;
-    e2 += p2;
-    float th = fmode == 2 ? p2 : (fmode == 1 ? s : powf(s, sp.flat_power));
-    th = fmaxf(sp.flat_amin, th);
-    am += th;
-    lg += __log2f(th);
+    if (need_m1) m1 = fmaf(freq[k], s, m1);
+    if (need_e2 | need_flat) {
+      const float p2 = s * s;
+      e2 += p2;
+      if (need_flat) {
+        float th = fmode == 2 ? p2 : (fmode == 1 ? s : powf(s, sp.flat_power));
+        th = fmaxf(sp.flat_amin, th);
+        am += th;
+        lg += __log2f(th);
+      }
+    }
   }
   *negative = __any_sync(0xffffffffu, neg);
   // exclusive scan of the chunk totals
@@ -62,12 +71,14 @@ __device__ inline float frame_stats(const float* row, const float* freq, int F, 
   const float thr = sp.roll_percent * total;
   const bool p_is_2 = sp.bw_p == 2.0f;
   float bw = 0.0f, rmin = INFINITY;
-  for (int k = k0; k < k1; ++k) {
-    const float s = row[k], fk = freq[k];
-    run += s;
-    if (run >= thr) rmin = fminf(rmin, fk);
-    const float d = fabsf(fk - centroid);
-    bw = fmaf(s, p_is_2 ? d * d : powf(d, sp.bw_p), bw);
+  if (need_pass2) {
+    for (int k = k0; k < k1; ++k) {
+      const float s = row[k], fk = freq[k];
+      run += s;
+      if (run >= thr) rmin = fminf(rmin, fk);
+      const float d = fabsf(fk - centroid);
+      bw = fmaf(s, p_is_2 ? d * d : powf(d, sp.bw_p), bw);
+    }
   }
   float bwt = warp_sum(bw);
   if (sp.bw_norm) bwt /= norm;

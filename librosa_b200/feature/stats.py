@@ -52,9 +52,10 @@ def _freq_table(freq, sr, n_fft, n_bins):
     return freq, ("freq", pl.digest(np.ascontiguousarray(freq, dtype=np.float64))), freq.dtype
 
 
-def _desc(*, roll_percent=0.85, amin=1e-10, power=2.0, p=2.0, norm=True, frame_length=2):
+def _desc(row, *, roll_percent=0.85, amin=1e-10, power=2.0, p=2.0, norm=True, frame_length=2):
+    """struct b2l_stats_desc asking for statistic ``row`` only (the kernel skips what the others need)."""
     return nat.StatsDesc(roll_percent=float(roll_percent), flat_amin=float(amin), flat_power=float(power),
-                         bw_p=float(p), bw_norm=int(bool(norm)), frame_length=int(frame_length))
+                         bw_p=float(p), bw_norm=int(bool(norm)), frame_length=int(frame_length), want=1 << row)
 
 
 def _take_row(ctx, stats, lead, T, row, on_device, res_dtype):
@@ -185,7 +186,7 @@ def spectral_centroid(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, h
                       win_length: Optional[int] = None, window="hann", center: bool = True, pad_mode="constant"):
     """Spectral centroid per frame, shape ``(..., 1, t)``; same contract as ``librosa.feature.spectral_centroid``
     (``freq`` must be 1-D or None on the GPU)."""
-    return _statistic(nat.STAT_CENTROID, "Spectral centroid", _desc(), lambda s, f: np.result_type(s, f),
+    return _statistic(nat.STAT_CENTROID, "Spectral centroid", _desc(nat.STAT_CENTROID), lambda s, f: np.result_type(s, f),
                       y=y, S=S, sr=sr, n_fft=n_fft, hop_length=hop_length, freq=freq, win_length=win_length,
                       window=window, center=center, pad_mode=pad_mode)
 
@@ -199,7 +200,7 @@ def spectral_bandwidth(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, 
         raise nat.UnsupportedOnGPU("spectral_bandwidth(centroid=...) is not supported on the GPU (no CPU fallback)")
     if not p > 0:
         raise ParameterError(f"p={p} must be strictly positive")
-    return _statistic(nat.STAT_BANDWIDTH, "Spectral bandwidth", _desc(p=p, norm=norm),
+    return _statistic(nat.STAT_BANDWIDTH, "Spectral bandwidth", _desc(nat.STAT_BANDWIDTH, p=p, norm=norm),
                       lambda s, f: np.result_type(s, f),
                       y=y, S=S, sr=sr, n_fft=n_fft, hop_length=hop_length, freq=freq, win_length=win_length,
                       window=window, center=center, pad_mode=pad_mode)
@@ -211,7 +212,7 @@ def spectral_rolloff(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, ho
     """Roll-off frequency per frame; same contract as ``librosa.feature.spectral_rolloff``."""
     if not 0.0 < roll_percent < 1.0:
         raise ParameterError("roll_percent must lie in the range (0, 1)")
-    return _statistic(nat.STAT_ROLLOFF, "Spectral rolloff", _desc(roll_percent=roll_percent),
+    return _statistic(nat.STAT_ROLLOFF, "Spectral rolloff", _desc(nat.STAT_ROLLOFF, roll_percent=roll_percent),
                       lambda s, f: np.result_type(s, f),
                       y=y, S=S, sr=sr, n_fft=n_fft, hop_length=hop_length, freq=freq, win_length=win_length,
                       window=window, center=center, pad_mode=pad_mode)
@@ -223,7 +224,7 @@ def spectral_flatness(*, y=None, S=None, n_fft: int = 2048, hop_length: int = 51
     """Spectral flatness per frame; same contract as ``librosa.feature.spectral_flatness``."""
     if amin <= 0:
         raise ParameterError("amin must be strictly positive")
-    return _statistic(nat.STAT_FLATNESS, "Spectral flatness", _desc(amin=amin, power=power), lambda s, f: np.dtype(s),
+    return _statistic(nat.STAT_FLATNESS, "Spectral flatness", _desc(nat.STAT_FLATNESS, amin=amin, power=power), lambda s, f: np.dtype(s),
                       y=y, S=S, sr=22050, n_fft=n_fft, hop_length=hop_length, freq=None, win_length=win_length,
                       window=window, center=center, pad_mode=pad_mode)
 
@@ -290,7 +291,7 @@ def rms(*, y=None, S=None, frame_length: int = 2048, hop_length: int = 512, cent
         if not isinstance(S, nat.DeviceArray) and np.iscomplexobj(S):
             raise nat.UnsupportedOnGPU("rms(S=...) with a complex S is not supported on the GPU: pass np.abs(S)")
         # rms only squares S, so the sign of an entry is irrelevant (no non-negativity requirement)
-        stats, ctx, lead, T, on_device, _, _ = _stats_from_S(S, _desc(frame_length=frame_length), None, 22050,
+        stats, ctx, lead, T, on_device, _, _ = _stats_from_S(S, _desc(nat.STAT_RMS, frame_length=frame_length), None, 22050,
                                                              frame_length, "rms", check_negative=False)
         return _take_row(ctx, stats, lead, T, nat.STAT_RMS, on_device, np.dtype(dtype))
     raise ParameterError("Either `y` or `S` must be input.")

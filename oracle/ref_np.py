@@ -363,6 +363,26 @@ def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0):
     return out[()]
 
 
+def amplitude_to_db(S, ref=1.0, amin=1e-5, top_db=80.0):
+    """librosa/core/spectrum.py:2000-2038 (``axes='auto'``): power_to_db of the squared magnitudes."""
+    S = np.asarray(S)
+    magnitude = np.abs(S)
+    axes = (-2, -1) if magnitude.ndim >= 2 else ((-1,) if magnitude.ndim == 1 else None)
+    ref_value = ref(magnitude, axis=axes, keepdims=True) if callable(ref) else np.abs(ref)
+    power = np.square(magnitude, out=magnitude if isinstance(magnitude, np.ndarray) else None)
+    return power_to_db(power, ref=ref_value ** 2, amin=amin ** 2, top_db=top_db)
+
+
+def db_to_power(S_db, ref=1.0):
+    """librosa/core/spectrum.py:1925."""
+    return ref * np.power(10.0, S_db * 0.1)
+
+
+def db_to_amplitude(S_db, ref=1.0):
+    """librosa/core/spectrum.py:2081."""
+    return db_to_power(S_db, ref=ref ** 2) ** 0.5
+
+
 def melspectrogram(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None,
                    window="hann", center=True, pad_mode="constant", power=2.0, **mel_kwargs):
     """librosa/feature/spectral.py:2145-2161."""

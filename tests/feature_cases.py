@@ -56,6 +56,18 @@ FEATURE_CASES = [
     dict(name="zcr_ref_magnitude_A", fn="zero_crossing_rate", mix="A", shape=(5000,), pos=True, kw=dict(threshold=0.5, ref_magnitude=0.1, frame_length=256, hop_length=64)),
 ]
 
+FEATURE_CASES += [
+    # ---- dB conversions (top-level functions): amplitude_to_db, db_to_power, db_to_amplitude
+    dict(name="amp_to_db_stft", fn="amplitude_to_db", ns="top", arg="stft_2048_512_A", arg_op="abs", kw=dict()),
+    dict(name="amp_to_db_refmax_stereo", fn="amplitude_to_db", ns="top", arg="stft_512_stereo_A", arg_op="abs", kw=dict(ref=np.max)),
+    dict(name="amp_to_db_top40_amin", fn="amplitude_to_db", ns="top", arg="stft_2048_C_burst", arg_op="abs", kw=dict(top_db=40.0, amin=1e-3, ref=2.0)),
+    dict(name="amp_to_db_notop", fn="amplitude_to_db", ns="top", arg="stft_64_16_B", arg_op="abs", kw=dict(top_db=None)),
+    dict(name="db_to_power_default", fn="db_to_power", ns="top", arg="const/power_to_db_out", kw=dict()),
+    dict(name="db_to_power_ref", fn="db_to_power", ns="top", arg="mfcc_16000_1024_A", kw=dict(ref=3.5)),
+    dict(name="db_to_amplitude_default", fn="db_to_amplitude", ns="top", arg="const/power_to_db_out", kw=dict()),
+    dict(name="db_to_amplitude_ref", fn="db_to_amplitude", ns="top", arg="const/power_to_db_out_top40", kw=dict(ref=0.25)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 
@@ -64,6 +76,10 @@ def case_args(case, golden):
     import signals
 
     kw = dict(case["kw"])
+    if "arg" in case:           # positional array taken from the hot-path fixtures, optionally transformed
+        x = golden[case["arg"]]
+        x = {"abs": np.abs, None: lambda v: v, "neg": lambda v: -np.abs(v)}[case.get("arg_op")](x)
+        return (x,), kw
     if "src" in case:
         kw["S"] = np.abs(golden[case["src"]])
         return (), kw
@@ -76,6 +92,14 @@ def case_args(case, golden):
     return (), kw
 
 
-def call(namespace, case, golden):
+def resolve(root, case):
+    """``root`` is the reference / the drop-in package (functions under ``.feature`` or at top level) or the
+    flat oracle module."""
+    if case.get("ns") == "top":
+        return getattr(root, case["fn"])
+    return getattr(getattr(root, "feature", root), case["fn"])
+
+
+def call(root, case, golden):
     args, kw = case_args(case, golden)
-    return getattr(namespace, case["fn"])(*args, **kw)
+    return resolve(root, case)(*args, **kw)

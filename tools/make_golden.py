@@ -80,7 +80,7 @@ def main():
     for case in FEATURE_CASES:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            out = call(ref.feature, case, store)
+            out = call(ref, case, store)
         feats[case["name"]] = np.ascontiguousarray(out)
         print(f"{case['name']:40s} {out.shape} {out.dtype}")
     path = os.path.join(ROOT, "tests", "golden", "features_v1.npz")
