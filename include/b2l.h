@@ -159,6 +159,18 @@ int b2l_mel_project(b2l_ctx* ctx, const b2l_plan* plan, const float* d_S, int64_
  * (core/spectrum.py:1839-1883); in place when d_out == d_in. */
 int b2l_power_to_db(b2l_ctx* ctx, const float* d_in, int64_t n_clips, int64_t per_clip, float amin,
                     float ref_value, float top_db, float* d_out);
+/* Spectral-flux onset strength envelope of a dB-scaled spectrogram d_S [n_clips][n_rows][n_frames]
+ * (librosa/onset.py:445-640 onset_strength_multi; :217-367 onset_strength is channel 0 of the default call):
+ *   out [n_clips][n_channels][n_frames], channel c = mean over rows bounds[c] .. bounds[c+1]-1 of
+ *   max(0, S[m][t + lag] - maxfilter_rows(S, max_size)[m][t]), shifted right by pad_width frames
+ *   (lag, plus n_fft // (2 hop) when centred), optionally detrended (lfilter([1,-1],[1,-0.99])).
+ *   n_channels == 0: no aggregation, out [n_clips][n_rows][n_frames]. */
+typedef struct b2l_onset_desc {
+  int32_t lag, max_size, pad_width, detrend, n_channels;
+  int32_t bounds[33];
+} b2l_onset_desc;
+int b2l_onset_from_spec(b2l_ctx* ctx, const b2l_onset_desc* desc, const float* d_S, int64_t n_clips, int64_t n_rows,
+                        int64_t n_frames, float* d_out);
 /* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
  *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
  *                                                        of the squared magnitudes with ref^2 / amin^2

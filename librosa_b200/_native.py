@@ -65,6 +65,18 @@ class StatsDesc(C.Structure):
     ]
 
 
+class OnsetDesc(C.Structure):
+    """struct b2l_onset_desc (include/b2l.h)."""
+    _fields_ = [
+        ("lag", C.c_int32),
+        ("max_size", C.c_int32),
+        ("pad_width", C.c_int32),
+        ("detrend", C.c_int32),
+        ("n_channels", C.c_int32),
+        ("bounds", C.c_int32 * 33),
+    ]
+
+
 N_STATS = 6
 STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
 FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
@@ -116,6 +128,7 @@ def _declare(lib):
         "b2l_istft": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64]),
         "b2l_mel_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_power_to_db": (C.c_int, [_vp, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp]),
+        "b2l_onset_from_spec": (C.c_int, [_vp, P(OnsetDesc), _vp, _i64, _i64, _i64, _vp]),
         "b2l_unary": (C.c_int, [_vp, C.c_int32, _vp, _i64, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),

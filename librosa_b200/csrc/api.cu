@@ -1289,6 +1289,43 @@ extern "C" int b2l_power_to_db(b2l_ctx* c, const float* d_in, int64_t n_clips, i
   return B2L_OK;
 }
 
+extern "C" int b2l_onset_from_spec(b2l_ctx* c, const b2l_onset_desc* d, const float* d_S, int64_t n_clips,
+                                   int64_t n_rows, int64_t n_frames, float* d_out) {
+  if (!c || !d || !d_S || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (d->lag < 1) return fail(B2L_ERR_INVALID, "lag=%d must be a positive integer", d->lag);
+  if (d->max_size < 1) return fail(B2L_ERR_INVALID, "max_size=%d must be a positive integer", d->max_size);
+  if (d->pad_width < 0) return fail(B2L_ERR_INVALID, "negative pad_width");
+  if (d->n_channels < 0 || d->n_channels > 32) return fail(B2L_ERR_UNSUPPORTED, "at most 32 onset channels");
+  if (n_clips <= 0 || n_rows <= 0 || n_frames <= 0) return B2L_OK;
+  if (n_clips > 65535 || n_rows > 0x7fffffffLL || n_frames > 0x7fffffffLL)
+    return fail(B2L_ERR_UNSUPPORTED, "onset: batch too large");
+  OnsetArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i <= d->n_channels; ++i) {
+    a.bounds[i] = d->bounds[i];
+    if (a.bounds[i] < 0 || a.bounds[i] > n_rows || (i > 0 && a.bounds[i] < a.bounds[i - 1]))
+      return fail(B2L_ERR_INVALID, "channel boundaries must be non-decreasing row indices");
+  }
+  a.n_ch = d->n_channels;
+  a.lag = d->lag;
+  a.max_size = d->max_size;
+  a.pad_width = d->pad_width;
+  a.n_rows = (int)n_rows;
+  a.T = (int)n_frames;
+  DeviceGuard g(c->device);
+  dim3 grid((unsigned)((n_frames + 127) / 128), (unsigned)n_clips);
+  onset_kernel<<<grid, 128, 0, c->stream>>>(d_S, a, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  if (d->detrend) {
+    const long long rows = (long long)n_clips * (a.n_ch > 0 ? a.n_ch : a.n_rows);
+    detrend_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, c->stream>>>(d_out, rows, a.T);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  return B2L_OK;
+}
+
 extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);

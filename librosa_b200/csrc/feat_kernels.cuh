@@ -83,6 +83,65 @@ __global__ void frame_td_kernel(const float* __restrict__ y, long long clip_stri
   }
 }
 
+// Spectral-flux onset strength (librosa/onset.py:445-640, onset_strength_multi) from a dB-scaled spectrogram
+// S [clip][rows][T]:  env[c][t'] = mean_{m in channel c} max(0, S[m][t' + lag] - ref[m][t']),  ref = S after a
+// maximum filter of `max_size` rows (scipy.ndimage.maximum_filter1d, reflect boundary), then shifted right by
+// pad_width = lag (+ n_fft // (2 hop) when centred) and cut to T frames.  One thread per output frame, so
+// every row access is coalesced; n_ch == 0 writes the un-aggregated flux of every row (aggregate=False).
+struct OnsetArgs {
+  int bounds[33];
+  int n_ch, lag, max_size, pad_width, n_rows, T;
+};
+__global__ void onset_kernel(const float* __restrict__ S, OnsetArgs a, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.T) return;
+  const long long clip = blockIdx.y;
+  const float* Sc = S + clip * (long long)a.n_rows * a.T;
+  const int tp = t - a.pad_width;
+  const bool live = tp >= 0 && tp + a.lag < a.T;
+  const int n_out = a.n_ch > 0 ? a.n_ch : a.n_rows;
+  float* oc = out + clip * (long long)n_out * a.T + t;
+  auto flux = [&](int m) -> float {
+    float ref;
+    if (a.max_size == 1) {
+      ref = Sc[(long long)m * a.T + tp];
+    } else {
+      ref = -INFINITY;
+      const int lo = m - a.max_size / 2;
+      for (int j = 0; j < a.max_size; ++j) {
+        int mm = lo + j;
+        while (mm < 0 || mm >= a.n_rows) mm = mm < 0 ? -mm - 1 : 2 * a.n_rows - mm - 1;
+        ref = fmaxf(ref, Sc[(long long)mm * a.T + tp]);
+      }
+    }
+    return fmaxf(0.0f, Sc[(long long)m * a.T + tp + a.lag] - ref);
+  };
+  if (a.n_ch == 0) {
+    for (int m = 0; m < a.n_rows; ++m) oc[(long long)m * a.T] = live ? flux(m) : 0.0f;
+    return;
+  }
+  for (int c = 0; c < a.n_ch; ++c) {
+    float acc = 0.0f;
+    const int m0 = a.bounds[c], m1 = a.bounds[c + 1];
+    if (live)
+      for (int m = m0; m < m1; ++m) acc += flux(m);
+    oc[(long long)c * a.T] = live && m1 > m0 ? acc / (float)(m1 - m0) : (live ? __int_as_float(0x7fc00000) : 0.0f);
+  }
+}
+// detrend: scipy.signal.lfilter([1, -1], [1, -0.99]) along time (direct form II transposed), one thread per row
+__global__ void detrend_kernel(float* __restrict__ x, long long n_rows, int T) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  float* xr = x + r * T;
+  float z = 0.0f;
+  for (int t = 0; t < T; ++t) {
+    const float in = xr[t];
+    const float y = in + z;
+    z = -in + 0.99f * y;
+    xr[t] = y;
+  }
+}
+
 // Elementwise helpers of the dB conversions (librosa/core/spectrum.py):
 //   UNARY_SQUARE           x*x                        amplitude_to_db squares |S| before power_to_db (:2032-2037)
 //   UNARY_DB_TO_POWER      ref * 10^(0.1 x)           db_to_power (:1899-1925)

@@ -550,6 +550,75 @@ def zero_crossing_rate(y, frame_length=2048, hop_length=512, center=True, **kwar
     return np.mean(crossings, axis=-2, keepdims=True)
 
 
+# --------------------------------------------------------------------------- onset strength
+def _channel_slices(channels, n_rows, pad):
+    """``util.sync`` index handling (librosa/util/utils.py: sync, index_to_slice, fix_frames)."""
+    if all(isinstance(c, slice) for c in channels):
+        return list(channels)
+    frames = np.asarray(channels)
+    if np.any(frames < 0):
+        raise ParameterError("Negative frame index detected")
+    if pad:
+        frames = np.concatenate((np.asarray([0, n_rows]), np.clip(frames, 0, n_rows)))
+    frames = frames[(frames >= 0) & (frames <= n_rows)]
+    edges = np.unique(frames).astype(int)
+    return [slice(a, b) for a, b in zip(edges[:-1], edges[1:])]
+
+
+def onset_strength_multi(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, lag=1, max_size=1, ref=None,
+                         detrend=False, center=True, aggregate=None, channels=None, **kwargs):
+    """librosa/onset.py:566-640 with ``feature=melspectrogram``."""
+    import scipy.ndimage
+    import scipy.signal
+
+    kwargs.setdefault("fmax", 0.5 * sr)
+    if aggregate is None:
+        aggregate = np.mean
+    if not (isinstance(lag, (int, np.integer)) and lag > 0):
+        raise ParameterError(f"lag={lag} must be a positive integer")
+    if not (isinstance(max_size, (int, np.integer)) and max_size > 0):
+        raise ParameterError(f"max_size={max_size} must be a positive integer")
+    if S is None:
+        S = power_to_db(np.abs(melspectrogram(y=y, sr=sr, n_fft=n_fft, hop_length=hop_length, **kwargs)))
+    S = np.atleast_2d(S)
+    if ref is None:
+        ref = S if max_size == 1 else scipy.ndimage.maximum_filter1d(S, max_size, axis=-2)
+    elif ref.shape != S.shape:
+        raise ParameterError(f"Reference spectrum shape {ref.shape} must match input spectrum {S.shape}")
+    onset_env = np.maximum(0.0, S[..., lag:] - ref[..., :-lag])
+    pad = True
+    if channels is None:
+        channels = [slice(None)]
+    else:
+        pad = False
+    if callable(aggregate):
+        slices = _channel_slices(channels, onset_env.shape[-2], pad)
+        agg = np.empty(onset_env.shape[:-2] + (len(slices), onset_env.shape[-1]), dtype=onset_env.dtype)
+        for i, seg in enumerate(slices):
+            agg[..., i, :] = aggregate(onset_env[..., seg, :], axis=-2)
+        onset_env = agg
+    pad_width = lag
+    if center:
+        pad_width += n_fft // (2 * hop_length)
+    padding = [(0, 0)] * onset_env.ndim
+    padding[-1] = (int(pad_width), 0)
+    onset_env = np.pad(onset_env, padding, mode="constant")
+    if detrend:
+        onset_env = scipy.signal.lfilter([1.0, -1.0], [1.0, -0.99], onset_env, axis=-1)
+    if center:
+        onset_env = onset_env[..., : S.shape[-1]]
+    return onset_env
+
+
+def onset_strength(y=None, sr=22050, S=None, lag=1, max_size=1, ref=None, detrend=False, center=True,
+                   aggregate=None, **kwargs):
+    """librosa/onset.py:346-367."""
+    if aggregate is False:
+        raise ParameterError("aggregate parameter cannot be False when computing full-spectrum onset strength.")
+    return onset_strength_multi(y=y, sr=sr, S=S, lag=lag, max_size=max_size, ref=ref, detrend=detrend, center=center,
+                                aggregate=aggregate, channels=None, **kwargs)[..., 0, :]
+
+
 def griffinlim(S, n_iter=32, hop_length=None, win_length=None, n_fft=None, window="hann", center=True,
                dtype=None, length=None, pad_mode="constant", momentum=0.99, init="random", rng=None):
     """Fast Griffin-Lim, restating librosa/core/spectrum.py:2819-2917 (first "next" row of SURVEY 8f)."""

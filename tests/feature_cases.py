@@ -68,6 +68,18 @@ FEATURE_CASES += [
     dict(name="db_to_amplitude_ref", fn="db_to_amplitude", ns="top", arg="const/power_to_db_out_top40", kw=dict(ref=0.25)),
 ]
 
+FEATURE_CASES += [
+    # ---- onset strength (librosa.onset): default mel / dB / flux, sub-bands, max filter, detrend, S= input
+    dict(name="onset_default_A", fn="onset_strength", ns="onset", mix="A", shape=(20000,), kw=dict(sr=22050)),
+    dict(name="onset_default_C_burst", fn="onset_strength", ns="onset", mix="C", shape=(20000,), kw=dict(sr=22050)),
+    dict(name="onset_stereo_lag2_max3_B", fn="onset_strength", ns="onset", mix="B", shape=(2, 16000), kw=dict(sr=16000, lag=2, max_size=3, n_fft=1024, hop_length=256)),
+    dict(name="onset_detrend_nocenter_C", fn="onset_strength", ns="onset", mix="C", shape=(20000,), kw=dict(sr=22050, detrend=True, center=False)),
+    dict(name="onset_max4_nmels64_A", fn="onset_strength", ns="onset", mix="A", shape=(12000,), kw=dict(sr=22050, max_size=4, n_mels=64, fmax=8000.0)),
+    dict(name="onset_multi_4bands_C", fn="onset_strength_multi", ns="onset", mix="C", shape=(20000,), kw=dict(sr=22050, channels=[0, 32, 64, 96, 128])),
+    dict(name="onset_multi_noagg_B", fn="onset_strength_multi", ns="onset", mix="B", shape=(9000,), kw=dict(sr=22050, aggregate=False, n_mels=40)),
+    dict(name="onset_fromS_db", fn="onset_strength", ns="onset", src_db="mel_22050_2048_C", kw=dict(sr=22050)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 
@@ -80,6 +92,10 @@ def case_args(case, golden):
         x = golden[case["arg"]]
         x = {"abs": np.abs, None: lambda v: v, "neg": lambda v: -np.abs(v)}[case.get("arg_op")](x)
         return (x,), kw
+    if "src_db" in case:        # S= form of the onset functions: a dB-scaled mel spectrogram
+        p = golden[case["src_db"]]
+        kw["S"] = (10.0 * np.log10(np.maximum(1e-10, p))).astype(np.float32)
+        return (), kw
     if "src" in case:
         kw["S"] = np.abs(golden[case["src"]])
         return (), kw
@@ -97,6 +113,8 @@ def resolve(root, case):
     flat oracle module."""
     if case.get("ns") == "top":
         return getattr(root, case["fn"])
+    if case.get("ns") == "onset":
+        return getattr(getattr(root, "onset", root), case["fn"])
     return getattr(getattr(root, "feature", root), case["fn"])
 
 

@@ -10,6 +10,7 @@ Stated tolerances (float32 pipeline vs the reference's float64 FFT):
     spectral_flatness               rtol 1e-4, atol 1e-7
     rms                             rtol 1e-4, atol 1e-7 * max|ref|
     zero_crossing_rate              exact
+    onset_strength(_multi)          rtol 1e-4, atol 1e-3 (dB-domain, as for mfcc)
     amplitude_to_db                 rtol 1e-5, atol 1e-4 dB (elementwise on identical input)
     db_to_power / db_to_amplitude   rtol 1e-5
 """
@@ -87,6 +88,8 @@ def test_feature_case_against_oracle_and_reference_fixture(case, lb, oracle, gol
             _close(got, ref, 1e-4, 1e-7)
         elif fn == "rms":
             _close(got, ref, 1e-4, 1e-7 * scale)
+        elif fn in ("onset_strength", "onset_strength_multi"):
+            _close(got, ref, 1e-4, 1e-3)          # means of dB differences: same absolute term as mfcc
         elif fn == "amplitude_to_db":
             _close(got, ref, 1e-5, 1e-4)          # same input array on both sides: only log10f rounding
         elif fn in ("db_to_power", "db_to_amplitude"):
