@@ -171,6 +171,17 @@ typedef struct b2l_onset_desc {
 } b2l_onset_desc;
 int b2l_onset_from_spec(b2l_ctx* ctx, const b2l_onset_desc* desc, const float* d_S, int64_t n_clips, int64_t n_rows,
                         int64_t n_frames, float* d_out);
+/* Per-channel energy normalisation, librosa.pcen (core/spectrum.py:2396-2666), of d_S [n_clips][n_rows][n_frames]
+ * along time: first-order IIR smoother with coefficient b (lfilter([b], [1, b-1])), adaptive gain and root
+ * compression.  d_zi / d_zf: optional initial / final filter state, one float per (clip, row) (NULL: the
+ * lfilter_zi steady state 1 - b / not returned).  max_size > 1 max-filters the smoother's input over rows
+ * (scipy.ndimage.maximum_filter1d) into d_scratch (same size as S).  In place when d_out == d_S and max_size == 1. */
+typedef struct b2l_pcen_desc {
+  float gain, bias, power, eps, b;
+  int32_t max_size;
+} b2l_pcen_desc;
+int b2l_pcen(b2l_ctx* ctx, const b2l_pcen_desc* desc, const float* d_S, int64_t n_clips, int64_t n_rows,
+             int64_t n_frames, const float* d_zi, float* d_zf, float* d_scratch, float* d_out);
 /* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
  *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
  *                                                        of the squared magnitudes with ref^2 / amin^2

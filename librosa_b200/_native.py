@@ -77,6 +77,12 @@ class OnsetDesc(C.Structure):
     ]
 
 
+class PcenDesc(C.Structure):
+    """struct b2l_pcen_desc (include/b2l.h)."""
+    _fields_ = [("gain", C.c_float), ("bias", C.c_float), ("power", C.c_float), ("eps", C.c_float), ("b", C.c_float),
+                ("max_size", C.c_int32)]
+
+
 N_STATS = 6
 STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
 FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
@@ -129,6 +135,7 @@ def _declare(lib):
         "b2l_mel_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_power_to_db": (C.c_int, [_vp, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp]),
         "b2l_onset_from_spec": (C.c_int, [_vp, P(OnsetDesc), _vp, _i64, _i64, _i64, _vp]),
+        "b2l_pcen": (C.c_int, [_vp, P(PcenDesc), _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
         "b2l_unary": (C.c_int, [_vp, C.c_int32, _vp, _i64, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),

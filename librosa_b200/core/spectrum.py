@@ -17,7 +17,7 @@ from .. import _native as nat
 from .. import _pipeline as pl
 from .. import filters
 from ..util.exceptions import ParameterError
-from ..util.utils import dtype_c2r, dtype_r2c, fix_length, tiny
+from ..util.utils import dtype_c2r, dtype_r2c, fix_length, is_positive_int, tiny
 
 _vp = C.c_void_p
 
@@ -363,6 +363,96 @@ def db_to_power(S_db, *, ref: float = 1.0):
 def db_to_amplitude(S_db, *, ref: float = 1.0):
     """``db_to_power(S_db, ref=ref**2) ** 0.5``; mirror of core/spectrum.py:2054-2081."""
     return _db_inverse(S_db, nat.UNARY_DB_TO_AMPLITUDE, float(ref) ** 2)
+
+
+def pcen(S, *, sr: float = 22050, hop_length: int = 512, gain: float = 0.98, bias: float = 2, power: float = 0.5,
+         time_constant: float = 0.400, eps: float = 1e-6, b: Optional[float] = None, max_size: int = 1, ref=None,
+         axis: int = -1, max_axis: Optional[int] = None, zi=None, return_zf: bool = False):
+    """Per-channel energy normalisation; mirror of core/spectrum.py:2396-2666 for spectrograms laid out
+    ``(..., bins, frames)`` (``axis=-1``, ``max_axis=-2``).  Like the reference, host results are float64
+    (SciPy's ``lfilter`` promotes); the arithmetic on the GPU is float32."""
+    if power < 0:
+        raise ParameterError(f"power={power} must be nonnegative")
+    if gain < 0:
+        raise ParameterError(f"gain={gain} must be non-negative")
+    if bias < 0:
+        raise ParameterError(f"bias={bias} must be non-negative")
+    if eps <= 0:
+        raise ParameterError(f"eps={eps} must be strictly positive")
+    if time_constant <= 0:
+        raise ParameterError(f"time_constant={time_constant} must be strictly positive")
+    if not is_positive_int(max_size):
+        raise ParameterError(f"max_size={max_size} must be a positive integer")
+    if b is None:
+        t_frames = time_constant * sr / float(hop_length)
+        b = (np.sqrt(1 + 4 * t_frames ** 2) - 1) / (2 * t_frames ** 2)
+    if not 0 <= b <= 1:
+        raise ParameterError(f"b={b} must be between 0 and 1")
+    on_device = isinstance(S, nat.DeviceArray)
+    if not on_device:
+        S = np.asarray(S)
+        if np.issubdtype(S.dtype, np.complexfloating):
+            warnings.warn("pcen was called on complex input so phase information will be discarded. "
+                          "To suppress this warning, call pcen(np.abs(D)) instead.", stacklevel=2)
+            S = np.abs(S)
+    ndim = S.ndim
+    if ref is not None:
+        raise nat.UnsupportedOnGPU("pcen(ref=...) is not supported on the GPU (no CPU fallback)")
+    if axis not in (-1, ndim - 1):
+        raise nat.UnsupportedOnGPU("pcen on the GPU filters along the last axis (axis=-1)")
+    if max_size > 1:
+        if ndim == 1:
+            raise ParameterError("Max-filtering cannot be applied to 1-dimensional input")
+        if max_axis is None:
+            if ndim != 2:
+                raise ParameterError(f"Max-filtering a {ndim:d}-dimensional spectrogram requires you to specify max_axis")
+            max_axis = 0
+        if max_axis not in (-2, ndim - 2):
+            raise nat.UnsupportedOnGPU("pcen on the GPU max-filters along the second-to-last axis (max_axis=-2)")
+    ctx = S.ctx if on_device else nat.default_context()
+    if on_device:
+        if S.dtype != np.float32 or S.layout != "c":
+            raise ParameterError("device input must be a C-ordered float32 DeviceArray")
+        dev, req = S, np.dtype(np.float32)
+    else:
+        if not np.issubdtype(S.dtype, np.floating):
+            S = S.astype(np.float32)
+        req = pl.check_real_dtype(S.dtype, "pcen input")
+        dev = ctx.to_device(np.ascontiguousarray(S, dtype=np.float32))
+    T = dev.shape[-1]
+    rows = dev.shape[-2] if ndim >= 2 else 1
+    lead = dev.shape[:-2] if ndim >= 2 else ()
+    n_lead = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    state_shape = dev.shape[:-1] + (1,)
+    d_zi = None
+    if zi is not None:
+        zi = np.asarray(zi, dtype=np.float64)
+        try:
+            zi_full = np.broadcast_to(zi, state_shape)
+        except ValueError as exc:
+            raise ValueError(f"zi has shape {zi.shape}, expected a shape broadcastable to {state_shape}") from exc
+        d_zi = ctx.to_device(np.ascontiguousarray(zi_full, dtype=np.float32))
+    d_zf = nat.DeviceArray.empty(ctx, state_shape, np.float32) if return_zf else None
+    out = nat.DeviceArray.empty(ctx, dev.shape, np.float32)
+    scratch = nat.DeviceArray.empty(ctx, dev.shape, np.float32) if max_size > 1 else None
+    desc = nat.PcenDesc(gain=float(gain), bias=float(bias), power=float(power), eps=float(eps), b=float(b),
+                        max_size=int(max_size))
+    nat.check(nat.lib().b2l_pcen(ctx.handle, C.byref(desc), _vp(dev.ptr), n_lead, rows, T,
+                                 _vp(d_zi.ptr if d_zi is not None else None),
+                                 _vp(d_zf.ptr if d_zf is not None else None),
+                                 _vp(scratch.ptr if scratch is not None else None), _vp(out.ptr)))
+    if scratch is not None:
+        scratch.free()
+    if d_zi is not None:
+        d_zi.free()
+    if on_device:
+        return (out, d_zf) if return_zf else out
+    dev.free()
+    res_dtype = np.result_type(req, np.float64)
+    res = pl.finish(ctx, out, True, res_dtype)
+    if return_zf:
+        return res, pl.finish(ctx, d_zf, True, res_dtype)
+    return res
 
 
 def griffinlim(S, *, n_iter: int = 32, hop_length: Optional[int] = None, win_length: Optional[int] = None,

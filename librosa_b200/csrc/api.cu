@@ -1326,6 +1326,42 @@ extern "C" int b2l_onset_from_spec(b2l_ctx* c, const b2l_onset_desc* d, const fl
   return B2L_OK;
 }
 
+extern "C" int b2l_pcen(b2l_ctx* c, const b2l_pcen_desc* d, const float* d_S, int64_t n_clips, int64_t n_rows,
+                        int64_t n_frames, const float* d_zi, float* d_zf, float* d_scratch, float* d_out) {
+  if (!c || !d || !d_S || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (d->power < 0.0f) return fail(B2L_ERR_INVALID, "power=%g must be nonnegative", d->power);
+  if (d->gain < 0.0f) return fail(B2L_ERR_INVALID, "gain=%g must be non-negative", d->gain);
+  if (d->bias < 0.0f) return fail(B2L_ERR_INVALID, "bias=%g must be non-negative", d->bias);
+  if (!(d->eps > 0.0f)) return fail(B2L_ERR_INVALID, "eps=%g must be strictly positive", d->eps);
+  if (!(d->b >= 0.0f && d->b <= 1.0f)) return fail(B2L_ERR_INVALID, "b=%g must be between 0 and 1", d->b);
+  if (d->max_size < 1) return fail(B2L_ERR_INVALID, "max_size=%d must be a positive integer", d->max_size);
+  if (n_clips <= 0 || n_rows <= 0 || n_frames <= 0) return B2L_OK;
+  if (n_frames > 0x7fffffffLL || n_rows > 65535 || n_clips > 65535) return fail(B2L_ERR_UNSUPPORTED, "pcen: batch too large");
+  DeviceGuard g(c->device);
+  const float* ref = d_S;
+  if (d->max_size > 1) {
+    if (!d_scratch) return fail(B2L_ERR_INVALID, "max_size > 1 needs a scratch buffer of the size of S");
+    dim3 grid((unsigned)((n_frames + 127) / 128), (unsigned)n_rows, (unsigned)n_clips);
+    maxfilter_rows_kernel<<<grid, 128, 0, c->stream>>>(d_S, (int)n_rows, (int)n_frames, d->max_size, d_scratch);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    ref = d_scratch;
+  }
+  PcenArgs a;
+  a.gain = d->gain;
+  a.bias = d->bias;
+  a.power = d->power;
+  a.eps = d->eps;
+  a.b = d->b;
+  a.mode = d->power == 0.0f ? 0 : (d->bias == 0.0f ? 1 : 2);
+  const long long rows = (long long)n_clips * n_rows;
+  const long long blocks = (rows + 127) / 128;
+  pcen_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(d_S, ref, rows, (int)n_frames, a, d_zi, d_zf, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);

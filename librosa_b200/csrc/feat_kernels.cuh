@@ -142,6 +142,73 @@ __global__ void detrend_kernel(float* __restrict__ x, long long n_rows, int T) {
   }
 }
 
+// Per-channel energy normalisation (librosa/core/spectrum.py:2396-2666, pcen) of S [n_rows][T] (time contiguous):
+//   M[t] = b * ref[t] + (1 - b) * M[t-1]              scipy.signal.lfilter([b], [1, b-1], ref, zi)  (:2629)
+//   smooth = exp(-gain * (log(eps) + log1p(M / eps)))                                             (:2633)
+//   out = log1p(S*smooth) | exp(power*(log S + log smooth)) | bias^power * expm1(power*log1p(S*smooth/bias))
+// The recurrence is sequential in time and independent per row: a warp takes 32 rows, stages 32 x 32 tiles
+// through shared memory so that global accesses are coalesced along time while each lane walks its own row.
+struct PcenArgs {
+  float gain, bias, power, eps, b;
+  int mode;            // 0: power == 0, 1: bias == 0, 2: general
+};
+__global__ void pcen_kernel(const float* __restrict__ S, const float* __restrict__ ref, long long n_rows, int T,
+                            PcenArgs a, const float* __restrict__ zi, float* __restrict__ zf, float* __restrict__ out) {
+  __shared__ float s_s[4][32][33], s_r[4][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * 4 + warp) * 32;
+  if (row0 >= n_rows) return;
+  const long long my_row = row0 + lane;
+  float z = (my_row < n_rows && zi) ? zi[my_row] : 1.0f - a.b;      // lfilter_zi([b], [1, b-1]) = 1 - b
+  const float log_eps = logf(a.eps), inv_eps = 1.0f / a.eps, bias_pow = powf(a.bias, a.power);
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int tn = min(32, T - t0);
+    for (int r = 0; r < 32; ++r) {
+      const long long row = row0 + r;
+      if (row < n_rows && lane < tn) {
+        s_s[warp][r][lane] = S[row * T + t0 + lane];
+        s_r[warp][r][lane] = ref[row * T + t0 + lane];
+      }
+    }
+    __syncwarp();
+    if (my_row < n_rows) {
+      for (int i = 0; i < tn; ++i) {
+        const float x = s_s[warp][lane][i];
+        const float m = fmaf(a.b, s_r[warp][lane][i], z);
+        z = (1.0f - a.b) * m;
+        const float log_smooth = -a.gain * (log_eps + log1pf(m * inv_eps));
+        float o;
+        if (a.mode == 0) o = log1pf(x * expf(log_smooth));
+        else if (a.mode == 1) o = expf(a.power * (logf(x) + log_smooth));
+        else o = bias_pow * expm1f(a.power * log1pf(x * expf(log_smooth) / a.bias));
+        s_s[warp][lane][i] = o;
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+      const long long row = row0 + r;
+      if (row < n_rows && lane < tn) out[row * T + t0 + lane] = s_s[warp][r][lane];
+    }
+    __syncwarp();
+  }
+  if (zf && my_row < n_rows) zf[my_row] = z;
+}
+// scipy.ndimage.maximum_filter1d along the row axis of [clip][rows][T] blocks (reflect boundary)
+__global__ void maxfilter_rows_kernel(const float* __restrict__ S, int rows, int T, int size, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int m = blockIdx.y;
+  const float* Sc = S + (long long)blockIdx.z * rows * T;
+  float v = -INFINITY;
+  const int lo = m - size / 2;
+  for (int j = 0; j < size; ++j) {
+    int mm = lo + j;
+    while (mm < 0 || mm >= rows) mm = mm < 0 ? -mm - 1 : 2 * rows - mm - 1;
+    v = fmaxf(v, Sc[(long long)mm * T + t]);
+  }
+  out[((long long)blockIdx.z * rows + m) * T + t] = v;
+}
+
 // Elementwise helpers of the dB conversions (librosa/core/spectrum.py):
 //   UNARY_SQUARE           x*x                        amplitude_to_db squares |S| before power_to_db (:2032-2037)
 //   UNARY_DB_TO_POWER      ref * 10^(0.1 x)           db_to_power (:1899-1925)

@@ -550,6 +550,56 @@ def zero_crossing_rate(y, frame_length=2048, hop_length=512, center=True, **kwar
     return np.mean(crossings, axis=-2, keepdims=True)
 
 
+def pcen(S, sr=22050, hop_length=512, gain=0.98, bias=2, power=0.5, time_constant=0.400, eps=1e-6, b=None,
+         max_size=1, ref=None, axis=-1, max_axis=None, zi=None, return_zf=False):
+    """librosa/core/spectrum.py:2576-2666."""
+    import scipy.ndimage
+    import scipy.signal
+
+    if power < 0:
+        raise ParameterError(f"power={power} must be nonnegative")
+    if gain < 0:
+        raise ParameterError(f"gain={gain} must be non-negative")
+    if bias < 0:
+        raise ParameterError(f"bias={bias} must be non-negative")
+    if eps <= 0:
+        raise ParameterError(f"eps={eps} must be strictly positive")
+    if time_constant <= 0:
+        raise ParameterError(f"time_constant={time_constant} must be strictly positive")
+    if not (isinstance(max_size, (int, np.integer)) and max_size > 0):
+        raise ParameterError(f"max_size={max_size} must be a positive integer")
+    if b is None:
+        t_frames = time_constant * sr / float(hop_length)
+        b = (np.sqrt(1 + 4 * t_frames ** 2) - 1) / (2 * t_frames ** 2)
+    if not 0 <= b <= 1:
+        raise ParameterError(f"b={b} must be between 0 and 1")
+    if np.issubdtype(S.dtype, np.complexfloating):
+        S = np.abs(S)
+    if ref is None:
+        if max_size == 1:
+            ref = S
+        elif S.ndim == 1:
+            raise ParameterError("Max-filtering cannot be applied to 1-dimensional input")
+        else:
+            if max_axis is None:
+                if S.ndim != 2:
+                    raise ParameterError(f"Max-filtering a {S.ndim:d}-dimensional spectrogram requires you to specify max_axis")
+                max_axis = np.mod(1 - axis, 2)
+            ref = scipy.ndimage.maximum_filter1d(S, max_size, axis=max_axis)
+    if zi is None:
+        zi = np.empty(tuple([1] * ref.ndim))
+        zi[:] = scipy.signal.lfilter_zi([b], [1, b - 1])[:]
+    S_smooth, zf = scipy.signal.lfilter([b], [1, b - 1], ref, zi=zi, axis=axis)
+    smooth = np.exp(-gain * (np.log(eps) + np.log1p(S_smooth / eps)))
+    if power == 0:
+        S_out = np.log1p(S * smooth)
+    elif bias == 0:
+        S_out = np.exp(power * (np.log(S) + np.log(smooth)))
+    else:
+        S_out = (bias ** power) * np.expm1(power * np.log1p(S * smooth / bias))
+    return (S_out, zf) if return_zf else S_out
+
+
 # --------------------------------------------------------------------------- onset strength
 def _channel_slices(channels, n_rows, pad):
     """``util.sync`` index handling (librosa/util/utils.py: sync, index_to_slice, fix_frames)."""

@@ -80,6 +80,16 @@ FEATURE_CASES += [
     dict(name="onset_fromS_db", fn="onset_strength", ns="onset", src_db="mel_22050_2048_C", kw=dict(sr=22050)),
 ]
 
+FEATURE_CASES += [
+    # ---- pcen (top level): defaults on a mel power spectrogram scaled as in the reference's docstring
+    dict(name="pcen_default", fn="pcen", ns="top", arg="mel_22050_2048_B", arg_op="scale31", kw=dict(sr=22050)),
+    dict(name="pcen_stereo_explicit_b", fn="pcen", ns="top", arg="mel_16000_1024_stereo_A", arg_op="scale31", kw=dict(sr=16000, hop_length=256, b=0.1, gain=0.8, bias=10, power=0.25)),
+    dict(name="pcen_power0", fn="pcen", ns="top", arg="mel_22050_2048_C", arg_op="scale31", kw=dict(power=0)),
+    dict(name="pcen_bias0", fn="pcen", ns="top", arg="mel_22050_2048_A", kw=dict(bias=0, eps=1e-3)),
+    dict(name="pcen_max3", fn="pcen", ns="top", arg="mel_22050_2048_B", arg_op="scale31", kw=dict(max_size=3)),
+    dict(name="pcen_max2_stereo_maxaxis", fn="pcen", ns="top", arg="mel_16000_1024_stereo_A", arg_op="scale31", kw=dict(max_size=2, max_axis=-2, time_constant=0.1)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 
@@ -90,7 +100,7 @@ def case_args(case, golden):
     kw = dict(case["kw"])
     if "arg" in case:           # positional array taken from the hot-path fixtures, optionally transformed
         x = golden[case["arg"]]
-        x = {"abs": np.abs, None: lambda v: v, "neg": lambda v: -np.abs(v)}[case.get("arg_op")](x)
+        x = {"abs": np.abs, None: lambda v: v, "scale31": lambda v: v * np.float32(2 ** 31)}[case.get("arg_op")](x)
         return (x,), kw
     if "src_db" in case:        # S= form of the onset functions: a dB-scaled mel spectrogram
         p = golden[case["src_db"]]

@@ -11,6 +11,7 @@ Stated tolerances (float32 pipeline vs the reference's float64 FFT):
     rms                             rtol 1e-4, atol 1e-7 * max|ref|
     zero_crossing_rate              exact
     onset_strength(_multi)          rtol 1e-4, atol 1e-3 (dB-domain, as for mfcc)
+    pcen                            rtol 1e-4, atol 1e-6 * max|ref|
     amplitude_to_db                 rtol 1e-5, atol 1e-4 dB (elementwise on identical input)
     db_to_power / db_to_amplitude   rtol 1e-5
 """
@@ -90,6 +91,8 @@ def test_feature_case_against_oracle_and_reference_fixture(case, lb, oracle, gol
             _close(got, ref, 1e-4, 1e-7 * scale)
         elif fn in ("onset_strength", "onset_strength_multi"):
             _close(got, ref, 1e-4, 1e-3)          # means of dB differences: same absolute term as mfcc
+        elif fn == "pcen":
+            _close(got, ref, 1e-4, 1e-6 * scale)
         elif fn == "amplitude_to_db":
             _close(got, ref, 1e-5, 1e-4)          # same input array on both sides: only log10f rounding
         elif fn in ("db_to_power", "db_to_amplitude"):
@@ -133,6 +136,39 @@ def test_rms_from_rectangular_stft_matches_rms_from_samples(lb):
     a = lb.feature.rms(S=S)
     b = lb.feature.rms(y=y, center=False)
     np.testing.assert_allclose(a, b, rtol=2e-5)
+
+
+def test_pcen_streaming_state_matches_one_shot(lb, oracle, golden):
+    """zi / return_zf: filtering two halves with the carried state equals one call (the reference's streaming
+    contract, core/spectrum.py:2514-2527), and both match the oracle."""
+    S = (golden["mel_16000_1024_stereo_A"] * np.float32(2 ** 31)).astype(np.float32)
+    full, zf_full = lb.pcen(S, sr=16000, hop_length=256, return_zf=True)
+    a, zf_a = lb.pcen(S[..., :10], sr=16000, hop_length=256, return_zf=True)
+    b, zf_b = lb.pcen(S[..., 10:], sr=16000, hop_length=256, zi=zf_a, return_zf=True)
+    assert zf_a.shape == S.shape[:-1] + (1,) and full.dtype == np.float64
+    np.testing.assert_allclose(np.concatenate([a, b], axis=-1), full, rtol=2e-6)
+    np.testing.assert_allclose(zf_b, zf_full, rtol=2e-6)
+    want, want_zf = oracle.pcen(S, sr=16000, hop_length=256, return_zf=True)
+    np.testing.assert_allclose(full, want, rtol=1e-4, atol=1e-6 * float(want.max()))
+    np.testing.assert_allclose(zf_full, want_zf, rtol=1e-4)
+    d = lb.pcen(lb.to_device(S), sr=16000, hop_length=256)
+    assert isinstance(d, lb.DeviceArray)
+    np.testing.assert_allclose(d.get(), full.astype(np.float32), rtol=1e-6)
+
+
+def test_onset_device_resident_and_full_size(lb):
+    """cfg-2 sized batch through onset_strength on the device: mel -> dB -> flux, only the envelope comes back."""
+    rng = np.random.default_rng(1)
+    y = (0.1 * rng.standard_normal((256, 220500))).astype(np.float32)
+    y[:, 110250:110250 + 2048] *= 20.0                      # one loud burst in the middle of every clip
+    env = lb.onset.onset_strength(y=lb.to_device(y), sr=22050)
+    assert isinstance(env, lb.DeviceArray) and env.shape == (256, 431)
+    e = env.get()
+    assert np.all(e >= 0) and np.all(e[:, :3] == 0)          # lag + centring shift are zero filled
+    peak = e.argmax(axis=-1)
+    assert np.all(np.abs(peak - (110250 // 512 + 1)) <= 4)    # the flux peaks where the burst starts
+    h = lb.onset.onset_strength(y=y[:4], sr=22050)
+    np.testing.assert_allclose(h, e[:4], rtol=1e-5, atol=1e-5)
 
 
 def test_error_behaviour_on_device(lb):
