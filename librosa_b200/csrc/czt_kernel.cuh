@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
           a.out_c[o] = X;
         } else {
           float p2 = sqmag(X);
-          a.out_r[o] = a.power_mode == 2 ? p2 : power_from_sq(p2, a.power_mode, a.power);
+          a.out_r[o] = a.power_mode == 2 ? p2 : (a.power_mode == 1 ? sqrt_approx(p2) : power_from_sq(p2, a.power_mode, a.power));
         }
       }
     });

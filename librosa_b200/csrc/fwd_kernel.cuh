@@ -97,6 +97,11 @@ static __device__ __noinline__ float power_from_sq(float p2, int power_mode, flo
   return power_mode == 1 ? mag : powf(mag, power);
 }
 __device__ __forceinline__ float sqmag(float2 x) { return fmaf(x.x, x.x, x.y * x.y); }
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // Exchange-buffer slot of Z[M - k] for k = t + TPF*c (the partner of bin k in the real-FFT un-mix).
 // For warp-multiple groups the padded index is affine in the lane with a compile-time offset.
@@ -340,7 +345,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         r2c_pair(zc, zc, make_float2(0.0f, -1.0f), xa, xb);
         pw[PPT] = sqmag(xa);
       }
-      if (a.power_mode != 2) {   // warp-uniform, cold for the default power = 2
+      if (MODE == MODE_STATS || a.power_mode == 1) {
+        // |X| (power = 1; the statistics of MODE_STATS are defined on it): MUFU-based square root, inline.
+        // sqrt.approx.f32 is accurate to 2^-23 relative; 33 calls of an out-of-line IEEE square root per
+        // thread and frame would cost as much as half the FFT.
+        static_for<0, PPT + 1>([&](auto S) { pw[decltype(S)::value] = sqrt_approx(pw[decltype(S)::value]); });
+      } else if (a.power_mode != 2) {   // warp-uniform, cold: general exponent through powf
         static_for<0, PPT + 1>([&](auto S) {
           pw[decltype(S)::value] = power_from_sq(pw[decltype(S)::value], a.power_mode, a.power);
         });
