@@ -182,6 +182,19 @@ typedef struct b2l_pcen_desc {
 } b2l_pcen_desc;
 int b2l_pcen(b2l_ctx* ctx, const b2l_pcen_desc* desc, const float* d_S, int64_t n_clips, int64_t n_rows,
              int64_t n_frames, const float* d_zi, float* d_zf, float* d_scratch, float* d_out);
+/* Spectral contrast, librosa.feature.spectral_contrast (feature/spectral.py:355-532): per frame and octave band
+ * the mean of the k[b] largest (peak) and k[b] smallest (valley) magnitudes among bins lo[b] .. lo[b]+count[b]-1
+ * of d_S [n_clips][n_frames][n_bins]; peak / valley [n_clips][n_bands][n_frames].  The caller derives the bands
+ * from the bin frequencies (:483-499) and finishes with power_to_db(peak) - power_to_db(valley) (b2l_power_to_db,
+ * b2l_sub) or peak - valley (linear=True). */
+typedef struct b2l_contrast_desc {
+  int32_t n_bands;   /* reference's n_bands + 1, at most 16 */
+  int32_t lo[16], count[16], k[16];
+} b2l_contrast_desc;
+int b2l_spectral_contrast(b2l_ctx* ctx, const b2l_contrast_desc* desc, const float* d_S, int64_t n_clips,
+                          int64_t n_frames, int32_t n_bins, float* d_peak, float* d_valley);
+/* out = x - y over n floats */
+int b2l_sub(b2l_ctx* ctx, const float* d_x, const float* d_y, int64_t n, float* d_out);
 /* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
  *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
  *                                                        of the squared magnitudes with ref^2 / amin^2

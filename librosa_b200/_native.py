@@ -83,6 +83,11 @@ class PcenDesc(C.Structure):
                 ("max_size", C.c_int32)]
 
 
+class ContrastDesc(C.Structure):
+    """struct b2l_contrast_desc (include/b2l.h)."""
+    _fields_ = [("n_bands", C.c_int32), ("lo", C.c_int32 * 16), ("count", C.c_int32 * 16), ("k", C.c_int32 * 16)]
+
+
 N_STATS = 6
 STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
 FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
@@ -136,6 +141,8 @@ def _declare(lib):
         "b2l_power_to_db": (C.c_int, [_vp, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp]),
         "b2l_onset_from_spec": (C.c_int, [_vp, P(OnsetDesc), _vp, _i64, _i64, _i64, _vp]),
         "b2l_pcen": (C.c_int, [_vp, P(PcenDesc), _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+        "b2l_spectral_contrast": (C.c_int, [_vp, P(ContrastDesc), _vp, _i64, _i64, C.c_int32, _vp, _vp]),
+        "b2l_sub": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
         "b2l_unary": (C.c_int, [_vp, C.c_int32, _vp, _i64, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),

@@ -1362,6 +1362,54 @@ extern "C" int b2l_pcen(b2l_ctx* c, const b2l_pcen_desc* d, const float* d_S, in
   return B2L_OK;
 }
 
+extern "C" int b2l_spectral_contrast(b2l_ctx* c, const b2l_contrast_desc* d, const float* d_S, int64_t n_clips,
+                                     int64_t n_frames, int32_t n_bins, float* d_peak, float* d_valley) {
+  if (!c || !d || !d_S || !d_peak || !d_valley) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (d->n_bands < 1 || d->n_bands > 16) return fail(B2L_ERR_UNSUPPORTED, "1 to 16 bands (n_bands + 1) are supported");
+  if (n_clips <= 0 || n_frames <= 0) return B2L_OK;
+  ContrastArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_bands = d->n_bands;
+  int max_count = 1;
+  for (int b = 0; b < d->n_bands; ++b) {
+    if (d->lo[b] < 0 || d->count[b] < 0 || d->lo[b] + d->count[b] > n_bins || d->k[b] < 1)
+      return fail(B2L_ERR_INVALID, "band %d: bad bin range / tail length", b);
+    a.lo[b] = d->lo[b];
+    a.count[b] = d->count[b];
+    a.k[b] = d->k[b];
+    max_count = std::max(max_count, d->count[b]);
+  }
+  int cap = 1;
+  while (cap < max_count) cap <<= 1;
+  DeviceGuard g(c->device);
+  const size_t per_warp = ((size_t)((n_bins + 3) & ~3) + cap) * 4;
+  int nw = 8;
+  while (nw > 1 && per_warp * nw > c->smem_optin) nw >>= 1;
+  const size_t smem = per_warp * nw;
+  if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_bins=%d rows do not fit in shared memory", n_bins);
+  CUDA_TRY(cudaFuncSetAttribute(contrast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  const long long rows = (long long)n_clips * n_frames;
+  long long grid = (rows + nw - 1) / nw;
+  const long long lim = (long long)c->sm_count * 8;
+  if (grid > lim) grid = lim;
+  contrast_kernel<<<(int)grid, nw * 32, smem, c->stream>>>(d_S, rows, (int)n_frames, n_bins, cap, a, d_peak, d_valley);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
+extern "C" int b2l_sub(b2l_ctx* c, const float* d_x, const float* d_y, int64_t n, float* d_out) {
+  if (!c || !d_x || !d_y || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (n <= 0) return B2L_OK;
+  DeviceGuard g(c->device);
+  long long grid = (n + 256LL * 8 - 1) / (256LL * 8);
+  if (grid > 8LL * c->sm_count) grid = 8LL * c->sm_count;
+  sub_kernel<<<(int)grid, 256, 0, c->stream>>>(d_x, d_y, n, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);

@@ -209,6 +209,69 @@ __global__ void maxfilter_rows_kernel(const float* __restrict__ S, int rows, int
   out[((long long)blockIdx.z * rows + m) * T + t] = v;
 }
 
+// Spectral contrast (librosa/feature/spectral.py:355-532): for every frame and octave band, the mean of the
+// `k` smallest (valley) and `k` largest (peak) magnitudes of the band's bins.  S [n_rows][F] (one row per frame,
+// bins contiguous); peak / valley [clip][n_bands][n_frames].  One warp per frame: the row is copied to shared
+// memory once, each band is copied into a power-of-two scratch (padded with +inf), sorted with a bitonic
+// network by the warp, and the two tails are averaged.
+struct ContrastArgs {
+  int lo[16], count[16], k[16];   // first bin, bins in the sub-band, tail length (>= 1)
+  int n_bands;
+};
+__global__ void contrast_kernel(const float* __restrict__ S, long long n_rows, int n_frames, int F, int sort_cap,
+                                ContrastArgs a, float* __restrict__ peak, float* __restrict__ valley) {
+  extern __shared__ __align__(16) float s_dyn[];
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Fp = (F + 3) & ~3;
+  float* s_row = s_dyn + (size_t)warp * (Fp + sort_cap);
+  float* s_sort = s_row + Fp;
+  for (long long r = (long long)blockIdx.x * nw + warp; r < n_rows; r += (long long)gridDim.x * nw) {
+    const float* src = S + r * F;
+    for (int i = lane; i < F; i += 32) s_row[i] = __ldg(src + i);
+    __syncwarp();
+    const long long clip = r / n_frames, frame = r % n_frames;
+    for (int b = 0; b < a.n_bands; ++b) {
+      const int n = a.count[b];
+      int N = 1;
+      while (N < n) N <<= 1;
+      for (int i = lane; i < N; i += 32) s_sort[i] = i < n ? s_row[a.lo[b] + i] : INFINITY;
+      __syncwarp();
+      for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < N; i += 32) {
+            const int p = i ^ j;
+            if (p > i) {
+              const float x = s_sort[i], y = s_sort[p];
+              if ((x > y) == ((i & k) == 0)) {
+                s_sort[i] = y;
+                s_sort[p] = x;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      const int kk = min(a.k[b], n);
+      float lo_sum = 0.0f, hi_sum = 0.0f;
+      for (int i = lane; i < kk; i += 32) {
+        lo_sum += s_sort[i];
+        hi_sum += s_sort[n - 1 - i];
+      }
+      lo_sum = warp_sum(lo_sum);
+      hi_sum = warp_sum(hi_sum);
+      if (lane == 0) {
+        const long long o = (clip * a.n_bands + b) * n_frames + frame;
+        valley[o] = lo_sum / (float)kk;       // n == 0: 0/0 = NaN, like the mean of an empty slice
+        peak[o] = hi_sum / (float)kk;
+      }
+      __syncwarp();
+    }
+  }
+}
+__global__ void sub_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = x[i] - y[i];
+}
+
 // Elementwise helpers of the dB conversions (librosa/core/spectrum.py):
 //   UNARY_SQUARE           x*x                        amplitude_to_db squares |S| before power_to_db (:2032-2037)
 //   UNARY_DB_TO_POWER      ref * 10^(0.1 x)           db_to_power (:1899-1925)

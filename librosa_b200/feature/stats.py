@@ -229,6 +229,107 @@ def spectral_flatness(*, y=None, S=None, n_fft: int = 2048, hop_length: int = 51
                       window=window, center=center, pad_mode=pad_mode)
 
 
+def spectral_contrast(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_length: int = 512,
+                      win_length: Optional[int] = None, window="hann", center: bool = True, pad_mode="constant",
+                      freq=None, fmin: float = 200.0, n_bands: int = 6, quantile: float = 0.02,
+                      linear: bool = False):
+    """Spectral contrast, shape ``(..., n_bands + 1, t)``; same contract as
+    ``librosa.feature.spectral_contrast`` (the bins of every octave band must be contiguous, which holds for
+    any increasing ``freq``)."""
+    from ..core.spectrum import _spectrogram, power_to_db
+    from .spectral import _spec_to_device
+
+    to_host, validate = True, False
+    if S is None:
+        if y is None:
+            raise ParameterError("Input signal must be provided to compute a spectrogram")
+        _, req = pl.precheck_signal(y)
+        if isinstance(y, nat.DeviceArray):
+            ctx, yd, to_host = y.ctx, y, False
+        else:
+            ctx = nat.default_context()
+            staged = pl.StagedInput(ctx, y)
+            yd, validate = staged.dev, True
+        Sd, n_fft = _spectrogram(y=yd, n_fft=n_fft, hop_length=hop_length, power=1, win_length=win_length,
+                                 window=window, center=center, pad_mode=pad_mode)
+        if validate:
+            hop_eff, _ = pl.frame_params(n_fft, hop_length, win_length)
+            staged.scan_uncovered(n_fft, hop_eff, center, Sd.shape[-1])
+        own_S = True
+    else:
+        if not isinstance(S, nat.DeviceArray) and np.iscomplexobj(S):
+            raise nat.UnsupportedOnGPU("spectral_contrast of a complex S is not supported on the GPU: pass np.abs(S)")
+        ctx = S.ctx if isinstance(S, nat.DeviceArray) else nat.default_context()
+        Sd, req, on_device = _spec_to_device(ctx, S)
+        to_host, own_S = not on_device, not on_device
+        if n_fft is None or n_fft // 2 + 1 != Sd.shape[-2]:
+            n_fft = 2 * (Sd.shape[-2] - 1)
+    F, T = Sd.shape[-2], Sd.shape[-1]
+    if freq is None:
+        freq = fft_frequencies(sr=sr, n_fft=n_fft)
+    freq = np.atleast_1d(freq)
+    if freq.ndim != 1 or len(freq) != F:
+        raise ParameterError(f"freq.shape mismatch: expected ({F:d},)")
+    if n_bands < 1 or not isinstance(n_bands, (int, np.integer)):
+        raise ParameterError("n_bands must be a positive integer")
+    if not 0.0 < quantile < 1.0:
+        raise ParameterError("quantile must lie in the range (0, 1)")
+    if fmin <= 0:
+        raise ParameterError("fmin must be a positive number")
+    octa = np.zeros(n_bands + 2)
+    octa[1:] = fmin * (2.0 ** np.arange(0, n_bands + 1))
+    if np.any(octa[:-1] >= 0.5 * sr):
+        raise ParameterError("Frequency band exceeds Nyquist. Reduce either fmin or n_bands.")
+    if n_bands + 1 > 16:
+        raise nat.UnsupportedOnGPU("spectral_contrast: at most 15 octave bands on the GPU")
+    desc = nat.ContrastDesc(n_bands=n_bands + 1)
+    for k in range(n_bands + 1):
+        # the reference's band mask (feature/spectral.py:483-499), reduced to (first bin, count, tail length)
+        band = np.logical_and(freq >= octa[k], freq <= octa[k + 1])
+        idx = np.flatnonzero(band)
+        if k > 0:
+            band[idx[0] - 1] = True
+        if k == n_bands:
+            band[idx[-1] + 1:] = True
+        sel = np.flatnonzero(band)
+        if sel.size and sel[-1] - sel[0] + 1 != sel.size:
+            raise nat.UnsupportedOnGPU("spectral_contrast: non-contiguous band (freq must be increasing)")
+        count = sel.size - (1 if k < n_bands else 0)
+        desc.lo[k] = int(sel[0]) if sel.size else 0
+        desc.count[k] = max(int(count), 0)
+        desc.k[k] = int(max(np.rint(quantile * np.sum(band)), 1))
+    lead = Sd.shape[:-2]
+    n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    L = nat.lib()
+    if Sd.layout == "ft":
+        src = Sd
+    else:
+        src = nat.DeviceArray.empty(ctx, Sd.shape, np.float32, layout="ft")
+        if n_clips and F and T:
+            nat.check(L.b2l_transpose(ctx.handle, _vp(Sd.ptr), n_clips, F, T, 4, _vp(src.ptr)))
+    shape = tuple(lead) + (n_bands + 1, T)
+    peak = nat.DeviceArray.empty(ctx, shape, np.float32)
+    valley = nat.DeviceArray.empty(ctx, shape, np.float32)
+    nat.check(L.b2l_spectral_contrast(ctx.handle, C.byref(desc), _vp(src.ptr), n_clips, T, F, _vp(peak.ptr),
+                                      _vp(valley.ptr)))
+    if src is not Sd:
+        src.free()
+    if own_S:
+        Sd.free()
+    if not linear:
+        p_db, v_db = power_to_db(peak), power_to_db(valley)
+        peak.free()
+        valley.free()
+        peak, valley = p_db, v_db
+    out = nat.DeviceArray.empty(ctx, shape, np.float32)
+    nat.check(L.b2l_sub(ctx.handle, _vp(peak.ptr), _vp(valley.ptr), peak.size, _vp(out.ptr)))
+    peak.free()
+    valley.free()
+    if not to_host:
+        return out
+    return pl.finish(ctx, out, True, np.result_type(req, np.float64), validate=validate)
+
+
 # --------------------------------------------------------------------------------------------- time-domain framings
 def _frame_feature(what, y, frame_length, hop_length, center, pad_mode, *, threshold=0.0, zero_pos=1, pad_first=0,
                    out_scale=1.0, validate=False):

@@ -491,6 +491,50 @@ def spectral_flatness(y=None, S=None, n_fft=2048, hop_length=512, win_length=Non
     return gmean / amean
 
 
+def spectral_contrast(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                      center=True, pad_mode="constant", freq=None, fmin=200.0, n_bands=6, quantile=0.02,
+                      linear=False):
+    """librosa/feature/spectral.py:447-532."""
+    S, n_fft = _spec_or_S(y, S, n_fft, hop_length, 1, win_length, window, center, pad_mode)
+    if freq is None:
+        freq = fft_frequencies(sr=sr, n_fft=n_fft)
+    freq = np.atleast_1d(freq)
+    if freq.ndim != 1 or len(freq) != S.shape[-2]:
+        raise ParameterError(f"freq.shape mismatch: expected ({S.shape[-2]:d},)")
+    if n_bands < 1 or not isinstance(n_bands, (int, np.integer)):
+        raise ParameterError("n_bands must be a positive integer")
+    if not 0.0 < quantile < 1.0:
+        raise ParameterError("quantile must lie in the range (0, 1)")
+    if fmin <= 0:
+        raise ParameterError("fmin must be a positive number")
+    octa = np.zeros(n_bands + 2)
+    octa[1:] = fmin * (2.0 ** np.arange(0, n_bands + 1))
+    if np.any(octa[:-1] >= 0.5 * sr):
+        raise ParameterError("Frequency band exceeds Nyquist. Reduce either fmin or n_bands.")
+    shape = list(S.shape)
+    shape[-2] = n_bands + 1
+    valley = np.zeros(shape)
+    peak = np.zeros_like(valley)
+    for k, (f_low, f_high) in enumerate(zip(octa[:-1], octa[1:])):
+        current_band = np.logical_and(freq >= f_low, freq <= f_high)
+        idx = np.flatnonzero(current_band)
+        if k > 0:
+            current_band[idx[0] - 1] = True
+        if k == n_bands:
+            current_band[idx[-1] + 1:] = True
+        sub_band = S[..., current_band, :]
+        if k < n_bands:
+            sub_band = sub_band[..., :-1, :]
+        idx = np.rint(quantile * np.sum(current_band))
+        idx = int(np.maximum(idx, 1))
+        sortedr = np.sort(sub_band, axis=-2)
+        valley[..., k, :] = np.mean(sortedr[..., :idx, :], axis=-2)
+        peak[..., k, :] = np.mean(sortedr[..., -idx:, :], axis=-2)
+    if linear:
+        return peak - valley
+    return power_to_db(peak) - power_to_db(valley)
+
+
 def rms(y=None, S=None, frame_length=2048, hop_length=512, center=True, pad_mode="constant", dtype=np.float32):
     """librosa/feature/spectral.py:881-916 (``util.abs2`` = ``np.square`` for real input,
     ``re^2 + im^2`` for complex, librosa/util/utils.py:2479-2530)."""

@@ -90,6 +90,17 @@ FEATURE_CASES += [
     dict(name="pcen_max2_stereo_maxaxis", fn="pcen", ns="top", arg="mel_16000_1024_stereo_A", arg_op="scale31", kw=dict(max_size=2, max_axis=-2, time_constant=0.1)),
 ]
 
+FEATURE_CASES += [
+    # ---- spectral_contrast
+    dict(name="contrast_default_A", fn="spectral_contrast", mix="A", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="contrast_default_B", fn="spectral_contrast", mix="B", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="contrast_linear_stereo_B", fn="spectral_contrast", mix="B", shape=(2, 6000), kw=dict(sr=16000, n_fft=1024, hop_length=256, linear=True, n_bands=4)),
+    dict(name="contrast_q25_fmin100_A", fn="spectral_contrast", mix="A", shape=(6000,), kw=dict(sr=22050, n_fft=1024, hop_length=256, quantile=0.25, fmin=100.0)),
+    dict(name="contrast_C_burst", fn="spectral_contrast", mix="C", shape=(9000,), kw=dict(sr=22050)),
+    dict(name="contrast_fromS", fn="spectral_contrast", src="stft_4096_1024_A", kw=dict(sr=44100)),
+    dict(name="contrast_400_nonpow2_A", fn="spectral_contrast", mix="A", shape=(2, 8000), kw=dict(sr=16000, n_fft=400, hop_length=160, n_bands=5)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 

@@ -11,6 +11,7 @@ Stated tolerances (float32 pipeline vs the reference's float64 FFT):
     rms                             rtol 1e-4, atol 1e-7 * max|ref|
     zero_crossing_rate              exact
     onset_strength(_multi)          rtol 1e-4, atol 1e-3 (dB-domain, as for mfcc)
+    spectral_contrast               rtol 1e-4, atol 1e-3 dB (1e-6 * max|ref| with linear=True)
     pcen                            rtol 1e-4, atol 1e-6 * max|ref|
     amplitude_to_db                 rtol 1e-5, atol 1e-4 dB (elementwise on identical input)
     db_to_power / db_to_amplitude   rtol 1e-5
@@ -91,6 +92,9 @@ def test_feature_case_against_oracle_and_reference_fixture(case, lb, oracle, gol
             _close(got, ref, 1e-4, 1e-7 * scale)
         elif fn in ("onset_strength", "onset_strength_multi"):
             _close(got, ref, 1e-4, 1e-3)          # means of dB differences: same absolute term as mfcc
+        elif fn == "spectral_contrast":
+            linear = case["kw"].get("linear", False)
+            _close(got, ref, 1e-4, 1e-6 * scale if linear else 1e-3)
         elif fn == "pcen":
             _close(got, ref, 1e-4, 1e-6 * scale)
         elif fn == "amplitude_to_db":
