@@ -195,6 +195,34 @@ int b2l_spectral_contrast(b2l_ctx* ctx, const b2l_contrast_desc* desc, const flo
                           int64_t n_frames, int32_t n_bins, float* d_peak, float* d_valley);
 /* out = x - y over n floats */
 int b2l_sub(b2l_ctx* ctx, const float* d_x, const float* d_y, int64_t n, float* d_out);
+/* Tuning estimation for chroma_stft (feature/spectral.py:1137-1293): librosa.estimate_tuning
+ * (core/pitch.py:28-109) = piptrack peaks (:182-366) whose interpolated magnitude reaches the median of all
+ * peaks, histogrammed by pitch residual (pitch_tuning, :112-179).  One call = one pass over the magnitude /
+ * power spectrogram d_S [n_rows][n_bins] that re-detects the peaks among bins k_lo .. k_hi-1 and returns ONE
+ * histogram in h_hist (the call synchronises):
+ *   mode 0 / 1 / 2  digits 31..21 / 20..10 / 9..0 of the order-preserving key of the peak magnitudes (restricted
+ *                   to keys whose higher digits equal `prefix`): radix selection of the exact median on the host
+ *                   from three 2048 / 2048 / 1024-entry histograms;
+ *   mode 3          n_res_bins-bin histogram (edges h_edges[n_res_bins + 1], np.histogram semantics) of
+ *                   mod(bins_per_octave * log2(pitch / 27.5), 1) folded to [-0.5, 0.5) over peaks with
+ *                   mag >= mag_threshold. */
+typedef struct b2l_pip_desc {
+  int32_t k_lo, k_hi;      /* bins with fmin <= f < fmax */
+  float threshold;         /* peaks must exceed threshold * max over the frame ... */
+  float ref_abs;           /* ... or this absolute value when >= 0 (piptrack(ref=number)) */
+  double hz_per_bin;       /* sr / n_fft */
+  int32_t mode;
+  uint32_t prefix;
+  float mag_threshold;
+  float bins_per_octave;
+  int32_t n_res_bins;
+} b2l_pip_desc;
+int b2l_pip_pass(b2l_ctx* ctx, const b2l_pip_desc* desc, const float* d_S, int64_t n_rows, int32_t n_bins,
+                 const double* h_edges, uint64_t* h_hist);
+/* util.normalize(x, norm, axis=-2) of [n_clips][n_rows][n_frames] (util/utils.py:797-1026, default threshold and
+ * fill): norm_kind 0 = inf, 1 = -inf, 2 = number of non-zeros, 3 = p-norm (norm_p > 0). */
+int b2l_normalize_rows(b2l_ctx* ctx, const float* d_in, int64_t n_clips, int64_t n_rows, int64_t n_frames,
+                       int32_t norm_kind, float norm_p, float* d_out);
 /* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
  *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
  *                                                        of the squared magnitudes with ref^2 / amin^2

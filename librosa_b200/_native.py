@@ -88,6 +88,13 @@ class ContrastDesc(C.Structure):
     _fields_ = [("n_bands", C.c_int32), ("lo", C.c_int32 * 16), ("count", C.c_int32 * 16), ("k", C.c_int32 * 16)]
 
 
+class PipDesc(C.Structure):
+    """struct b2l_pip_desc (include/b2l.h)."""
+    _fields_ = [("k_lo", C.c_int32), ("k_hi", C.c_int32), ("threshold", C.c_float), ("ref_abs", C.c_float),
+                ("hz_per_bin", C.c_double), ("mode", C.c_int32), ("prefix", C.c_uint32), ("mag_threshold", C.c_float),
+                ("bins_per_octave", C.c_float), ("n_res_bins", C.c_int32)]
+
+
 N_STATS = 6
 STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
 FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
@@ -143,6 +150,8 @@ def _declare(lib):
         "b2l_pcen": (C.c_int, [_vp, P(PcenDesc), _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
         "b2l_spectral_contrast": (C.c_int, [_vp, P(ContrastDesc), _vp, _i64, _i64, C.c_int32, _vp, _vp]),
         "b2l_sub": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+        "b2l_pip_pass": (C.c_int, [_vp, P(PipDesc), _vp, _i64, C.c_int32, _vp, _vp]),
+        "b2l_normalize_rows": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, C.c_float, _vp]),
         "b2l_unary": (C.c_int, [_vp, C.c_int32, _vp, _i64, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),

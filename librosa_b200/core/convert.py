@@ -52,3 +52,10 @@ def mel_frequencies(n_mels: int = 128, *, fmin: float = 0.0, fmax: float = 11025
 
 def fft_frequencies(*, sr: float = 22050, n_fft: int = 2048):
     return np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+
+
+def hz_to_octs(frequencies, *, tuning: float = 0.0, bins_per_octave: int = 12):
+    """Octave number of each frequency relative to A0 = A440 / 16 (mirror of core/convert.py:hz_to_octs)."""
+    a440 = 440.0 * 2.0 ** (tuning / bins_per_octave)
+    octs = np.log2(np.asanyarray(frequencies) / (float(a440) / 16))
+    return octs[()]

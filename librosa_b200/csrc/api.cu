@@ -1410,6 +1410,76 @@ extern "C" int b2l_sub(b2l_ctx* c, const float* d_x, const float* d_y, int64_t n
   return B2L_OK;
 }
 
+extern "C" int b2l_pip_pass(b2l_ctx* c, const b2l_pip_desc* d, const float* d_S, int64_t n_rows, int32_t n_bins,
+                            const double* h_edges, uint64_t* h_hist) {
+  if (!c || !d || !d_S || !h_hist) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (d->mode < 0 || d->mode > 3) return fail(B2L_ERR_INVALID, "bad pass mode %d", d->mode);
+  if (d->mode == 3 && (!h_edges || d->n_res_bins < 1 || d->n_res_bins > 2048))
+    return fail(B2L_ERR_INVALID, "residual histogram needs 1..2048 bins and their edges");
+  if (d->k_lo < 0 || d->k_hi > n_bins) return fail(B2L_ERR_INVALID, "bad bin range");
+  const int n_hist = d->mode == 3 ? d->n_res_bins : (d->mode == 2 ? 1024 : 2048);
+  for (int i = 0; i < n_hist; ++i) h_hist[i] = 0;
+  if (n_rows <= 0 || d->k_hi <= d->k_lo) return B2L_OK;
+  DeviceGuard g(c->device);
+  const size_t need = 2048 * sizeof(unsigned long long) + 2049 * sizeof(double);
+  if (c->scratch_bytes < need) {
+    if (c->d_scratch) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      CUDA_TRY(cudaFree(c->d_scratch));
+      c->d_scratch = nullptr;
+      c->scratch_bytes = 0;
+    }
+    CUDA_TRY(cudaMalloc((void**)&c->d_scratch, need));
+    c->scratch_bytes = need;
+  }
+  unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(c->d_scratch);
+  double* d_edges = reinterpret_cast<double*>(d_hist + 2048);
+  CUDA_TRY(cudaMemsetAsync(d_hist, 0, 2048 * sizeof(unsigned long long), c->stream));
+  if (d->mode == 3)
+    CUDA_TRY(cudaMemcpyAsync(d_edges, h_edges, (size_t)(d->n_res_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  PipArgs a;
+  a.k_lo = d->k_lo;
+  a.k_hi = d->k_hi;
+  a.threshold = d->threshold;
+  a.ref_abs = d->ref_abs;
+  a.hz_per_bin = d->hz_per_bin;
+  a.mode = d->mode;
+  a.prefix = d->prefix;
+  a.mag_threshold = d->mag_threshold;
+  a.bins_per_octave = d->bins_per_octave;
+  a.n_res_bins = d->n_res_bins;
+  const size_t per_warp = (size_t)((n_bins + 3) & ~3) * 4;
+  int nw = 8;
+  while (nw > 1 && per_warp * nw + 8192 + 1024 > c->smem_optin) nw >>= 1;
+  const size_t smem = per_warp * nw;
+  if (smem + 8192 + 1024 > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_bins=%d rows do not fit in shared memory", n_bins);
+  CUDA_TRY(cudaFuncSetAttribute(pip_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 8192 - 1024)));
+  long long grid = (n_rows + nw - 1) / nw;
+  const long long lim = (long long)c->sm_count * 4;
+  if (grid > lim) grid = lim;
+  pip_pass_kernel<<<(int)grid, nw * 32, smem, c->stream>>>(d_S, n_rows, n_bins, a, d_edges, d_hist);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  CUDA_TRY(cudaMemcpyAsync(h_hist, d_hist, (size_t)n_hist * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return B2L_OK;
+}
+
+extern "C" int b2l_normalize_rows(b2l_ctx* c, const float* d_in, int64_t n_clips, int64_t n_rows, int64_t n_frames,
+                                  int32_t norm_kind, float norm_p, float* d_out) {
+  if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (norm_kind < 0 || norm_kind > 3) return fail(B2L_ERR_INVALID, "bad norm kind %d", norm_kind);
+  if (norm_kind == 3 && !(norm_p > 0.0f)) return fail(B2L_ERR_INVALID, "Unsupported norm: %g", norm_p);
+  if (n_clips <= 0 || n_rows <= 0 || n_frames <= 0) return B2L_OK;
+  if (n_clips > 65535 || n_rows > 0x7fffffffLL || n_frames > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "normalize: batch too large");
+  DeviceGuard g(c->device);
+  dim3 grid((unsigned)((n_frames + 127) / 128), (unsigned)n_clips);
+  normalize_rows_kernel<<<grid, 128, 0, c->stream>>>(d_in, (int)n_rows, (int)n_frames, norm_kind, norm_p, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);

@@ -272,6 +272,115 @@ __global__ void sub_kernel(const float* __restrict__ x, const float* __restrict_
     out[i] = x[i] - y[i];
 }
 
+// Tuning estimation (librosa/core/pitch.py:28-109 estimate_tuning -> :182-366 piptrack -> :112-179 pitch_tuning).
+// piptrack marks the bins k in [k_lo, k_hi) of a frame where the thresholded spectrum S * (S > ref) has a local
+// maximum, refines them by parabolic interpolation (pitch = (k + shift) * sr / n_fft, mag = S[k] + skew) and
+// estimate_tuning keeps the peaks whose mag reaches the MEDIAN mag of all peaks, then histograms the pitch
+// residuals modulo one chroma bin.  The peak list is never materialised: every pass re-detects the peaks from
+// the spectrogram (one warp per frame row) and accumulates one histogram —
+//   mode 0/1/2: radix-select digits (11 + 11 + 10 bits) of the order-preserving key of mag -> exact median
+//   mode 3:     residual histogram of the peaks with mag >= mag_threshold.
+struct PipArgs {
+  int k_lo, k_hi;
+  float threshold;          // relative to the frame maximum when ref_abs < 0, else unused
+  float ref_abs;            // >= 0: absolute reference value (piptrack(ref=number))
+  double hz_per_bin;        // sr / n_fft
+  int mode;
+  unsigned int prefix;      // digits selected so far (mode 1: top 11 bits, mode 2: top 22 bits)
+  float mag_threshold;
+  float bins_per_octave;
+  int n_res_bins;
+};
+__global__ void pip_pass_kernel(const float* __restrict__ S, long long n_rows, int F, PipArgs a,
+                                const double* __restrict__ edges, unsigned long long* __restrict__ hist) {
+  extern __shared__ __align__(16) float s_dyn[];
+  __shared__ unsigned int s_hist[2048];
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_row = s_dyn + (size_t)warp * ((F + 3) & ~3);
+  const int n_hist = a.mode == 3 ? a.n_res_bins : (a.mode == 2 ? 1024 : 2048);
+  for (int i = threadIdx.x; i < n_hist; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (long long r = (long long)blockIdx.x * nw + warp; r < n_rows; r += (long long)gridDim.x * nw) {
+    const float* src = S + r * F;
+    float mx = -INFINITY;
+    for (int i = lane; i < F; i += 32) {
+      const float v = __ldg(src + i);
+      s_row[i] = v;
+      mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncwarp();
+    const float ref = a.ref_abs >= 0.0f ? a.ref_abs : a.threshold * mx;
+    for (int k = a.k_lo + lane; k < a.k_hi; k += 32) {
+      if (k < 1) continue;
+      const float c = s_row[k], l = s_row[k - 1];
+      const float cm = c > ref ? c : 0.0f, lm = l > ref ? l : 0.0f;
+      bool is_peak;
+      float shift = 0.0f, avg;
+      if (k == F - 1) {
+        is_peak = cm > lm;
+        avg = c - l;                                   // np.gradient, one-sided at the edge
+      } else {
+        const float rr = s_row[k + 1];
+        const float rm = rr > ref ? rr : 0.0f;
+        is_peak = cm > lm && cm >= rm;
+        const float pa = rr + l - 2.0f * c, pb = (rr - l) * 0.5f;
+        if (fabsf(pb) < fabsf(pa)) shift = -pb / pa;
+        avg = (rr - l) * 0.5f;
+      }
+      if (!is_peak) continue;
+      const float pitch = (float)(((double)k + (double)shift) * a.hz_per_bin);
+      if (!(pitch > 0.0f)) continue;
+      const float mag = c + 0.5f * avg * shift;
+      const unsigned int key = float_to_key(mag);
+      if (a.mode == 0) {
+        atomicAdd(&s_hist[key >> 21], 1u);
+      } else if (a.mode == 1) {
+        if ((key >> 21) == a.prefix) atomicAdd(&s_hist[(key >> 10) & 0x7ffu], 1u);
+      } else if (a.mode == 2) {
+        if ((key >> 10) == a.prefix) atomicAdd(&s_hist[key & 0x3ffu], 1u);
+      } else if (mag >= a.mag_threshold) {
+        // residual of the pitch modulo one bin of the chroma scale (pitch_tuning, core/pitch.py:161-170)
+        const float x = a.bins_per_octave * log2f(pitch / 27.5f);
+        float res = x - floorf(x);
+        if (res >= 0.5f) res -= 1.0f;
+        int b = (int)floor(((double)res + 0.5) * a.n_res_bins);
+        b = max(0, min(a.n_res_bins - 1, b));
+        while (b > 0 && (double)res < edges[b]) --b;
+        while (b < a.n_res_bins - 1 && (double)res >= edges[b + 1]) ++b;
+        atomicAdd(&s_hist[b], 1u);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_hist; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+// util.normalize(S, norm, axis=-2) of [clip][rows][T] blocks with the default threshold / fill
+// (librosa/util/utils.py:797-1026): columns whose norm is below tiny(float32) are left unscaled.
+// norm_kind: 0 = inf (max |x|), 1 = -inf (min |x|), 2 = count of non-zeros, 3 = p-norm with p = norm_p.
+__global__ void normalize_rows_kernel(const float* __restrict__ x, int rows, int T, int norm_kind, float norm_p,
+                                      float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* xc = x + (long long)blockIdx.y * rows * T + t;
+  float* oc = out + (long long)blockIdx.y * rows * T + t;
+  float len = norm_kind == 1 ? INFINITY : 0.0f;
+  for (int r = 0; r < rows; ++r) {
+    const float v = fabsf(xc[(long long)r * T]);
+    if (norm_kind == 0) len = fmaxf(len, v);
+    else if (norm_kind == 1) len = fminf(len, v);
+    else if (norm_kind == 2) len += v > 0.0f ? 1.0f : 0.0f;
+    else len += norm_p == 1.0f ? v : (norm_p == 2.0f ? v * v : powf(v, norm_p));
+  }
+  if (norm_kind == 3 && norm_p != 1.0f) len = norm_p == 2.0f ? sqrtf(len) : powf(len, 1.0f / norm_p);
+  if (len < 1.17549435e-38f) len = 1.0f;
+  for (int r = 0; r < rows; ++r) oc[(long long)r * T] = xc[(long long)r * T] / len;
+}
+
 // Elementwise helpers of the dB conversions (librosa/core/spectrum.py):
 //   UNARY_SQUARE           x*x                        amplitude_to_db squares |S| before power_to_db (:2032-2037)
 //   UNARY_DB_TO_POWER      ref * 10^(0.1 x)           db_to_power (:1899-1925)

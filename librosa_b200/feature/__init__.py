@@ -1,7 +1,7 @@
 """``librosa.feature`` names of the FFT time-frequency path and of its frame-wise consumers."""
-from .spectral import melspectrogram, mfcc
+from .spectral import chroma_stft, melspectrogram, mfcc
 from .stats import (rms, spectral_bandwidth, spectral_centroid, spectral_contrast, spectral_flatness,
                     spectral_rolloff, zero_crossing_rate)
 
-__all__ = ["melspectrogram", "mfcc", "spectral_centroid", "spectral_bandwidth", "spectral_rolloff",
+__all__ = ["melspectrogram", "mfcc", "chroma_stft", "spectral_centroid", "spectral_bandwidth", "spectral_rolloff",
            "spectral_flatness", "spectral_contrast", "rms", "zero_crossing_rate"]

@@ -131,6 +131,88 @@ def _compose_nonpow2(y, tail, res_dtype, **spec_kw):
     return pl.finish(ctx, out, True, res_dtype, validate=True)
 
 
+def chroma_stft(*, y=None, sr: float = 22050, S=None, norm=np.inf, n_fft: int = 2048, hop_length: int = 512,
+                win_length: Optional[int] = None, window="hann", center: bool = True, pad_mode="constant",
+                tuning: Optional[float] = None, n_chroma: int = 12, **kwargs):
+    """Chromagram from a waveform or power spectrogram, shape ``(..., n_chroma, t)``; same contract as
+    ``librosa.feature.chroma_stft`` (feature/spectral.py:1137-1293).  ``kwargs`` go to ``filters.chroma``.
+    Power spectrogram, tuning estimation (when ``tuning`` is None), projection and per-frame normalisation all
+    run on the device; like the reference, ONE tuning value is estimated for the whole input."""
+    from .. import filters
+    from ..core.pitch import _tuning_from_device_spec
+    from ..core.spectrum import _spectrogram
+
+    to_host, validate, own = True, False, False
+    if S is None:
+        if y is None:
+            raise ParameterError("Input signal must be provided to compute a spectrogram")
+        _, req = pl.precheck_signal(y)
+        if isinstance(y, nat.DeviceArray):
+            ctx, yd, to_host = y.ctx, y, False
+        else:
+            ctx = nat.default_context()
+            staged = pl.StagedInput(ctx, y)
+            yd, validate = staged.dev, True
+        Sd, n_fft = _spectrogram(y=yd, n_fft=n_fft, hop_length=hop_length, power=2, win_length=win_length,
+                                 window=window, center=center, pad_mode=pad_mode)
+        own = True
+        if validate:
+            hop_eff, _ = pl.frame_params(n_fft, hop_length, win_length)
+            staged.scan_uncovered(n_fft, hop_eff, center, Sd.shape[-1])
+    else:
+        ctx = S.ctx if isinstance(S, nat.DeviceArray) else nat.default_context()
+        Sd, req, on_device = _spec_to_device(ctx, S)
+        to_host, own = not on_device, not on_device
+        if n_fft is None or n_fft // 2 + 1 != Sd.shape[-2]:
+            n_fft = 2 * (Sd.shape[-2] - 1)
+    F, T = Sd.shape[-2], Sd.shape[-1]
+    lead = Sd.shape[:-2]
+    n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    L = nat.lib()
+    if Sd.layout == "ft":
+        src = Sd
+    else:
+        src = nat.DeviceArray.empty(ctx, Sd.shape, np.float32, layout="ft")
+        if n_clips and F and T:
+            nat.check(L.b2l_transpose(ctx.handle, _vp(Sd.ptr), n_clips, F, T, 4, _vp(src.ptr)))
+        if own:
+            Sd.free()
+        own = True
+    try:
+        if tuning is None:
+            tuning = _tuning_from_device_spec(ctx, src, sr, n_fft, resolution=0.01, bins_per_octave=n_chroma,
+                                              fmin=150.0, fmax=4000.0, threshold=0.1, ref=None)
+        fb = filters.chroma(sr=sr, n_fft=n_fft, tuning=tuning, n_chroma=n_chroma, **kwargs)
+        if fb.shape[1] != F:
+            raise ParameterError(f"chroma filter bank has {fb.shape[1]} bins, the spectrogram {F}")
+        plan = nat.make_plan(ctx, ("chroma", n_fft, pl.digest(fb)), n_fft=n_fft, hop_length=1, center=True,
+                             pad_mode="constant", window=np.ones(n_fft), mel_basis=fb)
+        raw = nat.DeviceArray.empty(ctx, tuple(lead) + (fb.shape[0], T), np.float32)
+        nat.check(L.b2l_mel_project(ctx.handle, plan.handle, _vp(src.ptr), n_clips, T, _vp(raw.ptr)))
+    finally:
+        if own:
+            src.free()
+    if norm is None:
+        out = raw
+    else:
+        if norm == np.inf:
+            kind, p = 0, 0.0
+        elif norm == -np.inf:
+            kind, p = 1, 0.0
+        elif norm == 0:
+            kind, p = 2, 0.0
+        elif np.issubdtype(type(norm), np.number) and norm > 0:
+            kind, p = 3, float(norm)
+        else:
+            raise ParameterError(f"Unsupported norm: {repr(norm)}")
+        out = nat.DeviceArray.empty(ctx, raw.shape, np.float32)
+        nat.check(L.b2l_normalize_rows(ctx.handle, _vp(raw.ptr), n_clips, fb.shape[0], T, kind, p, _vp(out.ptr)))
+        raw.free()
+    if not to_host:
+        return out
+    return pl.finish(ctx, out, True, np.result_type(req, fb.dtype), validate=validate)
+
+
 def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float) -> np.ndarray:
     """Rows 0..n_mfcc-1 of the DCT applied along the mel axis, as an explicit matrix, with the
     sinusoidal lifter ``1 + (lifter/2) sin(pi (k+1) / lifter)`` folded in

@@ -11,7 +11,7 @@ import warnings
 import numpy as np
 import scipy.signal
 
-from .core.convert import fft_frequencies, mel_frequencies
+from .core.convert import fft_frequencies, hz_to_octs, mel_frequencies
 from .util.exceptions import ParameterError
 from .util.utils import normalize, pad_center
 
@@ -76,3 +76,27 @@ def window_sumsquare(*, window, n_frames: int, hop_length: int = 512, win_length
         s = i * hop_length
         x[s : min(n, s + n_fft)] += win_sq[: max(0, min(n_fft, n - s))]
     return x
+
+
+def chroma(*, sr: float, n_fft: int, n_chroma: int = 12, tuning: float = 0.0, ctroct: float = 5.0, octwidth=2,
+           norm=2, base_c: bool = True, dtype=np.float32) -> np.ndarray:
+    """Chroma filter bank ``(n_chroma, 1 + n_fft/2)`` projecting FFT bins onto pitch classes; host-side
+    constant with the values of ``librosa.filters.chroma`` (filters.py:254-392): Gaussian bumps around each
+    bin's pitch class, column-normalised, optionally weighted by a Gaussian over octaves."""
+    # position of every FFT bin (DC excluded) on the chroma axis, in bins
+    bin_hz = np.linspace(0, sr, n_fft, endpoint=False)[1:]
+    pos = n_chroma * hz_to_octs(bin_hz, tuning=tuning, bins_per_octave=n_chroma)
+    # the 0 Hz bin gets a made-up position 1.5 octaves below bin 1
+    pos = np.concatenate(([pos[0] - 1.5 * n_chroma], pos))
+    width = np.concatenate((np.maximum(pos[1:] - pos[:-1], 1.0), [1]))
+    half = np.round(float(n_chroma) / 2)
+    # signed distance of every bin to every pitch class, wrapped to [-n_chroma/2, n_chroma/2)
+    dist = np.subtract.outer(pos, np.arange(0, n_chroma, dtype="d")).T
+    dist = np.remainder(dist + half + 10 * n_chroma, n_chroma) - half
+    wts = np.exp(-0.5 * (2 * dist / np.tile(width, (n_chroma, 1))) ** 2)
+    wts = normalize(wts, norm=norm, axis=0)
+    if octwidth is not None:
+        wts *= np.exp(-0.5 * (((pos / n_chroma - ctroct) / octwidth) ** 2))[np.newaxis, :]
+    if base_c:
+        wts = np.roll(wts, -3 * (n_chroma // 12), axis=0)
+    return np.ascontiguousarray(wts[:, : int(1 + n_fft / 2)], dtype=dtype)

@@ -594,6 +594,116 @@ def zero_crossing_rate(y, frame_length=2048, hop_length=512, center=True, **kwar
     return np.mean(crossings, axis=-2, keepdims=True)
 
 
+# --------------------------------------------------------------------------- tuning / chroma
+def hz_to_octs(frequencies, tuning=0.0, bins_per_octave=12):
+    """librosa/core/convert.py (hz_to_octs)."""
+    A440 = 440.0 * 2.0 ** (tuning / bins_per_octave)
+    return np.log2(np.asanyarray(frequencies) / (float(A440) / 16))[()]
+
+
+def localmax(x, axis=0):
+    """librosa/util/utils.py:1029-1118: x[i] > x[i-1] and x[i] >= x[i+1]; first False, last x[-1] > x[-2]."""
+    xi = np.moveaxis(np.asarray(x), axis, -1)
+    out = np.zeros(xi.shape, dtype=bool)
+    out[..., 1:-1] = (xi[..., 1:-1] > xi[..., :-2]) & (xi[..., 1:-1] >= xi[..., 2:])
+    out[..., -1] = xi[..., -1] > xi[..., -2]
+    return np.moveaxis(out, -1, axis)
+
+
+def _parabolic_interpolation(x, axis=-2):
+    """librosa/core/pitch.py:422-477."""
+    xi = np.moveaxis(np.asarray(x), axis, -1)
+    shifts = np.zeros_like(xi)
+    a = xi[..., 2:] + xi[..., :-2] - 2 * xi[..., 1:-1]
+    b = (xi[..., 2:] - xi[..., :-2]) / 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inner = np.where(np.abs(b) >= np.abs(a), 0, -b / a)
+    shifts[..., 1:-1] = inner
+    return np.moveaxis(shifts, -1, axis)
+
+
+def piptrack(y=None, sr=22050, S=None, n_fft=2048, hop_length=None, fmin=150.0, fmax=4000.0, threshold=0.1,
+             win_length=None, window="hann", center=True, pad_mode="constant", ref=None):
+    """librosa/core/pitch.py:296-366."""
+    S, n_fft = _spec_or_S(y, S, n_fft, hop_length, 1, win_length, window, center, pad_mode)
+    if np.iscomplexobj(S) or S.min() < 0:
+        S = np.abs(S)
+    fmin = np.maximum(fmin, 0)
+    fmax = np.minimum(fmax, float(sr) / 2)
+    fft_freqs = fft_frequencies(sr=sr, n_fft=n_fft)
+    avg = np.gradient(S, axis=-2)
+    shift = _parabolic_interpolation(S, axis=-2)
+    dskew = 0.5 * avg * shift
+    pitches = np.zeros_like(S)
+    mags = np.zeros_like(S)
+    freq_mask = (fmin <= fft_freqs) & (fft_freqs < fmax)
+    freq_mask = freq_mask.reshape((1,) * (S.ndim - 2) + (-1, 1))
+    if ref is None:
+        ref = np.max
+    if callable(ref):
+        ref_value = np.expand_dims(threshold * ref(S, axis=-2), -2)
+    else:
+        ref_value = np.abs(ref)
+    idx = np.nonzero(freq_mask & localmax(S * (S > ref_value), axis=-2))
+    pitches[idx] = (idx[-2] + shift[idx]) * float(sr) / n_fft
+    mags[idx] = S[idx] + dskew[idx]
+    return pitches, mags
+
+
+def pitch_tuning(frequencies, resolution=0.01, bins_per_octave=12):
+    """librosa/core/pitch.py:150-179."""
+    frequencies = np.atleast_1d(frequencies)
+    frequencies = frequencies[frequencies > 0]
+    if not np.any(frequencies):
+        warnings.warn("Trying to estimate tuning from empty frequency set.", stacklevel=2)
+        return 0.0
+    residual = np.mod(bins_per_octave * hz_to_octs(frequencies), 1.0)
+    residual[residual >= 0.5] -= 1.0
+    bins = np.linspace(-0.5, 0.5, int(np.ceil(1.0 / resolution)) + 1)
+    counts, tuning = np.histogram(residual, bins)
+    return tuning[np.argmax(counts)]
+
+
+def estimate_tuning(y=None, sr=22050, S=None, n_fft=2048, resolution=0.01, bins_per_octave=12, **kwargs):
+    """librosa/core/pitch.py:95-109."""
+    pitch, mag = piptrack(y=y, sr=sr, S=S, n_fft=n_fft, **kwargs)
+    pitch_mask = pitch > 0
+    threshold = np.median(mag[pitch_mask]) if pitch_mask.any() else 0.0
+    return pitch_tuning(pitch[(mag >= threshold) & pitch_mask], resolution=resolution,
+                        bins_per_octave=bins_per_octave)
+
+
+def chroma_filter(sr, n_fft, n_chroma=12, tuning=0.0, ctroct=5.0, octwidth=2, norm=2, base_c=True,
+                  dtype=np.float32):
+    """``filters.chroma`` (librosa/filters.py:254-392)."""
+    wts = np.zeros((n_chroma, n_fft))
+    frequencies = np.linspace(0, sr, n_fft, endpoint=False)[1:]
+    frqbins = n_chroma * hz_to_octs(frequencies, tuning=tuning, bins_per_octave=n_chroma)
+    frqbins = np.concatenate(([frqbins[0] - 1.5 * n_chroma], frqbins))
+    binwidthbins = np.concatenate((np.maximum(frqbins[1:] - frqbins[:-1], 1.0), [1]))
+    D = np.subtract.outer(frqbins, np.arange(0, n_chroma, dtype="d")).T
+    n_chroma2 = np.round(float(n_chroma) / 2)
+    D = np.remainder(D + n_chroma2 + 10 * n_chroma, n_chroma) - n_chroma2
+    wts = np.exp(-0.5 * (2 * D / np.tile(binwidthbins, (n_chroma, 1))) ** 2)
+    wts = normalize(wts, norm=norm, axis=0)
+    if octwidth is not None:
+        wts *= np.exp(-0.5 * (((frqbins / n_chroma - ctroct) / octwidth) ** 2))[np.newaxis, :]
+    if base_c:
+        wts = np.roll(wts, -3 * (n_chroma // 12), axis=0)
+    return np.ascontiguousarray(wts[:, : int(1 + n_fft / 2)], dtype=dtype)
+
+
+def chroma_stft(y=None, sr=22050, S=None, norm=np.inf, n_fft=2048, hop_length=512, win_length=None,
+                window="hann", center=True, pad_mode="constant", tuning=None, n_chroma=12, **kwargs):
+    """librosa/feature/spectral.py:1253-1293."""
+    S, n_fft = _spec_or_S(y, S, n_fft, hop_length, 2, win_length, window, center, pad_mode)
+    if tuning is None:
+        tuning = estimate_tuning(S=S, sr=sr, bins_per_octave=n_chroma)
+    chromafb = chroma_filter(sr=sr, n_fft=n_fft, tuning=tuning, n_chroma=n_chroma, **kwargs)
+    raw_chroma = np.einsum("cf,...ft->...ct", chromafb, S, optimize=True)
+    return normalize(raw_chroma, norm=norm, axis=-2)
+
+
 def pcen(S, sr=22050, hop_length=512, gain=0.98, bias=2, power=0.5, time_constant=0.400, eps=1e-6, b=None,
          max_size=1, ref=None, axis=-1, max_axis=None, zi=None, return_zf=False):
     """librosa/core/spectrum.py:2576-2666."""

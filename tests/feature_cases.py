@@ -101,6 +101,21 @@ FEATURE_CASES += [
     dict(name="contrast_400_nonpow2_A", fn="spectral_contrast", mix="A", shape=(2, 8000), kw=dict(sr=16000, n_fft=400, hop_length=160, n_bands=5)),
 ]
 
+FEATURE_CASES += [
+    # ---- chroma_stft and estimate_tuning.  Mix T (detuned harmonic notes) gives the residual histogram of the
+    # tuning estimate one clear maximum; with noise-like signals its argmax is a coin toss between tied bins.
+    dict(name="chroma_default_T", fn="chroma_stft", mix="T", seed=0, shape=(20000,), kw=dict(sr=22050)),
+    dict(name="chroma_stereo_one_tuning_T", fn="chroma_stft", mix="T", seed=1, shape=(2, 16000), kw=dict(sr=16000, n_fft=1024, hop_length=256)),
+    dict(name="chroma_tuning_given_norm2_24_B", fn="chroma_stft", mix="B", shape=(9000,), kw=dict(sr=22050, tuning=0.13, norm=2, n_chroma=24, octwidth=None)),
+    dict(name="chroma_norm_none_A", fn="chroma_stft", mix="A", shape=(6000,), kw=dict(sr=22050, n_fft=1024, hop_length=256, tuning=0.0, norm=None)),
+    dict(name="chroma_norm1_C", fn="chroma_stft", mix="C", shape=(9000,), kw=dict(sr=22050, tuning=-0.2, norm=1)),
+    dict(name="chroma_fromS_power", fn="chroma_stft", mix="A", shape=(9000,), as_power_S=True, kw=dict(sr=22050, n_fft=2048, hop_length=512, tuning=0.05)),
+    dict(name="chroma_400_nonpow2_T", fn="chroma_stft", mix="T", seed=2, shape=(2, 8000), kw=dict(sr=16000, n_fft=400, hop_length=160, tuning=0.1, base_c=False)),
+    dict(name="tuning_y_T", fn="estimate_tuning", ns="top", mix="T", seed=5, shape=(20000,), kw=dict(sr=22050)),
+    dict(name="tuning_fromS_stereo_T", fn="estimate_tuning", ns="top", mix="T", seed=2, shape=(2, 16000), as_power_S=True, kw=dict(sr=16000, n_fft=1024, hop_length=256)),
+    dict(name="tuning_res05_bpo24_T", fn="estimate_tuning", ns="top", mix="T", seed=1, shape=(20000,), kw=dict(sr=22050, resolution=0.05, bins_per_octave=24, fmin=100.0, fmax=3000.0)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 
@@ -120,7 +135,14 @@ def case_args(case, golden):
     if "src" in case:
         kw["S"] = np.abs(golden[case["src"]])
         return (), kw
-    y = signals.make(case["mix"], case["shape"], seed=len(case["name"]), sr=kw.get("sr", 22050))
+    y = signals.make(case["mix"], case["shape"], seed=case.get("seed", len(case["name"])), sr=kw.get("sr", 22050))
+    if case.get("as_power_S"):  # S= form fed with |stft|**2 of the signal, computed by the flat oracle (float32)
+        from oracle import ref_np as O
+
+        spec_kw = {k: kw[k] for k in ("n_fft", "hop_length") if k in kw}
+        kw.pop("hop_length", None)
+        kw["S"] = O.spectrogram(y, power=2, **spec_kw)
+        return (), kw
     if "freq" in case:
         kw["freq"] = (np.linspace(0.0, 1.0, case["freq"]) ** 2 * 9000.0 + 20.0)
     if case.get("pos"):

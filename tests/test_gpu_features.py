@@ -12,6 +12,8 @@ Stated tolerances (float32 pipeline vs the reference's float64 FFT):
     zero_crossing_rate              exact
     onset_strength(_multi)          rtol 1e-4, atol 1e-3 (dB-domain, as for mfcc)
     spectral_contrast               rtol 1e-4, atol 1e-3 dB (1e-6 * max|ref| with linear=True)
+    chroma_stft                     rtol 1e-4, atol 2e-6 (chroma values lie in [0, 1])
+    estimate_tuning                 exact (a histogram bin centre)
     pcen                            rtol 1e-4, atol 1e-6 * max|ref|
     amplitude_to_db                 rtol 1e-5, atol 1e-4 dB (elementwise on identical input)
     db_to_power / db_to_amplitude   rtol 1e-5
@@ -76,8 +78,8 @@ def _rolloff_close(O, case, golden, got, ref):
 def test_feature_case_against_oracle_and_reference_fixture(case, lb, oracle, golden):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        got = call(lb, case, golden)
-        want = call(oracle, case, golden)
+        got = np.asarray(call(lb, case, golden))
+        want = np.asarray(call(oracle, case, golden))
     fixture = golden[case["name"]]
     fn = case["fn"]
     for ref in (want, fixture):
@@ -95,6 +97,10 @@ def test_feature_case_against_oracle_and_reference_fixture(case, lb, oracle, gol
         elif fn == "spectral_contrast":
             linear = case["kw"].get("linear", False)
             _close(got, ref, 1e-4, 1e-6 * scale if linear else 1e-3)
+        elif fn == "chroma_stft":
+            _close(got, ref, 1e-4, 2e-6)           # values in [0, 1]; same tuning on both sides (mix T, see cases)
+        elif fn == "estimate_tuning":
+            assert got.shape == ref.shape == () and float(got) == pytest.approx(float(ref), abs=1e-12)
         elif fn == "pcen":
             _close(got, ref, 1e-4, 1e-6 * scale)
         elif fn == "amplitude_to_db":

@@ -50,9 +50,19 @@ def test_frame_statistics_bit_exact(ref, oracle, golden):
     for case in FEATURE_CASES:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            a, b = call(ref, case, golden), call(oracle, case, golden)
+            a, b = np.asarray(call(ref, case, golden)), np.asarray(call(oracle, case, golden))
         assert a.dtype == b.dtype and a.shape == b.shape, case["name"]
         np.testing.assert_array_equal(a, b, err_msg=case["name"])
+
+
+def test_product_chroma_filter_matches_reference(ref):
+    import librosa_b200 as lb
+
+    for kw in [dict(sr=22050, n_fft=2048), dict(sr=16000, n_fft=1024, tuning=0.27), dict(sr=22050, n_fft=400, n_chroma=24, octwidth=None),
+               dict(sr=44100, n_fft=4096, norm=None, base_c=False, ctroct=4.0, octwidth=1.5), dict(sr=22050, n_fft=1025, tuning=-0.3)]:
+        np.testing.assert_array_equal(lb.filters.chroma(**kw), ref.filters.chroma(**kw))
+    f = np.array([27.5, 55.0, 440.0, 1234.5])
+    np.testing.assert_array_equal(lb.hz_to_octs(f, tuning=0.2, bins_per_octave=24), ref.hz_to_octs(f, tuning=0.2, bins_per_octave=24))
 
 
 def test_griffinlim_bit_exact(ref, oracle):

@@ -81,7 +81,7 @@ def main():
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             out = call(ref, case, store)
-        feats[case["name"]] = np.ascontiguousarray(out)
+        feats[case["name"]] = np.ascontiguousarray(out) if np.ndim(out) else np.asarray(out)
         print(f"{case['name']:40s} {out.shape} {out.dtype}")
     path = os.path.join(ROOT, "tests", "golden", "features_v1.npz")
     np.savez_compressed(path, **feats)
