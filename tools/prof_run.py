@@ -22,6 +22,8 @@ for _ in range(reps):
         lb.stft(dev, **kw).free()
     elif op == "mfcc":
         lb.feature.mfcc(y=dev, sr=sr, **kw).free()
+    elif op == "centroid":
+        lb.feature.spectral_centroid(y=dev, sr=sr, **kw).free()
     else:
         D = lb.stft(dev, **kw); lb.istft(D, hop_length=kw["hop_length"], length=w["n"]).free(); D.free()
 ctx.synchronize()
