@@ -223,6 +223,20 @@ int b2l_pip_pass(b2l_ctx* ctx, const b2l_pip_desc* desc, const float* d_S, int64
  * fill): norm_kind 0 = inf, 1 = -inf, 2 = number of non-zeros, 3 = p-norm (norm_p > 0). */
 int b2l_normalize_rows(b2l_ctx* ctx, const float* d_in, int64_t n_clips, int64_t n_rows, int64_t n_frames,
                        int32_t norm_kind, float norm_p, float* d_out);
+/* ---- harmonic / percussive separation, librosa.decompose.hpss (decompose.py:241-389) --------
+ * d_mag [n_clips][n_frames][n_bins] magnitudes.  harm / perc = running medians over win_harm frames / win_perc
+ * bins (scipy.ndimage.median_filter, reflect boundary), turned into soft masks (util.softmask, `power`, margins).
+ * mask_only: d_out_* receive the float32 masks.  Otherwise the masked spectrogram: complex64 S * mask when
+ * d_S_complex is given (the reference's (|S| * mask) * phase), else float32 d_mag * mask.  Windows up to 64. */
+typedef struct b2l_hpss_desc {
+  int32_t win_harm, win_perc;
+  float margin_harm, margin_perc, power;   /* power may be +inf (hard mask) */
+  int32_t mask_only;
+} b2l_hpss_desc;
+int b2l_hpss(b2l_ctx* ctx, const b2l_hpss_desc* desc, const float* d_mag, const void* d_S_complex, int64_t n_clips,
+             int64_t n_frames, int64_t n_bins, void* d_out_harm, void* d_out_perc);
+/* |z| of n complex64 values */
+int b2l_cabs(b2l_ctx* ctx, const void* d_complex, int64_t n, float* d_out);
 /* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
  *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
  *                                                        of the squared magnitudes with ref^2 / amin^2

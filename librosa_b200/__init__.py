@@ -6,7 +6,7 @@ window_sumsquare``, ``util.frame`` (and the small helpers around them) with libr
 shapes, dtypes, warnings and exceptions.  The arithmetic runs in hand-written CUDA kernels reached
 through a C ABI (``include/b2l.h``) with ctypes — no PyTorch, no Triton, no CPU fallback.
 """
-from . import core, feature, filters, onset, util
+from . import core, decompose, effects, feature, filters, onset, util
 from ._native import (
     Context,
     DeviceArray,
@@ -31,7 +31,7 @@ def to_device(arr, device=None):
 
 
 __all__ = [
-    "stft", "istft", "griffinlim", "power_to_db", "amplitude_to_db", "pcen", "db_to_power", "db_to_amplitude", "_spectrogram", "feature", "filters", "util", "core", "onset",
+    "stft", "istft", "griffinlim", "power_to_db", "amplitude_to_db", "pcen", "db_to_power", "db_to_amplitude", "_spectrogram", "feature", "filters", "util", "core", "onset", "decompose", "effects",
     "hz_to_mel", "mel_to_hz", "hz_to_octs", "estimate_tuning", "mel_frequencies", "fft_frequencies", "ParameterError", "LibrosaError",
     "Context", "DeviceArray", "default_context", "device_count", "pinned_empty", "to_device",
     "NativeLibraryError", "UnsupportedOnGPU",

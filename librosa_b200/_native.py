@@ -95,6 +95,12 @@ class PipDesc(C.Structure):
                 ("bins_per_octave", C.c_float), ("n_res_bins", C.c_int32)]
 
 
+class HpssDesc(C.Structure):
+    """struct b2l_hpss_desc (include/b2l.h)."""
+    _fields_ = [("win_harm", C.c_int32), ("win_perc", C.c_int32), ("margin_harm", C.c_float),
+                ("margin_perc", C.c_float), ("power", C.c_float), ("mask_only", C.c_int32)]
+
+
 N_STATS = 6
 STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
 FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
@@ -152,6 +158,8 @@ def _declare(lib):
         "b2l_sub": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
         "b2l_pip_pass": (C.c_int, [_vp, P(PipDesc), _vp, _i64, C.c_int32, _vp, _vp]),
         "b2l_normalize_rows": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, C.c_float, _vp]),
+        "b2l_hpss": (C.c_int, [_vp, P(HpssDesc), _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+        "b2l_cabs": (C.c_int, [_vp, _vp, _i64, _vp]),
         "b2l_unary": (C.c_int, [_vp, C.c_int32, _vp, _i64, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),

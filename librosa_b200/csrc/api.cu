@@ -1480,6 +1480,51 @@ extern "C" int b2l_normalize_rows(b2l_ctx* c, const float* d_in, int64_t n_clips
   return B2L_OK;
 }
 
+extern "C" int b2l_cabs(b2l_ctx* c, const void* d_complex, int64_t n, float* d_out) {
+  if (!c || !d_complex || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (n <= 0) return B2L_OK;
+  DeviceGuard g(c->device);
+  long long grid = (n + 256LL * 8 - 1) / (256LL * 8);
+  if (grid > 8LL * c->sm_count) grid = 8LL * c->sm_count;
+  cabs_kernel<<<(int)grid, 256, 0, c->stream>>>((const float2*)d_complex, n, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
+extern "C" int b2l_hpss(b2l_ctx* c, const b2l_hpss_desc* d, const float* d_mag, const void* d_S_complex,
+                        int64_t n_clips, int64_t n_frames, int64_t n_bins, void* d_out_harm, void* d_out_perc) {
+  if (!c || !d || !d_mag || !d_out_harm || !d_out_perc) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (d->win_harm < 1 || d->win_perc < 1) return fail(B2L_ERR_INVALID, "kernel sizes must be positive");
+  if (d->win_harm > 64 || d->win_perc > 64) return fail(B2L_ERR_UNSUPPORTED, "median filters longer than 64 are not supported");
+  if (d->margin_harm < 1.0f || d->margin_perc < 1.0f)
+    return fail(B2L_ERR_INVALID, "Margins must be >= 1.0. A typical range is between 1 and 10.");
+  if (!(d->power > 0.0f)) return fail(B2L_ERR_INVALID, "power must be strictly positive");
+  if (n_clips <= 0 || n_frames <= 0 || n_bins <= 0) return B2L_OK;
+  if (n_frames > 65535 || n_clips > 65535 || n_bins > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "hpss: batch too large");
+  HpssArgs a;
+  a.T = (int)n_frames;
+  a.F = (int)n_bins;
+  a.win_h = d->win_harm;
+  a.win_p = d->win_perc;
+  a.margin_h = d->margin_harm;
+  a.margin_p = d->margin_perc;
+  a.power = d->power;
+  a.split_zeros = (d->margin_harm == 1.0f && d->margin_perc == 1.0f) ? 1 : 0;
+  a.mode = d->mask_only ? 1 : 0;
+  DeviceGuard g(c->device);
+  const int w = std::max(d->win_harm, d->win_perc);
+  dim3 grid((unsigned)((n_bins + 127) / 128), (unsigned)n_frames, (unsigned)n_clips);
+  const float2* sc = d->mask_only ? nullptr : (const float2*)d_S_complex;
+  if (w <= 8) hpss_kernel<8><<<grid, 128, 0, c->stream>>>(d_mag, sc, a, (float*)d_out_harm, (float*)d_out_perc);
+  else if (w <= 16) hpss_kernel<16><<<grid, 128, 0, c->stream>>>(d_mag, sc, a, (float*)d_out_harm, (float*)d_out_perc);
+  else if (w <= 32) hpss_kernel<32><<<grid, 128, 0, c->stream>>>(d_mag, sc, a, (float*)d_out_harm, (float*)d_out_perc);
+  else hpss_kernel<64><<<grid, 128, 0, c->stream>>>(d_mag, sc, a, (float*)d_out_harm, (float*)d_out_perc);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);

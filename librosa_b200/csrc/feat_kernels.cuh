@@ -232,32 +232,60 @@ __global__ void contrast_kernel(const float* __restrict__ S, long long n_rows, i
     const long long clip = r / n_frames, frame = r % n_frames;
     for (int b = 0; b < a.n_bands; ++b) {
       const int n = a.count[b];
-      int N = 1;
-      while (N < n) N <<= 1;
-      for (int i = lane; i < N; i += 32) s_sort[i] = i < n ? s_row[a.lo[b] + i] : INFINITY;
-      __syncwarp();
-      for (int k = 2; k <= N; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = lane; i < N; i += 32) {
-            const int p = i ^ j;
-            if (p > i) {
-              const float x = s_sort[i], y = s_sort[p];
-              if ((x > y) == ((i & k) == 0)) {
-                s_sort[i] = y;
-                s_sort[p] = x;
-              }
-            }
-          }
-          __syncwarp();
-        }
       const int kk = min(a.k[b], n);
       float lo_sum = 0.0f, hi_sum = 0.0f;
-      for (int i = lane; i < kk; i += 32) {
-        lo_sum += s_sort[i];
-        hi_sum += s_sort[n - 1 - i];
+      if (kk <= 16) {
+        // short tails (the default quantile 0.02 gives k <= 9 for n_fft = 2048): extract the k extremes one
+        // at a time — lane-local scan of the lane's strided elements, one warp reduction on the
+        // order-preserving keys, the owning lane knocks its element out.  ~40 instructions per extreme
+        // instead of a full sort of the band.
+        for (int pass = 0; pass < 2; ++pass) {                  // 0: valley (minima), 1: peak (maxima)
+          for (int i = lane; i < n; i += 32) s_sort[i] = s_row[a.lo[b] + i];
+          __syncwarp();
+          float acc = 0.0f;
+          for (int e = 0; e < kk; ++e) {
+            unsigned int best = pass == 0 ? 0xffffffffu : 0u;
+            int best_i = -1;
+            for (int i = lane; i < n; i += 32) {
+              const unsigned int key = float_to_key(s_sort[i]);
+              if (pass == 0 ? key < best : key > best) { best = key; best_i = i; }
+              else if (best_i < 0 && key == best) best_i = i;
+            }
+            const unsigned int win = pass == 0 ? __reduce_min_sync(0xffffffffu, best) : __reduce_max_sync(0xffffffffu, best);
+            const unsigned int owners = __ballot_sync(0xffffffffu, best == win && best_i >= 0);
+            if (owners == 0u) break;                              // fewer than k finite candidates left
+            if (lane == __ffs(owners) - 1) s_sort[best_i] = pass == 0 ? INFINITY : -INFINITY;
+            acc += key_to_float(win);
+            __syncwarp();
+          }
+          if (pass == 0) lo_sum = acc; else hi_sum = acc;
+        }
+      } else {
+        int N = 1;
+        while (N < n) N <<= 1;
+        for (int i = lane; i < N; i += 32) s_sort[i] = i < n ? s_row[a.lo[b] + i] : INFINITY;
+        __syncwarp();
+        for (int k = 2; k <= N; k <<= 1)
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < N; i += 32) {
+              const int p = i ^ j;
+              if (p > i) {
+                const float x = s_sort[i], y = s_sort[p];
+                if ((x > y) == ((i & k) == 0)) {
+                  s_sort[i] = y;
+                  s_sort[p] = x;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        for (int i = lane; i < kk; i += 32) {
+          lo_sum += s_sort[i];
+          hi_sum += s_sort[n - 1 - i];
+        }
+        lo_sum = warp_sum(lo_sum);
+        hi_sum = warp_sum(hi_sum);
       }
-      lo_sum = warp_sum(lo_sum);
-      hi_sum = warp_sum(hi_sum);
       if (lane == 0) {
         const long long o = (clip * a.n_bands + b) * n_frames + frame;
         valley[o] = lo_sum / (float)kk;       // n == 0: 0/0 = NaN, like the mean of an empty slice
@@ -379,6 +407,99 @@ __global__ void normalize_rows_kernel(const float* __restrict__ x, int rows, int
   if (norm_kind == 3 && norm_p != 1.0f) len = norm_p == 2.0f ? sqrtf(len) : powf(len, 1.0f / norm_p);
   if (len < 1.17549435e-38f) len = 1.0f;
   for (int r = 0; r < rows; ++r) oc[(long long)r * T] = xc[(long long)r * T] / len;
+}
+
+// Median-filtering harmonic / percussive separation (librosa/decompose.py:241-389, hpss) on a magnitude
+// spectrogram M [clip][T][F] (bins contiguous):
+//   harm = median over `win_h` frames (scipy.ndimage.median_filter, reflect boundary, rank size // 2),
+//   perc = median over `win_p` bins,
+//   mask_h = softmask(harm, perc * margin_h), mask_p = softmask(perc, harm * margin_p)   (util/utils.py: softmask)
+// One thread per element: the window goes into a register array padded with +inf to NS = 8 / 16 / 32 / 64
+// entries and through a compile-time bitonic network (fminf / fmaxf pairs, no branches).  Neighbouring threads
+// share all but one of their inputs, so the loads are served by L1.
+template <int NS>
+__device__ __forceinline__ float median_of(float (&v)[NS], int rank) {
+#pragma unroll
+  for (int k = 2; k <= NS; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const int p = i ^ j;
+        if (p > i) {
+          const float x = v[i], y = v[p];
+          const float lo = fminf(x, y), hi = fmaxf(x, y);
+          const bool asc = (i & k) == 0;
+          v[i] = asc ? lo : hi;
+          v[p] = asc ? hi : lo;
+        }
+      }
+    }
+  }
+  float m = v[0];
+#pragma unroll
+  for (int i = 1; i < NS; ++i)
+    if (i == rank) m = v[i];
+  return m;
+}
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - i - 1;
+  return i;
+}
+__device__ __forceinline__ float soft_mask(float x, float x_ref, float power, int split_zeros) {
+  float z = fmaxf(x, x_ref);
+  const bool bad = z < 1.17549435e-38f;
+  if (bad) return split_zeros ? 0.5f : 0.0f;
+  if (isinf(power)) return x > x_ref ? 1.0f : 0.0f;
+  const float a = x / z, b = x_ref / z;
+  const float pa = power == 2.0f ? a * a : (power == 1.0f ? a : powf(a, power));
+  const float pb = power == 2.0f ? b * b : (power == 1.0f ? b : powf(b, power));
+  return pa / (pa + pb);
+}
+struct HpssArgs {
+  int T, F, win_h, win_p;
+  float margin_h, margin_p, power;
+  int split_zeros, mode;     // mode 0: masked components, 1: the masks
+};
+template <int NS>
+__global__ void hpss_kernel(const float* __restrict__ M, const float2* __restrict__ Sc, HpssArgs a,
+                            float* __restrict__ out_h, float* __restrict__ out_p) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (f >= a.F) return;
+  const long long base = (long long)blockIdx.z * a.T * a.F;
+  const float* Mc = M + base;
+  float v[NS];
+  const int t0 = t - a.win_h / 2;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) v[j] = j < a.win_h ? __ldg(Mc + (long long)reflect_index(t0 + j, a.T) * a.F + f) : INFINITY;
+  const float harm = median_of<NS>(v, a.win_h / 2);
+  const int f0 = f - a.win_p / 2;
+  const float* row = Mc + (long long)t * a.F;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) v[j] = j < a.win_p ? __ldg(row + reflect_index(f0 + j, a.F)) : INFINITY;
+  const float perc = median_of<NS>(v, a.win_p / 2);
+  const float mh = soft_mask(harm, perc * a.margin_h, a.power, a.split_zeros);
+  const float mp = soft_mask(perc, harm * a.margin_p, a.power, a.split_zeros);
+  const long long o = base + (long long)t * a.F + f;
+  if (a.mode == 1) {
+    out_h[o] = mh;
+    out_p[o] = mp;
+  } else if (Sc) {
+    const float2 s = Sc[o];
+    reinterpret_cast<float2*>(out_h)[o] = make_float2(s.x * mh, s.y * mh);
+    reinterpret_cast<float2*>(out_p)[o] = make_float2(s.x * mp, s.y * mp);
+  } else {
+    const float m = Mc[(long long)t * a.F + f];
+    out_h[o] = m * mh;
+    out_p[o] = m * mp;
+  }
+}
+__global__ void cabs_kernel(const float2* __restrict__ x, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float2 v = x[i];
+    out[i] = hypotf(v.x, v.y);
+  }
 }
 
 // Elementwise helpers of the dB conversions (librosa/core/spectrum.py):

@@ -1,0 +1,68 @@
+"""``librosa.effects.hpss`` / ``harmonic`` / ``percussive`` with librosa's signatures (reference:
+librosa/effects.py:58-131, :134-206, :209-281): stft -> decompose.hpss -> istft, every intermediate on the
+device (one upload of the signal, one download per returned component)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _native as nat
+from . import _pipeline as pl
+from .core.spectrum import istft, stft
+from .decompose import _hpss_device
+from .util.exceptions import ParameterError
+
+__all__ = ["hpss", "harmonic", "percussive"]
+
+
+def _separate(y, want, *, kernel_size, power, mask, margin, n_fft, hop_length, win_length, window, center, pad_mode):
+    # NB: like the reference (effects.py:87-94, :102-119) `window` is accepted but not forwarded to stft / istft.
+    if mask:
+        raise nat.UnsupportedOnGPU("effects.hpss(mask=True) inverts the masks themselves; not supported on the GPU")
+    n, req = pl.precheck_signal(y)
+    on_device = isinstance(y, nat.DeviceArray)
+    if on_device:
+        ctx, yd = y.ctx, y
+    else:
+        ctx = nat.default_context()
+        staged = pl.StagedInput(ctx, y)
+        yd = staged.dev
+    D = stft(yd, n_fft=n_fft, hop_length=hop_length, win_length=win_length, center=center, pad_mode=pad_mode)
+    if not on_device:
+        hop_eff, _ = pl.frame_params(n_fft, hop_length, win_length)
+        staged.scan_uncovered(n_fft, hop_eff, center, D.shape[-1])
+    harm, perc = _hpss_device(ctx, D, kernel_size=kernel_size, power=power, mask=False, margin=margin)
+    D.free()
+    outs = []
+    for name, comp in (("harm", harm), ("perc", perc)):
+        if name in want:
+            yd_out = istft(comp, n_fft=n_fft, hop_length=hop_length, win_length=win_length, center=center, length=n)
+            outs.append(yd_out if on_device else pl.finish(ctx, yd_out, True, req, validate=True))
+        comp.free()
+    return outs
+
+
+def hpss(y, *, kernel_size=31, power: float = 2.0, mask: bool = False, margin=1.0, n_fft: int = 2048,
+         hop_length: Optional[int] = None, win_length: Optional[int] = None, window="hann", center: bool = True,
+         pad_mode="constant"):
+    """Decompose a signal into harmonic and percussive components; same contract as ``librosa.effects.hpss``."""
+    h, p = _separate(y, ("harm", "perc"), kernel_size=kernel_size, power=power, mask=mask, margin=margin, n_fft=n_fft,
+                     hop_length=hop_length, win_length=win_length, window=window, center=center, pad_mode=pad_mode)
+    return h, p
+
+
+def harmonic(y, *, kernel_size=31, power: float = 2.0, mask: bool = False, margin=1.0, n_fft: int = 2048,
+             hop_length: Optional[int] = None, win_length: Optional[int] = None, window="hann", center: bool = True,
+             pad_mode="constant"):
+    """Harmonic component of a signal; same contract as ``librosa.effects.harmonic``."""
+    return _separate(y, ("harm",), kernel_size=kernel_size, power=power, mask=mask, margin=margin, n_fft=n_fft,
+                     hop_length=hop_length, win_length=win_length, window=window, center=center, pad_mode=pad_mode)[0]
+
+
+def percussive(y, *, kernel_size=31, power: float = 2.0, mask: bool = False, margin=1.0, n_fft: int = 2048,
+               hop_length: Optional[int] = None, win_length: Optional[int] = None, window="hann", center: bool = True,
+               pad_mode="constant"):
+    """Percussive component of a signal; same contract as ``librosa.effects.percussive``."""
+    return _separate(y, ("perc",), kernel_size=kernel_size, power=power, mask=mask, margin=margin, n_fft=n_fft,
+                     hop_length=hop_length, win_length=win_length, window=window, center=center, pad_mode=pad_mode)[0]

@@ -754,6 +754,90 @@ def pcen(S, sr=22050, hop_length=512, gain=0.98, bias=2, power=0.5, time_constan
     return (S_out, zf) if return_zf else S_out
 
 
+# --------------------------------------------------------------------------- harmonic / percussive separation
+def softmask(X, X_ref, power=1, split_zeros=False):
+    """librosa/util/utils.py (softmask)."""
+    if X.shape != X_ref.shape:
+        raise ParameterError(f"Shape mismatch: {X.shape}!={X_ref.shape}")
+    if np.any(X < 0) or np.any(X_ref < 0):
+        raise ParameterError("X and X_ref must be non-negative")
+    if power <= 0:
+        raise ParameterError("power must be strictly positive")
+    dtype = X.dtype if np.issubdtype(X.dtype, np.floating) else np.float32
+    Z = np.maximum(X, X_ref).astype(dtype)
+    bad_idx = Z < np.finfo(dtype).tiny
+    Z[bad_idx] = 1
+    if np.isfinite(power):
+        mask = (X / Z) ** power
+        ref_mask = (X_ref / Z) ** power
+        good_idx = ~bad_idx
+        mask[good_idx] /= mask[good_idx] + ref_mask[good_idx]
+        mask[bad_idx] = 0.5 if split_zeros else 0.0
+    else:
+        mask = X > X_ref
+    return mask
+
+
+def magphase(D, power=1):
+    """librosa/core/spectrum.py (magphase)."""
+    mag = np.abs(D)
+    zeros_to_ones = mag == 0
+    mag_nonzero = mag + zeros_to_ones
+    phase = np.empty_like(D, dtype=dtype_r2c(D.dtype))
+    phase.real = D.real / mag_nonzero + zeros_to_ones
+    phase.imag = D.imag / mag_nonzero
+    mag **= power
+    return mag, phase
+
+
+def decompose_hpss(S, kernel_size=31, power=2.0, mask=False, margin=1.0):
+    """librosa/decompose.py:338-389."""
+    from scipy.ndimage import median_filter
+
+    if np.iscomplexobj(S):
+        S, phase = magphase(S)
+    else:
+        phase = 1
+    win_harm, win_perc = kernel_size if isinstance(kernel_size, (tuple, list)) else (kernel_size, kernel_size)
+    margin_harm, margin_perc = margin if isinstance(margin, (tuple, list)) else (margin, margin)
+    if margin_harm < 1 or margin_perc < 1:
+        raise ParameterError("Margins must be >= 1.0. A typical range is between 1 and 10.")
+    harm_shape = [1] * S.ndim
+    harm_shape[-1] = int(win_harm)
+    perc_shape = [1] * S.ndim
+    perc_shape[-2] = int(win_perc)
+    harm = np.empty_like(S)
+    harm[:] = median_filter(S, size=harm_shape, mode="reflect")
+    perc = np.empty_like(S)
+    perc[:] = median_filter(S, size=perc_shape, mode="reflect")
+    split_zeros = margin_harm == 1 and margin_perc == 1
+    mask_harm = softmask(harm, perc * margin_harm, power=power, split_zeros=split_zeros)
+    mask_perc = softmask(perc, harm * margin_perc, power=power, split_zeros=split_zeros)
+    if mask:
+        return mask_harm, mask_perc
+    return ((S * mask_harm) * phase, (S * mask_perc) * phase)
+
+
+def effects_hpss(y, kernel_size=31, power=2.0, mask=False, margin=1.0, n_fft=2048, hop_length=None,
+                 win_length=None, window="hann", center=True, pad_mode="constant"):
+    """librosa/effects.py:58-131 (``window`` is accepted but, as in the reference, not forwarded)."""
+    D = stft(y, n_fft=n_fft, hop_length=hop_length, win_length=win_length, center=center, pad_mode=pad_mode)
+    Dh, Dp = decompose_hpss(D, kernel_size=kernel_size, power=power, mask=mask, margin=margin)
+    kw = dict(dtype=y.dtype, n_fft=n_fft, hop_length=hop_length, win_length=win_length, center=center,
+              length=y.shape[-1])
+    return istft(Dh, **kw), istft(Dp, **kw)
+
+
+def effects_harmonic(y, **kwargs):
+    """librosa/effects.py:134-206."""
+    return effects_hpss(y, **kwargs)[0]
+
+
+def effects_percussive(y, **kwargs):
+    """librosa/effects.py:209-281."""
+    return effects_hpss(y, **kwargs)[1]
+
+
 # --------------------------------------------------------------------------- onset strength
 def _channel_slices(channels, n_rows, pad):
     """``util.sync`` index handling (librosa/util/utils.py: sync, index_to_slice, fix_frames)."""

@@ -116,6 +116,18 @@ FEATURE_CASES += [
     dict(name="tuning_res05_bpo24_T", fn="estimate_tuning", ns="top", mix="T", seed=1, shape=(20000,), kw=dict(sr=22050, resolution=0.05, bins_per_octave=24, fmin=100.0, fmax=3000.0)),
 ]
 
+FEATURE_CASES += [
+    # ---- harmonic / percussive separation (decompose.hpss on spectrograms, effects.hpss on signals)
+    dict(name="hpss_stft_default", fn="hpss", ns="decompose", arg="stft_1024_256_reflect_B", kw=dict()),
+    dict(name="hpss_mag_stereo_k13_31_margin", fn="hpss", ns="decompose", arg="stft_512_stereo_A", arg_op="abs", kw=dict(kernel_size=(13, 31), margin=(1.0, 3.0))),
+    dict(name="hpss_masks_power1", fn="hpss", ns="decompose", arg="stft_2048_C_burst", kw=dict(mask=True, power=1.0)),
+    dict(name="hpss_hard_k8", fn="hpss", ns="decompose", arg="stft_64_16_B", arg_op="abs", kw=dict(power=np.inf, kernel_size=8)),
+    dict(name="hpss_k63", fn="hpss", ns="decompose", arg="stft_2048_512_A", arg_op="abs", kw=dict(kernel_size=(63, 5), margin=2.0)),
+    dict(name="effects_hpss_B", fn="hpss", ns="effects", mix="B", shape=(2, 12000), pos=True, kw=dict(n_fft=1024)),
+    dict(name="effects_harmonic_T", fn="harmonic", ns="effects", mix="T", seed=3, shape=(20000,), pos=True, kw=dict(margin=3.0)),
+    dict(name="effects_percussive_C", fn="percussive", ns="effects", mix="C", shape=(20000,), pos=True, kw=dict(kernel_size=17)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 
@@ -158,9 +170,21 @@ def resolve(root, case):
         return getattr(root, case["fn"])
     if case.get("ns") == "onset":
         return getattr(getattr(root, "onset", root), case["fn"])
+    if case.get("ns") in ("decompose", "effects"):     # oracle: flat names decompose_hpss / effects_hpss
+        sub = getattr(root, case["ns"], None)
+        return getattr(sub, case["fn"]) if sub is not None else getattr(root, f"{case['ns']}_{case['fn']}")
     return getattr(getattr(root, "feature", root), case["fn"])
 
 
 def call(root, case, golden):
     args, kw = case_args(case, golden)
     return resolve(root, case)(*args, **kw)
+
+
+def outputs(result):
+    """Results as a list of arrays (functions returning tuples are stored / compared element by element)."""
+    return [np.asarray(r) for r in result] if isinstance(result, tuple) else [np.asarray(result)]
+
+
+def fixture_names(case, n):
+    return [case["name"]] if n == 1 else [f"{case['name']}#{i}" for i in range(n)]

@@ -45,14 +45,16 @@ def test_features_bit_exact(ref, oracle):
 
 
 def test_frame_statistics_bit_exact(ref, oracle, golden):
-    from feature_cases import FEATURE_CASES, call
+    from feature_cases import FEATURE_CASES, call, outputs
 
     for case in FEATURE_CASES:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            a, b = np.asarray(call(ref, case, golden)), np.asarray(call(oracle, case, golden))
-        assert a.dtype == b.dtype and a.shape == b.shape, case["name"]
-        np.testing.assert_array_equal(a, b, err_msg=case["name"])
+            A, B = outputs(call(ref, case, golden)), outputs(call(oracle, case, golden))
+        assert len(A) == len(B)
+        for a, b in zip(A, B):
+            assert a.dtype == b.dtype and a.shape == b.shape, case["name"]
+            np.testing.assert_array_equal(a, b, err_msg=case["name"])
 
 
 def test_product_chroma_filter_matches_reference(ref):

@@ -74,15 +74,17 @@ def main():
     np.savez_compressed(path, **store)
     print("wrote", path, os.path.getsize(path), "bytes; reference", ref.__version__)
     # ---- frame-wise consumers (tests/feature_cases.py)
-    from feature_cases import FEATURE_CASES, call
+    from feature_cases import FEATURE_CASES, call, fixture_names, outputs
 
     feats = {}
     for case in FEATURE_CASES:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             out = call(ref, case, store)
-        feats[case["name"]] = np.ascontiguousarray(out) if np.ndim(out) else np.asarray(out)
-        print(f"{case['name']:40s} {out.shape} {out.dtype}")
+        outs = outputs(out)
+        for key, arr in zip(fixture_names(case, len(outs)), outs):
+            feats[key] = np.ascontiguousarray(arr) if arr.ndim else arr
+            print(f"{key:40s} {arr.shape} {arr.dtype}")
     path = os.path.join(ROOT, "tests", "golden", "features_v1.npz")
     np.savez_compressed(path, **feats)
     print("wrote", path, os.path.getsize(path), "bytes")
