@@ -29,6 +29,7 @@ T = 1 + host.shape[-1] // 512
 frames = clips * T
 mel_db = lb.power_to_db(lb.feature.melspectrogram(y=dev, sr=sr))
 mel_pw = lb.feature.melspectrogram(y=dev, sr=sr)
+dev128 = ctx.to_device(host[:128])
 
 
 def free(x):
@@ -48,6 +49,7 @@ FEATURES = {
     "chroma_stft(tuning=0)": (lambda: lb.feature.chroma_stft(y=dev, sr=sr, tuning=0.0), lambda y: O.chroma_stft(y=y, sr=sr, tuning=0.0)),
     "chroma_stft(estimated tuning)": (lambda: lb.feature.chroma_stft(y=dev, sr=sr), lambda y: O.chroma_stft(y=y, sr=sr)),
     "onset_strength": (lambda: lb.onset.onset_strength(y=dev, sr=sr), lambda y: O.onset_strength(y=y, sr=sr)),
+    "effects.hpss (128 clips)": (lambda: lb.effects.hpss(dev128), None),
     "pcen(mel)": (lambda: lb.pcen(mel_pw, sr=sr), None),
     "amplitude_to_db(mel)": (lambda: lb.amplitude_to_db(mel_pw), None),
 }
@@ -66,7 +68,9 @@ with warnings.catch_warnings():
         e1.record()
         ctx.synchronize()
         ms = e0.elapsed_ms(e1) / reps
-        row = {"gpu_ms": round(ms, 3), "gpu_frames_per_s": round(frames / ms * 1e3), "launches_per_call": (ctx.launch_count - l0) / reps}
+        nfr = 128 * T if "128 clips" in name else frames
+        row = {"gpu_ms": round(ms, 3), "frames": nfr, "gpu_frames_per_s": round(nfr / ms * 1e3),
+               "launches_per_call": (ctx.launch_count - l0) / reps}
         if cpu is not None:
             sample = host[:8]
             cpu(sample[:1])
