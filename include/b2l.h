@@ -237,6 +237,18 @@ int b2l_hpss(b2l_ctx* ctx, const b2l_hpss_desc* desc, const float* d_mag, const 
              int64_t n_frames, int64_t n_bins, void* d_out_harm, void* d_out_perc);
 /* |z| of n complex64 values */
 int b2l_cabs(b2l_ctx* ctx, const void* d_complex, int64_t n, float* d_out);
+/* Time-frequency reassignment, librosa.reassigned_spectrogram (core/spectrum.py:1019-1293 with
+ * __reassign_frequencies :646-856 and __reassign_times :859-1016): elementwise over the STFTs taken with the
+ * window (d_Sh), its cyclic derivative (d_Sdh) and the time-weighted window (d_Sth), all complex64
+ * [n_clips][n_frames][n_bins]; d_bin_freqs [n_bins] (Hz), d_frame_times [n_frames] (s).  Outputs float32 in the
+ * same layout.  mag_threshold = sqrt(ref_power); apply_threshold = ref_power > 0. */
+typedef struct b2l_reassign_desc {
+  float sr, mag_threshold, max_time;
+  int32_t reassign_frequencies, reassign_times, apply_threshold, fill_nan, clip;
+} b2l_reassign_desc;
+int b2l_reassign(b2l_ctx* ctx, const b2l_reassign_desc* desc, const void* d_Sh, const void* d_Sdh, const void* d_Sth,
+                 int64_t n_clips, int64_t n_frames, int64_t n_bins, const float* d_bin_freqs,
+                 const float* d_frame_times, float* d_freqs, float* d_times, float* d_mags);
 /* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
  *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
  *                                                        of the squared magnitudes with ref^2 / amin^2

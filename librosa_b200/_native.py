@@ -101,6 +101,13 @@ class HpssDesc(C.Structure):
                 ("margin_perc", C.c_float), ("power", C.c_float), ("mask_only", C.c_int32)]
 
 
+class ReassignDesc(C.Structure):
+    """struct b2l_reassign_desc (include/b2l.h)."""
+    _fields_ = [("sr", C.c_float), ("mag_threshold", C.c_float), ("max_time", C.c_float),
+                ("reassign_frequencies", C.c_int32), ("reassign_times", C.c_int32), ("apply_threshold", C.c_int32),
+                ("fill_nan", C.c_int32), ("clip", C.c_int32)]
+
+
 N_STATS = 6
 STAT_CENTROID, STAT_BANDWIDTH, STAT_ROLLOFF, STAT_FLATNESS, STAT_RMS, STAT_TOTAL = range(6)
 FRAME_RMS, FRAME_ZERO_CROSSINGS = 0, 1
@@ -160,6 +167,7 @@ def _declare(lib):
         "b2l_normalize_rows": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, C.c_float, _vp]),
         "b2l_hpss": (C.c_int, [_vp, P(HpssDesc), _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
         "b2l_cabs": (C.c_int, [_vp, _vp, _i64, _vp]),
+        "b2l_reassign": (C.c_int, [_vp, P(ReassignDesc), _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
         "b2l_unary": (C.c_int, [_vp, C.c_int32, _vp, _i64, C.c_float, _vp]),
         "b2l_dct_project": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
         "b2l_transpose": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, _vp]),

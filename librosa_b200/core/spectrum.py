@@ -17,7 +17,7 @@ from .. import _native as nat
 from .. import _pipeline as pl
 from .. import filters
 from ..util.exceptions import ParameterError
-from ..util.utils import dtype_c2r, dtype_r2c, fix_length, is_positive_int, tiny
+from ..util.utils import dtype_c2r, dtype_r2c, fix_length, is_positive_int, pad_center, tiny
 
 _vp = C.c_void_p
 
@@ -453,6 +453,84 @@ def pcen(S, *, sr: float = 22050, hop_length: int = 512, gain: float = 0.98, bia
     if return_zf:
         return res, pl.finish(ctx, d_zf, True, res_dtype)
     return res
+
+
+def reassigned_spectrogram(y, *, sr: float = 22050, S=None, n_fft: int = 2048, hop_length: Optional[int] = None,
+                           win_length: Optional[int] = None, window="hann", center: bool = True,
+                           reassign_frequencies: bool = True, reassign_times: bool = True, ref_power=1e-6,
+                           fill_nan: bool = False, clip: bool = True, dtype=None, pad_mode="constant"):
+    """Time-frequency reassigned spectrogram ``(freqs, times, mags)``; same contract as
+    ``librosa.reassigned_spectrogram`` (core/spectrum.py:1019-1293) for a numeric ``ref_power``.  The three
+    STFTs (window, cyclic window derivative, time-weighted window) and the reassignment arithmetic stay on the
+    device.  float32 arithmetic: cells whose magnitude is near float32 round-off of the loudest bin carry a
+    visibly larger relative error in the reassigned coordinates than the reference's float64 FFT."""
+    from ..util.utils import cyclic_gradient
+
+    if callable(ref_power):
+        raise nat.UnsupportedOnGPU("reassigned_spectrogram(ref_power=callable) is not supported on the GPU")
+    if ref_power < 0:
+        raise ParameterError("ref_power must be non-negative or callable.")
+    if not reassign_frequencies and not reassign_times:
+        raise ParameterError("reassign_frequencies or reassign_times must be True.")
+    if S is not None and isinstance(S, nat.DeviceArray):
+        raise nat.UnsupportedOnGPU("reassigned_spectrogram(S=DeviceArray) is not supported; pass y only")
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    n, req = pl.precheck_signal(y)
+    w = pad_center(filters.get_window(window, win_length, fftbins=True), size=n_fft)
+    on_device = isinstance(y, nat.DeviceArray)
+    if on_device:
+        ctx, yd = y.ctx, y
+    else:
+        ctx = nat.default_context()
+        staged = pl.StagedInput(ctx, y)
+        yd = staged.dev
+    kw = dict(n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=pad_mode)
+    if S is None:
+        Sh = stft(yd, window=w, **kw)
+    else:
+        S = np.asarray(S)
+        Sh_host = np.ascontiguousarray(np.swapaxes(S, -1, -2), dtype=np.complex64)       # memory [.., frame, bin]
+        Sh = nat.DeviceArray.empty(ctx, S.shape, np.complex64, layout="ft")
+        nat.check(nat.lib().b2l_h2d(ctx.handle, _vp(Sh.ptr), Sh_host.ctypes.data_as(_vp), Sh_host.nbytes))
+        ctx.synchronize()
+    F, T = Sh.shape[-2], Sh.shape[-1]
+    if not on_device:
+        staged.scan_uncovered(n_fft, hop_length, center, T)
+    Sdh = stft(yd, window=cyclic_gradient(w), **kw) if reassign_frequencies else None
+    Sth = None
+    if reassign_times:
+        half = n_fft // 2
+        window_times = np.arange(-half, half + 1) if n_fft % 2 else np.arange(0.5 - half, half)
+        Sth = stft(yd, window=w * window_times, **kw)
+    offset = 0 if center else int(n_fft // 2)
+    frame_times = (np.arange(T) * hop_length + offset).astype(int) / float(sr)
+    from ..feature.stats import _device_table
+    from .convert import fft_frequencies
+
+    d_bf = _device_table(ctx, ("fftfreq", float(sr), int(n_fft)), fft_frequencies(sr=sr, n_fft=n_fft))
+    d_ft = _device_table(ctx, ("frametimes", float(sr), int(hop_length), int(offset), int(T)), frame_times)
+    lead = Sh.shape[:-2]
+    n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    outs = [nat.DeviceArray.empty(ctx, Sh.shape, np.float32, layout="ft") for _ in range(3)]
+    desc = nat.ReassignDesc(sr=float(sr), mag_threshold=float(ref_power) ** 0.5, max_time=float(n) / float(sr),
+                            reassign_frequencies=int(bool(reassign_frequencies)), reassign_times=int(bool(reassign_times)),
+                            apply_threshold=int(ref_power > 0), fill_nan=int(bool(fill_nan)), clip=int(bool(clip)))
+    nat.check(nat.lib().b2l_reassign(ctx.handle, C.byref(desc), _vp(Sh.ptr), _vp(Sdh.ptr if Sdh is not None else None),
+                                     _vp(Sth.ptr if Sth is not None else None), n_clips, T, F, _vp(d_bf), _vp(d_ft),
+                                     _vp(outs[0].ptr), _vp(outs[1].ptr), _vp(outs[2].ptr)))
+    for tmp in (Sh, Sdh, Sth):
+        if tmp is not None:
+            tmp.free()
+    if on_device:
+        return tuple(outs)
+    wide = np.result_type(req, np.float64)
+    freqs = pl.finish(ctx, outs[0], True, wide, validate=True)
+    times = pl.finish(ctx, outs[1], True, wide)
+    mags = pl.finish(ctx, outs[2], True, req)
+    return freqs, times, mags
 
 
 def griffinlim(S, *, n_iter: int = 32, hop_length: Optional[int] = None, win_length: Optional[int] = None,

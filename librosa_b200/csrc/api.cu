@@ -1525,6 +1525,40 @@ extern "C" int b2l_hpss(b2l_ctx* c, const b2l_hpss_desc* d, const float* d_mag, 
   return B2L_OK;
 }
 
+extern "C" int b2l_reassign(b2l_ctx* c, const b2l_reassign_desc* d, const void* d_Sh, const void* d_Sdh,
+                            const void* d_Sth, int64_t n_clips, int64_t n_frames, int64_t n_bins,
+                            const float* d_bin_freqs, const float* d_frame_times, float* d_freqs, float* d_times,
+                            float* d_mags) {
+  if (!c || !d || !d_Sh || !d_bin_freqs || !d_frame_times || !d_freqs || !d_times || !d_mags)
+    return fail(B2L_ERR_INVALID, "NULL argument");
+  if ((d->reassign_frequencies && !d_Sdh) || (d->reassign_times && !d_Sth))
+    return fail(B2L_ERR_INVALID, "missing derivative / time-weighted STFT");
+  if (n_clips <= 0 || n_frames <= 0 || n_bins <= 0) return B2L_OK;
+  if (n_frames > 0x7fffffffLL || n_bins > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "reassign: too large");
+  ReassignArgs a;
+  a.T = (int)n_frames;
+  a.F = (int)n_bins;
+  a.freq_scale = (float)(0.5 * (double)d->sr / 3.14159265358979323846);
+  a.inv_sr = (float)(1.0 / (double)d->sr);
+  a.mag_threshold = d->mag_threshold;
+  a.max_freq = (float)(0.5 * (double)d->sr);
+  a.max_time = d->max_time;
+  a.do_freq = d->reassign_frequencies ? 1 : 0;
+  a.do_time = d->reassign_times ? 1 : 0;
+  a.apply_threshold = d->apply_threshold ? 1 : 0;
+  a.fill_nan = d->fill_nan ? 1 : 0;
+  a.clip = d->clip ? 1 : 0;
+  DeviceGuard g(c->device);
+  const long long n = (long long)n_clips * n_frames * n_bins;
+  long long grid = (n + 256LL * 4 - 1) / (256LL * 4);
+  if (grid > 16LL * c->sm_count) grid = 16LL * c->sm_count;
+  reassign_kernel<<<(int)grid, 256, 0, c->stream>>>((const float2*)d_Sh, (const float2*)d_Sdh, (const float2*)d_Sth,
+                                                    d_bin_freqs, d_frame_times, a, n, d_freqs, d_times, d_mags);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);

@@ -502,6 +502,53 @@ __global__ void cabs_kernel(const float2* __restrict__ x, long long n, float* __
   }
 }
 
+// Time-frequency reassignment (librosa/core/spectrum.py:646-1293, reassigned_spectrogram): elementwise over three
+// STFTs of the same signal taken with the window h, its cyclic derivative dh and the time-weighted window th
+// (all [clip][T][F], bins contiguous):
+//   freq = f_k - Im(S_dh / S_h) * sr / (2 pi)         (eq. 5.20, :847-853)
+//   time = t_frame + Re(S_th / S_h) / sr              (eq. 5.23, :1001-1016)
+//   mag  = |S_h|; cells with mag < sqrt(ref_power) become NaN, optionally refilled with the bin frequency /
+//   frame time, optionally clipped to [0, sr/2] / [0, duration]                         (:1240-1290)
+struct ReassignArgs {
+  int T, F;
+  float freq_scale;      // sr / (2 pi)
+  float inv_sr, mag_threshold, max_freq, max_time;
+  int do_freq, do_time, apply_threshold, fill_nan, clip;
+};
+__global__ void reassign_kernel(const float2* __restrict__ Sh, const float2* __restrict__ Sdh,
+                                const float2* __restrict__ Sth, const float* __restrict__ bin_freqs,
+                                const float* __restrict__ frame_times, ReassignArgs a, long long n,
+                                float* __restrict__ freqs, float* __restrict__ times, float* __restrict__ mags) {
+  const float nan = __int_as_float(0x7fc00000);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % a.F);
+    const int t = (int)((i / a.F) % a.T);
+    const float2 h = Sh[i];
+    const float den = fmaf(h.x, h.x, h.y * h.y);
+    const float mag = hypotf(h.x, h.y);
+    const bool low = a.apply_threshold && mag < a.mag_threshold;
+    mags[i] = mag;
+    const float bf = bin_freqs[f], ft = frame_times[t];
+    float fr = bf, tm = ft;
+    if (a.do_freq) {
+      const float2 d = Sdh[i];
+      fr = den > 0.0f ? bf - (d.y * h.x - d.x * h.y) / den * a.freq_scale : nan;
+      if (low) fr = nan;
+      if (a.fill_nan && isnan(fr)) fr = bf;
+      if (a.clip && !isnan(fr)) fr = fminf(fmaxf(fr, 0.0f), a.max_freq);
+    }
+    if (a.do_time) {
+      const float2 d = Sth[i];
+      tm = den > 0.0f ? ft + (d.x * h.x + d.y * h.y) / den * a.inv_sr : nan;
+      if (low) tm = nan;
+      if (a.fill_nan && isnan(tm)) tm = ft;
+      if (a.clip && !isnan(tm)) tm = fminf(fmaxf(tm, 0.0f), a.max_time);
+    }
+    freqs[i] = fr;
+    times[i] = tm;
+  }
+}
+
 // Elementwise helpers of the dB conversions (librosa/core/spectrum.py):
 //   UNARY_SQUARE           x*x                        amplitude_to_db squares |S| before power_to_db (:2032-2037)
 //   UNARY_DB_TO_POWER      ref * 10^(0.1 x)           db_to_power (:1899-1925)

@@ -186,3 +186,13 @@ def abs2(x, dtype=None):
     else:
         y = np.square(x)
     return y if dtype is None else y.astype(dtype)
+
+
+def cyclic_gradient(data: np.ndarray, *, edge_order: int = 1, axis: int = -1) -> np.ndarray:
+    """Gradient of a periodic array: wrap-pad, ``np.gradient``, un-pad (mirror of util/utils.py cyclic_gradient)."""
+    pad = [(0, 0)] * data.ndim
+    pad[axis] = (edge_order, edge_order)
+    grad = np.gradient(np.pad(data, pad, mode="wrap"), edge_order=edge_order, axis=axis)
+    keep = [slice(None)] * data.ndim
+    keep[axis] = slice(edge_order, -edge_order)
+    return grad[tuple(keep)]

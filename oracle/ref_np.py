@@ -754,6 +754,84 @@ def pcen(S, sr=22050, hop_length=512, gain=0.98, bias=2, power=0.5, time_constan
     return (S_out, zf) if return_zf else S_out
 
 
+# --------------------------------------------------------------------------- reassigned spectrogram
+def cyclic_gradient(data, edge_order=1, axis=-1):
+    """librosa/util/utils.py (cyclic_gradient)."""
+    padding = [(0, 0)] * data.ndim
+    padding[axis] = (edge_order, edge_order)
+    data_pad = np.pad(data, padding, mode="wrap")
+    grad = np.gradient(data_pad, edge_order=edge_order, axis=axis)
+    slices = [slice(None)] * data.ndim
+    slices[axis] = slice(edge_order, -edge_order)
+    return grad[tuple(slices)]
+
+
+def frames_to_time(frames, sr=22050, hop_length=512, n_fft=None):
+    """librosa/core/convert.py (frames_to_time via frames_to_samples / samples_to_time)."""
+    offset = int(n_fft // 2) if n_fft is not None else 0
+    samples = (np.asanyarray(frames) * hop_length + offset).astype(int)
+    return np.asanyarray(samples) / float(sr)
+
+
+def reassigned_spectrogram(y, sr=22050, S=None, n_fft=2048, hop_length=None, win_length=None, window="hann",
+                           center=True, reassign_frequencies=True, reassign_times=True, ref_power=1e-6,
+                           fill_nan=False, clip=True, dtype=None, pad_mode="constant"):
+    """librosa/core/spectrum.py:1185-1293 with __reassign_frequencies (:812-856) and __reassign_times (:957-1016)."""
+    if not callable(ref_power) and ref_power < 0:
+        raise ParameterError("ref_power must be non-negative or callable.")
+    if not reassign_frequencies and not reassign_times:
+        raise ParameterError("reassign_frequencies or reassign_times must be True.")
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    w = pad_center(get_window(window, win_length, fftbins=True), n_fft)
+    kw = dict(n_fft=n_fft, hop_length=hop_length, center=center, dtype=dtype, pad_mode=pad_mode)
+    if S is None:
+        S = stft(y, window=w, **kw)
+    freqs = times = None
+    if reassign_frequencies:
+        S_dh = stft(y, window=cyclic_gradient(w), **kw)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            correction = -np.imag(S_dh / S)
+        f = fft_frequencies(sr=sr, n_fft=n_fft)
+        freqs = f.reshape((1,) * (correction.ndim - 2) + (-1, 1)) + correction * (0.5 * sr / np.pi)
+    if reassign_times:
+        half_width = n_fft // 2
+        window_times = np.arange(-half_width, half_width + 1) if n_fft % 2 else np.arange(0.5 - half_width, half_width)
+        S_th = stft(y, window=w * window_times, **kw)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            correction = np.real(S_th / S)
+        t = frames_to_time(np.arange(S.shape[-1]), sr=sr, hop_length=hop_length, n_fft=None if center else n_fft)
+        times = t.reshape((1,) * (correction.ndim - 1) + (-1,)) + correction / sr
+    mags = np.abs(S)
+    if fill_nan or not reassign_frequencies or not reassign_times:
+        bin_freqs = fft_frequencies(sr=sr, n_fft=n_fft)
+        frame_times = frames_to_time(np.arange(S.shape[-1]), sr=sr, hop_length=hop_length,
+                                     n_fft=None if center else n_fft)
+    ref_p = ref_power(mags ** 2) if callable(ref_power) else ref_power
+    mags_low = np.less(mags, ref_p ** 0.5, where=~np.isnan(mags), out=None)
+    if reassign_frequencies:
+        if ref_p > 0:
+            freqs[mags_low] = np.nan
+        if fill_nan:
+            freqs = np.where(np.isnan(freqs), bin_freqs[:, np.newaxis], freqs)
+        if clip:
+            np.clip(freqs, 0, sr / 2.0, out=freqs)
+    else:
+        freqs = np.broadcast_to(bin_freqs[:, np.newaxis], S.shape)
+    if reassign_times:
+        if ref_p > 0:
+            times[mags_low] = np.nan
+        if fill_nan:
+            times = np.where(np.isnan(times), frame_times[np.newaxis, :], times)
+        if clip:
+            np.clip(times, 0, y.shape[-1] / float(sr), out=times)
+    else:
+        times = np.broadcast_to(frame_times[np.newaxis, :], S.shape)
+    return freqs, times, mags
+
+
 # --------------------------------------------------------------------------- harmonic / percussive separation
 def softmask(X, X_ref, power=1, split_zeros=False):
     """librosa/util/utils.py (softmask)."""

@@ -128,6 +128,15 @@ FEATURE_CASES += [
     dict(name="effects_percussive_C", fn="percussive", ns="effects", mix="C", shape=(20000,), pos=True, kw=dict(kernel_size=17)),
 ]
 
+FEATURE_CASES += [
+    # ---- reassigned_spectrogram (top level): three STFTs with the window, its derivative, its time-weighted form
+    dict(name="reassign_default_A", fn="reassigned_spectrogram", ns="top", mix="A", shape=(9000,), pos=True, kw=dict(sr=22050)),
+    dict(name="reassign_fill_stereo_B", fn="reassigned_spectrogram", ns="top", mix="B", shape=(2, 9000), pos=True, kw=dict(sr=22050, n_fft=1024, hop_length=200, fill_nan=True)),
+    dict(name="reassign_freq_only_noclip_A", fn="reassigned_spectrogram", ns="top", mix="A", shape=(6000,), pos=True, kw=dict(sr=16000, n_fft=512, reassign_times=False, clip=False)),
+    dict(name="reassign_times_only_nocenter_A", fn="reassigned_spectrogram", ns="top", mix="A", shape=(6000,), pos=True, kw=dict(sr=22050, n_fft=512, center=False, reassign_frequencies=False, ref_power=0.0)),
+    dict(name="reassign_1025_hamming_T", fn="reassigned_spectrogram", ns="top", mix="T", seed=4, shape=(12000,), pos=True, kw=dict(sr=22050, n_fft=1025, window="hamming", win_length=800)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 
