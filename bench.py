@@ -256,6 +256,10 @@ def run_ours(args, w, rank, world, local_rank):
 
         torch.cuda.set_device(local_rank)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    # one process per GPU: keep this process (and the pinned buffers it allocates) on the CPUs local to its GPU,
+    # as `numactl --cpunodebind` would; released again before the CPU baseline uses every core
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = None if os.environ.get("B2L_BENCH_NO_NUMA_BIND") else lb.bind_host_to_device(local_rank)
     ctx = lb.default_context(local_rank)
     kw, op, sr = w["kw"], w["op"], w["sr"]
     T = n_frames(w["n"], kw["n_fft"], kw["hop_length"])
@@ -361,6 +365,8 @@ def run_ours(args, w, rank, world, local_rank):
 
     # ---- CPU baseline on this box (bounded sample)
     cpu = None
+    if numa_cpus:
+        os.sched_setaffinity(0, all_cpus)
     if world == 1 and not args.no_cpu:
         port = CpuPort(w, cpu_sample_clips(w))
         port.step()
@@ -383,6 +389,7 @@ def run_ours(args, w, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "name": args.workload, "per_gpu_clips": w["clips"],
                    "frames_per_step_per_gpu": frames_per_step, "parallelism": f"clips sharded x{world}, no collective",
+                   "host_cpus_bound_to_gpu": len(numa_cpus) if numa_cpus else None,
                    "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no flush" % (w["clips"] * w["n"] * 4 / 1e6)},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(host.nbytes),

@@ -12,6 +12,7 @@ from ._native import (
     DeviceArray,
     NativeLibraryError,
     UnsupportedOnGPU,
+    bind_host_to_device,
     default_context,
     device_count,
     pinned_empty,
@@ -34,5 +35,5 @@ __all__ = [
     "stft", "istft", "griffinlim", "power_to_db", "amplitude_to_db", "pcen", "reassigned_spectrogram", "db_to_power", "db_to_amplitude", "_spectrogram", "feature", "filters", "util", "core", "onset", "decompose", "effects",
     "hz_to_mel", "mel_to_hz", "hz_to_octs", "estimate_tuning", "mel_frequencies", "fft_frequencies", "ParameterError", "LibrosaError",
     "Context", "DeviceArray", "default_context", "device_count", "pinned_empty", "to_device",
-    "NativeLibraryError", "UnsupportedOnGPU",
+    "NativeLibraryError", "UnsupportedOnGPU", "bind_host_to_device",
 ]

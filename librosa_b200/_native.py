@@ -355,6 +355,29 @@ def default_context(device: Optional[int] = None) -> Context:
     return ctx
 
 
+def bind_host_to_device(device: int = 0):
+    """Pin the calling thread to the CPUs that are local to GPU ``device`` (NUMA node of its PCIe root), so that
+    pinned host buffers allocated afterwards — and the staging copies into them — do not cross sockets.  The
+    same thing ``numactl --cpunodebind`` does for one-process-per-GPU launches.  Needs NVML (``nvidia-ml-py``);
+    returns the CPU list, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def device_count() -> int:
     n = C.c_int()
     check(lib().b2l_device_count(C.byref(n)))
