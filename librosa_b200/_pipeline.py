@@ -251,7 +251,7 @@ def host_chunks(n_clips: int, nbytes: int) -> int:
         return max(1, min(int(env), n_clips))
     if n_clips < 8 or nbytes < (32 << 20):
         return 1
-    return int(min(8, n_clips // 4))
+    return int(min(16, n_clips // 4))   # 16 chunks: the un-overlapped head / tail is 1/16 of the transfer
 
 
 def run_host_forward(y: np.ndarray, *, n_fft: int, hop_length: int, center: bool, n_frames: int,
