@@ -249,6 +249,14 @@ typedef struct b2l_reassign_desc {
 int b2l_reassign(b2l_ctx* ctx, const b2l_reassign_desc* desc, const void* d_Sh, const void* d_Sdh, const void* d_Sth,
                  int64_t n_clips, int64_t n_frames, int64_t n_bins, const float* d_bin_freqs,
                  const float* d_frame_times, float* d_freqs, float* d_times, float* d_mags);
+/* librosa.phase_vocoder (core/spectrum.py:1364-1530) on d_D [n_clips][n_frames][n_bins] complex64 ->
+ * d_out [n_clips][n_out][n_bins].  Per output frame t (device arrays of length n_out, built by the caller from
+ * `rate` / `t_out`): i0 = floor(t_out), i1 = min(i0 + 1, n_frames - 1) for the phase increments (:1498-1512);
+ * lo, dx = the segment and offset scipy.interpolate.interp1d(kind="linear", fill_value="extrapolate") uses for
+ * the magnitudes (:1517-1527). */
+int b2l_phase_vocoder(b2l_ctx* ctx, const void* d_D, int64_t n_clips, int64_t n_frames, int64_t n_bins,
+                      int64_t n_out, const int32_t* d_i0, const int32_t* d_i1, const int32_t* d_lo,
+                      const double* d_dx, void* d_out);
 /* Elementwise pieces of the dB conversions over n floats (in place when d_out == d_in):
  *   B2L_UNARY_SQUARE           x*x                       amplitude_to_db (core/spectrum.py:1946-2038) = power_to_db
  *                                                        of the squared magnitudes with ref^2 / amin^2

@@ -533,6 +533,86 @@ def reassigned_spectrogram(y, *, sr: float = 22050, S=None, n_fft: int = 2048, h
     return freqs, times, mags
 
 
+class _Deprecated:
+    """Marker for deprecated keyword arguments (the reference's ``util.decorators.Deprecated``)."""
+
+    def __repr__(self):
+        return "<DEPRECATED parameter>"
+
+
+def phase_vocoder(D, *, rate: Optional[float] = None, t_out=None, kind="linear", hop_length=_Deprecated(),
+                  n_fft=_Deprecated()):
+    """Phase vocoder: re-time an STFT by ``rate`` (or to the frame positions ``t_out``); same contract as
+    ``librosa.phase_vocoder`` (core/spectrum.py:1364-1530) for ``kind="linear"``.  ``D`` may be a complex NumPy
+    array ``(..., bins, frames)`` or a complex64 ``DeviceArray`` (result stays on the device)."""
+    for name, val in (("hop_length", hop_length), ("n_fft", n_fft)):
+        if not isinstance(val, _Deprecated):
+            warnings.warn(f"The `{name}` parameter is deprecated as of 1.0 and will be removed in 1.1. "
+                          "It is unused in the current implementation.", FutureWarning, stacklevel=2)
+    n_frames = D.shape[-1]
+    if (rate is None) == (t_out is None):
+        raise ParameterError("Must specify exactly one of `rate` or `t_out`")
+    if (rate is not None) and (rate <= 0):
+        raise ParameterError(f"rate={rate} must be a positive number")
+    if t_out is None:
+        t_out = np.arange(0.0, n_frames, rate)
+    t_out = np.asarray(t_out, dtype=float)
+    if np.any(t_out < 0) or np.any(t_out >= n_frames):
+        raise ParameterError("t_out values must be in the range [0, D.shape[-1])")
+    if np.any(np.diff(t_out) < 0):
+        warnings.warn("t_out is not monotonic; phase estimation may be unstable", stacklevel=2)
+    if kind != "linear":
+        raise nat.UnsupportedOnGPU(f"phase_vocoder(kind={kind!r}): only linear magnitude interpolation runs on the GPU")
+    if n_frames < 2:
+        raise nat.UnsupportedOnGPU("phase_vocoder needs at least two frames on the GPU")
+    on_device = isinstance(D, nat.DeviceArray)
+    if on_device:
+        if D.dtype != np.complex64:
+            raise ParameterError("device STFT must be complex64")
+        ctx, res_dtype = D.ctx, np.dtype(np.complex64)
+        if D.layout == "ft":
+            src = D
+        else:
+            src = nat.DeviceArray.empty(ctx, D.shape, np.complex64, layout="ft")
+            lead0 = int(np.prod(D.shape[:-2], dtype=np.int64)) if D.ndim > 2 else 1
+            nat.check(nat.lib().b2l_transpose(ctx.handle, _vp(D.ptr), lead0, D.shape[-2], n_frames, 8, _vp(src.ptr)))
+    else:
+        D = np.asarray(D)
+        if not np.iscomplexobj(D):
+            raise ParameterError("phase_vocoder expects a complex STFT matrix")
+        res_dtype = np.dtype(D.dtype)
+        if res_dtype == np.complex128 and not pl.wide_complex_ok("phase_vocoder input"):
+            raise ParameterError("complex128 input refused (B2L_FLOAT64=error)")
+        ctx = nat.default_context()
+        mem = np.ascontiguousarray(np.swapaxes(D, -1, -2), dtype=np.complex64)     # [.., frame, bin]
+        src = nat.DeviceArray.empty(ctx, D.shape, np.complex64, layout="ft")
+        if mem.nbytes:
+            nat.check(nat.lib().b2l_h2d(ctx.handle, _vp(src.ptr), mem.ctypes.data_as(_vp), mem.nbytes))
+            ctx.synchronize()
+    F = D.shape[-2]
+    lead = tuple(D.shape[:-2])
+    n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    n_out = int(t_out.shape[0])
+    # phase increments: frames floor(t), floor(t) + 1 (:1498-1512); magnitudes: the segment scipy's interp1d
+    # picks — searchsorted(x, t) clipped to [1, n - 1], minus one — and the offset inside it (:1517-1527)
+    i0 = np.floor(t_out).astype(np.int32)
+    i1 = np.minimum(i0 + 1, n_frames - 1).astype(np.int32)
+    hi = np.clip(np.searchsorted(np.arange(n_frames, dtype=float), t_out), 1, n_frames - 1)
+    lo = (hi - 1).astype(np.int32)
+    dx = np.ascontiguousarray(t_out - lo, dtype=np.float64)
+    tables = [ctx.to_device(np.ascontiguousarray(a)) for a in (i0, i1, lo, dx)]
+    out = nat.DeviceArray.empty(ctx, lead + (F, n_out), np.complex64, layout="ft")
+    nat.check(nat.lib().b2l_phase_vocoder(ctx.handle, _vp(src.ptr), n_clips, n_frames, F, n_out, _vp(tables[0].ptr),
+                                          _vp(tables[1].ptr), _vp(tables[2].ptr), _vp(tables[3].ptr), _vp(out.ptr)))
+    for tb in tables:
+        tb.free()
+    if src is not D:
+        src.free()
+    if on_device:
+        return out
+    return pl.finish(ctx, out, True, res_dtype)
+
+
 def griffinlim(S, *, n_iter: int = 32, hop_length: Optional[int] = None, win_length: Optional[int] = None,
                n_fft: Optional[int] = None, window="hann", center: bool = True, dtype=None,
                length: Optional[int] = None, pad_mode="constant", momentum: float = 0.99, init="random",

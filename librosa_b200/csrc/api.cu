@@ -1559,6 +1559,23 @@ extern "C" int b2l_reassign(b2l_ctx* c, const b2l_reassign_desc* d, const void* 
   return B2L_OK;
 }
 
+extern "C" int b2l_phase_vocoder(b2l_ctx* c, const void* d_D, int64_t n_clips, int64_t n_frames, int64_t n_bins,
+                                 int64_t n_out, const int32_t* d_i0, const int32_t* d_i1, const int32_t* d_lo,
+                                 const double* d_dx, void* d_out) {
+  if (!c || !d_D || !d_i0 || !d_i1 || !d_lo || !d_dx || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (n_clips <= 0 || n_bins <= 0 || n_out <= 0) return B2L_OK;
+  if (n_frames < 2) return fail(B2L_ERR_UNSUPPORTED, "phase_vocoder needs at least two input frames");
+  if (n_frames > 0x7fffffffLL || n_bins > 0x7fffffffLL || n_out > 0x7fffffffLL)
+    return fail(B2L_ERR_UNSUPPORTED, "phase_vocoder: too large");
+  DeviceGuard g(c->device);
+  const long long threads = (long long)n_clips * n_bins;
+  phase_vocoder_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(
+      (const float2*)d_D, (int)n_frames, (int)n_bins, n_clips, (int)n_out, d_i0, d_i1, d_lo, d_dx, (float2*)d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_unary(b2l_ctx* c, int32_t op, const float* d_in, int64_t n, float param, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (op < 0 || op > B2L_UNARY_DB_TO_AMPLITUDE) return fail(B2L_ERR_INVALID, "bad unary op %d", op);

@@ -549,6 +549,37 @@ __global__ void reassign_kernel(const float2* __restrict__ Sh, const float2* __r
   }
 }
 
+// Phase vocoder (librosa/core/spectrum.py:1364-1530): output frame t takes its magnitude by linear interpolation
+// of |D| at time t_out[t] and its phase as  angle(D[i0[0]]) + sum_{s<t} (angle(D[i1[s]]) - angle(D[i0[s]]))  —
+// a float32 running sum along time (np.cumsum), so one thread walks the output frames of one (clip, bin).
+// D [clip][T][F] complex64 (bins contiguous: neighbouring threads read neighbouring bins of the same frame).
+__global__ void phase_vocoder_kernel(const float2* __restrict__ D, int T, int F, long long n_clips, int n_out,
+                                     const int* __restrict__ i0, const int* __restrict__ i1,
+                                     const int* __restrict__ lo, const double* __restrict__ dx,
+                                     float2* __restrict__ out) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_clips * F) return;
+  const long long clip = id / F;
+  const int f = (int)(id % F);
+  const float2* Dc = D + clip * (long long)T * F + f;
+  float2* oc = out + clip * (long long)n_out * F + f;
+  float phase = 0.0f;
+  for (int t = 0; t < n_out; ++t) {
+    const float2 a = Dc[(long long)i0[t] * F];
+    if (t == 0) {
+      phase = atan2f(a.y, a.x);
+    }
+    const float2 m0 = Dc[(long long)lo[t] * F], m1 = Dc[(long long)(lo[t] + 1) * F];
+    const double y0 = (double)hypotf(m0.x, m0.y), y1 = (double)hypotf(m1.x, m1.y);
+    const double mag = (y1 - y0) * dx[t] + y0;
+    float sn, cs;
+    sincosf(phase, &sn, &cs);
+    oc[(long long)t * F] = make_float2((float)((double)cs * mag), (float)((double)sn * mag));
+    const float2 b = Dc[(long long)i1[t] * F];
+    phase += atan2f(b.y, b.x) - atan2f(a.y, a.x);
+  }
+}
+
 // Elementwise helpers of the dB conversions (librosa/core/spectrum.py):
 //   UNARY_SQUARE           x*x                        amplitude_to_db squares |S| before power_to_db (:2032-2037)
 //   UNARY_DB_TO_POWER      ref * 10^(0.1 x)           db_to_power (:1899-1925)

@@ -9,11 +9,11 @@ import numpy as np
 
 from . import _native as nat
 from . import _pipeline as pl
-from .core.spectrum import istft, stft
+from .core.spectrum import istft, phase_vocoder, stft
 from .decompose import _hpss_device
 from .util.exceptions import ParameterError
 
-__all__ = ["hpss", "harmonic", "percussive"]
+__all__ = ["hpss", "harmonic", "percussive", "time_stretch"]
 
 
 def _separate(y, want, *, kernel_size, power, mask, margin, n_fft, hop_length, win_length, window, center, pad_mode):
@@ -66,3 +66,29 @@ def percussive(y, *, kernel_size=31, power: float = 2.0, mask: bool = False, mar
     """Percussive component of a signal; same contract as ``librosa.effects.percussive``."""
     return _separate(y, ("perc",), kernel_size=kernel_size, power=power, mask=mask, margin=margin, n_fft=n_fft,
                      hop_length=hop_length, win_length=win_length, window=window, center=center, pad_mode=pad_mode)[0]
+
+
+def time_stretch(y, *, rate: float, **kwargs):
+    """Time-stretch a signal by ``rate`` (stft -> phase_vocoder -> istft, all on the device); same contract as
+    ``librosa.effects.time_stretch`` (effects.py:284-361).  ``kwargs`` go to ``stft`` and ``istft``."""
+    if rate <= 0:
+        raise ParameterError("rate must be a positive number")
+    n, req = pl.precheck_signal(y)
+    on_device = isinstance(y, nat.DeviceArray)
+    if on_device:
+        ctx, yd = y.ctx, y
+    else:
+        ctx = nat.default_context()
+        staged = pl.StagedInput(ctx, y)
+        yd = staged.dev
+    D = stft(yd, **kwargs)
+    if not on_device:
+        n_fft = kwargs.get("n_fft", 2048)
+        hop_eff, _ = pl.frame_params(n_fft, kwargs.get("hop_length"), kwargs.get("win_length"))
+        staged.scan_uncovered(n_fft, hop_eff, kwargs.get("center", True), D.shape[-1])
+    # the reference forwards these two (deprecated, unused) arguments, so its call always warns; same here
+    Ds = phase_vocoder(D, rate=rate, hop_length=kwargs.get("hop_length"), n_fft=kwargs.get("n_fft"))
+    D.free()
+    out = istft(Ds, length=round(n / rate), **kwargs)
+    Ds.free()
+    return out if on_device else pl.finish(ctx, out, True, req, validate=True)

@@ -15,8 +15,9 @@ The reference is pure Python; its arithmetic lives in third-party libraries that
 /root/reference and are called here exactly as the reference calls them:
 ``scipy.fft.rfft / irfft / dct`` (SciPy >= 1.15, ducc0 backend; this image: 1.18.1),
 ``numpy.einsum`` -> OpenBLAS sgemm (NumPy >= 2.1; this image: 2.3.5) and
-``scipy.signal.get_window``.  ``numba`` (used by the reference only to JIT two serial loops)
-is not needed: the loops are restated with NumPy slices.
+``scipy.signal.get_window``.  ``numba`` (used by the reference to JIT a few serial loops) is not needed
+here: the loops are restated with NumPy slices, and ``phasor`` (phase vocoder) calls libm's ``cosf`` /
+``sinf`` through ctypes, which is what the reference's numba ufunc lowers to.
 
 Each function cites the reference lines it restates (paths relative to /root/reference).
 """
@@ -830,6 +831,74 @@ def reassigned_spectrogram(y, sr=22050, S=None, n_fft=2048, hop_length=None, win
     else:
         times = np.broadcast_to(frame_times[np.newaxis, :], S.shape)
     return freqs, times, mags
+
+
+# --------------------------------------------------------------------------- phase vocoder / time stretch
+_LIBM = None
+
+
+def phasor(angles):
+    """``util.phasor`` (librosa/util/utils.py:2634-2710): cos + i sin.  The reference evaluates it through a
+    numba ufunc, which for float32 input calls libm's ``cosf`` / ``sinf`` — not NumPy's SIMD float32 kernels,
+    which differ in the last bit.  The same libm entry points are called here through ctypes (element by
+    element: this is the checker, not a fast path)."""
+    global _LIBM
+    angles = np.asarray(angles)
+    z = np.empty_like(angles, dtype=dtype_r2c(angles.dtype))
+    if angles.dtype != np.float32:
+        z.real, z.imag = np.cos(angles), np.sin(angles)
+        return z
+    if _LIBM is None:
+        import ctypes
+        import ctypes.util
+
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        for fn in (_LIBM.cosf, _LIBM.sinf):
+            fn.restype = ctypes.c_float
+            fn.argtypes = [ctypes.c_float]
+    flat = angles.reshape(-1)
+    re = np.fromiter((_LIBM.cosf(float(v)) for v in flat), dtype=np.float32, count=flat.size)
+    im = np.fromiter((_LIBM.sinf(float(v)) for v in flat), dtype=np.float32, count=flat.size)
+    z.real, z.imag = re.reshape(angles.shape), im.reshape(angles.shape)
+    return z
+
+
+def phase_vocoder(D, rate=None, t_out=None, kind="linear"):
+    """librosa/core/spectrum.py:1476-1530."""
+    import scipy.interpolate
+
+    n_frames = D.shape[-1]
+    if (rate is None) == (t_out is None):
+        raise ParameterError("Must specify exactly one of `rate` or `t_out`")
+    if (rate is not None) and (rate <= 0):
+        raise ParameterError(f"rate={rate} must be a positive number")
+    if t_out is None:
+        t_out = np.arange(0.0, n_frames, rate)
+    t_out = np.asarray(t_out, dtype=float)
+    if np.any(t_out < 0) or np.any(t_out >= n_frames):
+        raise ParameterError("t_out values must be in the range [0, D.shape[-1])")
+    i0 = np.floor(t_out).astype(int)
+    i1 = np.minimum(i0 + 1, n_frames - 1)
+    ph = np.angle(D)
+    diff = ph[..., i1] - ph[..., i0]
+    phase = np.empty_like(diff)
+    phase[..., 0] = np.angle(D[..., i0[0]])
+    phase[..., 1:] = diff[..., :-1]
+    np.cumsum(phase, axis=-1, out=phase)
+    mag_interp = scipy.interpolate.interp1d(np.arange(n_frames), np.abs(D), kind=kind, axis=-1,
+                                            fill_value="extrapolate", assume_sorted=True, copy=False)
+    z = phasor(phase)
+    z *= mag_interp(t_out)
+    return z
+
+
+def effects_time_stretch(y, rate, **kwargs):
+    """librosa/effects.py:284-361."""
+    if rate <= 0:
+        raise ParameterError("rate must be a positive number")
+    D = stft(y, **kwargs)
+    Ds = phase_vocoder(D, rate=rate)
+    return istft(Ds, dtype=y.dtype, length=round(y.shape[-1] / rate), **kwargs)
 
 
 # --------------------------------------------------------------------------- harmonic / percussive separation

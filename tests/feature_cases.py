@@ -137,6 +137,16 @@ FEATURE_CASES += [
     dict(name="reassign_1025_hamming_T", fn="reassigned_spectrogram", ns="top", mix="T", seed=4, shape=(12000,), pos=True, kw=dict(sr=22050, n_fft=1025, window="hamming", win_length=800)),
 ]
 
+FEATURE_CASES += [
+    # ---- phase_vocoder (top level, on fixture STFTs) and effects.time_stretch
+    dict(name="pv_rate2", fn="phase_vocoder", ns="top", arg="stft_1024_256_reflect_B", kw=dict(rate=2.0)),
+    dict(name="pv_rate_half_stereo", fn="phase_vocoder", ns="top", arg="stft_512_stereo_A", kw=dict(rate=0.5)),
+    dict(name="pv_rate137_C", fn="phase_vocoder", ns="top", arg="stft_2048_C_burst", kw=dict(rate=1.37)),
+    dict(name="pv_t_out", fn="phase_vocoder", ns="top", arg="stft_2048_512_A", kw=dict(t_out=np.array([0.0, 0.5, 3.2, 3.2, 10.9, 17.99]))),
+    dict(name="time_stretch_15_B", fn="time_stretch", ns="effects", mix="B", shape=(2, 12000), pos=True, kw=dict(rate=1.5, n_fft=1024)),
+    dict(name="time_stretch_07_T", fn="time_stretch", ns="effects", mix="T", seed=6, shape=(20000,), pos=True, kw=dict(rate=0.7)),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 
