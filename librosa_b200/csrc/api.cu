@@ -750,7 +750,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     if (span > 0x3fffffff) continue;
     const b2l_plan::RowTable* t = nullptr;
     if (mode == MODE_MEL) {
-      int rc = get_row_table(c, p, 32 / f, &t);
+      int rc = get_row_table(c, p, mel_rows_per_warp(f), &t);
       if (rc) return rc;
     }
     size_t off = 0;
@@ -770,7 +770,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     a.off_xbuf = (int)(off = align_up(off, 128));
     size_t xbytes = (size_t)f * cfg.xbuf_f2() * 8;
     if (mode == MODE_MEL || mode == MODE_STATS) {
-      const int Hh = 32 / f;                                      // MelLayout (common.cuh)
+      const int Hh = mel_rows_per_warp(f);                        // MelLayout (common.cuh)
       const int rs = ((M + 4 - Hh + 31) / 32) * 32 + Hh;
       size_t pbytes = (size_t)f * rs * 4;
       if (pbytes > xbytes) xbytes = pbytes;

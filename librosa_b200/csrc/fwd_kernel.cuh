@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   static_assert(NW % NSPLIT == 0, "the warps are split evenly");
   static_assert(TPF <= 32 || NH + NT / TPF <= 15, "named barriers: 1..NH for the halves, then one per frame group");
   static_assert(FT >= 1 && FT <= 32, "tile must hold 1..32 frames");
-  constexpr int H = 32 / FT;                   // mel rows handled concurrently by one warp
+  using ML = MelLayout<M, FT>;
+  constexpr int H = ML::H;                     // mel rows handled concurrently by one warp (common.cuh)
   constexpr int NPAIR = PPT / 2;               // bin pairs (k, M-k) per thread
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         half_sync();   // B1: every group finished reading its Z
         // P[f][k] frame-major with a bank-skewed row stride (MelLayout, common.cuh); bins M+1 .. M+3 of
         // every row are kept at zero so the 4-bin groups of the mel loop may run past the Nyquist bin.
-        constexpr int RS = MelLayout<M, FT>::RS;
+        constexpr int RS = ML::RS;
         float* prow = s_p + grp * RS;
         static_for<0, NPAIR>([&](auto C) {
           constexpr int c = decltype(C)::value;
@@ -393,36 +394,66 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
               a.out_r[((long long)clip * N_STATS + lane) * a.n_frames + t0 + f] = r;
           }
         } else {
-          // Work item = H adjacent mel rows; lane (f, j) accumulates row i*H + j for frame f over that
-          // row's padded band (host-built MelRow table: the rows of an item share one trip count, start
-          // bins are congruent to j mod H so the skewed tile reads conflict-free, weights are zero
-          // padded and 16-byte aligned).  No cross-lane reduction, one short loop per item.
+          // Work item = H adjacent mel rows; lane (fp, j) accumulates row item*H + j for the frame pair
+          // (fp, fp + FP) over that row's padded band (host-built MelRow table: the rows of an item share
+          // one trip count, start bins are congruent to j mod H so the skewed tile reads conflict-free,
+          // weights are zero padded and 16-byte aligned).  One weight fetch feeds both frames; no
+          // cross-lane reduction, one short loop per item.
+          constexpr int FP = ML::FP;
+          constexpr bool PAIR = ML::PAIR;
           const int hwarp = htid >> 5, lane = htid & 31;
-          const int f = lane & (FT - 1), j = lane / FT;
-          const bool ok = (t0 + f) < a.n_frames;
+          const int fp = lane & (FP - 1), j = lane / FP;
+          const bool ok_a = (t0 + fp) < a.n_frames;
+          const bool ok_b = PAIR && (t0 + fp + FP) < a.n_frames;
           float wmax = -INFINITY;
           const int n_items = a.n_mel_rows / H;
+          const float* pbase = s_p + fp * RS;
+          float* obase = a.out_r + (long long)clip * a.n_mels * a.n_frames + t0 + fp;
           for (int item = hwarp; item < n_items; item += HW) {
             const int m = item * H + j;
             const MelRow row = s_row[m];
             const float4* wp = reinterpret_cast<const float4*>(s_melw + row.off);
-            const float* pp = s_p + f * RS + row.lo;
+            const float* pa = pbase + row.lo;
             const float4* wend = wp + row.quads;
-            float acc0 = 0.0f, acc1 = 0.0f;
+            float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+            if constexpr (PAIR) {
+              const float* pb = pa + FP * RS;
 #pragma unroll 2
-            for (; wp != wend; ++wp, pp += 4) {
-              const float4 w = *wp;
-              acc0 = fmaf(w.x, pp[0], acc0);
-              acc1 = fmaf(w.y, pp[1], acc1);
-              acc0 = fmaf(w.z, pp[2], acc0);
-              acc1 = fmaf(w.w, pp[3], acc1);
+              for (; wp != wend; ++wp, pa += 4, pb += 4) {
+                const float4 w = *wp;
+                a0 = fmaf(w.x, pa[0], a0);
+                b0 = fmaf(w.x, pb[0], b0);
+                a1 = fmaf(w.y, pa[1], a1);
+                b1 = fmaf(w.y, pb[1], b1);
+                a0 = fmaf(w.z, pa[2], a0);
+                b0 = fmaf(w.z, pb[2], b0);
+                a1 = fmaf(w.w, pa[3], a1);
+                b1 = fmaf(w.w, pb[3], b1);
+              }
+            } else {
+#pragma unroll 2
+              for (; wp != wend; ++wp, pa += 4) {
+                const float4 w = *wp;
+                a0 = fmaf(w.x, pa[0], a0);
+                a1 = fmaf(w.y, pa[1], a1);
+                a0 = fmaf(w.z, pa[2], a0);
+                a1 = fmaf(w.w, pa[3], a1);
+              }
             }
-            float acc = acc0 + acc1;
-            if (a.log_mode) {
-              acc = 10.0f * log10f(fmaxf(a.amin, acc)) - a.db_sub;
-              if (ok && m < a.n_mels) wmax = fmaxf(wmax, acc);
+            float va = a0 + a1, vb = b0 + b1;
+            if (m < a.n_mels) {
+              if (a.log_mode) {
+                va = 10.0f * log10f(fmaxf(a.amin, va)) - a.db_sub;
+                if (ok_a) wmax = fmaxf(wmax, va);
+                if constexpr (PAIR) {
+                  vb = 10.0f * log10f(fmaxf(a.amin, vb)) - a.db_sub;
+                  if (ok_b) wmax = fmaxf(wmax, vb);
+                }
+              }
+              float* o = obase + (long long)m * a.n_frames;
+              if (ok_a) o[0] = va;
+              if (ok_b) o[FP] = vb;
             }
-            if (ok && m < a.n_mels) a.out_r[((long long)clip * a.n_mels + m) * a.n_frames + t0 + f] = acc;
           }
           if (a.log_mode) {
 #pragma unroll
