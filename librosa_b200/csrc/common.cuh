@@ -29,14 +29,15 @@ struct MelRow { unsigned short lo, quads; unsigned int off; };
 
 // Shared-memory layout of the power tile used by the mel phase: frame-major, P[f][k] at word f*RS + k.
 // A lane of the mel loop owns one mel row and a PAIR of frames (f, f + FT/2) — one weight fetch serves both —
-// so a warp covers FP = FT/2 frame pairs x H = 32/FP rows (FT odd, i.e. FT == 1: one frame, 32 rows).  With
+// so a warp covers FP = FT/2 frame pairs x H = 32/FP rows (tiles of fewer than 8 frames: one frame per lane,
+// H = 32/FT rows).  With
 // the row stride RS = (M + 4 rounded up) congruent to H modulo 32 the load of lane (fp, j) — bin k_j + i with
 // k_j = j mod H, see MelRow — hits bank fp*H + j + const: 32 distinct banks, for either frame of the pair.
 // The transposing store (lanes = consecutive bins of one frame) is contiguous.  Rows hold bins 0 .. M plus
 // three zero bins so that 4-bin groups may run past the Nyquist bin.
 template <int M, int FT>
 struct MelLayout {
-  static constexpr bool PAIR = (FT % 2) == 0;
+  static constexpr bool PAIR = (FT % 2) == 0 && FT >= 8;   // few frames per tile: H would exceed 8 rows sharing one trip count
   static constexpr int FP = PAIR ? FT / 2 : FT;     // lanes along the frame axis
   static constexpr int H = 32 / FP;                 // mel rows handled concurrently by one warp
   static constexpr int RS = ((M + 4 - H + 31) / 32) * 32 + H;
@@ -44,7 +45,7 @@ struct MelLayout {
   static constexpr size_t bytes() { return (size_t)FT * RS * 4; }
 };
 // host mirror of MelLayout<M, FT>::H
-__host__ __device__ inline int mel_rows_per_warp(int ft) { return 32 / ((ft % 2) == 0 ? ft / 2 : ft); }
+__host__ __device__ inline int mel_rows_per_warp(int ft) { return 32 / (((ft % 2) == 0 && ft >= 8) ? ft / 2 : ft); }
 
 // Per-frame spectral statistics (stats.cuh): the rows of the [clip][N_STATS][frame] output.
 enum StatRow : int { STAT_CENTROID = 0, STAT_BANDWIDTH = 1, STAT_ROLLOFF = 2, STAT_FLATNESS = 3, STAT_RMS = 4, STAT_TOTAL = 5 };
