@@ -189,6 +189,42 @@ def test_device_resident_inputs_and_S_path_agree(lb):
     np.testing.assert_allclose(z.get(), lb.feature.zero_crossing_rate(y), rtol=1e-6)
 
 
+def test_device_resident_variants_of_the_wider_features(lb):
+    """DeviceArray in -> DeviceArray out for the features that compose several kernels; the results equal the
+    host-input calls (same kernels, only the staging differs)."""
+    import signals
+
+    y = signals.make("T", (2, 30000), seed=9)
+    yd = lb.to_device(y)
+    D = lb.stft(yd)                                         # complex64, kernels' native layout
+    P = lb._spectrogram(y=yd, power=2)[0]
+    pairs = [
+        (lambda: lb.feature.chroma_stft(y=yd, sr=22050), lambda: lb.feature.chroma_stft(y=y, sr=22050)),
+        (lambda: lb.feature.chroma_stft(S=P, sr=22050, tuning=0.1), lambda: lb.feature.chroma_stft(y=y, sr=22050, tuning=0.1)),
+        (lambda: lb.feature.spectral_contrast(y=yd, sr=22050), lambda: lb.feature.spectral_contrast(y=y, sr=22050)),
+        (lambda: lb.onset.onset_strength_multi(y=yd, sr=22050, channels=[0, 64, 128]),
+         lambda: lb.onset.onset_strength_multi(y=y, sr=22050, channels=[0, 64, 128])),
+        (lambda: lb.decompose.hpss(D), lambda: lb.decompose.hpss(D.get())),
+        (lambda: lb.effects.hpss(yd), lambda: lb.effects.hpss(y)),
+        (lambda: lb.phase_vocoder(D, rate=1.25), lambda: lb.phase_vocoder(D.get(), rate=1.25)),
+        (lambda: lb.effects.time_stretch(yd, rate=1.25), lambda: lb.effects.time_stretch(y, rate=1.25)),
+        (lambda: lb.reassigned_spectrogram(yd, sr=22050, fill_nan=True), lambda: lb.reassigned_spectrogram(y, sr=22050, fill_nan=True)),
+    ]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for dev_fn, host_fn in pairs:
+            dev, host = dev_fn(), host_fn()
+            dev = dev if isinstance(dev, tuple) else (dev,)
+            host = host if isinstance(host, tuple) else (host,)
+            assert len(dev) == len(host)
+            for a, b in zip(dev, host):
+                assert isinstance(a, lb.DeviceArray) and a.shape == b.shape
+                np.testing.assert_allclose(a.get(), b.astype(a.dtype), rtol=1e-6, atol=1e-6 * float(np.abs(b).max()))
+        t_dev = lb.estimate_tuning(S=P, sr=22050)
+        t_host = lb.estimate_tuning(S=P.get(), sr=22050)
+        assert t_dev == t_host
+
+
 def test_rms_from_rectangular_stft_matches_rms_from_samples(lb):
     """The reference's own docstring property (feature/spectral.py:872-879): with a constant window and no
     centering, rms(S=|stft|) equals rms(y=...) frame by frame (Parseval)."""
