@@ -1,5 +1,10 @@
-import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+"""Latency of the public calls on ONE 60 s clip (BASELINE cfg 1): NumPy in -> NumPy out, median of 20 calls.
+
+    python tools/latency_cfg1.py
+"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, librosa_b200 as lb
 y = (0.1*np.random.default_rng(0).standard_normal(1323000)).astype(np.float32)
 for name, fn in [("stft", lambda: lb.stft(y)), ("mel", lambda: lb.feature.melspectrogram(y=y, sr=22050)), ("mfcc", lambda: lb.feature.mfcc(y=y, sr=22050)),
