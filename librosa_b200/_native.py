@@ -9,7 +9,7 @@ import ctypes as C
 import os
 import threading
 import weakref
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 

@@ -7,14 +7,14 @@ import hashlib
 import os
 import warnings
 from functools import lru_cache
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 
 from . import _native as nat
 from . import filters
 from .util.exceptions import ParameterError
-from .util.utils import is_positive_int, pad_center, valid_audio
+from .util.utils import is_positive_int, pad_center
 
 _UNSUPPORTED_PAD = ("wrap", "maximum", "mean", "median", "minimum")   # librosa/core/spectrum.py:253
 

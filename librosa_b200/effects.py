@@ -5,8 +5,6 @@ from __future__ import annotations
 
 from typing import Optional
 
-import numpy as np
-
 from . import _native as nat
 from . import _pipeline as pl
 from .core.spectrum import istft, phase_vocoder, stft

@@ -5,8 +5,6 @@ power_to_db on the device and feed the log-mel block straight to the spectral-fl
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
-
 import numpy as np
 
 from . import _native as nat
