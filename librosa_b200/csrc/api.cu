@@ -1218,23 +1218,17 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
   a.vec4 = (p->hop % 4 == 0) && (clen % 4 == 0) && (a.start % 4 == 0) && (y_stride % 4 == 0) &&
            (cfg.xbuf_f2() % 2 == 0) &&   // frame buffers 16-byte aligned inside the exchange area
            (((uintptr_t)d_y & 15) == 0) && (((uintptr_t)d_inv_wss & 15) == 0);
-  // segments: about six work items per resident half-CTA so the last wave is short; each at least 4 rounds
-  // long so the halo frames (recomputed at every segment start) stay a small fraction
-  {
-    const long long want = 6LL * c->sm_count * halves;
-    long long segs = (want + n_clips - 1) / n_clips;
-    const long long max_segs = (n_frames_used + 4LL * G - 1) / (4LL * G);
-    if (segs > max_segs) segs = max_segs;
-    if (segs < 1) segs = 1;
-    long long fps = (n_frames_used + segs - 1) / segs;
-    fps = (fps + G - 1) / G * G;
-    segs = (n_frames_used + fps - 1) / fps;
-    a.segs_per_clip = (int)segs;
-    a.frames_per_seg = (int)fps;
-  }
-  const long long items = (long long)a.segs_per_clip * n_clips;
+  // one slot of consecutive (clip, frame) pairs per resident half-CTA (1 CTA per SM): equal work everywhere,
+  // no partial last wave; slots are whole rounds of G frames, and at least 4 rounds long so that the halo
+  // frames recomputed at the start of a slot stay a small fraction
+  const long long total_frames = (long long)n_clips * n_frames_used;
+  long long fps = (total_frames + (long long)c->sm_count * halves - 1) / ((long long)c->sm_count * halves);
+  if (fps < 4LL * G) fps = 4LL * G;
+  fps = (fps + G - 1) / G * G;
+  if (fps > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "istft batch too large");
+  a.frames_per_slot = (int)fps;
+  const long long items = (total_frames + fps - 1) / fps;
   const long long grid = (items + halves - 1) / halves;
-  if (grid > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many istft segments");
   CUDA_TRY(op(OP_SET_SMEM, variant, &a, 0, smem, c->stream, nullptr));
   CUDA_TRY(op(OP_LAUNCH, variant, &a, (int)grid, smem, c->stream, nullptr));
   c->launches++;

@@ -105,7 +105,7 @@ struct InvArgs {
   const float* inv_wss;      // [out_len] 1/wss where wss > tiny else 1
   const float2* tw;
   const float2* twn;
-  int segs_per_clip, frames_per_seg;
+  int frames_per_slot;       // consecutive (clip, frame) pairs per half-CTA, a multiple of the round size
   int vec4;                  // gather 4 samples per thread (alignment conditions checked on the host)
   int off_win, off_tw, off_xbuf, off_acc;
   int xbuf_stride, acc_stride;   // per-half strides in bytes (DUAL)

@@ -3,7 +3,8 @@
 // Replaces librosa.istft's per-block  win * scipy.fft.irfft(D)  (librosa/core/spectrum.py:566, :598),
 // the numba __overlap_add loop (:629-643) and the window-sum-square division (:606-624).
 //
-// A half-CTA (see DUAL in fwd_kernel.cuh) owns one (clip, segment of frames).  It walks its frames G at
+// A half-CTA (see DUAL in fwd_kernel.cuh) owns one slot of consecutive (clip, frame) pairs and walks it clip
+// by clip ("pieces").  Inside a piece it takes its frames G at
 // a time (one frame per thread group): each group rebuilds the packed half-length spectrum from bin
 // pairs (c2r_pair) — the lower half lands directly in the registers that feed the first FFT pass, the
 // upper half crosses shared memory to its partner thread — runs the same register FFT as the forward
@@ -50,18 +51,26 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
   for (int i = tid; i < N; i += NT) s_win[i] = a.window[i];
   for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.tw[i];
   const int clen = a.n_fft > a.hop ? a.n_fft - a.hop : 0;
-  for (int i = htid; i < 2 * clen; i += HT) s_carry[i] = 0.0f;
   __syncthreads();
-
-  const long long item = (long long)blockIdx.x * NH + half;     // (clip, segment)
-  if (item >= (long long)a.n_clips * a.segs_per_clip) return;
-  const int clip = (int)(item / a.segs_per_clip);
-  const int seg = (int)(item % a.segs_per_clip);
-  const int fs = seg * a.frames_per_seg;
-  const int fe = min(a.n_frames, fs + a.frames_per_seg);
-  if (fs >= fe) return;
-  const bool last_seg = (fe == a.n_frames);
+  const float2 wt = __ldg(a.twn + t);                         // W_N^t, see unmix twiddle in fwd_kernel.cuh
   const int overlap = (a.n_fft + a.hop - 1) / a.hop;          // frames covering one sample
+
+  // Work distribution: the (clip, frame) pairs of the whole batch form one sequence of n_clips * n_frames
+  // frames, cut into equal slots — one per resident half-CTA, so every SM finishes at the same time (a
+  // (clip, segment) grid leaves the last wave mostly empty).  A slot is walked piece by piece: a piece is
+  // the part of the slot that lies inside one clip; it starts from an empty carry and first rebuilds it
+  // from the overlap - 1 halo frames before its first frame (transformed again, not emitted).
+  const long long slot = (long long)blockIdx.x * NH + half;
+  const long long total_frames = (long long)a.n_clips * a.n_frames;
+  const long long slot_end = min(total_frames, (slot + 1) * (long long)a.frames_per_slot);
+  for (long long gpos = slot * (long long)a.frames_per_slot; gpos < slot_end;) {
+  const int clip = (int)(gpos / a.n_frames);
+  const int fs = (int)(gpos % a.n_frames);
+  const int fe = (int)min((long long)a.n_frames, fs + (slot_end - gpos));
+  gpos += fe - fs;
+  for (int i = htid; i < 2 * clen; i += HT) s_carry[i] = 0.0f;
+  half_sync();
+  const bool last_seg = (fe == a.n_frames);
   const int fh = max(0, fs - (overlap - 1));                  // halo frames rebuild the carry
   const long long emit_lo = (long long)fs * a.hop;
   const long long emit_hi = last_seg ? (1LL << 62) : (long long)fe * a.hop;
@@ -70,7 +79,6 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
   float* yclip = a.y + (long long)clip * a.y_clip_stride;
   float* carry_cur = s_carry;
   float* carry_nxt = s_carry + clen;
-  const float2 wt = __ldg(a.twn + t);                         // W_N^t, see unmix twiddle in fwd_kernel.cuh
 
   // The spectrum row of the next round's frame is pulled into L2 while this round is gathered, so the
   // operand loads at the top of the next round see L2 latency instead of HBM latency (the registers
@@ -213,6 +221,8 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
     for (long long o = u0 + clen - a.start + htid; o < a.out_len; o += HT)
       if (o >= 0) yclip[o] = 0.0f;
   }
+  half_sync();   // the piece's last carry reads are done before the next piece clears the carry
+  }  // pieces of this slot
 }
 
 }  // namespace b2l
