@@ -1040,18 +1040,18 @@ extern "C" int b2l_melspectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_
 static int launch_dct(b2l_ctx* c, const b2l_plan* p, const float* d_L, int64_t n_clips, int64_t T, int clamp,
                       float* d_out) {
   const int KG = (p->n_mfcc + 7) / 8;
-  if (KG > 32) return fail(B2L_ERR_UNSUPPORTED, "n_mfcc=%d > 256 is not supported", p->n_mfcc);
+  if (KG > 16) return fail(B2L_ERR_UNSUPPORTED, "n_mfcc=%d > 128 is not supported", p->n_mfcc);
   size_t smem = ((size_t)p->n_mels * 8 * KG + 2 * (size_t)p->n_mels * DCT_TILE) * 4;
   if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_mels=%d is too large for the DCT kernel", p->n_mels);
   CUDA_TRY(cudaFuncSetAttribute(dct_clamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (int)((T + DCT_TILE - 1) / DCT_TILE);
   const long long total = (long long)tiles * n_clips;
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dct_clamp_kernel, KG * 32, smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dct_clamp_kernel, KG * 64, smem));
   if (occ < 1) return fail(B2L_ERR_CUDA, "DCT kernel does not fit on an SM");
   long long grid = (long long)c->sm_count * occ;
   if (grid > total) grid = total;
-  dct_clamp_kernel<<<(int)grid, KG * 32, smem, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
+  dct_clamp_kernel<<<(int)grid, KG * 64, smem, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
                                                             clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, (int)T,
                                                             tiles, total, d_out);
   CUDA_TRY(cudaGetLastError());

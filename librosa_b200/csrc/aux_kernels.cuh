@@ -12,10 +12,11 @@ namespace b2l {
 // scipy.fft.dct(S, axis=-2, type, norm)[..., :n_mfcc, :] (* lifter) (librosa/feature/spectral.py:2005-2015);
 // the DCT (any type / norm, lifter folded in) arrives transposed and zero padded: dctT[m][8*KG].
 //
-// Persistent blocks of KG warps walk (clip, 64-frame tile) pairs.  Warp w owns coefficients 8w..8w+7,
-// lane owns frames lane and lane+32 of the tile; DCT rows are warp-uniform float4 loads.  Tiles are
-// double buffered with cp.async (LDGSTS) so the next tile streams in while this one is multiplied; the
-// top_db clamp is applied as the values are read.
+// Persistent blocks of 2*KG warps walk (clip, 64-frame tile) pairs.  Warp w owns coefficients 8*(w % KG) ..
+// +7 for frames 32*(w / KG) + lane of the tile (one frame per lane: twice the warps of a two-frames-per-lane
+// layout for the same shared memory, which is what hides the shared-memory latency of the short inner loop);
+// DCT rows are warp-uniform float4 loads.  Tiles are double buffered with cp.async (LDGSTS) so the next
+// tile streams in while this one is multiplied; the top_db clamp is applied as the values are read.
 constexpr int DCT_TILE = 64;
 
 __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
@@ -35,11 +36,12 @@ __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __res
                                  int n_mfcc, int T, int tiles_per_clip, long long total_tiles,
                                  float* __restrict__ C) {
   extern __shared__ __align__(16) float s_dyn[];
-  const int KG = blockDim.x >> 5, KP = 8 * KG;
+  const int KG = blockDim.x >> 6, KP = 8 * KG;             // two warp sets: frames 0-31 and 32-63 of a tile
   float* s_dct = s_dyn;                                     // [n_mels][KP]
   float* s_tile0 = s_dyn + n_mels * KP;                     // 2 x [n_mels][DCT_TILE]
   const int tile_words = n_mels * DCT_TILE;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (tid >> 5) % KG, fhalf = (tid >> 5) / KG;
   for (int i = tid; i < n_mels * KP; i += blockDim.x) s_dct[i] = dctT[i];
   const bool vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(L) & 15) == 0);
 
@@ -79,30 +81,24 @@ __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __res
     const int t0 = (int)(tile % tiles_per_clip) * DCT_TILE;
     float floor_v = -INFINITY;
     if (clip_max != nullptr && top_db >= 0.0f) floor_v = key_to_float(clip_max[clip]) - top_db;
-    float acc[8][2];
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0f;
-#pragma unroll 4
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    const int fl = lane + 32 * fhalf;                 // frame of this lane inside the tile
+#pragma unroll 8
     for (int m = 0; m < n_mels; ++m) {
       const float4 d0 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp);
       const float4 d1 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp + 4);
       const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-      const float x0 = fmaxf(tile_s[m * DCT_TILE + lane], floor_v);
-      const float x1 = fmaxf(tile_s[m * DCT_TILE + lane + 32], floor_v);
+      const float x0 = fmaxf(tile_s[m * DCT_TILE + fl], floor_v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j][0] = fmaf(dv[j], x0, acc[j][0]);
-        acc[j][1] = fmaf(dv[j], x1, acc[j][1]);
-      }
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(dv[j], x0, acc[j]);
     }
     float* Cc = C + (long long)clip * n_mfcc * T;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = 8 * warp + j;
-      if (k < n_mfcc) {
-        if (t0 + lane < T) Cc[(long long)k * T + t0 + lane] = acc[j][0];
-        if (t0 + lane + 32 < T) Cc[(long long)k * T + t0 + lane + 32] = acc[j][1];
-      }
+      if (k < n_mfcc && t0 + fl < T) Cc[(long long)k * T + t0 + fl] = acc[j];
     }
     __syncthreads();   // tile consumed before the buffer is refilled two iterations later
   }
