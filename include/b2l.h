@@ -140,7 +140,8 @@ int b2l_melspectrogram(b2l_ctx* ctx, const b2l_plan* plan, const float* d_y, int
 
 /* librosa.feature.mfcc(y=...) — feature/spectral.py:1843-2019 incl. power_to_db
  * (core/spectrum.py:1735-1883, per-clip top_db reference max).  d_logmel is scratch of
- * n_clips*n_mels*n_frames floats (NULL: allocated and freed internally). */
+ * n_clips * n_mels * (n_frames rounded up to a multiple of 64) floats (internal tiled layout; NULL: allocated
+ * and freed internally). */
 int b2l_mfcc(b2l_ctx* ctx, const b2l_plan* plan, const float* d_y, int64_t n_clips, int64_t n,
              int64_t y_stride, float* d_mfcc, float* d_logmel);
 

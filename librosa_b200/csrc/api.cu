@@ -823,7 +823,8 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     a.mel_rows = rt->d_rows;
     a.n_mel_rows = rt->n_rows;
   }
-  a.log_mode = log_mode;
+  a.log_mode = log_mode ? 1 : 0;
+  a.out_tiled = log_mode == 2 ? 1 : 0;   // b2l_mfcc: log-mel goes to the tiled scratch
   a.amin = p->amin;
   a.db_sub = 10.0f * log10f(fmaxf(p->amin, fabsf(p->ref_value)));
   a.clip_max = c->d_clip_max;
@@ -1038,7 +1039,7 @@ extern "C" int b2l_melspectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_
 }
 
 static int launch_dct(b2l_ctx* c, const b2l_plan* p, const float* d_L, int64_t n_clips, int64_t T, int clamp,
-                      float* d_out) {
+                      float* d_out, int tiled = 0) {
   const int KG = (p->n_mfcc + 7) / 8;
   if (KG > 16) return fail(B2L_ERR_UNSUPPORTED, "n_mfcc=%d > 128 is not supported", p->n_mfcc);
   size_t smem = ((size_t)p->n_mels * 8 * KG + 2 * (size_t)p->n_mels * DCT_TILE) * 4;
@@ -1053,7 +1054,7 @@ static int launch_dct(b2l_ctx* c, const b2l_plan* p, const float* d_L, int64_t n
   if (grid > total) grid = total;
   dct_clamp_kernel<<<(int)grid, KG * 64, smem, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
                                                             clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, (int)T,
-                                                            tiles, total, d_out);
+                                                            tiles, total, tiled, d_out);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return B2L_OK;
@@ -1074,9 +1075,10 @@ extern "C" int b2l_mfcc(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(c->d_clip_max, 0, (size_t)n_clips * sizeof(unsigned int), c->stream));
   float* scratch = d_logmel;
-  if (!scratch) CUDA_TRY(cudaMalloc((void**)&scratch, (size_t)n_clips * p->n_mels * T * sizeof(float)));
-  rc = run_forward(c, p, MODE_MEL, 1, d_y, n_clips, n, y_stride, nullptr, scratch);
-  if (rc == B2L_OK) rc = launch_dct(c, p, scratch, n_clips, T, 1, d_mfcc);
+  // the log-mel scratch is tiled: [clip][ceil(T/64)][n_mels][64] (see dct_clamp_kernel)
+  if (!scratch) CUDA_TRY(cudaMalloc((void**)&scratch, (size_t)n_clips * p->n_mels * ((T + 63) / 64 * 64) * sizeof(float)));
+  rc = run_forward(c, p, MODE_MEL, 2, d_y, n_clips, n, y_stride, nullptr, scratch);
+  if (rc == B2L_OK) rc = launch_dct(c, p, scratch, n_clips, T, 1, d_mfcc, 1);
   if (!d_logmel) {
     cudaStreamSynchronize(c->stream);
     cudaFree(scratch);

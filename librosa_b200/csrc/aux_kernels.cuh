@@ -6,7 +6,9 @@
 namespace b2l {
 
 // ------------------------------------------------------------------ clamp + DCT (mfcc pass B)
-// in  L   [n_clips][n_mels][T]   log-mel (dB), not yet clamped
+// in  L   [n_clips][n_mels][T]   log-mel (dB), not yet clamped — or, `tiled`, the mfcc scratch of fwd_kernel:
+//         [n_clips][ceil(T/64)][n_mels][64], every 64-frame tile one contiguous block (full DRAM bursts
+//         instead of 256-byte pieces 4*T bytes apart)
 // out C   [n_clips][n_mfcc][T]   C[k][t] = sum_m dct[k][m] * max(L[m][t], clipmax - top_db)
 // Reference: np.maximum(log_spec, log_spec.max(...) - top_db) (librosa/core/spectrum.py:1881) followed by
 // scipy.fft.dct(S, axis=-2, type, norm)[..., :n_mfcc, :] (* lifter) (librosa/feature/spectral.py:2005-2015);
@@ -33,7 +35,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __restrict__ dctT,
                                  const unsigned int* __restrict__ clip_max, float top_db, int n_mels,
-                                 int n_mfcc, int T, int tiles_per_clip, long long total_tiles,
+                                 int n_mfcc, int T, int tiles_per_clip, long long total_tiles, int tiled,
                                  float* __restrict__ C) {
   extern __shared__ __align__(16) float s_dyn[];
   const int KG = blockDim.x >> 6, KP = 8 * KG;             // two warp sets: frames 0-31 and 32-63 of a tile
@@ -48,6 +50,13 @@ __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __res
   auto stage = [&](long long tile, float* buf) {
     const int clip = (int)(tile / tiles_per_clip);
     const int t0 = (int)(tile % tiles_per_clip) * DCT_TILE;
+    if (tiled) {
+      // scratch written by fwd_kernel (out_tiled): the tile is one contiguous, 16-byte aligned block
+      const float* Lt = L + ((long long)clip * tiles_per_clip + t0 / DCT_TILE) * tile_words;
+      for (int i = tid; i < tile_words / 4; i += blockDim.x) cp_async16(buf + 4 * i, Lt + 4 * i);
+      cp_async_commit();
+      return;
+    }
     const float* Lc = L + (long long)clip * n_mels * T + t0;
     if (vec_ok && t0 + DCT_TILE <= T) {
       for (int i = tid; i < n_mels * (DCT_TILE / 4); i += blockDim.x) {

@@ -408,7 +408,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
           float wmax = -INFINITY;
           const int n_items = a.n_mel_rows / H;
           const float* pbase = s_p + fp * RS;
-          float* obase = a.out_r + (long long)clip * a.n_mels * a.n_frames + t0 + fp;
+          // output row stride / base: the public [clip][mel][frame] layout, or the tiled mfcc scratch whose
+          // 64-frame tiles are contiguous 32 KB blocks for dct_clamp_kernel (t0 + fp and t0 + fp + FP share a tile)
+          const long long orow = a.out_tiled ? 64 : a.n_frames;
+          float* obase = a.out_tiled
+                             ? a.out_r + ((long long)clip * ((a.n_frames + 63) >> 6) + (t0 >> 6)) * a.n_mels * 64 + (t0 & 63) + fp
+                             : a.out_r + (long long)clip * a.n_mels * a.n_frames + t0 + fp;
           for (int item = hwarp; item < n_items; item += HW) {
             const int m = item * H + j;
             const MelRow row = s_row[m];
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
                   if (ok_b) wmax = fmaxf(wmax, vb);
                 }
               }
-              float* o = obase + (long long)m * a.n_frames;
+              float* o = obase + (long long)m * orow;
               if (ok_a) o[0] = va;
               if (ok_b) o[FP] = vb;
             }

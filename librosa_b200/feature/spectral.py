@@ -292,7 +292,7 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
         staged = pl.StagedInput(ctx, y)
         plan = make_plan(ctx)
         out = nat.DeviceArray.empty(ctx, staged.lead + (dct.shape[0], T), np.float32)
-        scratch = nat.DeviceArray.empty(ctx, (staged.n_clips, n_mels, T), np.float32)
+        scratch = nat.DeviceArray.empty(ctx, (staged.n_clips, n_mels, (T + 63) // 64 * 64), np.float32)
         nat.check(nat.lib().b2l_mfcc(ctx.handle, plan.handle, _vp(staged.dev.ptr), staged.n_clips, staged.n,
                                      staged.n, _vp(out.ptr), _vp(scratch.ptr)))
         scratch.free()   # stream-ordered pool: the block can be handed out again without a sync
@@ -303,5 +303,5 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
 
     res = pl.run_host_forward(y, n_fft=n_fft, hop_length=hop_length, center=center, n_frames=T,
                               out_mem_tail=(dct.shape[0], T), out_dtype=np.float32, make_plan=make_plan,
-                              launch=launch, scratch_per_clip=n_mels * T)
+                              launch=launch, scratch_per_clip=n_mels * ((T + 63) // 64 * 64))
     return res if res.dtype == res_dtype else res.astype(res_dtype)
