@@ -225,6 +225,46 @@ def test_device_resident_variants_of_the_wider_features(lb):
         assert t_dev == t_host
 
 
+def test_randomized_configurations_against_the_oracle(lb, oracle):
+    """Seeded sweep over transform sizes, hops, centring, padding modes, window specs and leading shapes for the
+    frame-wise features (the fixtures pin a few dozen hand-picked cases; this covers the cross product)."""
+    import signals
+
+    rng = np.random.default_rng(20260922)
+    pads = ["constant", "reflect", "edge", "symmetric"]
+    for trial in range(24):
+        n_fft = int(rng.choice([256, 512, 1024, 2048, 4096, 400, 1000]))
+        hop = int(rng.choice([n_fft // 4, n_fft // 2, n_fft // 8 + 3]))
+        center = bool(rng.integers(0, 2))
+        shape = [(7 * n_fft + int(rng.integers(0, 999)),), (2, 6 * n_fft + 5), (2, 2, 5 * n_fft)][int(rng.integers(0, 3))]
+        mix = "ABT"[int(rng.integers(0, 3))]
+        sr = int(rng.choice([16000, 22050, 44100]))
+        y = signals.make(mix, shape, seed=100 + trial, sr=sr)
+        kw = dict(n_fft=n_fft, hop_length=hop, center=center, pad_mode=pads[int(rng.integers(0, 4))],
+                  window=["hann", "hamming", ("tukey", 0.3)][int(rng.integers(0, 3))])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            checks = [
+                (lb.feature.spectral_centroid(y=y, sr=sr, **kw), oracle.spectral_centroid(y=y, sr=sr, **kw), 1e-4, 1e-6),
+                (lb.feature.spectral_flatness(y=y, **kw), oracle.spectral_flatness(y=y, **kw), 1e-4, 1e-7),
+                (lb.feature.rms(y=y, frame_length=n_fft, hop_length=hop, center=center),
+                 oracle.rms(y=y, frame_length=n_fft, hop_length=hop, center=center), 1e-4, 1e-7),
+                (lb.feature.zero_crossing_rate(y, frame_length=n_fft, hop_length=hop, center=center),
+                 oracle.zero_crossing_rate(y, frame_length=n_fft, hop_length=hop, center=center), 0.0, 0.0),
+            ]
+        for got, want, rtol, atol_rel in checks:
+            assert got.shape == want.shape and got.dtype == want.dtype, (trial, kw)
+            scale = float(np.abs(want).max()) or 1.0
+            np.testing.assert_allclose(got, want, rtol=rtol, atol=atol_rel * scale, err_msg=f"trial {trial} {kw} {shape}")
+        for pp in (2.0, 2.5):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                got = lb.feature.spectral_bandwidth(y=y, sr=sr, p=pp, **kw)
+                want = oracle.spectral_bandwidth(y=y, sr=sr, p=pp, **kw)
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6 * float(np.abs(want).max() or 1.0),
+                                       err_msg=f"trial {trial} bandwidth p={pp} {kw}")
+
+
 def test_rms_from_rectangular_stft_matches_rms_from_samples(lb):
     """The reference's own docstring property (feature/spectral.py:872-879): with a constant window and no
     centering, rms(S=|stft|) equals rms(y=...) frame by frame (Parseval)."""
