@@ -70,3 +70,35 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), f"{os.path.join(dirpath, f)} references the oracle"
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "c_abi_demo"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", os.path.join(ROOT, "librosa_b200", "csrc"), "-lb2l", "-lm",
+           "-o", str(exe)]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return exe
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """include/b2l.h compiles as C99 (no C++ / torch types in the signatures) and every symbol the demo uses
+    resolves against libb2l.so; running it needs a GPU (tests/test_gpu_parity.py)."""
+    exe = _build_c_demo(tmp_path)
+    assert exe.exists()
+
+
+@pytest.mark.gpu
+def test_c_program_runs_on_the_gpu(tmp_path):
+    import subprocess
+
+    exe = _build_c_demo(tmp_path)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "librosa_b200", "csrc") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([str(exe)], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "C ABI demo: OK" in out.stdout
