@@ -909,7 +909,8 @@ static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, in
   a.power_mode = p->power_mode;
   a.power = p->power;
   a.status = c->d_status;
-  const size_t smem = (size_t)((cfg.tw_count() + 15) & ~15) * 8 + (size_t)G * cfg.xbuf_f2() * 8;
+  const size_t smem = (size_t)((cfg.tw_count() + 15) & ~15) * 8 + (size_t)G * cfg.xbuf_f2() * 8 +
+                      ((size_t)(1 << p->log2p) + (size_t)((p->n_fft + 1) & ~1) + (size_t)a.n_bins) * 8;   // + the three tables
   czt_op_fn op = czt_table(p->log2p);
   const unsigned long long kkey = (1ULL << 63) | ((unsigned long long)p->log2p << 40);
   int occ = 0;
@@ -917,10 +918,13 @@ static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, in
   if (hit != c->launch_cache.end()) {
     occ = hit->second;
   } else {
-    CUDA_TRY(op(OP_SET_SMEM, &a, 0, smem, c->stream, nullptr));
-    CUDA_TRY(op(OP_OCCUPANCY, &a, 0, smem, c->stream, &occ));
+    // the table part of the shared memory depends on n_fft, not only on P: allow the device maximum once and
+    // size the grid for the largest case (the kernels run one block per SM anyway)
+    CUDA_TRY(op(OP_SET_SMEM, &a, 0, c->smem_optin, c->stream, nullptr));
+    CUDA_TRY(op(OP_OCCUPANCY, &a, 0, c->smem_optin / 2 + 1, c->stream, &occ));
     c->launch_cache[kkey] = occ;
   }
+  if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", p->n_fft);
   if (occ < 1) return fail(B2L_ERR_CUDA, "chirp-z kernel does not fit on an SM (smem %zu)", smem);
   const long long steps = ((long long)n_clips * T + G - 1) / G;
   long long grid = (long long)c->sm_count * occ;

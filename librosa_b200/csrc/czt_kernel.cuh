@@ -44,11 +44,19 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);
   float2* s_xall = s_tw + ((Cfg::TW_COUNT + 15) & ~15);
+  // the three per-plan tables (FFT_P(h)/P, window * chirp, output chirp) live in shared memory: every frame
+  // reads all of them, and as global loads they competed with the sample gather for the LSU
+  float2* s_hf = s_xall + G * Cfg::XBUF_F2;
+  float2* s_wb = s_hf + P;
+  float2* s_bk = s_wb + ((a.L + 1) & ~1);
   const int tid = threadIdx.x, grp = tid / TPF, t = tid % TPF;
   const int gbar = 2 + grp;
   float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
   // inter-pass twiddles of the engine (the host appends them to the FFT_P(h)/P table)
   for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.hf[P + i];   // appended after FFT_P(h)/P
+  for (int i = tid; i < P; i += NT) s_hf[i] = a.hf[i];
+  for (int i = tid; i < a.L; i += NT) s_wb[i] = a.wb[i];
+  for (int i = tid; i < a.n_bins; i += NT) s_bk[i] = a.bk[i];
   __syncthreads();
 
   const long long total = (long long)a.n_clips * a.n_frames;
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
     load_pass0<Cfg>(v, t, [&](int e) {
       if (e >= a.L) return make_float2(0.0f, 0.0f);
       const float x = load_padded(yc, a.n, s0 + e, a.pad_mode, a.pad);
-      const float2 w = __ldg(a.wb + e);
+      const float2 w = s_wb[e];
       return make_float2(x * w.x, x * w.y);
     });
     fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
     static_for<0, PPT>([&](auto S) {
       constexpr int slot = decltype(S)::value;
       const int idx = t + spectrum_offset<Cfg>(slot);
-      const float2 c = cmul(v[slot], __ldg(a.hf + idx));
+      const float2 c = cmul(v[slot], s_hf[idx]);
       xbuf[xphys(idx)] = make_float2(c.y, c.x);
     });
     group_sync<TPF>(gbar);
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
       constexpr int slot = decltype(S)::value;
       const int k = t + spectrum_offset<Cfg>(slot);
       if (k < a.n_bins && live) {
-        const float2 X = cmul(make_float2(v[slot].y, v[slot].x), __ldg(a.bk + k));
+        const float2 X = cmul(make_float2(v[slot].y, v[slot].x), s_bk[k]);
         const long long o = ((long long)clip * a.n_frames + frame) * a.n_bins + k;
         if (a.mode == 0) {
           a.out_c[o] = X;
