@@ -133,10 +133,18 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
   extern __shared__ __align__(128) unsigned char smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);
   float2* s_xall = s_tw + ((Cfg::TW_COUNT + 15) & ~15);
+  float2* s_hf = s_xall + G * Cfg::XBUF_F2;               // plan tables in shared memory, as in czt_kernel
+  float2* s_bfull = s_hf + P;
+  float2* s_wbi = s_bfull + ((a.L + 1) & ~1);
   const int tid = threadIdx.x, grp = tid / TPF, t = tid % TPF;
   const int gbar = 2 + grp;
   float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
   for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.hf[P + i];
+  for (int i = tid; i < P; i += NT) s_hf[i] = a.hf[i];
+  for (int i = tid; i < a.L; i += NT) {
+    s_bfull[i] = a.bfull[i];
+    s_wbi[i] = a.wbi[i];
+  }
   __syncthreads();
   const long long total = (long long)a.n_clips * a.n_frames;
   for (long long f0 = (long long)blockIdx.x * G; f0 < total; f0 += (long long)gridDim.x * G) {
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
         x = __ldg(Drow + (a.L - e));
         x.y = -x.y;                                      // Hermitian extension
       }
-      const float2 b = __ldg(a.bfull + e);
+      const float2 b = s_bfull[e];
       return cmul(x, make_float2(b.x, -b.y));            // Xfull[e] * conj(b[e])
     });
     fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
     static_for<0, PPT>([&](auto S) {
       constexpr int slot = decltype(S)::value;
       const int idx = t + spectrum_offset<Cfg>(slot);
-      const float2 h = __ldg(a.hf + idx);
+      const float2 h = s_hf[idx];
       const float2 c = cmul(v[slot], make_float2(h.x, -h.y));     // conj(FFT_P(h)) = FFT_P(conj h), h symmetric
       xbuf[xphys(idx)] = make_float2(c.y, c.x);
     });
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
       constexpr int slot = decltype(S)::value;
       const int nn = t + spectrum_offset<Cfg>(slot);
       if (nn < a.L && live) {
-        const float2 w = __ldg(a.wbi + nn);
+        const float2 w = s_wbi[nn];
         // Re( (c.re + i c.im) * w ) with c un-swapped: c.re = v.y, c.im = v.x
         a.ytmp[((long long)clip * a.n_frames + frame) * a.L + nn] = fmaf(v[slot].y, w.x, -v[slot].x * w.y);
       }
