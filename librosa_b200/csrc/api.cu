@@ -1130,7 +1130,7 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
     a.hf = p->d_czt_hf;
     a.ytmp = c->d_scratch;
     const size_t smem = (size_t)((cfg.tw_count() + 15) & ~15) * 8 + (size_t)G * cfg.xbuf_f2() * 8 +
-                        ((size_t)(1 << p->log2p) + 2 * (size_t)((L + 1) & ~1)) * 8;   // + FFT_P(h)/P, chirp, window * chirp
+                        ((size_t)(1 << p->log2p) + (size_t)((L + 1) & ~1)) * 8;   // + FFT_P(h)/P and window * chirp
     if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", L);
     czt_inv_op_fn op = czt_inv_table(p->log2p);
     const unsigned long long kkey = (3ULL << 62) | ((unsigned long long)p->log2p << 40);

@@ -134,17 +134,14 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
   float2* s_tw = reinterpret_cast<float2*>(smem);
   float2* s_xall = s_tw + ((Cfg::TW_COUNT + 15) & ~15);
   float2* s_hf = s_xall + G * Cfg::XBUF_F2;               // plan tables in shared memory, as in czt_kernel
-  float2* s_bfull = s_hf + P;
-  float2* s_wbi = s_bfull + ((a.L + 1) & ~1);
+  float2* s_wbi = s_hf + P;                               // (the input chirp stays in global memory: with it the
+                                                          //  P = 4096 configuration would not fit)
   const int tid = threadIdx.x, grp = tid / TPF, t = tid % TPF;
   const int gbar = 2 + grp;
   float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
   for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.hf[P + i];
   for (int i = tid; i < P; i += NT) s_hf[i] = a.hf[i];
-  for (int i = tid; i < a.L; i += NT) {
-    s_bfull[i] = a.bfull[i];
-    s_wbi[i] = a.wbi[i];
-  }
+  for (int i = tid; i < a.L; i += NT) s_wbi[i] = a.wbi[i];
   __syncthreads();
   const long long total = (long long)a.n_clips * a.n_frames;
   for (long long f0 = (long long)blockIdx.x * G; f0 < total; f0 += (long long)gridDim.x * G) {
@@ -163,7 +160,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
         x = __ldg(Drow + (a.L - e));
         x.y = -x.y;                                      // Hermitian extension
       }
-      const float2 b = s_bfull[e];
+      const float2 b = __ldg(a.bfull + e);
       return cmul(x, make_float2(b.x, -b.y));            // Xfull[e] * conj(b[e])
     });
     fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
