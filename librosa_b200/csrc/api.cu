@@ -926,7 +926,7 @@ static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, in
   }
   if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", p->n_fft);
   if (occ < 1) return fail(B2L_ERR_CUDA, "chirp-z kernel does not fit on an SM (smem %zu)", smem);
-  const long long steps = ((long long)n_clips * T + G - 1) / G;
+  const long long steps = (((long long)n_clips * T + 1) / 2 + G - 1) / G;     // the kernel transforms frames in pairs
   long long grid = (long long)c->sm_count * occ;
   if (grid > steps) grid = steps;
   CUDA_TRY(op(OP_LAUNCH, &a, (int)grid, smem, c->stream, nullptr));

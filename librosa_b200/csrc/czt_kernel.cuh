@@ -8,7 +8,8 @@
 // a[n] = x[n] w[n] b[n] zero-padded to P >= 2L-1 (a power of two), h[m] = conj(b[|m|]) wrapped to length P.
 // FFT_P(h)/P, w*b and b are precomputed on the host in double precision.
 //
-// One group of TPF = P/32 threads per frame (same engine configuration as an n_fft = 2P real frame);
+// One group of TPF = P/32 threads per PAIR of frames (same engine configuration as an n_fft = 2P real frame; the
+// two real frames are the real and imaginary part of one complex input);
 // frames are read straight from global memory through the np.pad index map (the 2-4x frame overlap is
 // served by L2), the product with FFT_P(h) is applied in registers, and the inverse transform reuses the
 // forward one with re/im swapped.
@@ -59,23 +60,33 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
   for (int i = tid; i < a.n_bins; i += NT) s_bk[i] = a.bk[i];
   __syncthreads();
 
+  // Two real frames ride through one complex chirp-z transform: z = xA + i xB gives Z = XA + i XB, and since
+  // XA, XB are spectra of real signals, XA[k] = (Z[k] + conj Z[L-k]) / 2 and XB[k] = (Z[k] - conj Z[L-k]) / 2i.
+  // Z[L-k] = c[L-k] * b[L-k] with b[L-k] = (-1)^L b[k], so the chirp table still only covers k <= L/2.
   const long long total = (long long)a.n_clips * a.n_frames;
-  for (long long f0 = (long long)blockIdx.x * G; f0 < total; f0 += (long long)gridDim.x * G) {
-    // groups past the end redo the last frame (their stores are masked): sub-warp groups share a warp
-    const long long fidx = min(f0 + grp, total - 1);
-    const bool live = f0 + grp < total;
-    const int clip = (int)(fidx / a.n_frames), frame = (int)(fidx % a.n_frames);
-    const float* yc = a.y + (long long)clip * a.clip_stride;
-    const long long s0 = (long long)frame * a.hop - a.pad;
+  const long long pairs = (total + 1) / 2;
+  const float sgn = (a.L & 1) ? -1.0f : 1.0f;
+  for (long long p0 = (long long)blockIdx.x * G; p0 < pairs; p0 += (long long)gridDim.x * G) {
+    // groups past the end redo the last pair (their stores are masked): sub-warp groups share a warp
+    const long long pidx = min(p0 + grp, pairs - 1);
+    const bool live_a = p0 + grp < pairs;
+    const long long fa = 2 * pidx, fb = min(2 * pidx + 1, total - 1);
+    const bool live_b = live_a && 2 * pidx + 1 < total;
+    const int clip_a = (int)(fa / a.n_frames), frame_a = (int)(fa % a.n_frames);
+    const int clip_b = (int)(fb / a.n_frames), frame_b = (int)(fb % a.n_frames);
+    const float* ya = a.y + (long long)clip_a * a.clip_stride;
+    const float* yb = a.y + (long long)clip_b * a.clip_stride;
+    const long long sa = (long long)frame_a * a.hop - a.pad, sb = (long long)frame_b * a.hop - a.pad;
     float2 v[PPT];
     load_pass0<Cfg>(v, t, [&](int e) {
       if (e >= a.L) return make_float2(0.0f, 0.0f);
-      const float x = load_padded(yc, a.n, s0 + e, a.pad_mode, a.pad);
+      const float xa = load_padded(ya, a.n, sa + e, a.pad_mode, a.pad);
+      const float xb = load_padded(yb, a.n, sb + e, a.pad_mode, a.pad);
       const float2 w = s_wb[e];
-      return make_float2(x * w.x, x * w.y);
+      return make_float2(fmaf(xa, w.x, -xb * w.y), fmaf(xa, w.y, xb * w.x));      // (xa + i xb) * w
     });
     fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
-    if (live && !(fabsf(v[0].x) + fabsf(v[0].y) <= 3.0e38f)) *a.status = 1;   // util.valid_audio
+    if (live_a && !(fabsf(v[0].x) + fabsf(v[0].y) <= 3.0e38f)) *a.status = 1;   // util.valid_audio
     // C = A . FFT(h)/P in registers, published (re/im swapped) for the inverse transform's first pass
     if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
     static_for<0, PPT>([&](auto S) {
@@ -88,22 +99,40 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
     load_pass0<Cfg>(v, t, [&](int e) { return xbuf[xphys(e)]; });
     group_sync<TPF>(gbar);
     fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
-    // X[k] = b[k] * c[k]  (un-swap), k <= L/2
+    // publish c[idx] (un-swapped) for idx < L so that every bin can reach its mirror L - k
+    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
+    static_for<0, PPT>([&](auto S) {
+      constexpr int slot = decltype(S)::value;
+      const int idx = t + spectrum_offset<Cfg>(slot);
+      if (idx < a.L) xbuf[xphys(idx)] = make_float2(v[slot].y, v[slot].x);
+    });
+    group_sync<TPF>(gbar);
+    // k <= L/2:  Z[k] = c[k] b[k],  conj Z[L-k] = sgn * conj(c[L-k]) conj(b[k])
     static_for<0, PPT>([&](auto S) {
       constexpr int slot = decltype(S)::value;
       const int k = t + spectrum_offset<Cfg>(slot);
-      if (k < a.n_bins && live) {
-        const float2 X = cmul(make_float2(v[slot].y, v[slot].x), s_bk[k]);
-        const long long o = ((long long)clip * a.n_frames + frame) * a.n_bins + k;
-        if (a.mode == 0) {
-          a.out_c[o] = X;
-        } else {
-          float p2 = sqmag(X);
-          a.out_r[o] = a.power_mode == 2 ? p2 : (a.power_mode == 1 ? sqrt_approx(p2) : power_from_sq(p2, a.power_mode, a.power));
-        }
+      if (k < a.n_bins) {
+        const float2 b = s_bk[k];
+        const float2 zk = cmul(make_float2(v[slot].y, v[slot].x), b);
+        const float2 cm = xbuf[xphys(k == 0 ? 0 : a.L - k)];
+        const float sk = k == 0 ? 1.0f : sgn;                                                  // Z[L] is Z[0] itself
+        const float2 zm = cmul(make_float2(cm.x, -cm.y), make_float2(sk * b.x, -sk * b.y));     // conj Z[L-k]
+        const float2 XA = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
+        const float2 XB = make_float2(0.5f * (zk.y - zm.y), -0.5f * (zk.x - zm.x));             // (zk - zm) / 2i
+        auto emit = [&](float2 X, int clip, int frame) {
+          const long long o = ((long long)clip * a.n_frames + frame) * a.n_bins + k;
+          if (a.mode == 0) {
+            a.out_c[o] = X;
+          } else {
+            const float p2 = sqmag(X);
+            a.out_r[o] = a.power_mode == 2 ? p2 : (a.power_mode == 1 ? sqrt_approx(p2) : power_from_sq(p2, a.power_mode, a.power));
+          }
+        };
+        if (live_a) emit(XA, clip_a, frame_a);
+        if (live_b) emit(XB, clip_b, frame_b);
       }
     });
-    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);   // exchange area reused by the next frame
+    group_sync<TPF>(gbar);   // mirror reads done before the next pair's exchange writes
   }
 }
 
