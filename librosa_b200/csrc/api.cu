@@ -1144,7 +1144,7 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
       c->launch_cache[kkey] = occ;
     }
     if (occ < 1) return fail(B2L_ERR_CUDA, "chirp-z inverse kernel does not fit on an SM");
-    const long long steps = ((long long)n_clips * n_frames_used + G - 1) / G;
+    const long long steps = (((long long)n_clips * n_frames_used + 1) / 2 + G - 1) / G;   // frames go in pairs
     long long grid = (long long)c->sm_count * occ;
     if (grid > steps) grid = steps;
     CUDA_TRY(op(OP_LAUNCH, &a, (int)grid, smem, c->stream, nullptr));

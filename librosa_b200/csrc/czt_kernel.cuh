@@ -172,25 +172,36 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
   for (int i = tid; i < P; i += NT) s_hf[i] = a.hf[i];
   for (int i = tid; i < a.L; i += NT) s_wbi[i] = a.wbi[i];
   __syncthreads();
+  // As in czt_kernel, two frames share one complex transform: U = X_A + i X_B (Hermitian extensions) inverts to
+  // u = y_A + i y_B because both signals are real.
   const long long total = (long long)a.n_clips * a.n_frames;
-  for (long long f0 = (long long)blockIdx.x * G; f0 < total; f0 += (long long)gridDim.x * G) {
-    const long long fidx = min(f0 + grp, total - 1);
-    const bool live = f0 + grp < total;
-    const int clip = (int)(fidx / a.n_frames), frame = (int)(fidx % a.n_frames);
-    const float2* Drow = a.D + (long long)clip * a.d_clip_stride + (long long)frame * a.n_bins;
+  const long long pairs = (total + 1) / 2;
+  for (long long p0 = (long long)blockIdx.x * G; p0 < pairs; p0 += (long long)gridDim.x * G) {
+    const long long pidx = min(p0 + grp, pairs - 1);
+    const bool live_a = p0 + grp < pairs;
+    const long long fa = 2 * pidx, fb = min(2 * pidx + 1, total - 1);
+    const bool live_b = live_a && 2 * pidx + 1 < total;
+    const int clip_a = (int)(fa / a.n_frames), frame_a = (int)(fa % a.n_frames);
+    const int clip_b = (int)(fb / a.n_frames), frame_b = (int)(fb % a.n_frames);
+    const float2* Da = a.D + (long long)clip_a * a.d_clip_stride + (long long)frame_a * a.n_bins;
+    const float2* Db = a.D + (long long)clip_b * a.d_clip_stride + (long long)frame_b * a.n_bins;
     float2 v[PPT];
     load_pass0<Cfg>(v, t, [&](int e) {
       if (e >= a.L) return make_float2(0.0f, 0.0f);
-      float2 x;
+      float2 xa, xb;
       if (e < a.n_bins) {
-        x = __ldg(Drow + e);
-        if (e == 0 || 2 * e == a.L) x.y = 0.0f;          // DC, and Nyquist when L is even
+        xa = __ldg(Da + e);
+        xb = __ldg(Db + e);
+        if (e == 0 || 2 * e == a.L) xa.y = xb.y = 0.0f;  // DC, and Nyquist when L is even
       } else {
-        x = __ldg(Drow + (a.L - e));
-        x.y = -x.y;                                      // Hermitian extension
+        xa = __ldg(Da + (a.L - e));
+        xb = __ldg(Db + (a.L - e));
+        xa.y = -xa.y;                                    // Hermitian extension
+        xb.y = -xb.y;
       }
+      const float2 x = make_float2(xa.x - xb.y, xa.y + xb.x);     // X_A + i X_B
       const float2 b = __ldg(a.bfull + e);
-      return cmul(x, make_float2(b.x, -b.y));            // Xfull[e] * conj(b[e])
+      return cmul(x, make_float2(b.x, -b.y));            // U[e] * conj(b[e])
     });
     fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
     if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
@@ -208,10 +219,11 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
     static_for<0, PPT>([&](auto S) {
       constexpr int slot = decltype(S)::value;
       const int nn = t + spectrum_offset<Cfg>(slot);
-      if (nn < a.L && live) {
+      if (nn < a.L) {
         const float2 w = s_wbi[nn];
-        // Re( (c.re + i c.im) * w ) with c un-swapped: c.re = v.y, c.im = v.x
-        a.ytmp[((long long)clip * a.n_frames + frame) * a.L + nn] = fmaf(v[slot].y, w.x, -v[slot].x * w.y);
+        // u = c * w with c un-swapped (c.re = v.y, c.im = v.x): frame A is its real part, frame B its imaginary part
+        if (live_a) a.ytmp[((long long)clip_a * a.n_frames + frame_a) * a.L + nn] = fmaf(v[slot].y, w.x, -v[slot].x * w.y);
+        if (live_b) a.ytmp[((long long)clip_b * a.n_frames + frame_b) * a.L + nn] = fmaf(v[slot].y, w.y, v[slot].x * w.x);
       }
     });
     if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
