@@ -266,6 +266,13 @@ def test_randomized_configurations_against_the_oracle(lb, oracle):
                                        err_msg=f"trial {trial} bandwidth p={pp} {kw}")
 
 
+def test_known_answers_of_the_reference_suite(lb):
+    """Same facts (tests/known_answers.py) through the CUDA path; nothing is skipped."""
+    import known_answers
+
+    assert known_answers.run(lb.feature, unsupported=(lb.UnsupportedOnGPU,)) == 36
+
+
 def test_rms_from_rectangular_stft_matches_rms_from_samples(lb):
     """The reference's own docstring property (feature/spectral.py:872-879): with a constant window and no
     centering, rms(S=|stft|) equals rms(y=...) frame by frame (Parseval)."""
