@@ -273,6 +273,40 @@ def test_known_answers_of_the_reference_suite(lb):
     assert known_answers.run(lb.feature, unsupported=(lb.UnsupportedOnGPU,)) == 36
 
 
+def test_algebraic_properties_of_the_wider_functions(lb):
+    """Size-independent identities (no oracle needed): dB conversions invert each other, PCEN with gain 0 /
+    bias 0 / power 1 is the identity, harmonic + percussive = input for unit margins, a phase vocoder at rate 1
+    returns its input, a time stretch at rate 1 returns the signal, a pure tone reassigns to its frequency."""
+    import signals
+
+    rng = np.random.default_rng(5)
+    x = rng.uniform(1e-3, 1e3, size=(3, 64, 50)).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.testing.assert_allclose(lb.db_to_power(lb.power_to_db(x, top_db=None)), x, rtol=2e-5)
+        np.testing.assert_allclose(lb.db_to_amplitude(lb.amplitude_to_db(x, top_db=None)), x, rtol=2e-5)
+        np.testing.assert_allclose(lb.amplitude_to_db(x), lb.power_to_db(x ** 2, amin=1e-10), atol=1e-4)
+        np.testing.assert_allclose(lb.pcen(x, gain=0.0, bias=0.0, power=1.0), x, rtol=1e-5)
+        assert not np.any(lb.onset.onset_strength(S=np.full((40, 30), -3.0, dtype=np.float32)))
+        y = signals.make("B", (2, 16000), seed=8)
+        D = lb.stft(y, n_fft=1024)
+        H, P = lb.decompose.hpss(D)
+        np.testing.assert_allclose(H + P, D, rtol=1e-4, atol=1e-5 * float(np.abs(D).max()))
+        Hm, Pm = lb.decompose.hpss(np.abs(D), mask=True)
+        np.testing.assert_allclose(Hm + Pm, 1.0, atol=1e-5)
+        np.testing.assert_allclose(lb.phase_vocoder(D, rate=1.0), D, rtol=1e-4, atol=2e-5 * float(np.abs(D).max()))
+        ys = lb.effects.time_stretch(y, rate=1.0, n_fft=1024)
+        assert ys.shape == y.shape
+        np.testing.assert_allclose(ys[..., 512:-512], y[..., 512:-512], atol=2e-4 * float(np.abs(y).max()))
+        sr, tone = 22050, 2000.0
+        t = np.arange(22050) / sr
+        f, tt, m = lb.reassigned_spectrogram((0.5 * np.sin(2 * np.pi * tone * t)).astype(np.float32), sr=sr, fill_nan=True)
+        k = int(round(tone * 2048 / sr))
+        assert np.allclose(f[k - 1:k + 2, 5:-5], tone, atol=1.0)        # the three bins of the main lobe
+        frames_t = np.arange(f.shape[-1]) * 512 / sr
+        assert np.allclose(tt[k, 5:-5], frames_t[5:-5], atol=2e-3)       # a stationary tone does not move in time
+
+
 def test_rms_from_rectangular_stft_matches_rms_from_samples(lb):
     """The reference's own docstring property (feature/spectral.py:872-879): with a constant window and no
     centering, rms(S=|stft|) equals rms(y=...) frame by frame (Parseval)."""
