@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
   __syncthreads();
   const float2 wt = __ldg(a.twn + t);                         // W_N^t, see unmix twiddle in fwd_kernel.cuh
   const int overlap = (a.n_fft + a.hop - 1) / a.hop;          // frames covering one sample
+  const int hop_shift = (a.hop & (a.hop - 1)) == 0 ? 31 - __clz(a.hop) : -1;   // log2(hop) when hop is a power of two
 
   // Work distribution: the (clip, frame) pairs of the whole batch form one sequence of n_clips * n_frames
   // frames, cut into equal slots — one per resident half-CTA, so every SM finishes at the same time (a
@@ -156,11 +157,17 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
       // start and the row strides are multiples of 4 and the buffers 16-byte aligned; host-checked)
       const int per = a.hop >> 2;
       for (int item = htid; item < per * n_chunks; item += HT) {
-        const int c = item / per;
+        // (chunk, offset) of the item and the number of earlier frames covering the offset: shifts when the
+        // hop is a power of two (the usual case) instead of two integer divisions per item
+        int c, q;
+        if (hop_shift >= 2) c = item >> (hop_shift - 2);
+        else c = item / per;
         const int i = (item - c * per) << 2;
         const int x = c * a.hop + i;
         if (x >= emit_n + clen) continue;
-        const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;
+        if (i >= a.n_fft) q = -1;
+        else if (hop_shift >= 0) q = (a.n_fft - 1 - i) >> hop_shift;
+        else q = (a.n_fft - 1 - i) / a.hop;
         float4 val = (x < clen) ? *reinterpret_cast<const float4*>(carry_cur + x) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
         const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
@@ -188,11 +195,14 @@ __global__ void __launch_bounds__(NW * 32, 1) inv_kernel(const InvArgs a) {
       }
     } else {
       for (int item = htid; item < a.hop * n_chunks; item += HT) {
-        const int c = item / a.hop;
+        const int c = hop_shift >= 0 ? item >> hop_shift : item / a.hop;
         const int i = item - c * a.hop;
         const int x = c * a.hop + i;
         if (x >= emit_n + clen) continue;
-        const int q = i < a.n_fft ? (a.n_fft - 1 - i) / a.hop : -1;   // hop > n_fft: gap positions see no frame
+        int q;                                                        // hop > n_fft: gap positions see no frame
+        if (i >= a.n_fft) q = -1;
+        else if (hop_shift >= 0) q = (a.n_fft - 1 - i) >> hop_shift;
+        else q = (a.n_fft - 1 - i) / a.hop;
         float val = (x < clen) ? carry_cur[x] : 0.0f;
         const int g_lo = max(0, c - q), g_hi = min(c, ng - 1);
         const float* yb = reinterpret_cast<const float*>(s_xall + g_lo * Cfg::XBUF_F2) + (c - g_lo) * a.hop + i;
