@@ -11,9 +11,13 @@ no collective on the data path; `value` = frames of all ranks / max-over-ranks d
 One JSON line on stdout (rank 0).  Extra keys beyond the base contract:
   roofline      dominant kernel vs the measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes
   cpu_baseline  the oracle port (oracle/ref_np.py == the reference's algorithm, bit-exact here) timed on
-                this box's host cores on a bounded sample
-  e2e           same metric through the public drop-in call with HOST (pinned) buffers, H2D + D2H inside
-  clocks        nvidia-smi samples taken during the timed region
+                this box's host cores on a bounded sample: the three ways SURVEY 8d lists (batched call /
+                one-process loop / forked workers), best reported, all listed under `variants`
+  e2e           same metric through the public drop-in call with HOST (pinned) buffers, H2D + D2H inside;
+                `pageable` = the same call on an ordinary ndarray; `h2d_ceiling_gbs_per_gpu` = plain upload
+                bandwidth with every rank transferring at once (the floor of the end-to-end step)
+  secondary     device-resident ms / frames/s / roofline of BASELINE.json configs 3, 4, 5 (per-GPU shards)
+  clocks        NVML samples taken during the timed region
 """
 from __future__ import annotations
 
@@ -34,8 +38,8 @@ WORKLOADS = {
     # name: (clips per GPU, channels, samples, sr, op, kwargs, algorithmic bytes per frame)
     "cfg2": dict(clips=1024, n=220500, sr=22050, op="mel", kw=dict(n_fft=2048, hop_length=512, n_mels=128, power=2.0),
                  desc="batch=1024 clips x10s mono sr=22050 -> melspectrogram n_fft=2048 hop=512 n_mels=128 power=2.0"),
-    "cfg3": dict(clips=1024, n=441000, sr=44100, op="stft", kw=dict(n_fft=4096, hop_length=1024),
-                 desc="1024 channel-clips (512 stereo) x10s sr=44100 -> stft n_fft=4096 hop=1024 per GPU"),
+    "cfg3": dict(clips=2048, n=441000, sr=44100, op="stft", kw=dict(n_fft=4096, hop_length=1024),
+                 desc="2048 channel-clips (1024 stereo, 1/8 of batch=8192) x10s sr=44100 -> stft n_fft=4096 hop=1024 per GPU"),
     "cfg4": dict(clips=512, n=480000, sr=16000, op="mfcc", kw=dict(n_mfcc=40, n_mels=128, n_fft=1024, hop_length=256),
                  desc="512 clips x30s mono sr=16000 -> mfcc n_mfcc=40 n_mels=128 n_fft=1024 hop=256 per GPU"),
     # frame-wise statistics fused with the stft (cfg-2 shapes); one launch yields all six rows
@@ -150,8 +154,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU port
-def _cpu_clip_job(args):
-    op, kw, sr, y = args
+_CPU_BATCH = None      # the sample batch; forked workers inherit it (no per-step pickling of audio)
+
+
+def _cpu_one(op, kw, sr, y):
     from oracle import ref_np as O
 
     if op == "mel":
@@ -163,8 +169,14 @@ def _cpu_clip_job(args):
     if op == "centroid":
         return O.spectral_centroid(y=y, sr=sr, **kw).shape[-1]
     D = O.stft(y, **kw)
-    O.istft(D, hop_length=kw["hop_length"], length=len(y))
+    O.istft(D, hop_length=kw["hop_length"], length=y.shape[-1])
     return D.shape[-1]
+
+
+def _cpu_range_job(args):
+    """A worker's share of one pass: the clips [lo, hi) of the inherited batch, one reference call per clip."""
+    op, kw, sr, lo, hi = args
+    return sum(_cpu_one(op, kw, sr, _CPU_BATCH[i]) for i in range(lo, hi))
 
 
 def _cpu_worker_init():
@@ -179,56 +191,109 @@ def _cpu_worker_init():
 
 
 class CpuPort:
-    """The reference's algorithm (oracle port) on the host cores: per-clip loop spread over a process pool,
-    one BLAS thread per worker — the fastest of the three ways SURVEY §8d lists to run the reference
-    (a single batched call is ~3x slower than a per-clip loop)."""
+    """The reference's algorithm (oracle port, bit-exact with librosa here) on the host cores, the three ways
+    SURVEY 8d lists: (i) one batched call, BLAS threads = all cores; (ii) per-clip loop in one process;
+    (iii) per-clip loop over persistent forked workers reading the clips of a batch they inherited at fork
+    (>= 4 clips per core and pass, jobs are clip indices, one BLAS thread each)."""
 
-    def __init__(self, w, sample_clips):
+    def __init__(self, w, clips_per_core=4, min_clips=64):
         import multiprocessing as mp
 
+        global _CPU_BATCH
         self.w = w
-        self.cores = os.cpu_count() or 1
-        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-        os.environ.setdefault("OMP_NUM_THREADS", "1")
-        self.batch = make_batch(dict(w, clips=sample_clips), rank=0)
+        self.cores = len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
+        self.clips = max(min_clips, clips_per_core * self.cores)
+        _CPU_BATCH = make_batch(dict(w, clips=self.clips), rank=0)
+        self.T = n_frames(w["n"], w["kw"]["n_fft"], w["kw"]["hop_length"])
         self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_worker_init)
-        self.jobs = [(w["op"], w["kw"], w["sr"], self.batch[i]) for i in range(sample_clips)]
+        # one clip per job, >= 4 jobs per core and pass: idle workers pull the next clip index (a few bytes)
+        self.jobs = [(w["op"], w["kw"], w["sr"], i, i + 1) for i in range(self.clips)]
+        self.pool.map(_cpu_range_job, [(w["op"], w["kw"], w["sr"], 0, 1)] * self.cores, chunksize=1)   # imports, FFT plans
 
-    def step(self):
+    def step_pool(self):
         t0 = time.perf_counter()
-        frames = sum(self.pool.map(_cpu_clip_job, self.jobs, chunksize=1))
+        frames = sum(self.pool.map(_cpu_range_job, self.jobs, chunksize=1))
         return frames, time.perf_counter() - t0
+
+    def step_loop(self, k):
+        w = self.w
+        t0 = time.perf_counter()
+        frames = sum(_cpu_one(w["op"], w["kw"], w["sr"], _CPU_BATCH[i]) for i in range(k))
+        return frames, time.perf_counter() - t0
+
+    def step_batched(self, k):
+        w = self.w
+        t0 = time.perf_counter()
+        frames = k * _cpu_one(w["op"], w["kw"], w["sr"], _CPU_BATCH[:k])
+        return frames, time.perf_counter() - t0
+
+    def variants(self, small=32):
+        """frames/s of the three ways on this box (a warm-up of each first; (i) and (ii) on `small` clips)."""
+        out = {}
+        k = min(small, self.clips)
+        self.step_batched(min(4, k))
+        f, s = self.step_batched(k)
+        out["batched_call_all_blas_threads"] = f / s
+        self.step_loop(2)
+        f, s = self.step_loop(min(16, k))
+        out["per_clip_loop_1_process"] = f / s
+        self.step_pool()
+        f, s = self.step_pool()
+        out[f"per_clip_loop_{self.cores}_forked_workers"] = f / s
+        return out
+
+    def describe(self, variants):
+        return (f"{self.clips} clips of the workload per pass ({self.clips // self.cores} per core), persistent forked "
+                f"workers read a fork-inherited batch; variants frames/s: "
+                + ", ".join(f"{k}={v:.0f}" for k, v in variants.items()))
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
-def cpu_sample_clips(w):
-    # sized for roughly 10-30 s of CPU work in total over warm-up + timed steps
-    return {"mel": 128, "stft": 128, "mfcc": 64, "roundtrip": 64, "centroid": 128}[w["op"]]
+def cpu_measure(w, seconds):
+    """Best of the three SURVEY 8d variants, the pool variant re-timed for `seconds`."""
+    port = CpuPort(w)
+    var = port.variants()
+    f = s = 0.0
+    t_end = time.perf_counter() + seconds
+    while True:
+        fi, si = port.step_pool()
+        f += fi
+        s += si
+        if time.perf_counter() > t_end:
+            break
+    pool_key = [k for k in var if k.endswith("forked_workers")][0]
+    var[pool_key] = f / s
+    best = max(var, key=var.get)
+    out = {"value": var[best], "unit": "frames/s", "cores": port.cores, "kind": "port", "best_variant": best,
+           "variants": var, "sample": port.describe(var)}
+    port.close()
+    return out
 
 
 def run_reference(args, w, rank, world):
     if rank != 0:
         return
-    # size the per-step sample so that warm-up + K timed steps take about a minute on this box
-    probe = CpuPort(w, 16)
-    probe.step()
-    _, s16 = probe.step()
-    probe.close()
-    budget_s = 60.0 / (args.steps + max(1, args.warmup))
-    clips = int(max(8, min(cpu_sample_clips(w) * 2, 16 * budget_s / max(s16, 1e-3))))
-    port = CpuPort(w, clips)
+    port = CpuPort(w)
+    var = port.variants()
+    best = max(var, key=var.get)
+    if best.startswith("batched"):
+        step = lambda: port.step_batched(min(64, port.clips))
+    elif best.startswith("per_clip_loop_1_"):
+        step = lambda: port.step_loop(min(32, port.clips))
+    else:
+        step = port.step_pool
     for _ in range(max(1, args.warmup)):
-        port.step()
+        step()
     frames = secs = 0.0
     for _ in range(args.steps):
-        f, s = port.step()
+        f, s = step()
         frames += f
         secs += s
-    port.close()
     value = frames / secs
+    var[best] = value
     line = {
         "impl": "reference", "metric": METRIC if w["op"] == "mel" else f"{w['op']} frames/sec", "value": value,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -236,36 +301,16 @@ def run_reference(args, w, rank, world):
         "dtype": "f32 in / f64 FFT (reference numerics)", "data": "synthetic",
         "config": {"workload": w["desc"], "name": args.workload},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": port.cores, "kind": "port",
-                         "sample": f"{len(port.jobs)} clips of the workload per step, per-clip loop over a "
-                                   f"{port.cores}-process pool (1 BLAS thread each)"},
+                         "best_variant": best, "variants": var, "sample": port.describe(var)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    port.close()
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-def run_ours(args, w, rank, world, local_rank):
-    import librosa_b200 as lb
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    # one process per GPU: keep this process (and the pinned buffers it allocates) on the CPUs local to its GPU,
-    # as `numactl --cpunodebind` would; released again before the CPU baseline uses every core
-    all_cpus = os.sched_getaffinity(0)
-    numa_cpus = None if os.environ.get("B2L_BENCH_NO_NUMA_BIND") else lb.bind_host_to_device(local_rank)
-    ctx = lb.default_context(local_rank)
+def make_steps(lb, w, dev, host):
     kw, op, sr = w["kw"], w["op"], w["sr"]
-    T = n_frames(w["n"], kw["n_fft"], kw["hop_length"])
-    frames_per_step = w["clips"] * T
-
-    host = lb.pinned_empty((w["clips"], w["n"]), np.float32)
-    host[...] = make_batch(w, rank)
-    dev = ctx.to_device(host)
 
     def step_resident():
         if op == "mel":
@@ -281,16 +326,41 @@ def run_ours(args, w, rank, world, local_rank):
             lb.istft(D, hop_length=kw["hop_length"], length=w["n"]).free()
             D.free()
 
-    def step_e2e():
+    def step_e2e(src=None):
+        y = host if src is None else src
         if op == "mel":
-            return lb.feature.melspectrogram(y=host, sr=sr, **kw)
+            return lb.feature.melspectrogram(y=y, sr=sr, **kw)
         if op == "stft":
-            return lb.stft(host, **kw)
+            return lb.stft(y, **kw)
         if op == "mfcc":
-            return lb.feature.mfcc(y=host, sr=sr, **kw)
+            return lb.feature.mfcc(y=y, sr=sr, **kw)
         if op == "centroid":
-            return lb.feature.spectral_centroid(y=host, sr=sr, **kw)
-        return lb.istft(lb.stft(host, **kw), hop_length=kw["hop_length"], length=w["n"])
+            return lb.feature.spectral_centroid(y=y, sr=sr, **kw)
+        return lb.istft(lb.stft(y, **kw), hop_length=kw["hop_length"], length=w["n"])
+
+    return step_resident, step_e2e
+
+
+KERNEL_NAMES = {"mel": "fwd_kernel<10,32,16,MODE_MEL>", "stft": "fwd_kernel<.,.,.,MODE_STFT>",
+                "mfcc": "fwd_kernel<.,.,.,MODE_MEL>+dct_clamp_kernel", "roundtrip": "fwd_kernel+inv_kernel",
+                "centroid": "fwd_kernel<10,32,16,MODE_STATS>"}
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import librosa_b200 as lb
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    # one process per GPU: keep this process (and the pinned buffers it allocates) on the CPUs local to its GPU,
+    # as `numactl --cpunodebind` would; released again before the CPU baseline uses every core
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = None if os.environ.get("B2L_BENCH_NO_NUMA_BIND") else lb.bind_host_to_device(local_rank)
+    ctx = lb.default_context(local_rank)
 
     def barrier():
         ctx.synchronize()
@@ -309,39 +379,100 @@ def run_ours(args, w, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    peak, peak_src = measured_peak()
+
+    def resident(wl, steps, warmup, sample_clocks):
+        """Device-resident timing of one workload: (ms per step max over ranks, launches, clocks, frames per GPU)."""
+        T = n_frames(wl["n"], wl["kw"]["n_fft"], wl["kw"]["hop_length"])
+        host = lb.pinned_empty((wl["clips"], wl["n"]), np.float32)
+        host[...] = make_batch(wl, rank)
+        dev = ctx.to_device(host)
+        step_resident, step_e2e = make_steps(lb, wl, dev, host)
+        for _ in range(max(3, warmup)):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        launches0 = ctx.launch_count
+        e0, e1 = ctx.event(), ctx.event()
+        e0.record()
+        for _ in range(steps):
+            step_resident()
+        e1.record()
+        ms = e0.elapsed_ms(e1)
+        barrier()
+        launches = ctx.launch_count - launches0
+        clocks = sampler.stop() if sampler else None
+        ms_per_step = max_over_ranks(ms) / steps
+        return dict(ms_per_step=ms_per_step, launches=launches, clocks=clocks, frames=wl["clips"] * T, host=host,
+                    dev=dev, step_e2e=step_e2e)
+
+    def roofline_of(wl, ms_per_step, name):
+        alg_bytes = algorithmic_bytes_per_step(wl)
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": KERNEL_NAMES[wl["op"]],
+                "note": "kernel time == step time (CUDA events on the launching stream); bytes = inputs read once + outputs written once"}
+
     # ---- device-resident: warm-up, then K steps between events (inputs 0.9 GB >> 126 MB L2: no flush needed)
-    for _ in range(max(3, args.warmup)):
-        step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = ctx.launch_count
-    e0, e1 = ctx.event(), ctx.event()
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-    e1.record()
-    ms = e0.elapsed_ms(e1)
-    barrier()
-    launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
-    ms = max_over_ranks(ms)
-    ms_per_step = ms / args.steps
+    r = resident(w, args.steps, args.warmup, True)
+    ms_per_step, launches, clocks, frames_per_step = r["ms_per_step"], r["launches"], r["clocks"], r["frames"]
+    host, dev, step_e2e = r["host"], r["dev"], r["step_e2e"]
     value = world * frames_per_step / (ms_per_step * 1e-3)
 
     # ---- end to end through the public call with host buffers (H2D + D2H inside the timed region)
+    def time_e2e(src, steps):
+        out = step_e2e(src)                   # warm-up: second stream, plans, device and pinned pools
+        nbytes = int(out.nbytes)
+        out2 = step_e2e(src)                  # a second result while the first is alive: both pinned buffers exist
+        del out, out2
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step_e2e(src)
+        ctx.synchronize()
+        sec = (time.perf_counter() - t0) / steps
+        del out
+        return max_over_ranks(sec), nbytes
+
     e2e_steps = max(3, min(args.steps, 10))
-    out = step_e2e()                      # warm-up: second stream, plans, device and pinned pools
-    d2h = int(out.nbytes)
-    out2 = step_e2e()                     # a second result while the first is alive: both pinned buffers exist
-    del out, out2
+    e2e_s, d2h = time_e2e(host, e2e_steps)
+    e2e_value = world * frames_per_step / e2e_s
+    # the same call on a PAGEABLE ndarray (what a drop-in user passes): the library stages it through pinned
+    # buffers with several host threads (b2l_h2d -> staged_h2d)
+    pageable = np.array(host)               # ordinary malloc'ed copy
+    e2e_pg_s, _ = time_e2e(pageable, max(3, e2e_steps // 2))
+    del pageable
+    # PCIe upload ceiling with every rank transferring at once: explains the end-to-end scaling
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out = step_e2e()
+    for _ in range(3):
+        tmp = ctx.to_device(host)
+        tmp.free()
     ctx.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_s = max_over_ranks(e2e_s)
-    e2e_value = world * frames_per_step / e2e_s
+    h2d_gbs = 3 * host.nbytes / max_over_ranks(time.perf_counter() - t0) / 1e9
+    h2d_bytes = int(host.nbytes)
+    dev.free()
+    del host
+
+    # ---- the other BASELINE.json configs, device-resident (driver-recorded secondary numbers)
+    secondary = []
+    if not args.no_secondary and args.workload == "cfg2":
+        for name in ("cfg3", "cfg4", "cfg5"):
+            wl = WORKLOADS[name]
+            try:
+                rr = resident(wl, max(5, args.steps // 2), 3, False)
+            except Exception as exc:                      # e.g. not enough free HBM next to another job
+                secondary.append({"name": name, "error": repr(exc)[:200]})
+                continue
+            rr["dev"].free()
+            ms2 = rr["ms_per_step"]
+            secondary.append({"name": name, "workload": wl["desc"], "metric": f"{wl['op']} frames/sec",
+                              "value": world * rr["frames"] / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2,
+                              "per_gpu_clips": wl["clips"], "gpu_launches": rr["launches"],
+                              "roofline": roofline_of(wl, ms2, name)})
+            del rr
+        ctx.empty_cache()
 
     if rank != 0:
         if dist is not None:
@@ -349,38 +480,16 @@ def run_ours(args, w, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (one launch per step for mel / stft)
-    peak, peak_src = measured_peak()
-    alg_bytes = algorithmic_bytes_per_step(w)
-    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = profiled_traffic(args.workload)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": {"mel": "fwd_kernel<10,32,16,MODE_MEL>", "stft": "fwd_kernel<.,.,.,MODE_STFT>",
-                           "mfcc": "fwd_kernel<.,.,.,MODE_MEL>+dct_clamp_kernel", "roundtrip": "fwd_kernel+inv_kernel",
-                           "centroid": "fwd_kernel<10,32,16,MODE_STATS>"}[op],
-                "note": "kernel time == step time (one launch per step, CUDA events on the launching stream)"}
+    roofline = roofline_of(w, ms_per_step, args.workload)
 
     # ---- CPU baseline on this box (bounded sample)
     cpu = None
     if numa_cpus:
         os.sched_setaffinity(0, all_cpus)
     if world == 1 and not args.no_cpu:
-        port = CpuPort(w, cpu_sample_clips(w))
-        port.step()
-        f = s = 0.0
-        t_end = time.perf_counter() + 12.0
-        while True:
-            fi, si = port.step()
-            f += fi
-            s += si
-            if time.perf_counter() > t_end:
-                break
-        port.close()
-        cpu = {"value": f / s, "unit": "frames/s", "cores": port.cores, "kind": "port",
-               "sample": f"{len(port.jobs)} clips of the workload per pass for ~12 s, per-clip loop over a "
-                         f"{port.cores}-process pool (1 BLAS thread each)"}
+        cpu = cpu_measure(w, 10.0)
 
+    op = w["op"]
     line = {
         "metric": METRIC if op == "mel" else f"{op} frames/sec", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
@@ -390,10 +499,14 @@ def run_ours(args, w, rank, world, local_rank):
                    "host_cpus_bound_to_gpu": len(numa_cpus) if numa_cpus else None,
                    "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no flush" % (w["clips"] * w["n"] * 4 / 1e6)},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(host.nbytes),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                "path": "librosa_b200 public call on a pinned host ndarray -> ndarray"},
-        "roofline": roofline, "cpu_baseline": cpu,
+                "path": "librosa_b200 public call on a pinned host ndarray -> ndarray",
+                "pageable": {"value": world * frames_per_step / e2e_pg_s, "ms_per_step": e2e_pg_s * 1e3,
+                             "path": "same call on an ordinary (pageable) ndarray; staged upload inside the library"},
+                "h2d_ceiling_gbs_per_gpu": h2d_gbs,
+                "h2d_floor_ms": h2d_bytes / (h2d_gbs * 1e9) * 1e3},
+        "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -409,6 +522,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 / cfg4 / cfg5 secondary numbers")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

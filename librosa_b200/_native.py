@@ -231,6 +231,24 @@ def check(status: int):
 
 
 # --------------------------------------------------------------------------------------------- context
+class LRUCache(dict):
+    """Insertion-ordered dict used as a least-recently-used cache: ``fetch`` moves a hit to the young end and
+    ``evict_oldest`` removes from the old end — so the entries handed out during the current call (always the
+    youngest) are never the ones released.  ``dict.popitem()`` would evict the NEWEST entry instead."""
+
+    def fetch(self, key):
+        try:
+            value = self.pop(key)
+        except KeyError:
+            return None
+        self[key] = value
+        return value
+
+    def evict_oldest(self):
+        key = next(iter(self))
+        return key, self.pop(key)
+
+
 class Context:
     """One CUDA device + stream.  Not thread-safe; create one per thread / per GPU."""
 
@@ -238,8 +256,8 @@ class Context:
         self._h = _vp()
         check(lib().b2l_ctx_create(int(device), C.byref(self._h)))
         self.device = int(device)
-        self._plans = {}
-        self._wss = {}
+        self._plans = LRUCache()
+        self._wss = LRUCache()
         self._pool = {}
         self._sizes = {}
         self._pooled_bytes = 0
@@ -569,7 +587,7 @@ def make_plan(ctx: Context, key, *, n_fft: int, hop_length: int, center: bool, p
               dct_basis: Optional[np.ndarray] = None, amin: float = 1e-10, ref_value: float = 1.0,
               top_db: Optional[float] = 80.0) -> Plan:
     """Create (or fetch from the context's cache) the device constants of one configuration."""
-    plan = ctx._plans.get(key)
+    plan = ctx._plans.fetch(key)
     if plan is not None:
         return plan
     win = np.ascontiguousarray(window, dtype=np.float64)
@@ -600,8 +618,8 @@ def make_plan(ctx: Context, key, *, n_fft: int, hop_length: int, center: bool, p
     h = _vp()
     check(lib().b2l_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
     plan = Plan(ctx, h, int(n_fft), int(hop_length), bool(center), n_mels, n_mfcc)
-    if len(ctx._plans) > 64:  # bound the cache
-        _, old = ctx._plans.popitem()
-        lib().b2l_plan_destroy(old.handle)
     ctx._plans[key] = plan
+    while len(ctx._plans) > 64:  # bound the cache: drop the least recently used plan (never the new one)
+        _, old = ctx._plans.evict_oldest()
+        lib().b2l_plan_destroy(old.handle)
     return plan

@@ -87,7 +87,7 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
 def _inv_wss(ctx, window, n_frames, win_length, n_fft, hop_length, start, out_len, wkey):
     """Reciprocal window-sum-square, trimmed as istft does (core/spectrum.py:606-624), cached on device."""
     key = ("wss", wkey, n_frames, n_fft, hop_length, start, out_len)
-    ptr = ctx._wss.get(key)
+    ptr = ctx._wss.fetch(key)
     if ptr is None:
         wss = filters.window_sumsquare(window=window, n_frames=n_frames, win_length=win_length, n_fft=n_fft,
                                        hop_length=hop_length, dtype=np.float32)
@@ -95,8 +95,8 @@ def _inv_wss(ctx, window, n_frames, win_length, n_fft, hop_length, start, out_le
         inv = np.ones(out_len, dtype=np.float32)
         nz = wss > tiny(wss)
         inv[nz] = (np.float32(1.0) / wss[nz]).astype(np.float32)
-        if len(ctx._wss) > 32:
-            _, old = ctx._wss.popitem()
+        while len(ctx._wss) >= 32:                 # least recently used first
+            _, old = ctx._wss.evict_oldest()
             ctx.free(old)
         ptr = ctx.alloc(max(inv.nbytes, 16))
         nat.check(nat.lib().b2l_h2d(ctx.handle, _vp(ptr), inv.ctypes.data_as(_vp), inv.nbytes))
@@ -676,6 +676,12 @@ def griffinlim(S, *, n_iter: int = 32, hop_length: Optional[int] = None, win_len
         inverse = istft(angles, **kw_i)
         rebuilt = stft(inverse, **kw_f)
         inverse.free()
+        if tuple(rebuilt.shape) != tuple(S_host_shape):
+            # a `length` that does not correspond to T frames: the reference fails at `angles[:] = rebuilt`
+            # (core/spectrum.py:2884) with a broadcast error; the update kernel would run out of bounds
+            shape = tuple(rebuilt.shape)
+            rebuilt.free()
+            raise ParameterError(f"length={length} gives an STFT of shape {shape}, expected {tuple(S_host_shape)}")
         nat.check(L.b2l_gl_update(ctx.handle, _vp(rebuilt.ptr), _vp(tprev.ptr) if tprev is not None else None,
                                   _vp(S_ft.ptr), scale, eps, _vp(angles.ptr), n_clips * F * T))
         if tprev is not None:

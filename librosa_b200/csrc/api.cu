@@ -9,8 +9,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b2l.h"
@@ -115,6 +117,9 @@ struct b2l_ctx {
   size_t scratch_bytes = 0;
   std::map<unsigned long long, int> launch_cache;   // (kernel variant, smem) -> blocks/SM, attribute already set
   size_t clip_max_cap = 0;
+  // pinned staging ring for uploads from pageable host memory (staged_h2d)
+  std::vector<void*> stage_bufs;
+  std::vector<cudaEvent_t> stage_evs;
 };
 
 struct b2l_event {
@@ -137,7 +142,7 @@ struct b2l_plan {
   MelBand* d_band = nullptr;
   std::vector<MelBand> h_band;
   std::vector<float> h_mel_w;
-  struct RowTable { MelRow* d_rows = nullptr; float* d_w = nullptr; int n_rows = 0, w_count = 0; };
+  struct RowTable { MelRow* d_rows = nullptr; float* d_w = nullptr; unsigned short* d_order = nullptr; int n_rows = 0, w_count = 0, list_len = 0; };
   mutable std::map<int, RowTable> row_tables;
   int power_mode = 2;
   float power = 2.0f;
@@ -212,6 +217,9 @@ extern "C" int b2l_ctx_destroy(b2l_ctx* c) {
   if (c->d_clip_max) cudaFree(c->d_clip_max);
   if (c->d_status) cudaFree(c->d_status);
   if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void* b : c->stage_bufs) cudaFreeHost(b);
+  for (cudaEvent_t e : c->stage_evs) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return B2L_OK;
@@ -291,9 +299,67 @@ extern "C" int b2l_memset(b2l_ctx* c, void* d_ptr, int value, size_t bytes) {
   CUDA_TRY(cudaMemsetAsync(d_ptr, value, bytes, c->stream));
   return B2L_OK;
 }
+// Upload from PAGEABLE host memory (what a drop-in caller's ndarray is): cudaMemcpyAsync would stage it through
+// the driver's single bounce buffer on the calling thread (10-20 GB/s).  Instead `nthreads` host threads copy
+// 4 MB pieces into a ring of pinned buffers (two per thread) and enqueue the DMA of each piece on the context's
+// stream as soon as it is staged, so the host-side copies run in parallel and overlap the PCIe transfer.
+// Piece order on the stream is arbitrary (the pieces are disjoint); work enqueued after the call returns is
+// ordered behind all of them.
+static const size_t kStagePiece = 4u << 20;
+static int staged_h2d(b2l_ctx* c, char* d_dst, const char* h_src, size_t bytes, int nthreads) {
+  const size_t want = 2 * (size_t)nthreads;
+  while (c->stage_bufs.size() < want) {
+    void* b = nullptr;
+    CUDA_TRY(cudaHostAlloc(&b, kStagePiece, cudaHostAllocPortable));
+    c->stage_bufs.push_back(b);
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->stage_evs.push_back(e);
+  }
+  std::atomic<size_t> next(0);
+  std::atomic<int> err(0);
+  auto worker = [&](int w) {
+    cudaSetDevice(c->device);
+    for (int k = 0;; ++k) {
+      const size_t off = next.fetch_add(1) * kStagePiece;
+      if (off >= bytes || err.load()) break;
+      const size_t len = std::min(kStagePiece, bytes - off);
+      const int b = 2 * w + (k & 1);
+      cudaError_t e = cudaEventSynchronize(c->stage_evs[b]);   // the DMA that last used this buffer is done
+      if (e == cudaSuccess) {
+        memcpy(c->stage_bufs[b], h_src + off, len);
+        e = cudaMemcpyAsync(d_dst + off, c->stage_bufs[b], len, cudaMemcpyHostToDevice, c->stream);
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(c->stage_evs[b], c->stream);
+      if (e != cudaSuccess) err.store((int)e);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < nthreads; ++w) pool.emplace_back(worker, w);
+  worker(0);
+  for (auto& t : pool) t.join();
+  if (err.load()) {
+    cudaGetLastError();
+    return fail(B2L_ERR_CUDA, "staged upload: %s", cudaGetErrorString((cudaError_t)err.load()));
+  }
+  return B2L_OK;
+}
+
 extern "C" int b2l_h2d(b2l_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
   if (!c) return fail(B2L_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(c->device);
+  if (bytes >= (16u << 20)) {
+    static int threads = -1;   // B2L_H2D_THREADS: staging threads for pageable sources (0 = plain cudaMemcpyAsync)
+    if (threads < 0) {
+      const char* e = getenv("B2L_H2D_THREADS");
+      threads = e && *e ? atoi(e) : 6;
+      if (threads > 32) threads = 32;
+    }
+    cudaPointerAttributes attr;
+    if (threads > 0 && cudaPointerGetAttributes(&attr, h_src) == cudaSuccess && attr.type == cudaMemoryTypeUnregistered)
+      return staged_h2d(c, (char*)d_dst, (const char*)h_src, bytes, threads);
+    cudaGetLastError();
+  }
   CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
   return B2L_OK;
 }
@@ -444,6 +510,7 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   for (auto& kv : p->row_tables) {
     cudaFree(kv.second.d_rows);
     cudaFree(kv.second.d_w);
+    cudaFree(kv.second.d_order);
   }
   cudaFree(p->d_dct);
   delete p;
@@ -644,33 +711,41 @@ static int ensure_clip_max(b2l_ctx* c, size_t n_clips) {
   return B2L_OK;
 }
 
-// MelRow table for warps that process H mel rows at a time (see MelRow in common.cuh).
-static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, const b2l_plan::RowTable** out) {
-  auto it = p->row_tables.find(H);
+// MelRow table for warps that process H mel rows at a time (see MelRow / MelLayout in common.cuh), plus the
+// work-item lists of the `hw` warps of a half: items sorted by length and dealt longest-first to the least
+// loaded warp (the bands of the highest mel rows are ten times longer than those of the lowest).
+static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, int hw, const b2l_plan::RowTable** out) {
+  const int key = H * 64 + hw;
+  auto it = p->row_tables.find(key);
   if (it != p->row_tables.end()) {
     *out = &it->second;
     return B2L_OK;
   }
   const int n_rows = (p->n_mels + H - 1) / H * H;
+  const int n_items = n_rows / H;
+  const int rsm = H < 4 ? 4 : H, G = rsm / 4;   // row starts: lo_j == 4*(j mod G) (mod rsm)
   std::vector<MelRow> rows(n_rows);
   std::vector<float> w;
-  for (int item = 0; item < n_rows / H; ++item) {
+  std::vector<int> item_quads(n_items, 0);
+  for (int item = 0; item < n_items; ++item) {
     std::vector<int> start(H), lenp(H);
     int quads = 0;
     for (int j = 0; j < H; ++j) {
       const int m = item * H + j;
       if (m < p->n_mels && p->h_band[m].len > 0) {
         const MelBand& b = p->h_band[m];
-        int st = b.lo - (((b.lo - j) % H) + H) % H;   // largest row <= lo congruent to j mod H
-        if (st < 0) st = b.lo;
+        const int want = 4 * (j % G);
+        int st = b.lo - ((((b.lo - want) % rsm) + rsm) % rsm);   // largest bin <= lo congruent to `want` mod rsm
+        if (st < 0) st = b.lo - (b.lo % 4);                       // lowest rows: keep the 16-byte alignment only
         start[j] = st;
         lenp[j] = b.lo + b.len - st;
       } else {
-        start[j] = j;
+        start[j] = 4 * (j % G);
         lenp[j] = 0;
       }
       quads = std::max(quads, (lenp[j] + 3) / 4);
     }
+    item_quads[item] = quads;
     for (int j = 0; j < H; ++j) {
       const int m = item * H + j;
       MelRow r;
@@ -686,26 +761,56 @@ static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, const b2l_plan::R
       rows[m] = r;
     }
   }
+  // longest-processing-time-first: cost of an item = its trip count + a fixed part (row fetch, stores)
+  std::vector<int> idx(n_items);
+  for (int i = 0; i < n_items; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return item_quads[x] > item_quads[y]; });
+  std::vector<std::vector<int>> lists(hw);
+  std::vector<int> load(hw, 0);
+  for (int i : idx) {
+    int best = 0;
+    for (int wv = 1; wv < hw; ++wv)
+      if (load[wv] < load[best]) best = wv;
+    lists[best].push_back(i);
+    load[best] += item_quads[i] + 3;
+  }
+  size_t list_len = 0;
+  for (auto& l : lists) list_len = std::max(list_len, l.size());
+  std::vector<unsigned short> order(list_len * hw, (unsigned short)0xffff);
+  for (int wv = 0; wv < hw; ++wv)
+    for (size_t k = 0; k < lists[wv].size(); ++k) order[k * hw + wv] = (unsigned short)lists[wv][k];
+  if (order.empty()) order.push_back(0xffff);
   b2l_plan::RowTable t;
   t.n_rows = n_rows;
   t.w_count = (int)w.size();
+  t.list_len = (int)list_len;
   int rc;
-  if ((rc = upload(c, rows, &t.d_rows)) || (rc = upload(c, w, &t.d_w))) return rc;
-  auto ins = p->row_tables.emplace(H, t);
+  if ((rc = upload(c, rows, &t.d_rows)) || (rc = upload(c, w, &t.d_w)) || (rc = upload(c, order, &t.d_order))) return rc;
+  auto ins = p->row_tables.emplace(key, t);
   *out = &ins.first->second;
   return B2L_OK;
 }
 
 // Kernel variants tried in order (first that fits shared memory wins): 116 = 16 warps as two independent
 // 8-warp halves, 16 / 8 = plain CTAs.  B2L_FWD_VARIANT forces one (A/B measurements).
-static int fwd_variants(const HostFftCfg& cfg, int out[3]) {
+#ifndef B2L_TMEM_DEFAULT
+#define B2L_TMEM_DEFAULT true
+#endif
+static int fwd_variants(const HostFftCfg& cfg, int out[6]) {
   int n = 0;
   const char* force = getenv("B2L_FWD_VARIANT");
   if (force && *force) {
     out[n++] = atoi(force);
     return n;
   }
-  if (cfg.log2m >= 9 && cfg.log2m <= 11) out[n++] = 116;
+  // + 1000: window / twiddle tables in Tensor Memory (B2L_TMEM=0 keeps them in shared memory)
+  const char* tm_env = getenv("B2L_TMEM");
+  const bool tm = tm_env && *tm_env ? atoi(tm_env) != 0 : B2L_TMEM_DEFAULT;
+  if (cfg.log2m >= 9 && cfg.log2m <= 11) {
+    if (tm) out[n++] = 1116;
+    out[n++] = 116;
+  }
+  if (tm && cfg.log2m == 12) out[n++] = 1016;
   int nws[2];
   const int k = cfg.nw_options(nws);
   for (int i = 0; i < k; ++i) out[n++] = nws[i];
@@ -732,7 +837,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   HostFftCfg cfg(p->log2m);
   const int N = p->n_fft, M = N / 2;
   fwd_op_fn op = fwd_table(p->log2m);
-  int variants[3];
+  int variants[6];
   const int n_opt = fwd_variants(cfg, variants);
   FwdArgs a;
   memset(&a, 0, sizeof(a));
@@ -741,8 +846,9 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   const b2l_plan::RowTable* rt = nullptr;
   for (int i = 0; i < n_opt && !variant; ++i) {
     const int v = variants[i];
-    const int nh = v == 116 ? 2 : 1;
-    const int nw = nh > 1 ? 16 : v;
+    const bool tmem = v >= 1000;
+    const int nh = (v % 1000) == 116 ? 2 : 1;
+    const int nw = nh > 1 ? 16 : v % 1000;
     if (nw * 32 % (cfg.tpf * nh) != 0) continue;
     const int f = nw * 32 / nh / cfg.tpf;
     if (f < 1 || f > 32) continue;
@@ -750,16 +856,17 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     if (span > 0x3fffffff) continue;
     const b2l_plan::RowTable* t = nullptr;
     if (mode == MODE_MEL) {
-      int rc = get_row_table(c, p, mel_rows_per_warp(f), &t);
+      int rc = get_row_table(c, p, mel_rows_per_warp(f), nw / nh, &t);
       if (rc) return rc;
     }
     size_t off = 0;
-    a.off_win = (int)off; off = align_up(off + (size_t)N * 4, 16);
-    a.off_tw = (int)off; off = align_up(off + (size_t)cfg.tw_count() * 8, 16);
-    a.off_bar = (int)off; off = align_up(off + 16, 16);
+    a.off_win = (int)off; if (!tmem) off = align_up(off + (size_t)N * 4, 16);       // TMEM variants keep these
+    a.off_tw = (int)off; if (!tmem) off = align_up(off + (size_t)cfg.tw_count() * 8, 16);   // tables off shared memory
+    a.off_bar = (int)off; off = align_up(off + 32, 16);   // one mbarrier per half + the TMEM base address
     if (t) {
       a.off_melw = (int)off; off = align_up(off + (size_t)t->w_count * 4, 16);
       a.off_melband = (int)off; off = align_up(off + (size_t)t->n_rows * sizeof(MelRow), 16);
+      a.off_melorder = (int)off; off = align_up(off + (size_t)std::max(1, t->list_len) * (nw / nh) * 2, 16);
     }
     if (mode == MODE_STATS) {   // bin frequencies take the place of the mel weights
       a.off_melw = (int)off; off = align_up(off + (size_t)(M + 1) * 4, 16);
@@ -770,10 +877,9 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     a.off_xbuf = (int)(off = align_up(off, 128));
     size_t xbytes = (size_t)f * cfg.xbuf_f2() * 8;
     if (mode == MODE_MEL || mode == MODE_STATS) {
-      const int Hh = mel_rows_per_warp(f);                        // MelLayout (common.cuh)
-      const int rs = ((M + 4 - Hh + 31) / 32) * 32 + Hh;
-      size_t pbytes = (size_t)f * rs * 4;
-      if (pbytes > xbytes) xbytes = pbytes;
+      // the power row of a frame lives in the (padded) exchange region of its group: MelLayout (common.cuh);
+      // slack after the last row: a short row of a work item may read up to one band length past bin M + 3
+      xbytes = (size_t)f * mel_group_stride(M, f) * 8 + (size_t)(M + 16) * 4;
     }
     a.xbuf_stride = (int)align_up(xbytes, 128);
     off += (size_t)a.xbuf_stride * nh;
@@ -822,6 +928,8 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     a.mel_w = rt->d_w;
     a.mel_rows = rt->d_rows;
     a.n_mel_rows = rt->n_rows;
+    a.mel_order = rt->d_order;
+    a.mel_list_len = rt->list_len;
   }
   a.log_mode = log_mode ? 1 : 0;
   a.out_tiled = log_mode == 2 ? 1 : 0;   // b2l_mfcc: log-mel goes to the tiled scratch

@@ -22,30 +22,40 @@ enum FwdMode : int {
 };
 
 struct MelBand { int lo, len, off, pad; };   // bins [lo, lo+len), weights at mel_w[off ..] (mel_project kernel)
-// Fused-kernel form of one mel row: `quads` groups of 4 consecutive bins starting at bin `lo`, weights at
-// mel_w[off ..] (zero padded to 4*quads, off % 4 == 0).  Rows are grouped H at a time (H = 32 / frames
-// per tile): the rows of a group share `quads` and their `lo` are congruent to their position mod H.
+// Fused-kernel form of one mel row: `quads` groups of 4 consecutive bins starting at bin `lo` (a multiple of
+// 4), weights at mel_w[off ..] (zero padded to 4*quads, off % 4 == 0).  Rows are grouped H at a time (a work
+// item; H = 32 / frame lanes): the rows of an item share `quads`, and their `lo` follow the bank rule of
+// MelLayout.
 struct MelRow { unsigned short lo, quads; unsigned int off; };
 
-// Shared-memory layout of the power tile used by the mel phase: frame-major, P[f][k] at word f*RS + k.
+// Shared-memory layout of the power tile used by the mel phase: frame f keeps its row in the exchange region of
+// its own frame group (so no other group has to be waited for before it is written), P[f][k] at word f*RS + k
+// with RS = 2 * GS, GS = the group stride in float2 — the exchange buffer (M + M/32 float2) plus a few pad
+// entries chosen so that RS is congruent to max(H, 4) modulo 32.
 // A lane of the mel loop owns one mel row and a PAIR of frames (f, f + FT/2) — one weight fetch serves both —
 // so a warp covers FP = FT/2 frame pairs x H = 32/FP rows (tiles of fewer than 8 frames: one frame per lane,
-// H = 32/FT rows).  With
-// the row stride RS = (M + 4 rounded up) congruent to H modulo 32 the load of lane (fp, j) — bin k_j + i with
-// k_j = j mod H, see MelRow — hits bank fp*H + j + const: 32 distinct banks, for either frame of the pair.
-// The transposing store (lanes = consecutive bins of one frame) is contiguous.  Rows hold bins 0 .. M plus
-// three zero bins so that 4-bin groups may run past the Nyquist bin.
+// H = 32/FT rows).  Weights and power values are both read four bins at a time (16-byte shared loads).  A
+// 16-byte load is served a quarter warp at a time: lanes (fp < min(FP, 8), j < 8/FP) — with RS as above and row
+// starts lo_j congruent to 4*(j mod G) modulo 4*G, G = max(H, 4)/4 (host: get_row_table), the eight 16-byte
+// pieces fall into eight different bank groups.  Rows hold bins 0 .. M plus three zero bins so that 4-bin
+// groups may run past the Nyquist bin.
 template <int M, int FT>
 struct MelLayout {
   static constexpr bool PAIR = (FT % 2) == 0 && FT >= 8;   // few frames per tile: H would exceed 8 rows sharing one trip count
   static constexpr int FP = PAIR ? FT / 2 : FT;     // lanes along the frame axis
   static constexpr int H = 32 / FP;                 // mel rows handled concurrently by one warp
-  static constexpr int RS = ((M + 4 - H + 31) / 32) * 32 + H;
-  static_assert(RS >= M + 4 && RS % 32 == H % 32, "row stride");
-  static constexpr size_t bytes() { return (size_t)FT * RS * 4; }
+  static constexpr int RSM = H < 4 ? 4 : H;         // residue of the row stride modulo 32
+  static constexpr int XB = M + M / 32;             // FftCfg::XBUF_F2
+  static constexpr int GS = XB + ((((RSM - 2 * XB) % 32) + 32) % 32) / 2;   // group stride, float2
+  static constexpr int RS = 2 * GS;                 // row stride, words
+  static_assert(RS >= M + 4 && RS % 32 == RSM % 32 && RS % 4 == 0, "row stride");
 };
-// host mirror of MelLayout<M, FT>::H
+// host mirrors of MelLayout<M, FT>
 __host__ __device__ inline int mel_rows_per_warp(int ft) { return 32 / (((ft % 2) == 0 && ft >= 8) ? ft / 2 : ft); }
+__host__ __device__ inline int mel_group_stride(int m, int ft) {
+  const int h = mel_rows_per_warp(ft), rsm = h < 4 ? 4 : h, xb = m + m / 32;
+  return xb + ((((rsm - 2 * xb) % 32) + 32) % 32) / 2;
+}
 
 // Per-frame spectral statistics (stats.cuh): the rows of the [clip][N_STATS][frame] output.
 enum StatRow : int { STAT_CENTROID = 0, STAT_BANDWIDTH = 1, STAT_ROLLOFF = 2, STAT_FLATNESS = 3, STAT_RMS = 4, STAT_TOTAL = 5 };
@@ -82,6 +92,8 @@ struct FwdArgs {
   const float* mel_w;        // padded weights of the MelRow table built for this tile geometry
   const MelRow* mel_rows;    // n_mel_rows = n_mels rounded up to a multiple of H
   int n_mel_rows;
+  const unsigned short* mel_order;   // [mel_list_len][warps per half]: k-th work item of each warp (0xffff: none)
+  int mel_list_len;
   int log_mode;              // 1: write 10*log10(max(amin, S)) - db_sub and track the per-clip max
   int out_tiled;             // MODE_MEL: out_r is the mfcc scratch [clip][tile of 64 frames][mel][64] (dct_clamp_kernel)
   float amin, db_sub;
@@ -89,7 +101,7 @@ struct FwdArgs {
   int* status;               // bit 0 is set when a non-finite sample reached a frame (util.valid_audio)
   StatsParams stats;         // MODE_STATS (the frequency table travels in mel_w / mel_w_count)
   // dynamic shared-memory layout (byte offsets)
-  int off_win, off_tw, off_in, off_xbuf, off_melw, off_melband, off_bar;
+  int off_win, off_tw, off_in, off_xbuf, off_melw, off_melband, off_melorder, off_bar;
   int in_stride, xbuf_stride; // per-half strides (bytes) of the staging / exchange areas (DUAL)
   int in_floats;             // staged span length (floats)
 };

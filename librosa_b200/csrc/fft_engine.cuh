@@ -103,11 +103,13 @@ __device__ __forceinline__ void bfly(float2& a, float2& b) {
   }
 }
 
-// In-register radix-R DFT on v[BASE .. BASE+R): input in bit-reversed slots, output natural.
-template <int R, int BASE, int N>
+// In-register radix-R DFT on v[BASE .. BASE+R): input in bit-reversed slots, output natural.  S0 = 1 skips
+// the first (twiddle-free) stage: the caller already formed the sums / differences of the slot pairs
+// (2j, 2j+1) — see load_pass0_windowed, which fuses them with the window product.
+template <int R, int BASE, int S0 = 0, int N>
 __device__ __forceinline__ void dft_reg(float2 (&v)[N]) {
   constexpr int LOGR = ilog2c(R);
-  static_for<0, LOGR>([&](auto S) {
+  static_for<S0, LOGR>([&](auto S) {
     constexpr int h = 1 << decltype(S)::value;
     static_for<0, R / 2>([&](auto I) {
       constexpr int i = decltype(I)::value;
@@ -176,6 +178,32 @@ __device__ __forceinline__ void load_pass0(float2 (&v)[Cfg::PPT], int t, LoadIn&
   });
 }
 
+// Pass-0 operand fetch fused with the window product and the first butterfly stage of dft_reg: the slots
+// (2j, 2j+1) of a radix-R block hold elements r and r + R/2, whose first-stage butterfly is twiddle free, so
+//     v[2j] = xa*wa + xb*wb ,  v[2j+1] = xa*wa - xb*wb        (1 FMUL + 2 FFMA per component instead of
+// 2 FMUL + 2 FADD).  load_x(e) returns the sample pair (x[2e], x[2e+1]); win(SLOT) the window pair of the
+// element that lands in that slot (a compile-time slot index: the window source may be a register chunk).
+// Requires radix(0) >= 2; run dft_reg<R, BASE, 1> afterwards.
+template <class Cfg, class LoadX, class Win>
+__device__ __forceinline__ void load_pass0_windowed(float2 (&v)[Cfg::PPT], int t, LoadX&& load_x, Win&& win) {
+  constexpr int R = Cfg::radix(0), LOGR = Cfg::log_radix(0), T = Cfg::M / R, NB = Cfg::PPT / R;
+  static_assert(R >= 2, "fused first stage needs a radix of at least 2");
+  static_for<0, NB>([&](auto B) {
+    constexpr int b = decltype(B)::value;
+    const int i = t + Cfg::TPF * b;
+    static_for<0, R / 2>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      constexpr int sa = b * R + 2 * j, sb = sa + 1;
+      constexpr int ra = bitrevc(2 * j, LOGR), rb = bitrevc(2 * j + 1, LOGR);   // rb == ra + R/2
+      const float2 xa = load_x(i + ra * T), xb = load_x(i + rb * T);
+      const float2 wa = win(std::integral_constant<int, sa>{}), wb = win(std::integral_constant<int, sb>{});
+      const float pr = xa.x * wa.x, pi = xa.y * wa.y;
+      v[sa] = make_float2(fmaf(xb.x, wb.x, pr), fmaf(xb.y, wb.y, pi));
+      v[sb] = make_float2(fmaf(-xb.x, wb.x, pr), fmaf(-xb.y, wb.y, pi));
+    });
+  });
+}
+
 // Element offset (index minus t) that load_pass0 puts in v[slot], and the slot that receives element
 // t + TPF*c — used by the inverse path, whose rebuilt spectrum values are born in registers.
 template <class Cfg>
@@ -183,6 +211,8 @@ __host__ __device__ constexpr int pass0_offset(int slot) {
   constexpr int R = Cfg::radix(0), LOGR = Cfg::log_radix(0), T = Cfg::M / R;
   return Cfg::TPF * (slot / R) + bitrevc(slot % R, LOGR) * T;   // bitrevc is an involution
 }
+template <class Cfg, int SLOT>
+__host__ __device__ constexpr int pass0_offset_c() { return pass0_offset<Cfg>(SLOT); }
 template <class Cfg>
 __host__ __device__ constexpr int pass0_slot_of_pair(int c) {
   for (int s = 0; s < Cfg::PPT; ++s)
@@ -190,11 +220,112 @@ __host__ __device__ constexpr int pass0_slot_of_pair(int c) {
   return -1;
 }
 
+// ------------------------------------------------------------------ constant tables: shared memory or TMEM
+// The window and the inter-pass twiddles are per-thread constants (thread t of a frame group always touches
+// the same elements), read once per frame: 2 x 8 KB per frame for n_fft = 2048, a fifth of the kernel's
+// shared-memory wavefronts.  Two sources with the same interface:
+//   SmemTab  tables staged in shared memory (any size)
+//   TmemTab  tables parked in Tensor Memory, one 32-bit column per value and thread (PPT == 32 only):
+//            lane = thread of the warp, read back 16 columns at a time with tcgen05.ld — a datapath that
+//            does not go through the shared-memory pipe.  Column map (NCOLS = 64 * NPASS):
+//              [0, 64)                   window pair of pass-0 slot s at columns 2s, 2s+1
+//              [64*s, 64*s + 64), s>=1   twiddle of flattened operand f = b*R_s + r of pass s at 2f, 2f+1
+//                                        (r == 0 entries are (1, 0) and never fetched)
+//              [64*NPASS, +32)           un-mix twiddle W_N^(t + TPF*c) of bin pair c at 2c, 2c+1
+// Protocol (both): begin_window() ... window<SLOT>(t) for SLOT = 0 .. PPT-1 in increasing order;
+// begin_pass<S>() ... step<S, F>() for every F = 0 .. PPT-1 in increasing order, twiddle<S, F>(i) after the
+// step of the same F when r > 0.
+template <class Cfg>
+struct SmemTab {
+  const float* win;        // [n_fft]
+  const float2* tw;        // FftCfg::tw_offset layout
+  __device__ __forceinline__ void begin_window() {}
+  template <int SLOT>
+  __device__ __forceinline__ float2 window(int t) {
+    return *reinterpret_cast<const float2*>(win + 2 * (t + pass0_offset_c<Cfg, SLOT>()));
+  }
+  template <int S>
+  __device__ __forceinline__ void begin_pass() {}
+  template <int S, int F>
+  __device__ __forceinline__ void step() {}
+  template <int S, int F>
+  __device__ __forceinline__ float2 twiddle(int i) {
+    constexpr int R = Cfg::radix(S), p = Cfg::sublen(S), r = F % R;
+    return tw[Cfg::tw_offset(S) + (r - 1) * p + (i & (p - 1))];
+  }
+  // un-mix twiddle of bin k = t + TPF*c:  W_N^k = W_N^t * W_(2*PPT)^c  (register x compile-time constant)
+  __device__ __forceinline__ void begin_unmix() {}
+  template <int C>
+  __device__ __forceinline__ float2 unmix(float2 wt) {
+    if constexpr (C == 0) return wt;
+    else return cmul(wt, make_float2(TwC<C, 2 * Cfg::PPT>::re, TwC<C, 2 * Cfg::PPT>::im));
+  }
+};
+
+template <class Cfg>
+struct TmemTab {
+  static constexpr int UNMIX_COL = 64 * Cfg::NPASS;
+  static constexpr int NCOLS = UNMIX_COL + Cfg::PPT;
+  uint32_t taddr;          // TMEM address of column 0 in this warp's lane quarter
+  uint32_t q[16];          // chunk in flight (16 columns = 8 slots / 8 twiddles)
+  float c[16];             // chunk being consumed
+  template <int COL>
+  __device__ __forceinline__ void issue() {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(taddr + COL));
+  }
+  // wait for the chunk in flight (the registers are in-out operands so that no use can move above the wait)
+  __device__ __forceinline__ void arrive() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+                   "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = __uint_as_float(q[i]);
+  }
+  template <int BASE, int F, int COUNT = Cfg::PPT>
+  __device__ __forceinline__ void advance() {   // called for every F in order: chunk hand-over every 8 entries
+    if constexpr (F % 8 == 0) {
+      arrive();
+      if constexpr (F + 8 < COUNT) issue<BASE + 2 * (F + 8)>();
+    }
+  }
+  __device__ __forceinline__ void begin_window() { issue<0>(); }
+  template <int SLOT>
+  __device__ __forceinline__ float2 window(int) {
+    advance<0, SLOT>();
+    return make_float2(c[2 * (SLOT % 8)], c[2 * (SLOT % 8) + 1]);
+  }
+  template <int S>
+  __device__ __forceinline__ void begin_pass() { issue<64 * S>(); }
+  template <int S, int F>
+  __device__ __forceinline__ void step() { advance<64 * S, F>(); }
+  template <int S, int F>
+  __device__ __forceinline__ float2 twiddle(int) {
+    return make_float2(c[2 * (F % 8)], c[2 * (F % 8) + 1]);
+  }
+  __device__ __forceinline__ void begin_unmix() { issue<UNMIX_COL>(); }
+  template <int C>
+  __device__ __forceinline__ float2 unmix(float2) {   // bin pairs in increasing order, each exactly once
+    advance<UNMIX_COL, C, Cfg::PPT / 2>();
+    return make_float2(c[2 * (C % 8)], c[2 * (C % 8) + 1]);
+  }
+};
+
 // v[] must hold the pass-0 operands (see load_pass0) and receives the spectrum:
 //   v[b*RL + q] = Z[t + TPF*b + q*pL]   (RL, pL = radix / sub-length of the last pass, b = 0 .. PPT/RL-1).
-template <class Cfg>
-__device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int barrier_id,
-                                            float2* __restrict__ xbuf, const float2* __restrict__ tw) {
+// FUSED0: the first butterfly stage of pass 0 was already done by load_pass0_windowed.
+// pre_store() runs once, right before the first write to xbuf (multi-pass schedules only): callers that share
+// the exchange area with something else (the power rows of the previous tile) synchronise there instead of
+// before the transform, so that the register-only part of pass 0 overlaps the wait.
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <class Cfg, bool FUSED0 = false, class Tab, class Pre = NoHook>
+__device__ __forceinline__ void fft_forward_tab(float2 (&v)[Cfg::PPT], int t, int barrier_id,
+                                                float2* __restrict__ xbuf, Tab& tab, Pre&& pre_store = Pre()) {
   constexpr int M = Cfg::M, TPF = Cfg::TPF, PPT = Cfg::PPT;
   static_for<0, Cfg::NPASS>([&](auto S) {
     constexpr int s = decltype(S)::value;
@@ -211,20 +342,19 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int ba
         constexpr int r = decltype(Rr)::value;
         constexpr int slot = b * R + bitrevc(r, LOGR);
         if constexpr (s > 0) {
+          tab.template step<s, b * R + r>();
           float2 x = xbuf[xphys(i + r * T)];
-          if constexpr (r > 0) {
-            const int k = i & (p - 1);
-            x = cmul(x, tw[Cfg::tw_offset(s) + (r - 1) * p + k]);
-          }
+          if constexpr (r > 0) x = cmul(x, tab.template twiddle<s, b * R + r>(i));
           v[slot] = x;
         }
       });
     });
     // ---- radix-R DFTs in registers
-    static_for<0, NB>([&](auto B) { dft_reg<R, decltype(B)::value * R>(v); });
+    static_for<0, NB>([&](auto B) { dft_reg<R, decltype(B)::value * R, (FUSED0 && s == 0) ? 1 : 0>(v); });
     // ---- store for the next pass
     if constexpr (s + 1 < Cfg::NPASS) {
       if constexpr (s > 0) group_sync<TPF>(barrier_id);   // everyone finished reading pass s-1 data
+      else pre_store();
       static_for<0, NB>([&](auto B) {
         constexpr int b = decltype(B)::value;
         const int i = t + TPF * b;
@@ -235,9 +365,17 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int ba
           xbuf[xphys(j + q * p)] = v[b * R + q];
         });
       });
+      tab.template begin_pass<s + 1>();   // TMEM: the first twiddle chunk travels while the group synchronises
       group_sync<TPF>(barrier_id);
     }
   });
+}
+// Table in shared memory, given as a bare pointer (inverse / chirp-z kernels).
+template <class Cfg>
+__device__ __forceinline__ void fft_forward(float2 (&v)[Cfg::PPT], int t, int barrier_id,
+                                            float2* __restrict__ xbuf, const float2* __restrict__ tw) {
+  SmemTab<Cfg> tab{nullptr, tw};
+  fft_forward_tab<Cfg, false>(v, t, barrier_id, xbuf, tab);
 }
 
 // Offset (index minus t) of the spectrum element held in v[slot] after fft_forward, and the inverse map

@@ -56,6 +56,28 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
       : "memory");
 }
 
+// ------------------------------------------------------------------ Tensor Memory as a per-thread constant store
+// (tcgen05.alloc / st / ld; SASS UTCALLOC, STTM, LDTM).  One warp allocates, the address comes back through
+// shared memory; a warp reaches only the 32 lanes of its own quarter (warp index mod 4).
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
+  constexpr int cols = NCOLS <= 32 ? 32 : NCOLS <= 64 ? 64 : NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_free(uint32_t taddr) {
+  constexpr int cols = NCOLS <= 32 ? 32 : NCOLS <= 64 ? 64 : NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_store1(uint32_t taddr, float v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
 // ------------------------------------------------------------------ padded sample fetch
 // Virtual sample j of a clip of n samples under np.pad semantics (librosa/core/spectrum.py:252-328,
 // equivalence to np.pad(y, n_fft//2, mode) per SURVEY Appendix A.2).
@@ -129,7 +151,9 @@ __device__ __forceinline__ int partner_slot(int t) {
 // tables are shared.  The halves drift apart, so the shared-memory-bound phases of one (operand fetch,
 // exchange, mel gather) overlap the FP32-bound butterflies of the other instead of all warps of the SM
 // hitting the same pipe at once.
-template <int LOG2M, int TPF, int NW, int MODE, int NSPLIT>
+// TM: the window and the inter-pass twiddles live in Tensor Memory (TmemTab, fft_engine.cuh) instead of shared
+// memory — a fifth of the shared-memory wavefronts of a frame move to the tcgen05.ld datapath.
+template <int LOG2M, int TPF, int NW, int MODE, int NSPLIT, bool TM>
 __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   using Cfg = FftCfg<LOG2M, TPF>;
   constexpr int M = Cfg::M, N = 2 * M, PPT = Cfg::PPT;
@@ -142,6 +166,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   static_assert(NW % NSPLIT == 0, "the warps are split evenly");
   static_assert(TPF <= 32 || NH + NT / TPF <= 15, "named barriers: 1..NH for the halves, then one per frame group");
   static_assert(FT >= 1 && FT <= 32, "tile must hold 1..32 frames");
+  static_assert(!TM || (PPT == 32 && NW >= 4 && (TPF <= 32 || (4 * 32) % TPF == 0)), "TMEM tables: 32 points per thread, all four lane quarters in use");
+  using Tab = typename std::conditional<TM, TmemTab<Cfg>, SmemTab<Cfg>>::type;
   using ML = MelLayout<M, FT>;
   constexpr int H = ML::H;                     // mel rows handled concurrently by one warp (common.cuh)
   constexpr int NPAIR = PPT / 2;               // bin pairs (k, M-k) per thread
@@ -156,13 +182,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   MelRow* s_row = reinterpret_cast<MelRow*>(smem + a.off_melband);
   float* s_in = reinterpret_cast<float*>(smem + a.off_in + half * a.in_stride);
   float2* s_xall = reinterpret_cast<float2*>(smem + a.off_xbuf + half * a.xbuf_stride);
-  float* s_p = reinterpret_cast<float*>(s_xall);               // P tile aliases the exchange area
+  float* s_p = reinterpret_cast<float*>(s_xall);               // P rows alias the exchange regions (MelLayout)
+  const unsigned short* s_order = reinterpret_cast<const unsigned short*>(smem + a.off_melorder);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + half;
 
   const int grp = htid / TPF;                  // frame group == local frame index
   const int t = htid % TPF;
   const int gbar = 1 + NH + half * FT + grp;   // named barrier of this frame group (used when TPF > 32)
-  float2* xbuf = s_xall + grp * Cfg::XBUF_F2;
+  // stride between the exchange regions of consecutive groups: padded in the modes that park the power row there
+  constexpr int GS = (MODE == MODE_MEL || MODE == MODE_STATS) ? ML::GS : Cfg::XBUF_F2;
+  float2* xbuf = s_xall + grp * GS;
 
   auto half_sync = [&]() {
     if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");   // ids 1 .. NH
@@ -170,11 +199,49 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   };
 
   // ---- one-time table staging (whole CTA)
-  for (int i = tid; i < N; i += NT) s_win[i] = a.window[i];
-  for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.tw[i];
+  Tab tab;
+  if constexpr (TM) {
+    // Warps 0..3 each fill the lane quarter they can reach: lane i of quarter q serves thread
+    // t = (i + 32 q) mod TPF of a frame group (every warp w of the CTA sits in quarter w mod 4).
+    uint32_t* s_taddr = reinterpret_cast<uint32_t*>(smem + a.off_bar + 8 * NH);
+    if (tid < 32) tmem_alloc<Tab::NCOLS>(s_taddr);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tbase = *s_taddr + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
+    if (tid < 128) {
+      const int tt = tid % TPF;
+      for (int col = 0; col < 64; ++col)          // window pair of pass-0 slot col/2
+        tmem_store1(tbase + col, a.window[2 * (tt + pass0_offset<Cfg>(col >> 1)) + (col & 1)]);
+      for (int sp = 1; sp < Cfg::NPASS; ++sp) {
+        const int R = Cfg::radix(sp), p = Cfg::sublen(sp);
+        for (int f = 0; f < PPT; ++f) {
+          const int b = f / R, r = f % R, k = (tt + TPF * b) & (p - 1);
+          const float2 w = r == 0 ? make_float2(1.0f, 0.0f) : a.tw[Cfg::tw_offset(sp) + (r - 1) * p + k];
+          tmem_store1(tbase + 64 * sp + 2 * f, w.x);
+          tmem_store1(tbase + 64 * sp + 2 * f + 1, w.y);
+        }
+      }
+      for (int cp = 0; cp < NPAIR; ++cp) {        // un-mix twiddles W_N^(t + TPF*c)
+        const float2 w = a.twn[tt + TPF * cp];
+        tmem_store1(tbase + Tab::UNMIX_COL + 2 * cp, w.x);
+        tmem_store1(tbase + Tab::UNMIX_COL + 2 * cp + 1, w.y);
+      }
+      tmem_wait_st();
+    }
+    tmem_fence_before_sync();
+    tab.taddr = tbase;
+  } else {
+    for (int i = tid; i < N; i += NT) s_win[i] = a.window[i];
+    for (int i = tid; i < Cfg::TW_COUNT; i += NT) s_tw[i] = a.tw[i];
+    tab.win = s_win;
+    tab.tw = s_tw;
+  }
   if constexpr (MODE == MODE_MEL) {
     for (int i = tid; i < a.mel_w_count; i += NT) s_melw[i] = a.mel_w[i];
     for (int i = tid; i < a.n_mel_rows; i += NT) s_row[i] = a.mel_rows[i];
+    unsigned short* so = reinterpret_cast<unsigned short*>(smem + a.off_melorder);
+    for (int i = tid; i < a.mel_list_len * HW; i += NT) so[i] = a.mel_order[i];
   }
   if constexpr (MODE == MODE_STATS) {
     for (int i = tid; i < a.mel_w_count; i += NT) s_melw[i] = a.mel_w[i];   // bin frequencies
@@ -184,106 +251,110 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     fence_mbar_init();
   }
   __syncthreads();
+  if constexpr (TM) tmem_fence_after_sync();
 
   const int span = a.in_floats;
   const bool hop_even = (a.hop & 1) == 0;
-  // un-mix twiddle of bin k = t + TPF*c:  W_N^k = W_N^t * W_(2*PPT)^c  (register x compile-time constant)
+  // un-mix twiddle of bin k = t + TPF*c: one register x compile-time constant (SmemTab) or a TMEM column pair
   const float2 wt = __ldg(a.twn + t);
-  auto unmix_tw = [&](auto C) -> float2 {
-    constexpr int c = decltype(C)::value;
-    if constexpr (c == 0) return wt;
-    else return cmul(wt, make_float2(TwC<c, 2 * PPT>::re, TwC<c, 2 * PPT>::im));
-  };
+  auto unmix_tw = [&](auto C) -> float2 { return tab.template unmix<decltype(C)::value>(wt); };
 
-  auto tile_origin = [&](long long tile, int& clip, int& t0, long long& s0) {
-    clip = (int)(tile / a.tiles_per_clip);
-    t0 = (int)(tile % a.tiles_per_clip) * FT;
-    s0 = (long long)t0 * a.hop - a.pad;
-  };
+  // Tile walk without divisions in the loop: tile = clip * tiles_per_clip + tix, advanced by the constant
+  // stride (step_c clips, step_t tiles) of this half.
   // How a tile's span gets into shared memory:
   //   TILE_TMA      entirely inside the clip and 16-byte aligned -> one bulk copy
   //   TILE_TMA_ZERO zero ("constant") padding, aligned: bulk-copy the in-range part, threads zero the rest
   //   TILE_GATHER   anything else (reflect / edge / ... padding, unaligned clips): per-sample gather
   enum { TILE_GATHER = 0, TILE_TMA = 1, TILE_TMA_ZERO = 2 };
-  auto tile_kind = [&](long long tile, int& lead, int& valid) -> int {
-    int clip, t0;
-    long long s0;
-    tile_origin(tile, clip, t0, s0);
-    lead = s0 < 0 ? (int)(-s0) : 0;                                   // floats before the clip starts
-    long long end = s0 + span;
-    valid = (int)((end > a.n ? (long long)a.n : end) - (s0 + lead));  // in-range floats
-    if (!a.tma_ok || ((s0 + lead) & 3) != 0) return TILE_GATHER;
-    if (lead == 0 && valid == span) return TILE_TMA;
-    if (a.pad_mode == PAD_CONSTANT && valid > 0 && (lead & 3) == 0 && (valid & 3) == 0) return TILE_TMA_ZERO;
-    return TILE_GATHER;
+  struct TileInfo { int clip, tix, kind, lead, valid; };
+  auto describe = [&](int clip, int tix) -> TileInfo {
+    TileInfo ti;
+    ti.clip = clip;
+    ti.tix = tix;
+    const long long s0 = (long long)tix * FT * a.hop - a.pad;
+    ti.lead = s0 < 0 ? (int)(-s0) : 0;                                      // floats before the clip starts
+    const long long end = s0 + span;
+    ti.valid = (int)((end > a.n ? (long long)a.n : end) - (s0 + ti.lead));  // in-range floats
+    if (!a.tma_ok || ((s0 + ti.lead) & 3) != 0) ti.kind = TILE_GATHER;
+    else if (ti.lead == 0 && ti.valid == span) ti.kind = TILE_TMA;
+    else if (a.pad_mode == PAD_CONSTANT && ti.valid > 0 && (ti.lead & 3) == 0 && (ti.valid & 3) == 0) ti.kind = TILE_TMA_ZERO;
+    else ti.kind = TILE_GATHER;
+    return ti;
   };
-  auto issue_tma = [&](long long tile, int lead, int valid) {
-    int clip, t0;
-    long long s0;
-    tile_origin(tile, clip, t0, s0);
-    fence_proxy_async();
-    mbar_expect_tx(s_bar, (uint32_t)valid * 4u);
-    tma_load_1d(s_in + lead, a.y + (long long)clip * a.clip_stride + s0 + lead, (uint32_t)valid * 4u, s_bar);
-  };
-  // Called by the whole half after the staging buffer has been released (B0): start the copy of `tile`.
-  auto prefetch = [&](long long tile) {
-    if (tile >= a.total_tiles) return;
-    int lead, valid;
-    const int kind = tile_kind(tile, lead, valid);
-    if (kind == TILE_GATHER) return;
-    if (htid == 0) issue_tma(tile, lead, valid);
-    if (kind == TILE_TMA_ZERO) {
-      for (int i = htid; i < lead; i += HT) s_in[i] = 0.0f;
-      for (int i = lead + valid + htid; i < span; i += HT) s_in[i] = 0.0f;
+  // Called by the whole half after the staging buffer has been released (B0): start the copy of the tile.
+  auto prefetch = [&](const TileInfo& ti) {
+    if (ti.clip >= a.n_clips || ti.kind == TILE_GATHER) return;
+    if (htid == 0) {
+      const long long s0 = (long long)ti.tix * FT * a.hop - a.pad;
+      fence_proxy_async();
+      mbar_expect_tx(s_bar, (uint32_t)ti.valid * 4u);
+      tma_load_1d(s_in + ti.lead, a.y + (long long)ti.clip * a.clip_stride + s0 + ti.lead, (uint32_t)ti.valid * 4u, s_bar);
+    }
+    if (ti.kind == TILE_TMA_ZERO) {
+      for (int i = htid; i < ti.lead; i += HT) s_in[i] = 0.0f;
+      for (int i = ti.lead + ti.valid + htid; i < span; i += HT) s_in[i] = 0.0f;
     }
   };
 
-  const long long tile_step = (long long)gridDim.x * NH;
-  long long tile = (long long)blockIdx.x * NH + half;
+  const int tile_step = (int)gridDim.x * NH;
+  const int step_c = tile_step / a.tiles_per_clip, step_t = tile_step - step_c * a.tiles_per_clip;
+  TileInfo cur;
+  {
+    const int first = (int)blockIdx.x * NH + half;
+    cur = describe(first / a.tiles_per_clip, first % a.tiles_per_clip);
+  }
   uint32_t phase = 0;
-  prefetch(tile);
+  prefetch(cur);
 
-  for (; tile < a.total_tiles; tile += tile_step) {
-    int clip, t0;
-    long long s0;
-    tile_origin(tile, clip, t0, s0);
+  for (; cur.clip < a.n_clips;) {
+    const int clip = cur.clip, t0 = cur.tix * FT;
     // ---------------- stage the tile's sample span
-    {
-      int lead, valid;
-      const int kind = tile_kind(tile, lead, valid);
-      if (kind == TILE_GATHER) {
-        const float* yc = a.y + (long long)clip * a.clip_stride;
-        for (int i = htid; i < span; i += HT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
-        half_sync();
-      } else {
-        mbar_wait(s_bar, phase);
-        phase ^= 1;
-        if (kind == TILE_TMA_ZERO) half_sync();   // zeros written by other threads
-      }
+    if constexpr (TM) tab.begin_window();   // first window chunk travels while the tile lands
+    if (cur.kind == TILE_GATHER) {
+      const float* yc = a.y + (long long)clip * a.clip_stride;
+      const long long s0 = (long long)t0 * a.hop - a.pad;
+      for (int i = htid; i < span; i += HT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
+      half_sync();
+    } else {
+      mbar_wait(s_bar, phase);
+      phase ^= 1;
+      if (cur.kind == TILE_TMA_ZERO) half_sync();   // zeros written by other threads
     }
 
-    // ---------------- windowed frame -> registers (pass-0 operands)
+    // ---------------- windowed frame -> registers (pass-0 operands, first butterfly stage fused in)
     float2 v[PPT];
     {
       const float* fr = s_in + grp * a.hop;
+      auto win = [&](auto S) { return tab.template window<decltype(S)::value>(t); };
       if (hop_even) {
-        load_pass0<Cfg>(v, t, [&](int e) {
-          float2 x = *reinterpret_cast<const float2*>(fr + 2 * e);
-          float2 w = *reinterpret_cast<const float2*>(s_win + 2 * e);
-          return make_float2(x.x * w.x, x.y * w.y);
-        });
+        load_pass0_windowed<Cfg>(v, t, [&](int e) { return *reinterpret_cast<const float2*>(fr + 2 * e); }, win);
       } else {
-        load_pass0<Cfg>(v, t, [&](int e) {
-          float2 w = *reinterpret_cast<const float2*>(s_win + 2 * e);
-          return make_float2(fr[2 * e] * w.x, fr[2 * e + 1] * w.y);
-        });
+        load_pass0_windowed<Cfg>(v, t, [&](int e) { return make_float2(fr[2 * e], fr[2 * e + 1]); }, win);
       }
     }
-    half_sync();   // B0: staging buffer consumed -> prefetch the next tile behind the math
-    prefetch(tile + tile_step);
+    // next tile of this half
+    TileInfo nxt;
+    {
+      int nc = cur.clip + step_c, nt = cur.tix + step_t;
+      if (nt >= a.tiles_per_clip) { nt -= a.tiles_per_clip; ++nc; }
+      nxt = describe(nc, nt);
+    }
+    // B0: staging buffer consumed -> prefetch the next tile behind the math.  In the modes whose power rows
+    // share the exchange regions (MEL / STATS) the same barrier also says "every warp is done with the rows
+    // of the previous tile", so it sits right before the first exchange write: the operand fetch and the
+    // register-only butterflies of pass 0 of the fast warps overlap the tail of the slow warps' mel items.
+    constexpr bool MERGED = (MODE == MODE_MEL || MODE == MODE_STATS);
+    auto release = [&]() {
+      half_sync();
+      prefetch(nxt);
+    };
+    if constexpr (!MERGED) release();
 
     // ---------------- M-point complex FFT
-    fft_forward<Cfg>(v, t, gbar, xbuf, s_tw);
+    fft_forward_tab<Cfg, true>(v, t, gbar, xbuf, tab, [&]() {
+      if constexpr (MERGED) release();
+    });
+    if constexpr (MERGED && Cfg::NPASS == 1) release();
     if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
     // Bin pair (k, M-k), k = t + TPF*c < M/2: Z[k] is already in one of this thread's registers; only the
     // upper half of the spectrum (indices >= M/2) goes through shared memory to reach its partner.
@@ -291,6 +362,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       constexpr int slot = decltype(S)::value;
       if constexpr (spectrum_offset<Cfg>(slot) >= M / 2) xbuf[xphys(t + spectrum_offset<Cfg>(slot))] = v[slot];
     });
+    tab.begin_unmix();
     group_sync<TPF>(gbar);
     auto pair_operands = [&](auto C, float2& A, float2& B) {
       constexpr int c = decltype(C)::value;
@@ -370,20 +442,25 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         group_sync<TPF>(gbar);
       } else {
         // ---------------- band-sparse mel projection over the tile
-        half_sync();   // B1: every group finished reading its Z
-        // P[f][k] frame-major with a bank-skewed row stride (MelLayout, common.cuh); bins M+1 .. M+3 of
-        // every row are kept at zero so the 4-bin groups of the mel loop may run past the Nyquist bin.
+        // The power row of frame f goes to the exchange region of its own group (P[f][k] at word f*RS + k,
+        // MelLayout): only the group itself has to be done with its Z before the row is written.  Bins
+        // M+1 .. M+3 of every row are kept at zero so that 4-bin groups may run past the Nyquist bin.
         constexpr int RS = ML::RS;
-        float* prow = s_p + grp * RS;
+        group_sync<TPF>(gbar);   // every thread of the group has fetched its pair operands
+        float* prow = reinterpret_cast<float*>(xbuf);
         static_for<0, NPAIR>([&](auto C) {
           constexpr int c = decltype(C)::value;
           const int k = t + TPF * c;
           prow[k] = pw[2 * c];
           prow[M - k] = pw[2 * c + 1];
         });
-        if (t == 0) prow[M / 2] = pw[PPT];
-        if (htid < 3 * FT) s_p[(htid / 3) * RS + M + 1 + (htid % 3)] = 0.0f;
-        half_sync();   // B2
+        if (t == 0) {
+          prow[M / 2] = pw[PPT];
+          prow[M + 1] = 0.0f;
+          prow[M + 2] = 0.0f;
+          prow[M + 3] = 0.0f;
+        }
+        half_sync();   // B2: the tile's rows are complete
         if constexpr (MODE == MODE_STATS) {
           // one warp per frame of the tile: statistics of the magnitude row (stats.cuh)
           const int hwarp = htid >> 5, lane = htid & 31;
@@ -396,9 +473,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         } else {
           // Work item = H adjacent mel rows; lane (fp, j) accumulates row item*H + j for the frame pair
           // (fp, fp + FP) over that row's padded band (host-built MelRow table: the rows of an item share
-          // one trip count, start bins are congruent to j mod H so the skewed tile reads conflict-free,
-          // weights are zero padded and 16-byte aligned).  One weight fetch feeds both frames; no
-          // cross-lane reduction, one short loop per item.
+          // one trip count, start bins follow the bank rule of MelLayout, weights are zero padded and 16-byte
+          // aligned).  One 16-byte weight fetch and one 16-byte power fetch per frame feed eight FMAs; no
+          // cross-lane reduction.  The items of a tile are dealt to the warps by the host (longest first,
+          // a.mel_order) because their lengths differ by an order of magnitude from the lowest to the highest rows.
           constexpr int FP = ML::FP;
           constexpr bool PAIR = ML::PAIR;
           const int hwarp = htid >> 5, lane = htid & 31;
@@ -406,7 +484,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
           const bool ok_a = (t0 + fp) < a.n_frames;
           const bool ok_b = PAIR && (t0 + fp + FP) < a.n_frames;
           float wmax = -INFINITY;
-          const int n_items = a.n_mel_rows / H;
           const float* pbase = s_p + fp * RS;
           // output row stride / base: the public [clip][mel][frame] layout, or the tiled mfcc scratch whose
           // 64-frame tiles are contiguous 32 KB blocks for dct_clamp_kernel (t0 + fp and t0 + fp + FP share a tile)
@@ -414,35 +491,37 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
           float* obase = a.out_tiled
                              ? a.out_r + ((long long)clip * ((a.n_frames + 63) >> 6) + (t0 >> 6)) * a.n_mels * 64 + (t0 & 63) + fp
                              : a.out_r + (long long)clip * a.n_mels * a.n_frames + t0 + fp;
-          for (int item = hwarp; item < n_items; item += HW) {
+          for (int li = 0; li < a.mel_list_len; ++li) {
+            const int item = s_order[li * HW + hwarp];
+            if (item == 0xffff) break;
             const int m = item * H + j;
             const MelRow row = s_row[m];
             const float4* wp = reinterpret_cast<const float4*>(s_melw + row.off);
-            const float* pa = pbase + row.lo;
+            const float4* pa = reinterpret_cast<const float4*>(pbase + row.lo);
             const float4* wend = wp + row.quads;
             float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
             if constexpr (PAIR) {
-              const float* pb = pa + FP * RS;
+              const float4* pb = pa + (FP * RS) / 4;
 #pragma unroll 2
-              for (; wp != wend; ++wp, pa += 4, pb += 4) {
-                const float4 w = *wp;
-                a0 = fmaf(w.x, pa[0], a0);
-                b0 = fmaf(w.x, pb[0], b0);
-                a1 = fmaf(w.y, pa[1], a1);
-                b1 = fmaf(w.y, pb[1], b1);
-                a0 = fmaf(w.z, pa[2], a0);
-                b0 = fmaf(w.z, pb[2], b0);
-                a1 = fmaf(w.w, pa[3], a1);
-                b1 = fmaf(w.w, pb[3], b1);
+              for (; wp != wend; ++wp, ++pa, ++pb) {
+                const float4 w = *wp, x = *pa, y = *pb;
+                a0 = fmaf(w.x, x.x, a0);
+                b0 = fmaf(w.x, y.x, b0);
+                a1 = fmaf(w.y, x.y, a1);
+                b1 = fmaf(w.y, y.y, b1);
+                a0 = fmaf(w.z, x.z, a0);
+                b0 = fmaf(w.z, y.z, b0);
+                a1 = fmaf(w.w, x.w, a1);
+                b1 = fmaf(w.w, y.w, b1);
               }
             } else {
 #pragma unroll 2
-              for (; wp != wend; ++wp, pa += 4) {
-                const float4 w = *wp;
-                a0 = fmaf(w.x, pa[0], a0);
-                a1 = fmaf(w.y, pa[1], a1);
-                a0 = fmaf(w.z, pa[2], a0);
-                a1 = fmaf(w.w, pa[3], a1);
+              for (; wp != wend; ++wp, ++pa) {
+                const float4 w = *wp, x = *pa;
+                a0 = fmaf(w.x, x.x, a0);
+                a1 = fmaf(w.y, x.y, a1);
+                a0 = fmaf(w.z, x.z, a0);
+                a1 = fmaf(w.w, x.w, a1);
               }
             }
             float va = a0 + a1, vb = b0 + b1;
@@ -466,8 +545,17 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
             if (lane == 0 && wmax > -INFINITY) atomicMax(a.clip_max + clip, float_to_key(wmax));
           }
         }
-        half_sync();   // B3: P reads done before the next tile's exchange writes
+        // no barrier here: the next tile's `release` (before its first exchange write) orders the P reads
       }
+    }
+    cur = nxt;
+  }
+  if constexpr (TM) {
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (tid < 32) {
+      tmem_fence_after_sync();
+      tmem_free<Tab::NCOLS>(tab.taddr);   // warp 0 sits in quarter 0: its address is the allocation base
     }
   }
 }

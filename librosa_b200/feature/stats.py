@@ -27,11 +27,11 @@ _NP_PAD_ONLY = ("maximum", "mean", "median", "minimum", "wrap")
 
 def _device_table(ctx, key, values: np.ndarray) -> int:
     """Small float32 constant (bin frequencies) cached on the device per context."""
-    ptr = ctx._wss.get(key)
+    ptr = ctx._wss.fetch(key)
     if ptr is None:
         arr = np.ascontiguousarray(values, dtype=np.float32)
-        if len(ctx._wss) > 32:
-            _, old = ctx._wss.popitem()
+        while len(ctx._wss) >= 32:                 # least recently used first: a table fetched earlier in
+            _, old = ctx._wss.evict_oldest()       # the same call is the youngest entry and stays
             ctx.free(old)
         ptr = ctx.alloc(max(arr.nbytes, 16))
         nat.check(nat.lib().b2l_h2d(ctx.handle, _vp(ptr), arr.ctypes.data_as(_vp), arr.nbytes))
