@@ -190,6 +190,27 @@ def _cpu_worker_init():
         _BLAS_LIMIT = None
 
 
+def cpu_quota():
+    """CPU time this container may use, in cores (cgroup v2 cpu.max / v1 cfs quota), or None if unlimited."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()[:2]
+        if quota != "max":
+            return float(quota) / float(period)
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fh:
+            quota = float(fh.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fh:
+            period = float(fh.read())
+        if quota > 0:
+            return quota / period
+    except Exception:
+        pass
+    return None
+
+
 class CpuPort:
     """The reference's algorithm (oracle port, bit-exact with librosa here) on the host cores, the three ways
     SURVEY 8d lists: (i) one batched call, BLAS threads = all cores; (ii) per-clip loop in one process;
@@ -201,7 +222,11 @@ class CpuPort:
 
         global _CPU_BATCH
         self.w = w
-        self.cores = len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
+        self.visible = len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
+        self.quota = cpu_quota()
+        # a container may show every core of the box and still be throttled to a few cores' worth of time
+        # (cgroup cpu.max): more workers than that only adds context switches
+        self.cores = self.visible if self.quota is None else max(1, min(self.visible, int(round(self.quota))))
         self.clips = max(min_clips, clips_per_core * self.cores)
         _CPU_BATCH = make_batch(dict(w, clips=self.clips), rank=0)
         self.T = n_frames(w["n"], w["kw"]["n_fft"], w["kw"]["hop_length"])
@@ -243,8 +268,9 @@ class CpuPort:
         return out
 
     def describe(self, variants):
-        return (f"{self.clips} clips of the workload per pass ({self.clips // self.cores} per core), persistent forked "
-                f"workers read a fork-inherited batch; variants frames/s: "
+        return (f"{self.clips} clips of the workload per pass ({self.clips // self.cores} per worker), {self.cores} persistent "
+                f"forked workers ({self.visible} CPUs visible, cgroup quota "
+                f"{'none' if self.quota is None else '%.1f cores' % self.quota}) read a fork-inherited batch; variants frames/s: "
                 + ", ".join(f"{k}={v:.0f}" for k, v in variants.items()))
 
     def close(self):
@@ -267,7 +293,8 @@ def cpu_measure(w, seconds):
     pool_key = [k for k in var if k.endswith("forked_workers")][0]
     var[pool_key] = f / s
     best = max(var, key=var.get)
-    out = {"value": var[best], "unit": "frames/s", "cores": port.cores, "kind": "port", "best_variant": best,
+    out = {"value": var[best], "unit": "frames/s", "cores": port.cores, "cpus_visible": port.visible,
+           "cgroup_cpu_quota": port.quota, "kind": "port", "best_variant": best,
            "variants": var, "sample": port.describe(var)}
     port.close()
     return out
@@ -300,7 +327,8 @@ def run_reference(args, w, rank, world):
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 in / f64 FFT (reference numerics)", "data": "synthetic",
         "config": {"workload": w["desc"], "name": args.workload},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": port.cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": port.cores, "cpus_visible": port.visible,
+                         "cgroup_cpu_quota": port.quota, "kind": "port",
                          "best_variant": best, "variants": var, "sample": port.describe(var)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -444,16 +472,68 @@ def run_ours(args, w, rank, world, local_rank):
     e2e_pg_s, _ = time_e2e(pageable, max(3, e2e_steps // 2))
     del pageable
     # PCIe upload ceiling with every rank transferring at once: explains the end-to-end scaling
+    import ctypes as C
+
+    from librosa_b200 import _native as nat
+
+    probe = ctx.empty(host.shape, np.float32)
+    nat.check(nat.lib().b2l_h2d(ctx.handle, C.c_void_p(probe.ptr), host.ctypes.data_as(C.c_void_p), host.nbytes))
     barrier()
     t0 = time.perf_counter()
     for _ in range(3):
-        tmp = ctx.to_device(host)
-        tmp.free()
+        nat.check(nat.lib().b2l_h2d(ctx.handle, C.c_void_p(probe.ptr), host.ctypes.data_as(C.c_void_p), host.nbytes))
     ctx.synchronize()
     h2d_gbs = 3 * host.nbytes / max_over_ranks(time.perf_counter() - t0) / 1e9
+    probe.free()
     h2d_bytes = int(host.nbytes)
     dev.free()
     del host
+
+    # ---- split / join over NVLink through the product's own NCCL path (b2l_comm_*, rendezvous over TCP, no
+    # torch): rank 0 holds the whole device-resident batch, scatters the shards, every rank runs its shard,
+    # rank 0 gathers the mel spectrograms.  Timed with CUDA events on rank 0's stream, max over ranks.
+    join = None
+    if world > 1 and not args.no_join and w["op"] == "mel":
+        from librosa_b200 import distributed as D
+
+        comm = D.init_from_env(ctx)
+        T = n_frames(w["n"], w["kw"]["n_fft"], w["kw"]["hop_length"])
+        shard = ctx.empty((w["clips"], w["n"]), np.float32)
+        full_in = full_out = None
+        if rank == 0:
+            full_in = ctx.empty((world * w["clips"], w["n"]), np.float32)
+            one = ctx.to_device(make_batch(w, 0))
+            for r_ in range(world):
+                lb.device_copy(ctx, full_in, r_ * one.nbytes, one)
+            one.free()
+            full_out = ctx.empty((world * w["clips"], w["kw"]["n_mels"], T), np.float32)
+
+        def join_step():
+            comm.scatter(full_in, shard)
+            M = lb.feature.melspectrogram(y=shard, sr=w["sr"], **w["kw"])
+            comm.gather(M, full_out)
+            M.free()
+
+        for _ in range(3):
+            join_step()
+        barrier()
+        js = max(3, min(args.steps, 10))
+        e0, e1 = ctx.event(), ctx.event()
+        e0.record()
+        for _ in range(js):
+            join_step()
+        e1.record()
+        jms = max_over_ranks(e0.elapsed_ms(e1)) / js
+        barrier()
+        comm.close()
+        shard.free()
+        if rank == 0:
+            full_in.free()
+            full_out.free()
+        moved = (world - 1) * (w["clips"] * w["n"] * 4 + w["clips"] * w["kw"]["n_mels"] * T * 4)
+        join = {"mode": "nccl scatter -> mel -> nccl gather (b2l_comm_*, root = rank 0)", "ms_per_step": jms,
+                "value": world * frames_per_step / (jms * 1e-3), "unit": "frames/s",
+                "nvlink_bytes_per_step": moved, "nvlink_gbs_at_root": moved / (jms * 1e-3) / 1e9}
 
     # ---- the other BASELINE.json configs, device-resident (driver-recorded secondary numbers)
     secondary = []
@@ -506,7 +586,7 @@ def run_ours(args, w, rank, world, local_rank):
                              "path": "same call on an ordinary (pageable) ndarray; staged upload inside the library"},
                 "h2d_ceiling_gbs_per_gpu": h2d_gbs,
                 "h2d_floor_ms": h2d_bytes / (h2d_gbs * 1e9) * 1e3},
-        "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
+        "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "join": join,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -523,6 +603,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 / cfg4 / cfg5 secondary numbers")
+    ap.add_argument("--no-join", action="store_true", help="skip the NCCL scatter -> mel -> gather leg (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -14,7 +14,8 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb2l.so")
+# B2L_LIB_PATH selects another build flavour of the same C ABI (A/B measurements); there is still no fallback.
+LIB_PATH = os.environ.get("B2L_LIB_PATH") or os.path.join(_HERE, "csrc", "libb2l.so")
 
 B2L_OK = 0
 B2L_ERR_INVALID = 1

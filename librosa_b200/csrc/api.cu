@@ -879,7 +879,8 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     if (mode == MODE_MEL || mode == MODE_STATS) {
       // the power row of a frame lives in the (padded) exchange region of its group: MelLayout (common.cuh);
       // slack after the last row: a short row of a work item may read up to one band length past bin M + 3
-      xbytes = (size_t)f * mel_group_stride(M, f) * 8 + (size_t)(M + 16) * 4;
+      // (only possible when 2 * GS < 2 * M + 8, i.e. M < 128)
+      xbytes = (size_t)f * mel_group_stride(M, f) * 8 + (M < 128 ? (size_t)(M + 16) * 4 : 0);
     }
     a.xbuf_stride = (int)align_up(xbytes, 128);
     off += (size_t)a.xbuf_stride * nh;
@@ -1289,6 +1290,48 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
   }
   InvArgs a;
   memset(&a, 0, sizeof(a));
+  // hop = n_fft / 4 or / 2, one or more whole warps per frame: autonomous frame groups with the overlap-add
+  // state in Tensor Memory (inv2_kernel.cuh); B2L_INV2=0 keeps the gather kernel
+  {
+    const char* e2 = getenv("B2L_INV2");
+    const bool want2 = !(e2 && *e2 && atoi(e2) == 0) && !(getenv("B2L_INV_VARIANT") && *getenv("B2L_INV_VARIANT"));
+    const int R = p->hop > 0 && N % p->hop == 0 ? N / p->hop : 0;
+    if (want2 && cfg.log2m >= 10 && cfg.log2m <= 12 && (R == 4 || R == 2)) {
+      const int NG = 16 * 32 / cfg.tpf;
+      size_t off = 0;
+      a.off_acc = (int)off; off = align_up(off + 16, 128);            // TMEM base address
+      a.off_xbuf = (int)off; off += (size_t)NG * cfg.xbuf_f2() * 8;
+      if (off <= c->smem_optin) {
+        a.D = (const float2*)d_D;
+        a.d_clip_stride = (long long)n_frames_stored * (M + 1);
+        a.n_clips = (int)n_clips;
+        a.n_frames = (int)n_frames_used;
+        a.n_fft = N;
+        a.hop = p->hop;
+        a.start = p->center ? N / 2 : 0;
+        a.out_len = (int)out_len;
+        a.y_clip_stride = y_stride;
+        a.y = d_y;
+        a.window = p->d_win_inv;
+        a.inv_wss = d_inv_wss;
+        a.tw = p->d_tw;
+        a.twn = p->d_twn;
+        a.vec4 = (y_stride % 2 == 0) && (((uintptr_t)d_y & 7) == 0) && (((uintptr_t)d_inv_wss & 7) == 0);   // 8-byte stores
+        const long long total_frames = (long long)n_clips * n_frames_used;
+        const long long groups = (long long)c->sm_count * NG;
+        long long fps = (total_frames + groups - 1) / groups;
+        if (fps < 8) fps = 8;                                          // replayed frames stay a bounded fraction
+        a.frames_per_slot = (int)fps;
+        const long long runs = (total_frames + fps - 1) / fps;
+        const long long grid = (runs + NG - 1) / NG;
+        const int v2 = 2000 + R;
+        CUDA_TRY(op(OP_SET_SMEM, v2, &a, 0, off, c->stream, nullptr));
+        CUDA_TRY(op(OP_LAUNCH, v2, &a, (int)grid, off, c->stream, nullptr));
+        c->launches++;
+        return B2L_OK;
+      }
+    }
+  }
   int variant = 0, G = 0, halves = 1;
   size_t smem = 0;
   const int clen = N > p->hop ? N - p->hop : 0;

@@ -16,6 +16,10 @@
 #include "fft_engine.cuh"
 #include "stats.cuh"
 
+#ifndef B2L_UNMIX_SHFL
+#define B2L_UNMIX_SHFL 0   // 1: real-FFT un-mix partners travel by warp shuffle where a warp owns a whole frame
+#endif
+
 namespace b2l {
 
 // ------------------------------------------------------------------ mbarrier / TMA (PTX)
@@ -355,24 +359,40 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       if constexpr (MERGED) release();
     });
     if constexpr (MERGED && Cfg::NPASS == 1) release();
-    if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
     // Bin pair (k, M-k), k = t + TPF*c < M/2: Z[k] is already in one of this thread's registers; only the
-    // upper half of the spectrum (indices >= M/2) goes through shared memory to reach its partner.
-    static_for<0, PPT>([&](auto S) {
-      constexpr int slot = decltype(S)::value;
-      if constexpr (spectrum_offset<Cfg>(slot) >= M / 2) xbuf[xphys(t + spectrum_offset<Cfg>(slot))] = v[slot];
-    });
+    // upper half of the spectrum (indices >= M/2) has to reach its partner thread — through shared memory,
+    // or (one warp per frame, M = 1024: v[q] = Z[t + 32 q], so Z[M-k] is register 31-c of lane 32-t) with
+    // warp shuffles, which keeps 64 wavefronts per frame off the shared-memory pipe.
+    constexpr bool SHFL_UNMIX = B2L_UNMIX_SHFL && TPF == 32 && PPT == 32 && M == 1024;
+    if constexpr (!SHFL_UNMIX) {
+      if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
+      static_for<0, PPT>([&](auto S) {
+        constexpr int slot = decltype(S)::value;
+        if constexpr (spectrum_offset<Cfg>(slot) >= M / 2) xbuf[xphys(t + spectrum_offset<Cfg>(slot))] = v[slot];
+      });
+    }
     tab.begin_unmix();
-    group_sync<TPF>(gbar);
+    if constexpr (!SHFL_UNMIX) group_sync<TPF>(gbar);
     auto pair_operands = [&](auto C, float2& A, float2& B) {
       constexpr int c = decltype(C)::value;
       constexpr int sa = slot_of_pair<Cfg>(c);
       static_assert(sa >= 0, "pair operand must be register resident");
       A = v[sa];
-      B = xbuf[partner_slot<M, TPF, c>(t)];
-      if constexpr (c == 0) {
-        if (t == 0) B = A;   // k = 0 pairs with itself (Z[M] == Z[0])
+      if constexpr (SHFL_UNMIX) {
+        const int src = (32 - t) & 31;
+        B.x = __shfl_sync(0xffffffffu, v[31 - c].x, src);
+        B.y = __shfl_sync(0xffffffffu, v[31 - c].y, src);
+        if (t == 0) B = v[c == 0 ? 0 : 32 - c];   // lane 0 pairs with itself: Z[M - 32c] = its register 32-c (Z[M] == Z[0])
+      } else {
+        B = xbuf[partner_slot<M, TPF, c>(t)];
+        if constexpr (c == 0) {
+          if (t == 0) B = A;   // k = 0 pairs with itself (Z[M] == Z[0])
+        }
       }
+    };
+    auto middle_bin = [&]() -> float2 {   // Z[M/2], needed by t == 0 only
+      if constexpr (SHFL_UNMIX) return v[16];
+      else return xbuf[xphys(M / 2)];
     };
 
     const int frame = t0 + grp;
@@ -396,7 +416,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       });
       if (t == 0) {
         float2 xa, xb;
-        float2 zc = xbuf[xphys(M / 2)];
+        float2 zc = middle_bin();
         r2c_pair(zc, zc, make_float2(0.0f, -1.0f), xa, xb);   // W_N^(M/2) = -i
         if (frame_ok) orow[M / 2] = xa;
       }
@@ -414,7 +434,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       pw[PPT] = 0.0f;
       if (t == 0) {
         float2 xa, xb;
-        float2 zc = xbuf[xphys(M / 2)];
+        float2 zc = middle_bin();
         r2c_pair(zc, zc, make_float2(0.0f, -1.0f), xa, xb);
         pw[PPT] = sqmag(xa);
       }

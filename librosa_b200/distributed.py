@@ -3,8 +3,10 @@ collective inside the compute.  NCCL (through the C ABI, ``b2l_comm_*``) is used
 device-resident batch from a root GPU and to gather the results back over NVLink; host-resident batches
 are simply sliced per rank and uploaded directly (no funnel through one GPU).
 
-The rendezvous (rank, world size, exchanging the 128-byte NCCL id) is the launcher's job: under
-``torchrun`` use ``init_from_torch()``; any other mechanism can pass its own ``bcast_bytes`` callable.
+The rendezvous (rank, world size, exchanging the 128-byte NCCL id) needs no framework: ``init_from_env()``
+reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT (what ``torchrun`` or any launcher exports)
+and rank 0 hands the id to the other ranks over a plain TCP socket (``tcp_bcast_bytes``).  Any other
+mechanism can pass its own ``bcast_bytes`` callable to ``Communicator``.  No PyTorch import anywhere.
 """
 from __future__ import annotations
 
@@ -78,21 +80,75 @@ class Communicator:
         nat.check(nat.lib().b2l_comm_destroy(self.ctx.handle))
 
 
-def torch_bcast_bytes(payload: Optional[bytes]) -> bytes:
-    """Broadcast helper for processes launched by torchrun (torch.distributed must be initialised)."""
-    import torch.distributed as dist
+def rendezvous_endpoint() -> Tuple[str, int]:
+    """(host, port) of the id exchange: B2L_RDZV_PORT, else MASTER_PORT + 23 (the launcher's own store keeps
+    MASTER_PORT itself), on MASTER_ADDR (default 127.0.0.1)."""
+    host = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = os.environ.get("B2L_RDZV_PORT")
+    if port is None:
+        port = int(os.environ.get("MASTER_PORT", "29500")) + 23
+    return host, int(port)
 
-    box = [payload]
-    dist.broadcast_object_list(box, src=0)
-    return box[0]
+
+def tcp_bcast_bytes(payload: Optional[bytes], rank: int, world: int, *, host: Optional[str] = None,
+                    port: Optional[int] = None, timeout: float = 120.0) -> bytes:
+    """Rank 0 serves ``payload`` to the world - 1 other ranks over TCP; everyone returns it.
+
+    The message is length-prefixed; clients retry the connection until the server is up (ranks start in any
+    order) and fail after ``timeout`` seconds."""
+    import socket
+    import struct
+    import time
+
+    if world <= 1:
+        return payload
+    ep_host, ep_port = rendezvous_endpoint()
+    host = ep_host if host is None else host
+    port = ep_port if port is None else port
+    if rank == 0:
+        if payload is None:
+            raise ValueError("rank 0 must supply the payload")
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind(("" if host not in ("127.0.0.1", "localhost") else "127.0.0.1", port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        try:
+            for _ in range(world - 1):
+                conn, _addr = srv.accept()
+                with conn:
+                    conn.sendall(struct.pack("<I", len(payload)) + payload)
+        finally:
+            srv.close()
+        return payload
+    deadline = time.monotonic() + timeout
+    while True:
+        try:
+            with socket.create_connection((host, port), timeout=5.0) as conn:
+                conn.settimeout(timeout)
+                head = _recv_exact(conn, 4)
+                (size,) = struct.unpack("<I", head)
+                return _recv_exact(conn, size)
+        except (ConnectionRefusedError, ConnectionResetError, socket.timeout, OSError):
+            if time.monotonic() > deadline:
+                raise TimeoutError(f"rank {rank}: no NCCL id from {host}:{port} within {timeout} s")
+            time.sleep(0.05)
 
 
-def init_from_torch(ctx: Optional[nat.Context] = None) -> Communicator:
-    import torch.distributed as dist
+def _recv_exact(conn, size: int) -> bytes:
+    buf = bytearray()
+    while len(buf) < size:
+        chunk = conn.recv(size - len(buf))
+        if not chunk:
+            raise ConnectionResetError("peer closed during the id exchange")
+        buf += chunk
+    return bytes(buf)
 
+
+def init_from_env(ctx: Optional[nat.Context] = None) -> Communicator:
+    """One process per GPU under any launcher that exports RANK / WORLD_SIZE / LOCAL_RANK (torchrun, mpirun
+    wrappers, a shell loop): create the NCCL communicator of this rank's context."""
     rank, world, local = env_rank_world()
     if ctx is None:
         ctx = nat.default_context(local)
-    if not dist.is_initialized():
-        dist.init_process_group(backend="gloo")
-    return Communicator(ctx, rank, world, torch_bcast_bytes)
+    return Communicator(ctx, rank, world, lambda payload: tcp_bcast_bytes(payload, rank, world))

@@ -40,9 +40,11 @@ def _worker(rank, world, port, out_dir):
     gathered = [None] * world
     dist.all_gather_object(gathered, part)
     full = D.join_batches(gathered)
-    # broadcast of an opaque id (what Communicator does with the NCCL unique id)
-    uid = D.torch_bcast_bytes(bytes(range(128)) if rank == 0 else None)
+    # broadcast of an opaque id (what Communicator does with the NCCL unique id): the product's own TCP
+    # rendezvous, no torch involved
+    uid = D.tcp_bcast_bytes(bytes(range(128)) if rank == 0 else None, rank, world)
     assert uid == bytes(range(128))
+    assert D.rendezvous_endpoint() == ("127.0.0.1", port + 23)
     # max-over-ranks of a per-rank time, as bench.py reports it
     t = torch.tensor([10.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -66,3 +68,42 @@ def test_two_rank_split_join(tmp_path):
     want = O.melspectrogram(y=batch, sr=16000, n_fft=1024, hop_length=256)
     got = np.load(os.path.join(str(tmp_path), "full.npy"))
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
+
+
+def _tcp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from librosa_b200 import distributed as D
+
+    got = D.tcp_bcast_bytes(os.urandom(128) if rank == 0 else None, rank, world)
+    q.put((rank, got, "torch" in sys.modules))
+
+
+def test_tcp_rendezvous_three_ranks_without_torch():
+    """The id exchange of librosa_b200.distributed works for any launcher and never imports torch."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tcp_worker, args=(r, 3, port, q)) for r in (2, 1, 0)]   # server starts last
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=60) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    payloads = {g[1] for g in got}
+    assert len(payloads) == 1 and len(next(iter(payloads))) == 128
+    assert not any(g[2] for g in got), "librosa_b200.distributed pulled in torch"
+
+
+def test_shard_ranges_cover_the_batch():
+    sys.path.insert(0, ROOT)
+    from librosa_b200 import distributed as D
+
+    for n in (0, 1, 5, 8, 1024, 8191):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

@@ -377,6 +377,28 @@ def test_launch_counter_and_no_fallback(lb):
     assert ctx.launch_count == before + 3   # fused mel kernel + clamp/DCT kernel
 
 
+def test_single_rank_communicator_roundtrip(lb, oracle):
+    """b2l_comm_* through NCCL on ONE GPU (world = 1): unique id, init, broadcast, scatter, compute, gather,
+    barrier, destroy — the product's split / join path exercised on a box that has a single GPU."""
+    import signals
+    from librosa_b200 import distributed as D
+
+    ctx = lb.Context(0)
+    comm = D.Communicator(ctx, 0, 1, lambda payload: payload)
+    Y = signals.make("A", (6, 30000), seed=78)
+    full = ctx.to_device(Y)
+    shard = ctx.empty(Y.shape, np.float32)
+    comm.scatter(full, shard)
+    comm.broadcast(shard)
+    M = lb.feature.melspectrogram(y=shard, sr=22050)
+    out = ctx.empty(M.shape, np.float32)
+    comm.gather(M, out)
+    comm.barrier()
+    ctx.synchronize()
+    close(out.get(), oracle.melspectrogram(y=Y, sr=22050), **TOL["mel"])
+    comm.close()
+
+
 @pytest.mark.skipif("__import__('librosa_b200').device_count() < 2")
 def test_two_rank_split_join_on_gpu(lb, oracle):
     """Two GPUs of one box: scatter a device-resident batch from rank 0 over NCCL, compute per rank,
