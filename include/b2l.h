@@ -317,6 +317,46 @@ int b2l_frame_feature(b2l_ctx* ctx, int32_t what, const float* d_y, int64_t n_cl
                       int32_t frame_length, int32_t hop_length, int32_t center, int32_t pad_mode, float threshold,
                       int32_t zero_pos, int32_t pad_first, float out_scale, float* d_out);
 
+/* ---- double-precision path: float64 audio / complex128 spectra ---------------------------------
+ * librosa computes a float64 signal in float64 (dtype_r2c, core/spectrum.py:341; the window product :388 and the
+ * irfft :598 follow the input's precision; the mel einsum feature/spectral.py:2160 and scipy.fft.dct :2005
+ * too).  These entry points do the same on the device in FP64 (f64_kernels.cuh): a correctness path next to
+ * the float32 hot path.  Device arrays are double / double2 in the layouts of the float32 functions; constants
+ * come as HOST pointers and are uploaded stream-ordered. */
+/* librosa.stft for float64 y — core/spectrum.py:58-391; h_window: [n_fft] (get_window + pad_center);
+ * d_out: [n_clips][n_frames][1 + n_fft/2] complex128; power-of-two n_fft up to 2^20 (in-place FFT, work area in
+ * shared memory up to 16384 and in global memory above), any other n_fft up to 65536 (direct DFT). */
+int b2l_stft_f64(b2l_ctx* ctx, const double* d_y, int64_t n_clips, int64_t n, int64_t y_stride, int32_t n_fft,
+                 int32_t hop_length, int32_t center, int32_t pad_mode, const double* h_window, void* d_out);
+/* librosa.istft for complex128 D — core/spectrum.py:395-643; h_inv_wss: [out_len] reciprocal trimmed
+ * window-sum-square in float64 (filters.py:1268-1339), 1 where wss <= tiny. */
+int b2l_istft_f64(b2l_ctx* ctx, const void* d_D, int64_t n_clips, int64_t n_frames_stored, int64_t n_frames_used,
+                  int32_t n_fft, int32_t hop_length, int32_t center, const double* h_window,
+                  const double* h_inv_wss, int64_t out_len, double* d_y, int64_t y_stride);
+/* np.abs(D)**power — core/spectrum.py:3000-3013; n complex128 elements in, n float64 out. */
+int b2l_f64_abs_pow(b2l_ctx* ctx, const void* d_D, int64_t n, double power, double* d_S);
+/* einsum("...ft,mf->...mt", S, mel_basis) — feature/spectral.py:2160; d_S [n_clips][n_frames][n_bins] float64,
+ * h_mel [n_mels][n_bins] float32 (filters.mel), d_out [n_clips][n_mels][n_frames] float64. */
+int b2l_f64_mel(b2l_ctx* ctx, const double* d_S, int64_t n_clips, int64_t n_frames, int32_t n_bins,
+                const float* h_mel, int32_t n_mels, double* d_out);
+/* power_to_db on float64 — core/spectrum.py:1866-1881; the top_db reference maximum is per clip
+ * (per_clip elements); top_db < 0: no floor. */
+int b2l_f64_db(b2l_ctx* ctx, const double* d_in, int64_t n_clips, int64_t per_clip, double amin, double ref_value,
+               double top_db, double* d_out);
+/* scipy.fft.dct(S, axis=-2, type, norm)[:n_mfcc] (* lifter) as the explicit matrix h_dct [n_mfcc][n_mels] —
+ * feature/spectral.py:2005-2015; d_L [n_clips][n_mels][n_frames] -> d_out [n_clips][n_mfcc][n_frames]. */
+int b2l_f64_dct(b2l_ctx* ctx, const double* d_L, int64_t n_clips, int32_t n_mels, int64_t n_frames,
+                const double* h_dct, int32_t n_mfcc, double* d_out);
+
+/* ---- feature.inverse ------------------------------------------------------------------------- */
+/* librosa.feature.inverse.mel_to_stft — feature/inverse.py:28-114 (util.nnls, util/_nnls.py:22-175):
+ * min |A X - B|^2 over X >= 0 per frame, A = h_basis [n_mels][n_bins] (triangular: every bin in <= 2 rows),
+ * started from max(0, pinv(A) B) (h_pinv [n_bins][n_mels]) and refined by n_iter accelerated projected-gradient
+ * steps of size `step` (1 / sigma_max(A)^2); the result is raised to inv_power = 1 / power.
+ * d_mel [n_clips][n_mels][n_frames] -> d_out [n_clips][n_bins][n_frames]. */
+int b2l_nnls_mel(b2l_ctx* ctx, const float* d_mel, int64_t n_clips, int64_t n_frames, int32_t n_mels, int32_t n_bins,
+                 const float* h_basis, const float* h_pinv, float step, int32_t n_iter, float inv_power, float* d_out);
+
 /* ---- multi-GPU split / join (one process per GPU; NCCL over NVLink) --------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and handed to the other ranks by the launcher. */
 int b2l_comm_unique_id(void* id128);

@@ -178,6 +178,16 @@ def _declare(lib):
         "b2l_spectral_stats_from_spec": (C.c_int, [_vp, P(StatsDesc), _vp, _i64, _i64, C.c_int32, _vp, _vp]),
         "b2l_frame_feature": (C.c_int, [_vp, C.c_int32, _vp, _i64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_float, _vp]),
+        "b2l_stft_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   P(C.c_double), _vp]),
+        "b2l_istft_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32, P(C.c_double),
+                                    P(C.c_double), _i64, _vp, _i64]),
+        "b2l_f64_abs_pow": (C.c_int, [_vp, _vp, _i64, C.c_double, _vp]),
+        "b2l_f64_mel": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int32, P(C.c_float), C.c_int32, _vp]),
+        "b2l_f64_db": (C.c_int, [_vp, _vp, _i64, _i64, C.c_double, C.c_double, C.c_double, _vp]),
+        "b2l_f64_dct": (C.c_int, [_vp, _vp, _i64, C.c_int32, _i64, P(C.c_double), C.c_int32, _vp]),
+        "b2l_nnls_mel": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int32, C.c_int32, P(C.c_float), P(C.c_float), C.c_float,
+                                   C.c_int32, C.c_float, _vp]),
         "b2l_comm_unique_id": (C.c_int, [_vp]),
         "b2l_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
         "b2l_comm_destroy": (C.c_int, [_vp]),

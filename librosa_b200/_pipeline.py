@@ -20,10 +20,20 @@ _UNSUPPORTED_PAD = ("wrap", "maximum", "mean", "median", "minimum")   # librosa/
 
 
 def float64_policy() -> str:
-    """``B2L_FLOAT64``: the kernels compute in float32.  "downcast" (default) accepts float64 / complex128
-    data, computes in float32, returns arrays of the dtype librosa would return and warns once;
-    "error" refuses such requests (``UnsupportedOnGPU``); "quiet" is "downcast" without the warning."""
-    return os.environ.get("B2L_FLOAT64", "downcast").lower()
+    """``B2L_FLOAT64``: what happens to float64 / complex128 data.
+
+    * "native" (default) — the hot-path functions (stft, istft, _spectrogram, melspectrogram, mfcc,
+      power_to_db) compute in FP64 on the GPU like the reference does (``_f64.py``); the wider functions,
+      which have float32 kernels only, fall back to "downcast" for such inputs;
+    * "downcast" — compute in float32, return arrays of the dtype librosa would return, warn once;
+    * "quiet" — "downcast" without the warning;
+    * "error" — refuse (``UnsupportedOnGPU``)."""
+    return os.environ.get("B2L_FLOAT64", "native").lower()
+
+
+def native_float64(dtype) -> bool:
+    """True when data of this dtype should take the FP64 kernels."""
+    return np.dtype(dtype) in (np.dtype(np.float64), np.dtype(np.complex128)) and float64_policy() == "native"
 
 
 _warned_float64 = False
@@ -31,18 +41,22 @@ _warned_float64 = False
 
 def _note_float64(what: str):
     global _warned_float64
-    if float64_policy() == "downcast" and not _warned_float64:
+    if float64_policy() in ("downcast", "native") and not _warned_float64:
         _warned_float64 = True
-        warnings.warn(f"{what}: float64 data is computed in float32 on the GPU (results agree with librosa to "
-                      "about 1e-6 relative, not to float64 precision); set B2L_FLOAT64=error to refuse instead, "
-                      "or B2L_FLOAT64=quiet to silence this warning", stacklevel=4)
+        warnings.warn(f"{what}: float64 data is computed in float32 by this function on the GPU (results agree with "
+                      "librosa to about 1e-6 relative, not to float64 precision; stft / istft / melspectrogram / mfcc "
+                      "/ power_to_db have FP64 kernels); set B2L_FLOAT64=error to refuse instead, or B2L_FLOAT64=quiet "
+                      "to silence this warning", stacklevel=4)
 
 
-def check_real_dtype(dtype, what: str) -> np.dtype:
+def check_real_dtype(dtype, what: str, native_ok: bool = False) -> np.dtype:
+    """``native_ok``: the caller has an FP64 path for float64 data (no downcast, no warning)."""
     dtype = np.dtype(dtype)
     if dtype == np.float32:
         return dtype
     if np.issubdtype(dtype, np.floating):
+        if native_ok and dtype == np.float64 and float64_policy() == "native":
+            return dtype
         if float64_policy() == "error":
             raise nat.UnsupportedOnGPU(
                 f"{what}: dtype {dtype} is not supported by the float32 sm_100a kernels and B2L_FLOAT64=error "
@@ -53,7 +67,7 @@ def check_real_dtype(dtype, what: str) -> np.dtype:
 
 
 def wide_complex_ok(what: str) -> bool:
-    """complex128 requests (stft dtype=, istft input) under the float64 policy."""
+    """complex128 requests served by the float32 kernels (stft dtype= on float32 data) under the float64 policy."""
     if float64_policy() == "error":
         return False
     _note_float64(what)
@@ -126,11 +140,13 @@ def check_stft_geometry(n: int, n_fft: int, center: bool, pad_mode):
     return pad_mode if (center and isinstance(pad_mode, str)) else "constant"
 
 
-def precheck_signal(y):
+def precheck_signal(y, native_ok: bool = False):
     """Host-side validation of an input signal, done before any GPU resource is touched so that
     argument errors surface exactly as in the reference (util.valid_audio, core/spectrum.py:240).
-    Returns ``(length, requested dtype)``."""
+    Returns ``(length, requested dtype)``.  ``native_ok``: the caller has an FP64 path."""
     if isinstance(y, nat.DeviceArray):
+        if native_ok and y.dtype == np.float64 and y.layout == "c" and y.ndim > 0:
+            return y.shape[-1], np.dtype(np.float64)
         if y.dtype != np.float32 or y.layout != "c":
             raise ParameterError("device input must be a C-ordered float32 DeviceArray")
         if y.ndim == 0:
@@ -144,7 +160,7 @@ def precheck_signal(y):
         raise ParameterError("Audio data must be floating-point")
     if y.ndim == 0:
         raise ParameterError(f"Audio data must be at least one-dimensional, given y.shape={y.shape}")
-    return y.shape[-1], check_real_dtype(y.dtype, "input signal")
+    return y.shape[-1], check_real_dtype(y.dtype, "input signal", native_ok)
 
 
 MIN_N_FFT, MAX_N_FFT = 8, 8192   # powers of two: kMinLog2M / kMaxLog2M in csrc/internal.h
@@ -169,6 +185,26 @@ def require_supported_n_fft(n_fft: int, inverse: bool = False):
     if not (3 <= n_fft <= MAX_CZT_N_FFT):
         raise nat.UnsupportedOnGPU(f"n_fft={n_fft}: non-power-of-two sizes are supported from 3 to {MAX_CZT_N_FFT} "
                                    "(no CPU fallback)")
+
+
+def f32_kernels_cover(n_fft: int) -> bool:
+    """True when the float32 hot-path kernels are built for this frame length."""
+    n_fft = int(n_fft)
+    if is_pow2(n_fft):
+        return MIN_N_FFT <= n_fft <= MAX_N_FFT
+    return 3 <= n_fft <= MAX_CZT_N_FFT
+
+
+def wide_route(y, req_dtype, n_fft: int) -> bool:
+    """Should this call take the FP64 kernels?  Yes for float64 data under the "native" policy, and for float32
+    HOST data whose n_fft the float32 kernels are not built for (2^14 ... 2^20, non-powers of two above 2047):
+    librosa accepts any frame length (its tests go to 2^16, tests/test_core.py:308-314), so those sizes run on
+    the FP64 kernels and the result is rounded to the dtype librosa would return."""
+    from . import _f64
+
+    if np.dtype(req_dtype) == np.float64 and native_float64(req_dtype):
+        return True
+    return (not isinstance(y, nat.DeviceArray)) and not f32_kernels_cover(n_fft) and _f64.supported(n_fft)
 
 
 def context_for(x):

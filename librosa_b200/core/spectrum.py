@@ -13,6 +13,7 @@ from typing import Optional
 
 import numpy as np
 
+from .. import _f64 as f64
 from .. import _native as nat
 from .. import _pipeline as pl
 from .. import filters
@@ -31,12 +32,15 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
     """
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
     # host-side validation in the reference's order (valid_audio, window, padding), before any GPU work
-    n, req_dtype = pl.precheck_signal(y)
+    n, req_dtype = pl.precheck_signal(y, native_ok=True)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     if dtype is None:
         dtype = dtype_r2c(req_dtype)
     dtype = np.dtype(dtype)
+    if pl.wide_route(y, req_dtype, n_fft):
+        y64 = y if req_dtype == np.float64 else np.asarray(y, dtype=np.float64)
+        return _stft_f64(y64, n, n_fft, hop_length, center, mode, win, dtype, out)
     if dtype != np.complex64 and not (dtype.kind == "c" and pl.wide_complex_ok("stft dtype")):
         raise nat.UnsupportedOnGPU(f"stft dtype={dtype}: only complex64 is computed on the GPU "
                                    "(B2L_FLOAT64=error forbids returning float32 results in a wider dtype)")
@@ -84,6 +88,47 @@ def stft(y, *, n_fft: int = 2048, hop_length: Optional[int] = None, win_length: 
     return target
 
 
+def _check_out(out, shape):
+    if isinstance(out, nat.DeviceArray):
+        raise ParameterError("out= must be a NumPy array")
+    if not (tuple(out.shape[:-1]) == tuple(shape[:-1]) and out.shape[-1] >= shape[-1]):
+        raise ParameterError(f"Shape mismatch for provided output array out.shape={out.shape} and "
+                             f"target shape={list(shape)}")
+    if not np.iscomplexobj(out):
+        raise ParameterError(f"output with dtype={out.dtype} is not of complex type")
+
+
+def _stft_f64(y, n, n_fft, hop_length, center, mode, win, dtype, out):
+    """float64 signal -> complex128 STFT in FP64 on the device (what the reference computes: dtype_r2c,
+    core/spectrum.py:341; window product and rfft in double, :388)."""
+    if dtype.kind != "c":
+        raise ParameterError(f"stft dtype={dtype} is not complex")
+    F = 1 + n_fft // 2
+    T = 1 + (n + (2 * (n_fft // 2) if center else 0) - n_fft) // hop_length
+    shape = tuple(y.shape[:-1]) + (F, T)
+    if out is not None:
+        _check_out(out, shape)
+    f64.require_supported(n_fft)
+    on_device = isinstance(y, nat.DeviceArray)
+    ctx = y.ctx if on_device else nat.default_context()
+    if not on_device:
+        nat.check(nat.lib().b2l_status_reset(ctx.handle))
+    yd = y if on_device else f64.to_device(ctx, y)
+    D = f64.stft(ctx, yd, n_fft=n_fft, hop_length=hop_length, center=center, mode=mode, win=win)
+    if not on_device:
+        yd.free()
+    if on_device and out is None:
+        return D
+    res = f64.fetch(ctx, D, validate=not on_device)
+    if res.dtype != dtype:
+        res = res.astype(dtype)
+    if out is None:
+        return res
+    target = out if out.shape[-1] == shape[-1] else out[..., : shape[-1]]
+    target[...] = res
+    return target
+
+
 def _inv_wss(ctx, window, n_frames, win_length, n_fft, hop_length, start, out_len, wkey):
     """Reciprocal window-sum-square, trimmed as istft does (core/spectrum.py:606-624), cached on device."""
     key = ("wss", wkey, n_frames, n_fft, hop_length, start, out_len)
@@ -103,6 +148,59 @@ def _inv_wss(ctx, window, n_frames, win_length, n_fft, hop_length, start, out_le
         ctx.synchronize()
         ctx._wss[key] = ptr
     return ptr
+
+
+def _istft_f64(stft_matrix, on_device, n_frames, T_stored, F, n_fft, hop_length, win_length, window, win, center,
+               dtype, length, out):
+    """complex128 STFT -> float64 signal in FP64 on the device (core/spectrum.py:506-626 in double)."""
+    if dtype is None:
+        dtype = np.float64
+    dtype = np.dtype(dtype)
+    if not np.issubdtype(dtype, np.floating):
+        raise ParameterError(f"istft dtype={dtype} must be a floating-point type")
+    full_len = n_fft + hop_length * (n_frames - 1)
+    if length:
+        out_len = int(length)
+    elif center:
+        out_len = full_len - 2 * (n_fft // 2)
+    else:
+        out_len = full_len
+    lead = tuple(stft_matrix.shape[:-2])
+    shape = lead + (out_len,)
+    if out is not None:
+        if isinstance(out, nat.DeviceArray):
+            raise ParameterError("out= must be a NumPy array")
+        if tuple(out.shape) != shape:
+            raise ParameterError(f"Shape mismatch for provided output array out.shape={out.shape} != {list(shape)}")
+    f64.require_supported(n_fft)
+    ctx = stft_matrix.ctx if on_device else nat.default_context()
+    if on_device:
+        if stft_matrix.layout != "ft":
+            raise ParameterError("device complex128 stft_matrix must be in the native [frame][bin] layout")
+        Dd, own = stft_matrix, False
+    else:
+        mem = np.ascontiguousarray(np.swapaxes(stft_matrix, -1, -2))      # [..., frame, bin]
+        Dd = nat.DeviceArray(ctx, ctx.alloc(max(mem.nbytes, 16)), stft_matrix.shape, np.complex128, layout="ft")
+        if mem.nbytes:
+            nat.check(nat.lib().b2l_h2d(ctx.handle, _vp(Dd.ptr), mem.ctypes.data_as(_vp), mem.nbytes))
+            ctx.synchronize()
+        own = True
+    start = n_fft // 2 if center else 0
+    inv = f64.inv_wss(window, n_frames, win_length, n_fft, hop_length, start, out_len)
+    y = f64.istft(ctx, Dd, n_frames_used=n_frames, n_fft=n_fft, hop_length=hop_length, center=center, win=win,
+                  inv=inv, out_len=out_len)
+    if own:
+        ctx.synchronize()
+        Dd.free()
+    if on_device and out is None:
+        return y
+    res = f64.fetch(ctx, y)
+    if res.dtype != dtype:
+        res = res.astype(dtype)
+    if out is None:
+        return res
+    out[...] = res
+    return out
 
 
 def istft(stft_matrix, *, hop_length: Optional[int] = None, win_length: Optional[int] = None,
@@ -130,6 +228,11 @@ def istft(stft_matrix, *, hop_length: Optional[int] = None, win_length: Optional
     else:
         n_frames = T_stored
     in_dtype = np.dtype(stft_matrix.dtype)
+    if (in_dtype == np.complex128 and pl.native_float64(in_dtype)) or \
+            (in_dtype == np.complex64 and not on_device and not pl.f32_kernels_cover(n_fft) and f64.supported(n_fft)):
+        wide = stft_matrix if in_dtype == np.complex128 else stft_matrix.astype(np.complex128)
+        return _istft_f64(wide, on_device, n_frames, T_stored, F, n_fft, hop_length, win_length, window, win,
+                          center, dtype if dtype is not None else dtype_c2r(in_dtype), length, out)
     if in_dtype != np.complex64:
         if in_dtype.kind == "c" and pl.wide_complex_ok("istft input"):
             pass
@@ -219,9 +322,24 @@ def _spectrogram(*, y=None, S=None, n_fft: Optional[int] = 2048, hop_length: Opt
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    n, req_dtype = pl.precheck_signal(y)
+    n, req_dtype = pl.precheck_signal(y, native_ok=True)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
+    if pl.wide_route(y, req_dtype, n_fft):
+        f64.require_supported(n_fft)
+        on_device = isinstance(y, nat.DeviceArray)
+        ctx = y.ctx if on_device else nat.default_context()
+        if not on_device:
+            nat.check(nat.lib().b2l_status_reset(ctx.handle))
+        yd = y if on_device else f64.to_device(ctx, y)
+        D = f64.stft(ctx, yd, n_fft=n_fft, hop_length=hop_length, center=center, mode=mode, win=win)
+        Sd = f64.abs_pow(ctx, D, power)
+        D.free()
+        if not on_device:
+            yd.free()
+            res = f64.fetch(ctx, Sd, validate=True)
+            return (res if res.dtype == req_dtype else res.astype(req_dtype)), n_fft
+        return Sd, n_fft
     pl.require_supported_n_fft(n_fft)
     key = ("spec", n_fft, hop_length, bool(center), mode, wkey, float(power))
     F = 1 + n_fft // 2
@@ -277,11 +395,29 @@ def _to_db(S, ref, amin, top_db, axes, amplitude: bool):
         warnings.warn(f"{name} was called on complex input so phase information will be discarded. "
                       f"To suppress this warning, call {hint} instead.", stacklevel=3)
         S = np.abs(S)
-    if axes != "auto":
-        raise nat.UnsupportedOnGPU(f"{name}: only axes='auto' is computed on the GPU")
     if top_db is not None and top_db < 0:
         raise ParameterError("top_db must be non-negative")
+    if not (isinstance(axes, str) and axes == "auto"):
+        # explicit reduction axes for the top_db maximum / callable ref (core/spectrum.py:1855-1881): bring the
+        # reduced axes to the end, run the "auto" kernel on (kept, 1, reduced), undo the permutation
+        if on_device:
+            raise nat.UnsupportedOnGPU(f"{name}: explicit axes need a host array")
+        if S.ndim == 0:
+            return _to_db(S, ref, amin, top_db, "auto", amplitude)
+        ax = tuple(range(S.ndim)) if axes is None else tuple(np.atleast_1d(axes).astype(int).tolist())
+        ax = tuple(sorted({a % S.ndim if -S.ndim <= a < S.ndim else a for a in ax}))
+        if any(not (0 <= a < S.ndim) for a in ax):
+            raise np.exceptions.AxisError(f"axis {axes} is out of bounds for array of dimension {S.ndim}")
+        kept = [i for i in range(S.ndim) if i not in ax]
+        perm = kept + list(ax)
+        Sp = np.transpose(S, perm)
+        n_keep = int(np.prod([S.shape[i] for i in kept], dtype=np.int64)) if kept else 1
+        flat = np.ascontiguousarray(Sp).reshape(n_keep, 1, -1)
+        res = _to_db(flat, ref, amin, top_db, "auto", amplitude)
+        return np.transpose(np.asarray(res).reshape(Sp.shape), np.argsort(perm))[()]
     ctx = S.ctx if on_device else nat.default_context()
+    if not on_device and S.dtype == np.float64 and pl.native_float64(S.dtype) and S.ndim >= 1:
+        return _to_db_f64(ctx, S, ref, amin, top_db, amplitude)
     if on_device:
         if S.dtype != np.float32:
             raise ParameterError("device input must be float32")
@@ -332,6 +468,39 @@ def _to_db(S, ref, amin, top_db, axes, amplitude: bool):
         return out
     res = pl.finish(ctx, out, True, req)
     return res[()]
+
+
+def _to_db_f64(ctx, S, ref, amin, top_db, amplitude):
+    """power_to_db / amplitude_to_db of a float64 host array in FP64 (core/spectrum.py:1866-1881, :1990-2038)."""
+    shape = S.shape
+    work = S if S.ndim >= 2 else S.reshape(1, -1)
+    lead = work.shape[:-2]
+    n_lead = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    mag = np.abs(work) if amplitude else work
+    if callable(ref):
+        try:
+            ref_value = np.asarray(ref(mag, axis=(-2, -1), keepdims=True), dtype=np.float64).reshape(-1)
+        except TypeError as exc:
+            raise ParameterError("The provided reference function must support 'axis' and 'keepdims' "
+                                 "arguments for proper multichannel processing.") from exc
+    else:
+        ref_value = np.asarray([np.abs(ref)], dtype=np.float64)
+    if amplitude:                                   # 20 log10(|S| / ref) == 10 log10(|S|^2 / ref^2), amin^2
+        power, amin, ref_value = mag ** 2, float(amin) ** 2, ref_value ** 2
+    else:
+        power = mag
+    dev = ctx.to_device(np.ascontiguousarray(power, dtype=np.float64).reshape((n_lead,) + work.shape[-2:]))
+    if ref_value.size > 1:
+        parts = []
+        for i in range(n_lead):                     # one reference level per leading index
+            one = nat.DeviceArray(ctx, dev.ptr + 8 * i * work.shape[-2] * work.shape[-1], (1,) + work.shape[-2:], np.float64,
+                                  owner=False)
+            parts.append(f64.power_to_db(ctx, one, ref_value=float(ref_value[i]), amin=amin, top_db=top_db))
+        res = np.concatenate([f64.fetch(ctx, p) for p in parts], axis=0)
+    else:
+        res = f64.fetch(ctx, f64.power_to_db(ctx, dev, ref_value=float(ref_value[0]), amin=amin, top_db=top_db))
+    dev.free()
+    return res.reshape(shape)[()]
 
 
 def _db_inverse(S_db, op, param):

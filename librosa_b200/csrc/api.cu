@@ -173,6 +173,23 @@ struct DeviceGuard {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ------------------------------------------------------------------ glue for the other translation units
+cudaStream_t b2l_internal_stream(b2l_ctx* c) { return c->stream; }
+int b2l_internal_device(b2l_ctx* c) { return c->device; }
+int* b2l_internal_status(b2l_ctx* c) { return c->d_status; }
+size_t b2l_internal_smem_optin(b2l_ctx* c) { return c->smem_optin; }
+int b2l_internal_sm_count(b2l_ctx* c) { return c->sm_count; }
+void b2l_internal_count_launches(b2l_ctx* c, int n) { c->launches += n; }
+int b2l_internal_fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
 // ------------------------------------------------------------------ library / device
 extern "C" int b2l_version(void) { return B2L_VERSION; }
 extern "C" const char* b2l_last_error(void) { return g_last_error.c_str(); }
@@ -1131,6 +1148,22 @@ extern "C" int b2l_frame_feature(b2l_ctx* c, int32_t what, const float* d_y, int
   if (!d_y || !d_out) return fail(B2L_ERR_INVALID, "NULL device pointer");
   if (T > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "too many frames");
   DeviceGuard g(c->device);
+  // frame_length a multiple of hop_length: block form, every sample read once (feat_kernels.cuh)
+  {
+    const char* env = getenv("B2L_TD_BLOCK");
+    const long long tiles = (T + TD_FRAMES - 1) / TD_FRAMES;
+    if (!(env && *env && atoi(env) == 0) && frame_length % hop_length == 0 && frame_length / hop_length <= 64 &&
+        n_clips <= 65535 && tiles <= 0x7fffffffLL) {
+      const int R = frame_length / hop_length;
+      const size_t smem = (size_t)(TD_FRAMES + R - 1) * 8;
+      frame_td_block_kernel<<<dim3((unsigned)tiles, (unsigned)n_clips), 256, smem, c->stream>>>(
+          d_y, y_stride, (int)n, frame_length, hop_length, pad, pad_mode, (int)T, what, threshold, zero_pos, pad_first,
+          out_scale, d_out, c->d_status);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+      return B2L_OK;
+    }
+  }
   const long long rows = (long long)n_clips * T;
   long long grid = (rows + 7) / 8;
   const long long cap = (long long)c->sm_count * 8;

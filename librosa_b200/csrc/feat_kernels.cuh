@@ -83,6 +83,90 @@ __global__ void frame_td_kernel(const float* __restrict__ y, long long clip_stri
   }
 }
 
+// The same two features when frame_length is a multiple of hop_length (the usual 2048 / 512): every sample is
+// read ONCE.  The padded signal is cut into blocks of hop samples; a CTA takes FRAMES consecutive frames of one
+// clip, reduces the FRAMES + R - 1 blocks they cover (R = frame_length / hop) — one warp per block, 16-byte
+// coalesced loads for blocks inside the clip, the np.pad index map for the few that touch the padding — and
+// then every frame is the sum of R block values:
+//   rms:  block value = sum of squares;
+//   zero crossings:  block value = number of positions p in the block whose sample differs in sign class from
+//         the sample at p - 1 (which may lie in the previous block); a frame counts the crossings at its
+//         positions 1 .. L-1, i.e. the block sum minus the crossing AT its first position, plus `pad_first`.
+// frame_td_kernel (one warp per frame) re-reads every sample frame_length / hop times through a 64-bit modulo
+// index map: 1.96 ms / 3.5 ms for the 903 MB of cfg-2 shapes against a 0.14 ms traffic floor.
+constexpr int TD_FRAMES = 64;
+__global__ void __launch_bounds__(256) frame_td_block_kernel(const float* __restrict__ y, long long clip_stride, int n, int L,
+                                                             int hop, int pad, int pad_mode, int n_frames, int what,
+                                                             float threshold, int zero_pos, int pad_first, float out_scale,
+                                                             float* __restrict__ out, int* status) {
+  extern __shared__ __align__(16) unsigned char s_td[];
+  const int R = L / hop;
+  const int nblk = TD_FRAMES + R - 1;
+  float* s_val = reinterpret_cast<float*>(s_td);             // per block: sum of squares / crossing count
+  int* s_first = reinterpret_cast<int*>(s_val + nblk);       // per block: crossing at its first position
+  const int clip = blockIdx.y, t0 = blockIdx.x * TD_FRAMES;
+  const float* yc = y + (long long)clip * clip_stride;
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(yc) & 15) == 0) && (hop % 4 == 0) && (pad % 4 == 0);
+  bool bad = false;
+  auto cls = [&](float x) -> int {
+    if (!(fabsf(x) <= 3.0e38f)) bad = true;
+    if (fabsf(x) <= threshold) x = 0.0f;
+    return zero_pos ? (int)(x < 0.0f) : (x > 0.0f) - (x < 0.0f);
+  };
+  for (int b = warp; b < nblk; b += nw) {
+    const long long p0 = (long long)(t0 + b) * hop - pad;      // first position of the block
+    const bool inside = p0 >= 1 && p0 + hop <= n;              // the sample before the block is in range too
+    float acc = 0.0f;
+    int cnt = 0, first = 0;
+    if (what == 0) {
+      if (inside && vec_ok) {
+        const float4* src = reinterpret_cast<const float4*>(yc + p0);
+        for (int i = lane; i < hop / 4; i += 32) {
+          const float4 v = __ldg(src + i);
+          acc = fmaf(v.x, v.x, acc);
+          acc = fmaf(v.y, v.y, acc);
+          acc = fmaf(v.z, v.z, acc);
+          acc = fmaf(v.w, v.w, acc);
+        }
+      } else {
+        for (int i = lane; i < hop; i += 32) {
+          const float x = load_padded(yc, n, p0 + i, pad_mode, pad);
+          acc = fmaf(x, x, acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) s_val[b] = acc;
+    } else {
+      for (int base = 0; base < hop; base += 32) {
+        const int i = base + lane;
+        const int c = i < hop ? cls(inside ? __ldg(yc + p0 + i) : load_padded(yc, n, p0 + i, pad_mode, pad)) : 0;
+        int prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0 && i < hop) prev = cls(inside ? __ldg(yc + p0 + i - 1) : load_padded(yc, n, p0 + i - 1, pad_mode, pad));
+        const bool cross = i < hop && c != prev;
+        const unsigned m = __ballot_sync(0xffffffffu, cross);
+        cnt += __popc(m);
+        if (base == 0) first = (int)(m & 1u);
+      }
+      if (lane == 0) {
+        s_val[b] = (float)cnt;
+        s_first[b] = first;
+      }
+    }
+  }
+  if (what != 0 && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, 1);
+  __syncthreads();
+  for (int f = threadIdx.x; f < TD_FRAMES; f += blockDim.x) {
+    const int t = t0 + f;
+    if (t >= n_frames) break;
+    float acc = 0.0f;
+    for (int r = 0; r < R; ++r) acc += s_val[f + r];
+    float* o = out + (long long)clip * n_frames + t;
+    if (what == 0) *o = sqrtf(acc / (float)L);
+    else *o = (acc - (float)s_first[f] + (float)(pad_first != 0)) * out_scale;
+  }
+}
+
 // Spectral-flux onset strength (librosa/onset.py:445-640, onset_strength_multi) from a dB-scaled spectrogram
 // S [clip][rows][T]:  env[c][t'] = mean_{m in channel c} max(0, S[m][t' + lag] - ref[m][t']),  ref = S after a
 // maximum filter of `max_size` rows (scipy.ndimage.maximum_filter1d, reflect boundary), then shifted right by

@@ -60,3 +60,13 @@ struct HostFftCfg {
 };
 
 }  // namespace b2l
+
+// ---- glue for translation units other than api.cu (f64_api.cu): the context stays opaque to them
+struct b2l_ctx;
+cudaStream_t b2l_internal_stream(b2l_ctx* c);
+int b2l_internal_device(b2l_ctx* c);
+int* b2l_internal_status(b2l_ctx* c);
+size_t b2l_internal_smem_optin(b2l_ctx* c);
+int b2l_internal_sm_count(b2l_ctx* c);
+void b2l_internal_count_launches(b2l_ctx* c, int n);
+int b2l_internal_fail(int code, const char* fmt, ...);

@@ -13,6 +13,7 @@ from typing import Optional
 import numpy as np
 import scipy.fft
 
+from .. import _f64 as f64
 from .. import _native as nat
 from .. import _pipeline as pl
 from ..core.spectrum import power_to_db
@@ -69,10 +70,17 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    n, req_dtype = pl.precheck_signal(y)
+    n, req_dtype = pl.precheck_signal(y, native_ok=True)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     basis, bkey = pl.mel_basis(sr, n_fft, kwargs)
+    if pl.wide_route(y, req_dtype, n_fft):
+        ctx, mel_d, on_device = _mel_f64(y, n_fft, hop_length, center, mode, win, power, basis)
+        if on_device:
+            return mel_d
+        res = f64.fetch(ctx, mel_d, validate=True)
+        res_dtype = np.result_type(req_dtype, basis.dtype)
+        return res if res.dtype == res_dtype else res.astype(res_dtype)
     pl.require_supported_n_fft(n_fft)
     if not pl.is_pow2(n_fft):
         # chirp-z frames: |STFT|**power on the device, then the band-sparse projection (two kernels)
@@ -104,6 +112,25 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
     res = pl.run_host_forward(y, n_fft=n_fft, hop_length=hop_length, center=center, n_frames=T,
                               out_mem_tail=(n_mels, T), out_dtype=np.float32, make_plan=make_plan, launch=launch)
     return res if res.dtype == res_dtype else res.astype(res_dtype)
+
+
+def _mel_f64(y, n_fft, hop_length, center, mode, win, power, basis):
+    """float64 signal -> float64 mel spectrogram on the device in FP64: stft, |.|**power, band projection
+    (feature/spectral.py:2145-2160 in the input's precision).  Returns (ctx, DeviceArray, input was on device)."""
+    f64.require_supported(n_fft)
+    on_device = isinstance(y, nat.DeviceArray)
+    ctx = y.ctx if on_device else nat.default_context()
+    if not on_device:
+        nat.check(nat.lib().b2l_status_reset(ctx.handle))
+    yd = y if on_device else f64.to_device(ctx, y)
+    D = f64.stft(ctx, yd, n_fft=n_fft, hop_length=hop_length, center=center, mode=mode, win=win)
+    Sd = f64.abs_pow(ctx, D, power)
+    D.free()
+    mel_d = f64.mel(ctx, Sd, basis)
+    Sd.free()
+    if not on_device:
+        yd.free()
+    return ctx, mel_d, on_device
 
 
 def _compose_nonpow2(y, tail, res_dtype, **spec_kw):
@@ -213,7 +240,7 @@ def chroma_stft(*, y=None, sr: float = 22050, S=None, norm=np.inf, n_fft: int = 
     return pl.finish(ctx, out, True, np.result_type(req, fb.dtype), validate=validate)
 
 
-def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float) -> np.ndarray:
+def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float, dtype=np.float32) -> np.ndarray:
     """Rows 0..n_mfcc-1 of the DCT applied along the mel axis, as an explicit matrix, with the
     sinusoidal lifter ``1 + (lifter/2) sin(pi (k+1) / lifter)`` folded in
     (feature/spectral.py:2005-2015).  Built in float64 from scipy.fft.dct itself, so every
@@ -222,7 +249,7 @@ def _dct_basis(n_mels: int, n_mfcc: int, dct_type: int, norm, lifter: float) -> 
     if lifter > 0:
         lift = 1 + (lifter / 2) * np.sin(np.pi * np.arange(1, 1 + basis.shape[0], dtype=np.float64) / lifter)
         basis = basis * lift[:, np.newaxis]
-    return np.ascontiguousarray(basis, dtype=np.float32)
+    return np.ascontiguousarray(basis, dtype=dtype)
 
 
 def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int = 2, norm="ortho",
@@ -259,13 +286,26 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
     if y is None:
         raise ParameterError("Input signal must be provided to compute a spectrogram")
     hop_length, win_length = pl.frame_params(n_fft, hop_length, win_length)
-    n, req_dtype = pl.precheck_signal(y)
+    n, req_dtype = pl.precheck_signal(y, native_ok=True)
     win, wkey = pl.resolve_window(window, win_length, n_fft)
     mode = pl.check_stft_geometry(n, n_fft, center, pad_mode)
     mel_kwargs = dict(kwargs)
     mel_kwargs["norm"] = mel_norm
     basis, bkey = pl.mel_basis(sr, n_fft, mel_kwargs)
     n_mels = basis.shape[0]
+    if pl.wide_route(y, req_dtype, n_fft):
+        # float64 signal (or a frame length only the FP64 kernels cover): mel -> power_to_db (ref 1.0, amin 1e-10,
+        # top_db 80) -> DCT, all in FP64
+        ctx, mel_d, on_device = _mel_f64(y, n_fft, hop_length, center, mode, win, power, basis)
+        db_d = f64.power_to_db(ctx, mel_d, ref_value=1.0, amin=1e-10, top_db=80.0)
+        mel_d.free()
+        out = f64.dct(ctx, db_d, _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter, dtype=np.float64))
+        db_d.free()
+        if on_device:
+            return out
+        res = f64.fetch(ctx, out, validate=True)
+        res_dtype = np.result_type(req_dtype, basis.dtype)
+        return res if res.dtype == res_dtype else res.astype(res_dtype)
     dct = _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter)
     pl.require_supported_n_fft(n_fft)
     if not pl.is_pow2(n_fft):

@@ -346,14 +346,15 @@ def spectrogram(y, n_fft=2048, hop_length=512, power=1.0, win_length=None, windo
                        window=window, center=center, pad_mode=pad_mode)) ** power
 
 
-def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0):
-    """librosa/core/spectrum.py:1839-1883 for real input, scalar or callable ``ref``,
-    ``axes='auto'`` (reduce over the last two axes, per leading index)."""
+def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0, axes="auto"):
+    """librosa/core/spectrum.py:1839-1883 for real input, scalar or callable ``ref``;
+    ``axes='auto'`` reduces over the last two axes, per leading index (:1855-1861)."""
     S = np.asarray(S)
     if amin <= 0:
         raise ParameterError("amin must be strictly positive")
     mag = np.abs(S) if np.iscomplexobj(S) else S
-    axes = (-2, -1) if mag.ndim >= 2 else ((-1,) if mag.ndim == 1 else None)
+    if isinstance(axes, str) and axes == "auto":
+        axes = (-2, -1) if mag.ndim >= 2 else ((-1,) if mag.ndim == 1 else None)
     ref_value = ref(mag, axis=axes, keepdims=True) if callable(ref) else np.abs(ref)
     out = 10.0 * np.log10(np.maximum(amin, mag))
     out -= 10.0 * np.log10(np.maximum(amin, ref_value))
@@ -1087,3 +1088,74 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, n_fft=None, windo
         angles *= S
         tprev = rebuilt
     return istft(angles, **kw_i)
+
+
+# ------------------------------------------------------------------ feature.inverse
+MAX_MEM_BLOCK = 2 ** 8 * 2 ** 10   # librosa/util/utils.py:41
+
+
+def _nnls_obj(x, shape, A, B):
+    """librosa/util/_nnls.py:22-41: objective and gradient of the block problem."""
+    x = x.reshape(shape)
+    diff = np.einsum("mf,...ft->...mt", A, x, optimize=True) - B
+    value = (1 / B.size) * 0.5 * np.sum(diff ** 2)
+    grad = (1 / B.size) * np.einsum("mf,...mt->...ft", A, diff, optimize=True)
+    return value, grad.flatten()
+
+
+def _nnls_lbfgs_block(A, B, x_init=None, **kwargs):
+    """librosa/util/_nnls.py:44-89: L-BFGS-B from the clipped pseudo-inverse solution."""
+    import scipy.optimize
+
+    if x_init is None:
+        x_init = np.einsum("fm,...mt->...ft", np.linalg.pinv(A), B, optimize=True)
+        np.clip(x_init, 0, None, out=x_init)
+    kwargs.setdefault("m", A.shape[1])
+    bounds = [(0, None)] * x_init.size
+    shape = x_init.shape
+    x, _obj, _diag = scipy.optimize.fmin_l_bfgs_b(_nnls_obj, x_init, args=(shape, A, B), bounds=bounds, **kwargs)
+    return x.reshape(shape)
+
+
+def nnls(A, B, **kwargs):
+    """librosa/util/_nnls.py:92-175."""
+    import scipy.optimize
+
+    if B.ndim == 1:
+        return scipy.optimize.nnls(A, B)[0]
+    n_columns = int(MAX_MEM_BLOCK // (np.prod(B.shape[:-1]) * A.itemsize))
+    n_columns = max(n_columns, 1)
+    if B.shape[-1] <= n_columns:
+        return _nnls_lbfgs_block(A, B, **kwargs).astype(A.dtype)
+    x = np.einsum("fm,...mt->...ft", np.linalg.pinv(A), B, optimize=True)
+    np.clip(x, 0, None, out=x)
+    x_init = x
+    for bl_s in range(0, x.shape[-1], n_columns):
+        bl_t = min(bl_s + n_columns, B.shape[-1])
+        x[..., bl_s:bl_t] = _nnls_lbfgs_block(A, B[..., bl_s:bl_t], x_init=x_init[..., bl_s:bl_t], **kwargs)
+    return x
+
+
+def mel_to_stft(M, sr=22050, n_fft=2048, power=2.0, **kwargs):
+    """librosa/feature/inverse.py:104-114."""
+    mel_basis = mel(sr=sr, n_fft=n_fft, n_mels=M.shape[-2], dtype=M.dtype, **kwargs)
+    inverse = nnls(mel_basis, M)
+    np.power(inverse, 1.0 / power, out=inverse)
+    return inverse
+
+
+def mfcc_to_mel(mfcc, n_mels=128, dct_type=2, norm="ortho", ref=1.0, lifter=0):
+    """librosa/feature/inverse.py:265-287."""
+    if lifter > 0:
+        n_mfcc = mfcc.shape[-2]
+        idx = np.arange(1, 1 + n_mfcc, dtype=mfcc.dtype)
+        idx = idx.reshape([-1 if i == mfcc.ndim - 2 else 1 for i in range(mfcc.ndim)])
+        lifter_sine = 1 + lifter * 0.5 * np.sin(np.pi * idx / lifter)
+        if np.any(np.abs(lifter_sine) < np.finfo(lifter_sine.dtype).eps):
+            warnings.warn(message="lifter array includes critical values that may invoke underflow.",
+                          category=UserWarning, stacklevel=2)
+        mfcc = mfcc / (lifter_sine + tiny(mfcc))
+    elif lifter != 0:
+        raise ParameterError("MFCC to mel lifter must be a non-negative number.")
+    logmel = scipy.fft.idct(mfcc, axis=-2, type=dct_type, norm=norm, n=n_mels)
+    return db_to_power(logmel, ref=ref)

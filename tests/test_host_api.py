@@ -163,9 +163,8 @@ def strict_float64(monkeypatch):
 
 
 @pytest.mark.parametrize("call", [
-    lambda: lb.stft(Y, n_fft=3001),         # non power of two beyond the chirp-z range (<= 2047)
-    lambda: lb.istft(np.zeros((1501, 9), dtype=np.complex64), n_fft=3001),
-    lambda: lb.stft(np.zeros(40000, dtype=np.float32), n_fft=16384),
+    lambda: lb.stft(np.zeros(3_000_000, dtype=np.float32), n_fft=70001),   # beyond the FP64 direct-DFT range too
+    lambda: lb.stft(lb.DeviceArray(None, 0, (40000,), np.float32, owner=False), n_fft=16384),  # device f32, FP64-only size
     lambda: lb.stft(Y.astype(np.float64)),  # float64 needs an explicit opt-in to be computed in float32
     lambda: lb.stft(Y, dtype=np.complex128),
     lambda: lb.stft(Y, pad_mode=lambda *a, **k: None),
@@ -176,16 +175,36 @@ def test_unsupported_is_loud(call, strict_float64):
         call()
 
 
-def test_float64_policy_warns_by_default(monkeypatch):
+def test_float64_policy_native_by_default(monkeypatch):
+    """float64 audio takes the FP64 kernels by default (no downcast, no warning); a function that has float32
+    kernels only warns once that it computes in float32; B2L_FLOAT64=downcast restores the old behaviour."""
+    import warnings
+
     import librosa_b200._pipeline as pl
 
     monkeypatch.delenv("B2L_FLOAT64", raising=False)
     monkeypatch.setattr(pl, "_warned_float64", False)
+    assert pl.float64_policy() == "native" and pl.native_float64(np.float64) and pl.native_float64(np.complex128)
+    assert not pl.native_float64(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        try:
+            lb.stft(Y.astype(np.float64))          # FP64 path: no warning before the device is touched
+        except lb.NativeLibraryError:
+            pass
+    with pytest.warns(UserWarning, match="computed in float32"):
+        try:
+            lb.feature.spectral_centroid(y=Y.astype(np.float64))   # float32 kernels only
+        except lb.NativeLibraryError:
+            pass
+    monkeypatch.setenv("B2L_FLOAT64", "downcast")
+    monkeypatch.setattr(pl, "_warned_float64", False)
+    assert not pl.native_float64(np.float64)
     with pytest.warns(UserWarning, match="computed in float32"):
         try:
             lb.stft(Y.astype(np.float64))
         except lb.NativeLibraryError:
-            pass   # no GPU here: the policy is applied before the device is touched
+            pass
 
 
 def test_warnings_match_reference():

@@ -100,3 +100,39 @@ def test_product_host_constants_match_reference(ref):
     np.testing.assert_array_equal(ref.util.pad_center(np.ones(5), size=12), lb.util.pad_center(np.ones(5), size=12))
     np.testing.assert_array_equal(ref.util.fix_length(np.ones(5), size=3), lb.util.fix_length(np.ones(5), size=3))
     assert ref.util.tiny(np.float32(1)) == lb.util.tiny(np.float32(1))
+
+
+def test_power_to_db_axes_and_float64_bit_exact(ref, oracle):
+    """power_to_db with explicit reduction axes, and the float64 behaviour of the whole path (the reference
+    computes float64 audio in float64: complex128 STFT, float64 mel / MFCC)."""
+    rng = np.random.default_rng(9)
+    P = np.abs(rng.standard_normal((2, 3, 40, 30))) ** 2
+    for kw in (dict(), dict(axes=(-1,)), dict(axes=(-2,)), dict(axes=None, ref=np.max), dict(axes=(0, -1), top_db=30.0),
+               dict(axes=(-1,), ref=np.max)):
+        np.testing.assert_array_equal(ref.power_to_db(P, **kw), oracle.power_to_db(P, **kw))
+    y = 0.1 * rng.standard_normal((2, 9000))
+    for fn_ref, fn_or, kw in ((ref.stft, oracle.stft, dict(n_fft=1024, hop_length=256)),
+                              (ref.stft, oracle.stft, dict(n_fft=1000, hop_length=250, pad_mode="reflect"))):
+        a, b = fn_ref(y, **kw), fn_or(y, **kw)
+        assert a.dtype == b.dtype == np.complex128
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(ref.istft(a, hop_length=kw["hop_length"], n_fft=kw["n_fft"]),
+                                      oracle.istft(a, hop_length=kw["hop_length"], n_fft=kw["n_fft"]))
+    m_ref, m_or = ref.feature.melspectrogram(y=y, sr=16000, n_fft=1024), oracle.melspectrogram(y=y, sr=16000, n_fft=1024)
+    assert m_ref.dtype == m_or.dtype == np.float64
+    np.testing.assert_array_equal(m_ref, m_or)
+    np.testing.assert_array_equal(ref.feature.mfcc(y=y, sr=16000, n_fft=1024), oracle.mfcc(y=y, sr=16000, n_fft=1024))
+
+
+def test_feature_inverse_bit_exact(ref, oracle):
+    """mel_to_stft (NNLS through SciPy's L-BFGS-B) and mfcc_to_mel restated in the oracle."""
+    rng = np.random.default_rng(21)
+    for dtype in (np.float32, np.float64):
+        basis = ref.filters.mel(sr=22050, n_fft=1024, n_mels=64, dtype=dtype)
+        S = np.abs(rng.standard_normal((513, 6))).astype(dtype) ** 2
+        M = basis.dot(S)
+        np.testing.assert_array_equal(ref.feature.inverse.mel_to_stft(M, n_fft=1024, power=2.0),
+                                      oracle.mel_to_stft(M, n_fft=1024, power=2.0))
+    mf = rng.standard_normal((2, 13, 20)).astype(np.float32) * 10
+    for kw in (dict(), dict(lifter=3, dct_type=3), dict(n_mels=64, norm=None), dict(ref=2.5, lifter=22)):
+        np.testing.assert_array_equal(ref.feature.inverse.mfcc_to_mel(mf, **kw), oracle.mfcc_to_mel(mf, **kw))
