@@ -227,6 +227,8 @@ class CpuPort:
         # a container may show every core of the box and still be throttled to a few cores' worth of time
         # (cgroup cpu.max): more workers than that only adds context switches
         self.cores = self.visible if self.quota is None else max(1, min(self.visible, int(round(self.quota))))
+        if os.environ.get("B2L_CPU_WORKERS"):
+            self.cores = max(1, int(os.environ["B2L_CPU_WORKERS"]))
         self.clips = max(min_clips, clips_per_core * self.cores)
         _CPU_BATCH = make_batch(dict(w, clips=self.clips), rank=0)
         self.T = n_frames(w["n"], w["kw"]["n_fft"], w["kw"]["hop_length"])

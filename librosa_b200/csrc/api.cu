@@ -282,12 +282,13 @@ extern "C" int b2l_scan_finite(b2l_ctx* c, const float* d_y, int64_t n_clips, in
                                int64_t begin) {
   if (!c || !d_y) return fail(B2L_ERR_INVALID, "NULL argument");
   if (n_clips <= 0 || begin >= n) return B2L_OK;
-  if (n_clips > 65535 || n > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "scan_finite: batch too large");
+  if (n > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "scan_finite: clips longer than 2^31-1 samples");
   DeviceGuard g(c->device);
   long long bx = ((n - begin) + 1023) / 1024;
   if (bx > 64) bx = 64;
-  dim3 grid((unsigned)bx, (unsigned)n_clips);
-  finite_scan_kernel<<<grid, 256, 0, c->stream>>>(d_y, y_stride, (int)n, (int)(begin < 0 ? 0 : begin), c->d_status);
+  dim3 grid((unsigned)bx, (unsigned)(n_clips > 65535 ? 65535 : n_clips));
+  finite_scan_kernel<<<grid, 256, 0, c->stream>>>(d_y, y_stride, (int)n, (int)(begin < 0 ? 0 : begin), n_clips,
+                                                  c->d_status);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return B2L_OK;
@@ -810,6 +811,9 @@ static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, int hw, const b2l
 
 // Kernel variants tried in order (first that fits shared memory wins): 116 = 16 warps as two independent
 // 8-warp halves, 16 / 8 = plain CTAs.  B2L_FWD_VARIANT forces one (A/B measurements).
+#ifndef B2L_DCT_FPL_DEFAULT
+#define B2L_DCT_FPL_DEFAULT 2
+#endif
 #ifndef B2L_TMEM_DEFAULT
 #define B2L_TMEM_DEFAULT true
 #endif
@@ -1189,18 +1193,33 @@ static int launch_dct(b2l_ctx* c, const b2l_plan* p, const float* d_L, int64_t n
   const int KG = (p->n_mfcc + 7) / 8;
   if (KG > 16) return fail(B2L_ERR_UNSUPPORTED, "n_mfcc=%d > 128 is not supported", p->n_mfcc);
   size_t smem = ((size_t)p->n_mels * 8 * KG + 2 * (size_t)p->n_mels * DCT_TILE) * 4;
-  if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_mels=%d is too large for the DCT kernel", p->n_mels);
-  CUDA_TRY(cudaFuncSetAttribute(dct_clamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > c->smem_optin) {
+    // too many input rows for the shared-memory tile (e.g. mfcc(S=...) of a 1025-bin spectrogram): generic kernel
+    if (tiled) return fail(B2L_ERR_UNSUPPORTED, "n_mels=%d is too large for the fused mfcc path", p->n_mels);
+    if (n_clips > 65535) return fail(B2L_ERR_UNSUPPORTED, "dct: more than 65535 leading indices");
+    dct_generic_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)n_clips), 128, 0, c->stream>>>(
+        d_L, p->d_dct, clamp ? c->d_clip_max : nullptr, clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, 8 * KG, (int)T,
+        d_out);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return B2L_OK;
+  }
+  // frames per lane: 2 halves the shared-memory traffic per FMA (B2L_DCT_FPL=1 selects the two-warp-set form)
+  const char* env = getenv("B2L_DCT_FPL");
+  const int fpl = env && *env ? atoi(env) : B2L_DCT_FPL_DEFAULT;
+  auto kern = fpl == 2 ? dct_clamp_kernel<2> : dct_clamp_kernel<1>;
+  const int threads = fpl == 2 ? KG * 32 : KG * 64;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (int)((T + DCT_TILE - 1) / DCT_TILE);
   const long long total = (long long)tiles * n_clips;
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dct_clamp_kernel, KG * 64, smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) return fail(B2L_ERR_CUDA, "DCT kernel does not fit on an SM");
   long long grid = (long long)c->sm_count * occ;
   if (grid > total) grid = total;
-  dct_clamp_kernel<<<(int)grid, KG * 64, smem, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
-                                                            clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, (int)T,
-                                                            tiles, total, tiled, d_out);
+  kern<<<(int)grid, threads, smem, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
+                                                clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, (int)T, tiles, total,
+                                                tiled, d_out);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return B2L_OK;
@@ -1355,6 +1374,10 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
         long long fps = (total_frames + groups - 1) / groups;
         if (fps < 8) fps = 8;                                          // replayed frames stay a bounded fraction
         a.frames_per_slot = (int)fps;
+        {
+          const char* ea = getenv("B2L_INV2_AHEAD");           // spectrum rows prefetched to L2 ahead of the transform
+          a.acc_floats = ea && *ea ? std::max(1, std::min(4, atoi(ea))) : 1;
+        }
         const long long runs = (total_frames + fps - 1) / fps;
         const long long grid = (runs + NG - 1) / NG;
         const int v2 = 2000 + R;

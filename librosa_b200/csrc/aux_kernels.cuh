@@ -33,12 +33,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// FPL = frames per lane: 1 -> two warp sets per tile (frames 0-31 / 32-63), 2 -> one warp set whose lanes own
+// frames (lane, lane + 32): the two warp-uniform coefficient fetches of a mel row (eight shared-memory
+// wavefronts) then feed 16 FMAs instead of 8 — the kernel is bound by the shared-memory pipe.
+template <int FPL>
 __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __restrict__ dctT,
                                  const unsigned int* __restrict__ clip_max, float top_db, int n_mels,
                                  int n_mfcc, int T, int tiles_per_clip, long long total_tiles, int tiled,
                                  float* __restrict__ C) {
   extern __shared__ __align__(16) float s_dyn[];
-  const int KG = blockDim.x >> 6, KP = 8 * KG;             // two warp sets: frames 0-31 and 32-63 of a tile
+  const int KG = FPL == 1 ? blockDim.x >> 6 : blockDim.x >> 5, KP = 8 * KG;   // FPL 1: two warp sets, frames 0-31 / 32-63
   float* s_dct = s_dyn;                                     // [n_mels][KP]
   float* s_tile0 = s_dyn + n_mels * KP;                     // 2 x [n_mels][DCT_TILE]
   const int tile_words = n_mels * DCT_TILE;
@@ -90,10 +94,10 @@ __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __res
     const int t0 = (int)(tile % tiles_per_clip) * DCT_TILE;
     float floor_v = -INFINITY;
     if (clip_max != nullptr && top_db >= 0.0f) floor_v = key_to_float(clip_max[clip]) - top_db;
-    float acc[8];
+    float acc[8], acc2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    const int fl = lane + 32 * fhalf;                 // frame of this lane inside the tile
+    for (int j = 0; j < 8; ++j) acc[j] = acc2[j] = 0.0f;
+    const int fl = lane + 32 * (FPL == 1 ? fhalf : 0);   // (first) frame of this lane inside the tile
 #pragma unroll 8
     for (int m = 0; m < n_mels; ++m) {
       const float4 d0 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp);
@@ -102,14 +106,52 @@ __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __res
       const float x0 = fmaxf(tile_s[m * DCT_TILE + fl], floor_v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(dv[j], x0, acc[j]);
+      if constexpr (FPL == 2) {
+        const float x1 = fmaxf(tile_s[m * DCT_TILE + fl + 32], floor_v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc2[j] = fmaf(dv[j], x1, acc2[j]);
+      }
     }
     float* Cc = C + (long long)clip * n_mfcc * T;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = 8 * warp + j;
       if (k < n_mfcc && t0 + fl < T) Cc[(long long)k * T + t0 + fl] = acc[j];
+      if constexpr (FPL == 2) {
+        if (k < n_mfcc && t0 + fl + 32 < T) Cc[(long long)k * T + t0 + fl + 32] = acc2[j];
+      }
     }
     __syncthreads();   // tile consumed before the buffer is refilled two iterations later
+  }
+}
+
+// Same product without a shared-memory tile, for inputs whose row count does not fit (mfcc(S=...) on a full
+// 1025-bin dB spectrogram, as the reference's multichannel tests do): one thread per frame, eight coefficients
+// at a time, the input column re-read from L1 / L2 for every group of eight.
+__global__ void dct_generic_kernel(const float* __restrict__ L, const float* __restrict__ dctT,
+                                   const unsigned int* __restrict__ clip_max, float top_db, int n_mels, int n_mfcc,
+                                   int KP, int T, float* __restrict__ C) {
+  const int clip = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* Lc = L + (long long)clip * n_mels * T + t;
+  float* Cc = C + (long long)clip * n_mfcc * T + t;
+  float floor_v = -INFINITY;
+  if (clip_max != nullptr && top_db >= 0.0f) floor_v = key_to_float(clip_max[clip]) - top_db;
+  for (int k0 = 0; k0 < n_mfcc; k0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    for (int m = 0; m < n_mels; ++m) {
+      const float x = fmaxf(Lc[(long long)m * T], floor_v);
+      const float4 d0 = __ldg(reinterpret_cast<const float4*>(dctT + (long long)m * KP + k0));
+      const float4 d1 = __ldg(reinterpret_cast<const float4*>(dctT + (long long)m * KP + k0 + 4));
+      acc[0] = fmaf(d0.x, x, acc[0]); acc[1] = fmaf(d0.y, x, acc[1]); acc[2] = fmaf(d0.z, x, acc[2]); acc[3] = fmaf(d0.w, x, acc[3]);
+      acc[4] = fmaf(d1.x, x, acc[4]); acc[5] = fmaf(d1.y, x, acc[5]); acc[6] = fmaf(d1.z, x, acc[6]); acc[7] = fmaf(d1.w, x, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (k0 + j < n_mfcc) Cc[(long long)(k0 + j) * T] = acc[j];
   }
 }
 
@@ -168,12 +210,16 @@ __global__ void db_clamp_kernel(float* __restrict__ x, long long per_clip, const
 // ------------------------------------------------------------------ finite scan of samples no frame reads
 // y [n_clips][stride]; checks samples [begin, n) of every clip (the uncovered tail when the last frame
 // ends before the clip does, or the whole clip when hop > n_fft leaves gaps).
-__global__ void finite_scan_kernel(const float* __restrict__ y, long long stride, int n, int begin, int* status) {
-  const float* yc = y + (long long)blockIdx.y * stride;
+// grid.x = blocks per clip (bx), grid.y strides the clips: any number of clips, like the kernels it accompanies.
+__global__ void finite_scan_kernel(const float* __restrict__ y, long long stride, int n, int begin, long long n_clips,
+                                   int* status) {
   bool bad = false;
-  for (long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    bad |= !(fabsf(yc[i]) <= 3.0e38f);
+  for (long long clip = blockIdx.y; clip < n_clips; clip += gridDim.y) {
+    const float* yc = y + clip * stride;
+    for (long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+      bad |= !(fabsf(yc[i]) <= 3.0e38f);
+  }
   if (bad) *status = 1;
 }
 

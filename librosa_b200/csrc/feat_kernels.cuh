@@ -137,6 +137,30 @@ __global__ void __launch_bounds__(256) frame_td_block_kernel(const float* __rest
       }
       acc = warp_sum(acc);
       if (lane == 0) s_val[b] = acc;
+    } else if (inside && vec_ok) {
+      // four consecutive samples per lane: three comparisons inside the lane, one with the previous lane's last
+      // sample (the lane before lane 0 of a 128-sample step is the previous step's lane 31, or the sample before
+      // the block)
+      const float4* src = reinterpret_cast<const float4*>(yc + p0);
+      int carry = cls(__ldg(yc + p0 - 1));            // class of the sample before the current 128-sample step
+      for (int base = 0; base < hop / 4; base += 32) {
+        const int i = base + lane;
+        const bool live = i < hop / 4;
+        const float4 v = live ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c0 = cls(v.x), c1 = cls(v.y), c2 = cls(v.z), c3 = cls(v.w);
+        int prev = __shfl_up_sync(0xffffffffu, c3, 1);
+        if (lane == 0) prev = carry;
+        const int x0 = live && c0 != prev;
+        if (base == 0 && lane == 0) first = x0;
+        cnt += live ? x0 + (c1 != c0) + (c2 != c1) + (c3 != c2) : 0;
+        carry = __shfl_sync(0xffffffffu, c3, 31);
+      }
+      cnt = (int)warp_sum((float)cnt);                 // counts stay far below 2^24: exact in float
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (lane == 0) {
+        s_val[b] = (float)cnt;
+        s_first[b] = first;
+      }
     } else {
       for (int base = 0; base < hop; base += 32) {
         const int i = base + lane;

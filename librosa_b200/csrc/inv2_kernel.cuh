@@ -169,11 +169,12 @@ __global__ void __launch_bounds__(NW * 32, 1) inv2_kernel(const InvArgs a) {
       const char* row = reinterpret_cast<const char*>(Dclip + (long long)frame * (M + 1));
       for (int off = t * 128; off < (M + 1) * 8; off += TPF * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
     };
+    const int ahead = a.acc_floats;                          // rows prefetched ahead of the one being transformed (host: 1 or 2)
     prefetch_row(fh);
-    if (fh + 1 < fe) prefetch_row(fh + 1);
+    if (ahead > 1 && fh + 1 < fe) prefetch_row(fh + 1);
     for (int frame = fh; frame < fe; ++frame) {
       const float2* Drow = Dclip + (long long)frame * (M + 1);
-      if (frame + 2 < fe) prefetch_row(frame + 2);           // two rows ahead -> L2 while this frame is transformed
+      if (frame + ahead < fe) prefetch_row(frame + ahead);   // next row(s) -> L2 while this frame is transformed
       // ---- bin pairs -> packed spectrum Z (re/im swapped: the forward engine then computes the inverse)
       float2 v[PPT];
       tab.begin_unmix();

@@ -260,3 +260,31 @@ def test_frame_statistics_argument_errors_before_any_gpu_work():
         lb.feature.rms(y=y, pad_mode="wrap")
     with pytest.raises(ValueError):
         lb.feature.rms(y=y, pad_mode="nonsense")
+
+
+def test_stream_blocks_line_up_with_frames():
+    """librosa.stream's block geometry (core/audio.py:407-408) over an in-memory signal: stft(center=False) of the
+    blocks, concatenated, is stft(center=False) of the whole signal (checked with the oracle: no GPU here)."""
+    from oracle import ref_np as O
+
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(50000).astype(np.float32)
+    for block_length, frame_length, hop in ((16, 1024, 256), (7, 512, 512), (5, 400, 100)):
+        blocks = list(lb.stream(y, block_length=block_length, frame_length=frame_length, hop_length=hop))
+        size = (block_length - 1) * hop + frame_length
+        assert all(b.shape[-1] == size for b in blocks[:-1]) and blocks[-1].shape[-1] <= size
+        parts = [O.stft(b, n_fft=frame_length, hop_length=hop, center=False) for b in blocks if b.shape[-1] >= frame_length]
+        whole = O.stft(y, n_fft=frame_length, hop_length=hop, center=False)
+        got = np.concatenate(parts, axis=-1)
+        assert got.shape == whole.shape
+        np.testing.assert_array_equal(got, whole)
+    st = np.stack([y, -y])
+    b0 = next(lb.stream(st, block_length=4, frame_length=64, hop_length=16, mono=False))
+    assert b0.shape == (2, 3 * 16 + 64)
+    assert next(lb.stream(st, block_length=4, frame_length=64, hop_length=16)).shape == (3 * 16 + 64,)
+    last = list(lb.stream(y[:1000], block_length=4, frame_length=256, hop_length=64, fill_value=0.0))[-1]
+    assert last.shape == (3 * 64 + 256,)
+    with pytest.raises(UnsupportedOnGPU):
+        next(lb.stream("song.wav", block_length=4, frame_length=64, hop_length=16))
+    with pytest.raises(lb.ParameterError):
+        next(lb.stream(y, block_length=0, frame_length=64, hop_length=16))
