@@ -335,7 +335,7 @@ def run_reference(args, w, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     port.close()
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -590,13 +590,31 @@ def run_ours(args, w, rank, world, local_rank):
                 "h2d_floor_ms": h2d_bytes / (h2d_gbs * 1e9) * 1e3},
         "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "join": join,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else that libraries print on file
+    descriptor 1 while the benchmark runs (NCCL's version banner, torchrun notices) was redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

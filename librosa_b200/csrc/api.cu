@@ -782,13 +782,20 @@ static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, int hw, const b2l
   // longest-processing-time-first: cost of an item = its trip count + a fixed part (row fetch, stores)
   std::vector<int> idx(n_items);
   for (int i = 0; i < n_items; ++i) idx[i] = i;
-  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return item_quads[x] > item_quads[y]; });
+  {
+    const char* lpt = getenv("B2L_MEL_LPT");   // 0: natural order, dealt round-robin (the round-1 assignment)
+    if (!(lpt && *lpt && atoi(lpt) == 0))
+      std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return item_quads[x] > item_quads[y]; });
+  }
+  const bool round_robin = getenv("B2L_MEL_LPT") && atoi(getenv("B2L_MEL_LPT")) == 0;
   std::vector<std::vector<int>> lists(hw);
   std::vector<int> load(hw, 0);
+  int rr = 0;
   for (int i : idx) {
     int best = 0;
     for (int wv = 1; wv < hw; ++wv)
       if (load[wv] < load[best]) best = wv;
+    if (round_robin) best = (rr++) % hw;
     lists[best].push_back(i);
     load[best] += item_quads[i] + 3;
   }
@@ -1056,7 +1063,7 @@ static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, in
   }
   if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", p->n_fft);
   if (occ < 1) return fail(B2L_ERR_CUDA, "chirp-z kernel does not fit on an SM (smem %zu)", smem);
-  const long long steps = (((long long)n_clips * T + 1) / 2 + G - 1) / G;     // the kernel transforms frames in pairs
+  const long long steps = ((long long)n_clips * ((T + 1) / 2) + G - 1) / G;   // frames go in pairs inside a clip
   long long grid = (long long)c->sm_count * occ;
   if (grid > steps) grid = steps;
   CUDA_TRY(op(OP_LAUNCH, &a, (int)grid, smem, c->stream, nullptr));
@@ -1305,7 +1312,7 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
       c->launch_cache[kkey] = occ;
     }
     if (occ < 1) return fail(B2L_ERR_CUDA, "chirp-z inverse kernel does not fit on an SM");
-    const long long steps = (((long long)n_clips * n_frames_used + 1) / 2 + G - 1) / G;   // frames go in pairs
+    const long long steps = ((long long)n_clips * ((n_frames_used + 1) / 2) + G - 1) / G;   // frames go in pairs inside a clip
     long long grid = (long long)c->sm_count * occ;
     if (grid > steps) grid = steps;
     CUDA_TRY(op(OP_LAUNCH, &a, (int)grid, smem, c->stream, nullptr));

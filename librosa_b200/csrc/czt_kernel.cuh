@@ -63,25 +63,27 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_kernel(const CztArgs a) {
   // Two real frames ride through one complex chirp-z transform: z = xA + i xB gives Z = XA + i XB, and since
   // XA, XB are spectra of real signals, XA[k] = (Z[k] + conj Z[L-k]) / 2 and XB[k] = (Z[k] - conj Z[L-k]) / 2i.
   // Z[L-k] = c[L-k] * b[L-k] with b[L-k] = (-1)^L b[k], so the chirp table still only covers k <= L/2.
-  const long long total = (long long)a.n_clips * a.n_frames;
-  const long long pairs = (total + 1) / 2;
+  // Frames are paired INSIDE a clip (frames 2j, 2j+1; the odd last frame of a clip rides alone with a zero
+  // partner): a non-finite or much louder neighbouring clip can then never leak into this one through the
+  // un-mix (Z[k] +- conj Z[L-k]) / 2, whose round-off scales with the louder partner.
+  const int ppc = (a.n_frames + 1) / 2;                       // pairs per clip
+  const long long pairs = (long long)a.n_clips * ppc;
   const float sgn = (a.L & 1) ? -1.0f : 1.0f;
   for (long long p0 = (long long)blockIdx.x * G; p0 < pairs; p0 += (long long)gridDim.x * G) {
     // groups past the end redo the last pair (their stores are masked): sub-warp groups share a warp
     const long long pidx = min(p0 + grp, pairs - 1);
     const bool live_a = p0 + grp < pairs;
-    const long long fa = 2 * pidx, fb = min(2 * pidx + 1, total - 1);
-    const bool live_b = live_a && 2 * pidx + 1 < total;
-    const int clip_a = (int)(fa / a.n_frames), frame_a = (int)(fa % a.n_frames);
-    const int clip_b = (int)(fb / a.n_frames), frame_b = (int)(fb % a.n_frames);
+    const int clip_a = (int)(pidx / ppc), frame_a = 2 * (int)(pidx % ppc);
+    const int clip_b = clip_a, frame_b = min(frame_a + 1, a.n_frames - 1);
+    const bool live_b = live_a && frame_a + 1 < a.n_frames;
     const float* ya = a.y + (long long)clip_a * a.clip_stride;
-    const float* yb = a.y + (long long)clip_b * a.clip_stride;
+    const float* yb = ya;
     const long long sa = (long long)frame_a * a.hop - a.pad, sb = (long long)frame_b * a.hop - a.pad;
     float2 v[PPT];
     load_pass0<Cfg>(v, t, [&](int e) {
       if (e >= a.L) return make_float2(0.0f, 0.0f);
       const float xa = load_padded(ya, a.n, sa + e, a.pad_mode, a.pad);
-      const float xb = load_padded(yb, a.n, sb + e, a.pad_mode, a.pad);
+      const float xb = live_b ? load_padded(yb, a.n, sb + e, a.pad_mode, a.pad) : 0.0f;
       const float2 w = s_wb[e];
       return make_float2(fmaf(xa, w.x, -xb * w.y), fmaf(xa, w.y, xb * w.x));      // (xa + i xb) * w
     });
@@ -174,15 +176,14 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
   __syncthreads();
   // As in czt_kernel, two frames share one complex transform: U = X_A + i X_B (Hermitian extensions) inverts to
   // u = y_A + i y_B because both signals are real.
-  const long long total = (long long)a.n_clips * a.n_frames;
-  const long long pairs = (total + 1) / 2;
+  const int ppc = (a.n_frames + 1) / 2;                       // pairs stay inside a clip (see czt_kernel)
+  const long long pairs = (long long)a.n_clips * ppc;
   for (long long p0 = (long long)blockIdx.x * G; p0 < pairs; p0 += (long long)gridDim.x * G) {
     const long long pidx = min(p0 + grp, pairs - 1);
     const bool live_a = p0 + grp < pairs;
-    const long long fa = 2 * pidx, fb = min(2 * pidx + 1, total - 1);
-    const bool live_b = live_a && 2 * pidx + 1 < total;
-    const int clip_a = (int)(fa / a.n_frames), frame_a = (int)(fa % a.n_frames);
-    const int clip_b = (int)(fb / a.n_frames), frame_b = (int)(fb % a.n_frames);
+    const int clip_a = (int)(pidx / ppc), frame_a = 2 * (int)(pidx % ppc);
+    const int clip_b = clip_a, frame_b = min(frame_a + 1, a.n_frames - 1);
+    const bool live_b = live_a && frame_a + 1 < a.n_frames;
     const float2* Da = a.D + (long long)clip_a * a.d_clip_stride + (long long)frame_a * a.n_bins;
     const float2* Db = a.D + (long long)clip_b * a.d_clip_stride + (long long)frame_b * a.n_bins;
     float2 v[PPT];
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(NW * 32, 1) czt_inv_kernel(const CztInvArgs a)
         xa.y = -xa.y;                                    // Hermitian extension
         xb.y = -xb.y;
       }
+      if (!live_b) xb = make_float2(0.0f, 0.0f);         // odd last frame of a clip: no partner
       const float2 x = make_float2(xa.x - xb.y, xa.y + xb.x);     // X_A + i X_B
       const float2 b = __ldg(a.bfull + e);
       return cmul(x, make_float2(b.x, -b.y));            // U[e] * conj(b[e])

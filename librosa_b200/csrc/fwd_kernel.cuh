@@ -19,6 +19,12 @@
 #ifndef B2L_UNMIX_SHFL
 #define B2L_UNMIX_SHFL 0   // 1: real-FFT un-mix partners travel by warp shuffle where a warp owns a whole frame
 #endif
+#ifndef B2L_MEL_PVEC
+#define B2L_MEL_PVEC 4     // power values fetched per shared-memory load in the mel loop: 4 (16 bytes), 2 or 1
+#endif
+#ifndef B2L_DEFER_BARRIER
+#define B2L_DEFER_BARRIER 1   // 1: "previous tile's power rows consumed" merged into the barrier before the first exchange write
+#endif
 
 namespace b2l {
 
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     // share the exchange regions (MEL / STATS) the same barrier also says "every warp is done with the rows
     // of the previous tile", so it sits right before the first exchange write: the operand fetch and the
     // register-only butterflies of pass 0 of the fast warps overlap the tail of the slow warps' mel items.
-    constexpr bool MERGED = (MODE == MODE_MEL || MODE == MODE_STATS);
+    constexpr bool MERGED = B2L_DEFER_BARRIER && (MODE == MODE_MEL || MODE == MODE_STATS);
     auto release = [&]() {
       half_sync();
       prefetch(nxt);
@@ -524,7 +530,22 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
               const float4* pb = pa + (FP * RS) / 4;
 #pragma unroll 2
               for (; wp != wend; ++wp, ++pa, ++pb) {
-                const float4 w = *wp, x = *pa, y = *pb;
+                const float4 w = *wp;
+                float4 x, y;
+                if constexpr (B2L_MEL_PVEC == 4) {
+                  x = *pa;
+                  y = *pb;
+                } else if constexpr (B2L_MEL_PVEC == 2) {
+                  const float2 x0 = reinterpret_cast<const float2*>(pa)[0], x1 = reinterpret_cast<const float2*>(pa)[1];
+                  const float2 y0 = reinterpret_cast<const float2*>(pb)[0], y1 = reinterpret_cast<const float2*>(pb)[1];
+                  x = make_float4(x0.x, x0.y, x1.x, x1.y);
+                  y = make_float4(y0.x, y0.y, y1.x, y1.y);
+                } else {
+                  const float* xa = reinterpret_cast<const float*>(pa);
+                  const float* ya = reinterpret_cast<const float*>(pb);
+                  x = make_float4(xa[0], xa[1], xa[2], xa[3]);
+                  y = make_float4(ya[0], ya[1], ya[2], ya[3]);
+                }
                 a0 = fmaf(w.x, x.x, a0);
                 b0 = fmaf(w.x, y.x, b0);
                 a1 = fmaf(w.y, x.y, a1);
@@ -565,7 +586,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
             if (lane == 0 && wmax > -INFINITY) atomicMax(a.clip_max + clip, float_to_key(wmax));
           }
         }
-        // no barrier here: the next tile's `release` (before its first exchange write) orders the P reads
+        // deferred form: the next tile's `release` (before its first exchange write) orders the P reads
+        if constexpr (!B2L_DEFER_BARRIER) half_sync();
       }
     }
     cur = nxt;

@@ -441,3 +441,29 @@ def test_two_rank_split_join_on_gpu(lb, oracle):
     [t.join(timeout=120) for t in threads]
     assert not errors, errors
     close(results["mel"], oracle.melspectrogram(y=Y, sr=22050), **TOL["mel"])
+
+
+def test_chirpz_frames_are_paired_inside_a_clip(lb, oracle):
+    """Two frames share one complex chirp-z transform; the pairs must not straddle clips: a clip 80 dB louder
+    (or a non-finite one) next to a quiet clip may not touch the quiet clip's spectrum.  Per-clip tolerance."""
+    import signals
+
+    quiet = signals.make("A", (1, 4000), seed=3)[0] * 1e-4
+    loud = signals.make("A", (1, 4000), seed=4)[0]
+    Y = np.stack([loud, quiet, loud]).astype(np.float32)
+    kw = dict(n_fft=400, hop_length=160)                     # 26 frames per clip would pair evenly; 4001 -> odd count
+    Yo = np.concatenate([Y, Y[:, :1]], axis=1)               # 4001 samples: 26 frames -> use hop 150 for an odd count
+    kw = dict(n_fft=400, hop_length=150)
+    D, Do = lb.stft(Yo, **kw), oracle.stft(Yo, **kw)
+    assert D.shape[-1] % 2 == 1                              # odd frame count: the last frame of a clip rides alone
+    for c in range(3):
+        close(D[c], Do[c], rtol=1e-4, atol=1e-5 * float(np.abs(Do[c]).max()))
+    yr, yo = lb.istft(Do, hop_length=150, n_fft=400, length=Yo.shape[-1]), oracle.istft(Do, hop_length=150, n_fft=400,
+                                                                                      length=Yo.shape[-1])
+    for c in range(3):
+        close(yr[c], yo[c], rtol=1e-4, atol=2e-5 * float(np.abs(yo[c]).max()))
+    # a clip with a NaN poisons only itself (device-resident input: no valid_audio check in front)
+    Yn = Yo.copy()
+    Yn[0, 100] = np.nan
+    Dn = lb.stft(lb.to_device(Yn), **kw).get()
+    assert np.isnan(Dn[0]).any() and np.isfinite(Dn[1]).all() and np.isfinite(Dn[2]).all()
