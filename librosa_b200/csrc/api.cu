@@ -782,12 +782,13 @@ static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, int hw, const b2l
   // longest-processing-time-first: cost of an item = its trip count + a fixed part (row fetch, stores)
   std::vector<int> idx(n_items);
   for (int i = 0; i < n_items; ++i) idx[i] = i;
-  {
-    const char* lpt = getenv("B2L_MEL_LPT");   // 0: natural order, dealt round-robin (the round-1 assignment)
-    if (!(lpt && *lpt && atoi(lpt) == 0))
-      std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return item_quads[x] > item_quads[y]; });
-  }
-  const bool round_robin = getenv("B2L_MEL_LPT") && atoi(getenv("B2L_MEL_LPT")) == 0;
+  // B2L_MEL_LPT=1: longest-first deal to the least loaded warp.  Measured neutral to slightly negative on cfg 2
+  // (1.148 vs 1.139 ms): the natural order, dealt round-robin, keeps neighbouring rows (whose bands overlap
+  // in shared memory) on warps that run at the same time.  Default: round-robin.
+  const char* lpt_env = getenv("B2L_MEL_LPT");
+  const bool round_robin = !(lpt_env && *lpt_env && atoi(lpt_env) != 0);
+  if (!round_robin)
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return item_quads[x] > item_quads[y]; });
   std::vector<std::vector<int>> lists(hw);
   std::vector<int> load(hw, 0);
   int rr = 0;
@@ -818,6 +819,9 @@ static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, int hw, const b2l
 
 // Kernel variants tried in order (first that fits shared memory wins): 116 = 16 warps as two independent
 // 8-warp halves, 16 / 8 = plain CTAs.  B2L_FWD_VARIANT forces one (A/B measurements).
+#ifndef B2L_MEL2_DEFAULT
+#define B2L_MEL2_DEFAULT false
+#endif
 #ifndef B2L_DCT_FPL_DEFAULT
 #define B2L_DCT_FPL_DEFAULT 2
 #endif
@@ -869,6 +873,69 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
   const int n_opt = fwd_variants(cfg, variants);
   FwdArgs a;
   memset(&a, 0, sizeof(a));
+  // melspectrogram, n_fft = 2048, hop = n_fft / 4, no dB epilogue: autonomous frame groups (mel2_kernel.cuh);
+  // B2L_MEL2=0 keeps fwd_kernel
+  {
+    const char* e2 = getenv("B2L_MEL2");
+    const bool forced = getenv("B2L_FWD_VARIANT") && *getenv("B2L_FWD_VARIANT");
+    if (mode == MODE_MEL && !log_mode && p->log2m == 10 && 4 * p->hop == N && !forced &&
+        (e2 && *e2 ? atoi(e2) != 0 : B2L_MEL2_DEFAULT)) {
+      const b2l_plan::RowTable* t = nullptr;
+      int rc = get_row_table(c, p, mel_rows_per_warp(8), 8, &t);
+      if (rc) return rc;
+      const int PRS = ((M + 4 + 31) / 32) * 32 + 8;
+      size_t off = 0;
+      a.off_bar = (int)off; off = align_up(off + 64, 128);
+      a.off_win = (int)off; off = align_up(off + 2 * 8 * sizeof(long long), 128);       // per-row output offsets
+      a.off_melw = (int)off; off = align_up(off + (size_t)t->w_count * 4, 16);
+      a.off_melband = (int)off; off = align_up(off + (size_t)t->n_rows * sizeof(MelRow), 16);
+      a.off_melorder = (int)off; off = align_up(off + (size_t)std::max(1, t->list_len) * 8 * 2, 128);
+      a.off_in = (int)off; off = align_up(off + (size_t)2 * 8 * PRS * 4, 128);           // power tiles of the two halves
+      a.off_xbuf = (int)off; off += (size_t)16 * cfg.xbuf_f2() * 8;
+      if (off <= c->smem_optin) {
+        a.y = d_y;
+        a.clip_stride = y_stride;
+        a.n = (int)n;
+        a.n_clips = (int)n_clips;
+        a.n_fft = N;
+        a.hop = p->hop;
+        a.pad = p->center ? N / 2 : 0;
+        a.pad_mode = p->pad_mode;
+        a.n_frames = (int)T;
+        a.tma_ok = (((uintptr_t)d_y & 7) == 0) && (y_stride % 2 == 0) && (a.pad % 2 == 0);   // 8-byte sample loads
+        a.window = p->d_win_fwd;
+        a.tw = p->d_tw;
+        a.twn = p->d_twn;
+        a.out_r = out_r;
+        a.power_mode = p->power_mode;
+        a.power = p->power;
+        a.n_mels = p->n_mels;
+        a.mel_w_count = t->w_count;
+        a.mel_w = t->d_w;
+        a.mel_rows = t->d_rows;
+        a.n_mel_rows = t->n_rows;
+        a.mel_order = t->d_order;
+        a.mel_list_len = t->list_len;
+        a.status = c->d_status;
+        const long long total_frames = (long long)n_clips * T;
+        long long grid = c->sm_count;
+        if (grid * 16 > total_frames) grid = (total_frames + 15) / 16;
+        const long long fpg = (total_frames + grid * 16 - 1) / (grid * 16);
+        if (fpg <= 0x7fffffffLL) {
+          a.tiles_per_clip = (int)fpg;                     // steps: frames per frame group
+          const unsigned long long kkey = (7ULL << 60);
+          if (c->launch_cache.find(kkey) == c->launch_cache.end()) {
+            CUDA_TRY(op(OP_SET_SMEM, 3016, mode, &a, 0, c->smem_optin, c->stream, nullptr));
+            c->launch_cache[kkey] = 1;
+          }
+          CUDA_TRY(op(OP_LAUNCH, 3016, mode, &a, (int)grid, off, c->stream, nullptr));
+          c->launches++;
+          return B2L_OK;
+        }
+      }
+      memset(&a, 0, sizeof(a));
+    }
+  }
   int variant = 0, ft = 0, halves = 1;
   size_t smem = 0;
   const b2l_plan::RowTable* rt = nullptr;

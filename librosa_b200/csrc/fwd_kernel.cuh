@@ -23,7 +23,7 @@
 #define B2L_MEL_PVEC 4     // power values fetched per shared-memory load in the mel loop: 4 (16 bytes), 2 or 1
 #endif
 #ifndef B2L_DEFER_BARRIER
-#define B2L_DEFER_BARRIER 1   // 1: "previous tile's power rows consumed" merged into the barrier before the first exchange write
+#define B2L_DEFER_BARRIER 0   // 1: "previous tile's power rows consumed" merged into the barrier before the first exchange write
 #endif
 
 namespace b2l {
