@@ -272,7 +272,9 @@ class Context:
         self._pool = {}
         self._sizes = {}
         self._pooled_bytes = 0
-        self.pool_limit_bytes = int(os.environ.get("B2L_POOL_LIMIT_MB", "65536")) << 20
+        # cached (released but not returned to the driver) device memory: blocks are exact-size, so variable-length
+        # workloads reuse little — keep the cache well below the 180 GB of the device
+        self.pool_limit_bytes = int(os.environ.get("B2L_POOL_LIMIT_MB", "32768")) << 20
         self._finalizer = weakref.finalize(self, Context._destroy, self._h, self._plans, self._wss, self._sizes)
 
     @staticmethod
@@ -523,7 +525,7 @@ class _PinnedPool:
     def __init__(self):
         self.free = {}
         self.pooled = 0
-        self.limit = int(os.environ.get("B2L_PINNED_POOL_MB", "16384")) << 20
+        self.limit = int(os.environ.get("B2L_PINNED_POOL_MB", "8192")) << 20
         self.lock = threading.Lock()
 
     def take(self, nbytes: int):

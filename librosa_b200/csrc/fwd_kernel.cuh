@@ -353,7 +353,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     // share the exchange regions (MEL / STATS) the same barrier also says "every warp is done with the rows
     // of the previous tile", so it sits right before the first exchange write: the operand fetch and the
     // register-only butterflies of pass 0 of the fast warps overlap the tail of the slow warps' mel items.
-    constexpr bool MERGED = B2L_DEFER_BARRIER && (MODE == MODE_MEL || MODE == MODE_STATS);
+    // B2L_DEFER_BARRIER: 0 = three barriers per tile (staging released early, "rows consumed" at the end of the
+    // tile); 1 = the two merged into one barrier before the first exchange write (late prefetch: measured 2 %
+    // slower); 2 = staging released early AND "rows consumed" deferred to just before the first exchange write.
+    constexpr bool ROWS = (MODE == MODE_MEL || MODE == MODE_STATS);
+    constexpr bool MERGED = B2L_DEFER_BARRIER == 1 && ROWS;
+    constexpr bool LATE_ROWS = B2L_DEFER_BARRIER == 2 && ROWS;
     auto release = [&]() {
       half_sync();
       prefetch(nxt);
@@ -363,8 +368,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     // ---------------- M-point complex FFT
     fft_forward_tab<Cfg, true>(v, t, gbar, xbuf, tab, [&]() {
       if constexpr (MERGED) release();
+      if constexpr (LATE_ROWS) half_sync();
     });
     if constexpr (MERGED && Cfg::NPASS == 1) release();
+    if constexpr (LATE_ROWS && Cfg::NPASS == 1) half_sync();
     // Bin pair (k, M-k), k = t + TPF*c < M/2: Z[k] is already in one of this thread's registers; only the
     // upper half of the spectrum (indices >= M/2) has to reach its partner thread — through shared memory,
     // or (one warp per frame, M = 1024: v[q] = Z[t + 32 q], so Z[M-k] is register 31-c of lane 32-t) with
@@ -587,7 +594,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
           }
         }
         // deferred form: the next tile's `release` (before its first exchange write) orders the P reads
-        if constexpr (!B2L_DEFER_BARRIER) half_sync();
+        if constexpr (B2L_DEFER_BARRIER == 0) half_sync();
       }
     }
     cur = nxt;
