@@ -957,7 +957,7 @@ static int run_forward(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, co
     size_t off = 0;
     a.off_win = (int)off; if (!tmem) off = align_up(off + (size_t)N * 4, 16);       // TMEM variants keep these
     a.off_tw = (int)off; if (!tmem) off = align_up(off + (size_t)cfg.tw_count() * 8, 16);   // tables off shared memory
-    a.off_bar = (int)off; off = align_up(off + 32, 16);   // one mbarrier per half + the TMEM base address
+    a.off_bar = (int)off; off = align_up(off + 64, 16);   // "tile landed" mbarrier per half, TMEM base address, "staging consumed" mbarriers
     if (t) {
       a.off_melw = (int)off; off = align_up(off + (size_t)t->w_count * 4, 16);
       a.off_melband = (int)off; off = align_up(off + (size_t)t->n_rows * sizeof(MelRow), 16);

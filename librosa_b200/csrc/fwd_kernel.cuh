@@ -23,7 +23,7 @@
 #define B2L_MEL_PVEC 4     // power values fetched per shared-memory load in the mel loop: 4 (16 bytes), 2 or 1
 #endif
 #ifndef B2L_DEFER_BARRIER
-#define B2L_DEFER_BARRIER 0   // 1: "previous tile's power rows consumed" merged into the barrier before the first exchange write
+#define B2L_DEFER_BARRIER 2   // barrier placement of the row modes, see the comment at `release` in fwd_kernel
 #endif
 
 namespace b2l {
@@ -56,6 +56,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(phase)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   float* s_p = reinterpret_cast<float*>(s_xall);               // P rows alias the exchange regions (MelLayout)
   const unsigned short* s_order = reinterpret_cast<const unsigned short*>(smem + a.off_melorder);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + half;
+  uint64_t* s_empty = reinterpret_cast<uint64_t*>(smem + a.off_bar + 32) + half;   // "staging consumed" (B2L_DEFER_BARRIER == 3)
 
   const int grp = htid / TPF;                  // frame group == local frame index
   const int t = htid % TPF;
@@ -258,6 +262,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   }
   if (htid == 0) {
     mbar_init(s_bar, 1);
+    mbar_init(s_empty, HW);
     fence_mbar_init();
   }
   __syncthreads();
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     return ti;
   };
   // Called by the whole half after the staging buffer has been released (B0): start the copy of the tile.
-  auto prefetch = [&](const TileInfo& ti) {
+  auto prefetch_copy = [&](const TileInfo& ti) {          // the bulk copy of the tile's in-range part (one thread)
     if (ti.clip >= a.n_clips || ti.kind == TILE_GATHER) return;
     if (htid == 0) {
       const long long s0 = (long long)ti.tix * FT * a.hop - a.pad;
@@ -300,10 +305,15 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       mbar_expect_tx(s_bar, (uint32_t)ti.valid * 4u);
       tma_load_1d(s_in + ti.lead, a.y + (long long)ti.clip * a.clip_stride + s0 + ti.lead, (uint32_t)ti.valid * 4u, s_bar);
     }
-    if (ti.kind == TILE_TMA_ZERO) {
-      for (int i = htid; i < ti.lead; i += HT) s_in[i] = 0.0f;
-      for (int i = ti.lead + ti.valid + htid; i < span; i += HT) s_in[i] = 0.0f;
-    }
+  };
+  auto prefetch_zeros = [&](const TileInfo& ti) {         // the zero padding around it (every thread of the half)
+    if (ti.clip >= a.n_clips || ti.kind != TILE_TMA_ZERO) return;
+    for (int i = htid; i < ti.lead; i += HT) s_in[i] = 0.0f;
+    for (int i = ti.lead + ti.valid + htid; i < span; i += HT) s_in[i] = 0.0f;
+  };
+  auto prefetch = [&](const TileInfo& ti) {
+    prefetch_copy(ti);
+    prefetch_zeros(ti);
   };
 
   const int tile_step = (int)gridDim.x * NH;
@@ -313,7 +323,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     const int first = (int)blockIdx.x * NH + half;
     cur = describe(first / a.tiles_per_clip, first % a.tiles_per_clip);
   }
-  uint32_t phase = 0;
+  uint32_t phase = 0, ephase = 0;
   prefetch(cur);
 
   for (; cur.clip < a.n_clips;) {
@@ -356,22 +366,38 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     // B2L_DEFER_BARRIER: 0 = three barriers per tile (staging released early, "rows consumed" at the end of the
     // tile); 1 = the two merged into one barrier before the first exchange write (late prefetch: measured 2 %
     // slower); 2 = staging released early AND "rows consumed" deferred to just before the first exchange write.
+    // 3 = as 2, and "staging consumed" is an mbarrier on which every warp ARRIVES but only the thread that issues
+    // the bulk copy WAITS: seven of the eight warps of a half never stop there (the zero padding of edge tiles,
+    // written by all threads, moves behind the "rows consumed" barrier, which every warp passes after its fetch).
     constexpr bool ROWS = (MODE == MODE_MEL || MODE == MODE_STATS);
     constexpr bool MERGED = B2L_DEFER_BARRIER == 1 && ROWS;
-    constexpr bool LATE_ROWS = B2L_DEFER_BARRIER == 2 && ROWS;
+    constexpr bool LATE_ROWS = B2L_DEFER_BARRIER >= 2 && ROWS;
+    constexpr bool ARRIVE_ONLY = B2L_DEFER_BARRIER == 3 && ROWS;
     auto release = [&]() {
+      if constexpr (ARRIVE_ONLY) {
+        __syncwarp();
+        if ((htid & 31) == 0) mbar_arrive(s_empty);
+        if (htid == 0) mbar_wait(s_empty, ephase);
+        ephase ^= 1;
+        prefetch_copy(nxt);
+      } else {
+        half_sync();
+        prefetch(nxt);
+      }
+    };
+    auto rows_consumed = [&]() {
       half_sync();
-      prefetch(nxt);
+      if constexpr (ARRIVE_ONLY) prefetch_zeros(nxt);
     };
     if constexpr (!MERGED) release();
 
     // ---------------- M-point complex FFT
     fft_forward_tab<Cfg, true>(v, t, gbar, xbuf, tab, [&]() {
       if constexpr (MERGED) release();
-      if constexpr (LATE_ROWS) half_sync();
+      if constexpr (LATE_ROWS) rows_consumed();
     });
     if constexpr (MERGED && Cfg::NPASS == 1) release();
-    if constexpr (LATE_ROWS && Cfg::NPASS == 1) half_sync();
+    if constexpr (LATE_ROWS && Cfg::NPASS == 1) rows_consumed();
     // Bin pair (k, M-k), k = t + TPF*c < M/2: Z[k] is already in one of this thread's registers; only the
     // upper half of the spectrum (indices >= M/2) has to reach its partner thread — through shared memory,
     // or (one warp per frame, M = 1024: v[q] = Z[t + 32 q], so Z[M-k] is register 31-c of lane 32-t) with

@@ -52,9 +52,6 @@ __device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&r)[16])
         "r"(__float_as_uint(r[14])), "r"(__float_as_uint(r[15]))
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <int LOG2M>
 __global__ void __launch_bounds__(512, 1) mel2_kernel(const FwdArgs a) {
