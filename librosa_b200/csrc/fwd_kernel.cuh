@@ -22,6 +22,9 @@
 #ifndef B2L_MEL_PVEC
 #define B2L_MEL_PVEC 4     // power values fetched per shared-memory load in the mel loop: 4 (16 bytes), 2 or 1
 #endif
+#ifndef B2L_PIPELINE
+#define B2L_PIPELINE 0     // 1: row modes fetch the next tile's operands in front of the mel phase (one rendezvous less)
+#endif
 #ifndef B2L_DEFER_BARRIER
 #define B2L_DEFER_BARRIER 2   // barrier placement of the row modes, see the comment at `release` in fwd_kernel
 #endif
@@ -326,38 +329,56 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   uint32_t phase = 0, ephase = 0;
   prefetch(cur);
 
-  for (; cur.clip < a.n_clips;) {
-    const int clip = cur.clip, t0 = cur.tix * FT;
-    // ---------------- stage the tile's sample span
+  // B2L_PIPELINE (row modes): the operand fetch of tile i+1 is hoisted in front of the mel phase of tile i, so
+  // that the "staging consumed" barrier that follows the fetch also says "the power rows of tile i are complete"
+  // (every warp stores its row before it fetches): one rendezvous per tile less.
+  constexpr bool ROWS = (MODE == MODE_MEL || MODE == MODE_STATS);
+  constexpr bool PIPE = B2L_PIPELINE && ROWS && B2L_DEFER_BARRIER == 2;
+  float2 v[PPT];
+  TileInfo nxt;
+  // ---------------- stage a tile's sample span and turn it into windowed pass-0 operands (first stage fused in)
+  auto stage_and_fetch = [&](const TileInfo& ti) {
     if constexpr (TM) tab.begin_window();   // first window chunk travels while the tile lands
-    if (cur.kind == TILE_GATHER) {
-      const float* yc = a.y + (long long)clip * a.clip_stride;
-      const long long s0 = (long long)t0 * a.hop - a.pad;
+    if (ti.kind == TILE_GATHER) {
+      const float* yc = a.y + (long long)ti.clip * a.clip_stride;
+      const long long s0 = (long long)ti.tix * FT * a.hop - a.pad;
       for (int i = htid; i < span; i += HT) s_in[i] = load_padded(yc, a.n, s0 + i, a.pad_mode, a.pad);
       half_sync();
     } else {
       mbar_wait(s_bar, phase);
       phase ^= 1;
-      if (cur.kind == TILE_TMA_ZERO) half_sync();   // zeros written by other threads
+      if (ti.kind == TILE_TMA_ZERO) half_sync();   // zeros written by other threads
     }
+    const float* fr = s_in + grp * a.hop;
+    auto win = [&](auto S) { return tab.template window<decltype(S)::value>(t); };
+    if (hop_even) {
+      load_pass0_windowed<Cfg>(v, t, [&](int e) { return *reinterpret_cast<const float2*>(fr + 2 * e); }, win);
+    } else {
+      load_pass0_windowed<Cfg>(v, t, [&](int e) { return make_float2(fr[2 * e], fr[2 * e + 1]); }, win);
+    }
+  };
+  auto advance = [&](const TileInfo& ti) -> TileInfo {   // next tile of this half
+    int nc = ti.clip + step_c, nt = ti.tix + step_t;
+    if (nt >= a.tiles_per_clip) { nt -= a.tiles_per_clip; ++nc; }
+    return describe(nc, nt);
+  };
+  auto release_staging = [&]() {   // B0: staging buffer consumed -> prefetch the next tile behind the math
+    half_sync();
+    prefetch(nxt);
+  };
+  if constexpr (PIPE) {
+    if (cur.clip < a.n_clips) {
+      stage_and_fetch(cur);
+      nxt = advance(cur);
+      release_staging();
+    }
+  }
 
-    // ---------------- windowed frame -> registers (pass-0 operands, first butterfly stage fused in)
-    float2 v[PPT];
-    {
-      const float* fr = s_in + grp * a.hop;
-      auto win = [&](auto S) { return tab.template window<decltype(S)::value>(t); };
-      if (hop_even) {
-        load_pass0_windowed<Cfg>(v, t, [&](int e) { return *reinterpret_cast<const float2*>(fr + 2 * e); }, win);
-      } else {
-        load_pass0_windowed<Cfg>(v, t, [&](int e) { return make_float2(fr[2 * e], fr[2 * e + 1]); }, win);
-      }
-    }
-    // next tile of this half
-    TileInfo nxt;
-    {
-      int nc = cur.clip + step_c, nt = cur.tix + step_t;
-      if (nt >= a.tiles_per_clip) { nt -= a.tiles_per_clip; ++nc; }
-      nxt = describe(nc, nt);
+  for (; cur.clip < a.n_clips;) {
+    const int clip = cur.clip, t0 = cur.tix * FT;
+    if constexpr (!PIPE) {
+      stage_and_fetch(cur);
+      nxt = advance(cur);
     }
     // B0: staging buffer consumed -> prefetch the next tile behind the math.  In the modes whose power rows
     // share the exchange regions (MEL / STATS) the same barrier also says "every warp is done with the rows
@@ -369,20 +390,20 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
     // 3 = as 2, and "staging consumed" is an mbarrier on which every warp ARRIVES but only the thread that issues
     // the bulk copy WAITS: seven of the eight warps of a half never stop there (the zero padding of edge tiles,
     // written by all threads, moves behind the "rows consumed" barrier, which every warp passes after its fetch).
-    constexpr bool ROWS = (MODE == MODE_MEL || MODE == MODE_STATS);
     constexpr bool MERGED = B2L_DEFER_BARRIER == 1 && ROWS;
     constexpr bool LATE_ROWS = B2L_DEFER_BARRIER >= 2 && ROWS;
     constexpr bool ARRIVE_ONLY = B2L_DEFER_BARRIER == 3 && ROWS;
     auto release = [&]() {
-      if constexpr (ARRIVE_ONLY) {
+      if constexpr (PIPE) {
+        // (done right after the fetch, in front of the previous tile's mel phase)
+      } else if constexpr (ARRIVE_ONLY) {
         __syncwarp();
         if ((htid & 31) == 0) mbar_arrive(s_empty);
         if (htid == 0) mbar_wait(s_empty, ephase);
         ephase ^= 1;
         prefetch_copy(nxt);
       } else {
-        half_sync();
-        prefetch(nxt);
+        release_staging();
       }
     };
     auto rows_consumed = [&]() {
@@ -519,7 +540,20 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
           prow[M + 2] = 0.0f;
           prow[M + 3] = 0.0f;
         }
-        half_sync();   // B2: the tile's rows are complete
+        // B2: the tile's rows are complete.  Pipelined form: fetch the next tile's operands first — the barrier
+        // after that fetch is the same rendezvous.
+        if constexpr (PIPE) {
+          cur = nxt;
+          if (cur.clip < a.n_clips) {
+            stage_and_fetch(cur);
+            nxt = advance(cur);
+            release_staging();
+          } else {
+            half_sync();
+          }
+        } else {
+          half_sync();
+        }
         if constexpr (MODE == MODE_STATS) {
           // one warp per frame of the tile: statistics of the magnitude row (stats.cuh)
           const int hwarp = htid >> 5, lane = htid & 31;
@@ -623,7 +657,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         if constexpr (B2L_DEFER_BARRIER == 0) half_sync();
       }
     }
-    cur = nxt;
+    if constexpr (!PIPE) cur = nxt;   // (pipelined form: already advanced in front of the mel phase)
   }
   if constexpr (TM) {
     tmem_fence_before_sync();
