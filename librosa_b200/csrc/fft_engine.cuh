@@ -335,6 +335,12 @@ __device__ __forceinline__ void fft_forward_tab(float2 (&v)[Cfg::PPT], int t, in
     constexpr int T = M / R;
     constexpr int NB = PPT / R;
     // ---- load (+ inter-pass twiddle)
+    // Padded addresses: xphys(A + D) == xphys(A) + D + D/32 whenever the low five bits of A and D do not carry.
+    // For groups of whole warps every offset below is a multiple of 32, so one run-time base per pass and
+    // compile-time displacements replace an OR + shift-add + scale per access (a tenth of the instructions of the
+    // n_fft = 4096 kernel, whose t spans two warps and keeps the compiler from folding the padding itself).
+    constexpr bool AFFINE_LD = s > 0 && (TPF % 32 == 0) && (T % 32 == 0);
+    const float2* ld_base = xbuf + xphys(t);
     static_for<0, NB>([&](auto B) {
       constexpr int b = decltype(B)::value;
       const int i = t + TPF * b;
@@ -343,7 +349,13 @@ __device__ __forceinline__ void fft_forward_tab(float2 (&v)[Cfg::PPT], int t, in
         constexpr int slot = b * R + bitrevc(r, LOGR);
         if constexpr (s > 0) {
           tab.template step<s, b * R + r>();
-          float2 x = xbuf[xphys(i + r * T)];
+          float2 x;
+          if constexpr (AFFINE_LD) {
+            constexpr int D = TPF * b + r * T;
+            x = ld_base[D + D / 32];
+          } else {
+            x = xbuf[xphys(i + r * T)];
+          }
           if constexpr (r > 0) x = cmul(x, tab.template twiddle<s, b * R + r>(i));
           v[slot] = x;
         }
@@ -355,16 +367,34 @@ __device__ __forceinline__ void fft_forward_tab(float2 (&v)[Cfg::PPT], int t, in
     if constexpr (s + 1 < Cfg::NPASS) {
       if constexpr (s > 0) group_sync<TPF>(barrier_id);   // everyone finished reading pass s-1 data
       else pre_store();
-      static_for<0, NB>([&](auto B) {
-        constexpr int b = decltype(B)::value;
-        const int i = t + TPF * b;
-        const int k = i & (p - 1);
-        const int j = (i - k) * R + k;
-        static_for<0, R>([&](auto Q) {
-          constexpr int q = decltype(Q)::value;
-          xbuf[xphys(j + q * p)] = v[b * R + q];
+      // butterfly i = t + TPF*b writes j(b) + q*p with j(b) = (i - k)*R + k, k = i mod p.  When TPF*b is a multiple
+      // of p, k does not depend on b and j(b) = j(0) + TPF*b*R: displacement D = TPF*b*R + q*p from j(0).  It is
+      // carry-free when j(0) is a multiple of 32 (pass 0: j(0) = 32 t) or D is (later passes: p >= 32).
+      constexpr bool AFFINE_ST = (TPF % 32 == 0) && (R == 32 ? true : false) && (p == 1 || p % 32 == 0) && ((TPF * R) % 32 == 0) &&
+                                 (p == 1 ? (R % 32 == 0) : true) && (TPF % p == 0 || p == 1);
+      if constexpr (AFFINE_ST) {
+        const int k0 = t & (p - 1);
+        float2* st_base = xbuf + xphys((t - k0) * R + k0);
+        static_for<0, NB>([&](auto B) {
+          constexpr int b = decltype(B)::value;
+          static_for<0, R>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            constexpr int D = TPF * b * R + q * p;
+            st_base[D + D / 32] = v[b * R + q];
+          });
         });
-      });
+      } else {
+        static_for<0, NB>([&](auto B) {
+          constexpr int b = decltype(B)::value;
+          const int i = t + TPF * b;
+          const int k = i & (p - 1);
+          const int j = (i - k) * R + k;
+          static_for<0, R>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            xbuf[xphys(j + q * p)] = v[b * R + q];
+          });
+        });
+      }
       tab.template begin_pass<s + 1>();   // TMEM: the first twiddle chunk travels while the group synchronises
       group_sync<TPF>(barrier_id);
     }

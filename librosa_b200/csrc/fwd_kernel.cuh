@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
   // stride between the exchange regions of consecutive groups: padded in the modes that park the power row there
   constexpr int GS = (MODE == MODE_MEL || MODE == MODE_STATS) ? ML::GS : Cfg::XBUF_F2;
   float2* xbuf = s_xall + grp * GS;
+  float2* xb_t = xbuf + xphys(t);                                   // &xbuf[xphys(t)]: base of the affine accesses
+  const float2* xb_neg = xbuf - xphys(t) + ((t & 31) == 0 ? 1 : 0);  // base of the mirror (partner) accesses
 
   auto half_sync = [&]() {
     if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(HT) : "memory");   // ids 1 .. NH
@@ -428,7 +430,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
       if constexpr (Cfg::NPASS > 1) group_sync<TPF>(gbar);
       static_for<0, PPT>([&](auto S) {
         constexpr int slot = decltype(S)::value;
-        if constexpr (spectrum_offset<Cfg>(slot) >= M / 2) xbuf[xphys(t + spectrum_offset<Cfg>(slot))] = v[slot];
+        constexpr int D = spectrum_offset<Cfg>(slot);
+        if constexpr (D >= M / 2) {
+          if constexpr (TPF % 32 == 0 && D % 32 == 0) xb_t[D + D / 32] = v[slot];   // xphys(t + D), D a multiple of 32
+          else xbuf[xphys(t + D)] = v[slot];
+        }
       });
     }
     tab.begin_unmix();
@@ -444,9 +450,17 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         B.y = __shfl_sync(0xffffffffu, v[31 - c].y, src);
         if (t == 0) B = v[c == 0 ? 0 : 32 - c];   // lane 0 pairs with itself: Z[M - 32c] = its register 32-c (Z[M] == Z[0])
       } else {
-        B = xbuf[partner_slot<M, TPF, c>(t)];
-        if constexpr (c == 0) {
-          if (t == 0) B = A;   // k = 0 pairs with itself (Z[M] == Z[0])
+        if constexpr (TPF % 32 == 0) {
+          // padded slot of Z[M - k], k = t + TPF*c:  K_c - xphys(t) (+ 1 in lane 0 of a warp), K_c a constant —
+          // see partner_slot; folded into one pointer per thread
+          constexpr int K = 33 * (M / 32 - 1 - (TPF / 32) * c) + 32;
+          if constexpr (c == 0) B = t == 0 ? A : xb_neg[K];   // k = 0 pairs with itself (Z[M] == Z[0])
+          else B = xb_neg[K];
+        } else {
+          B = xbuf[partner_slot<M, TPF, c>(t)];
+          if constexpr (c == 0) {
+            if (t == 0) B = A;   // k = 0 pairs with itself (Z[M] == Z[0])
+          }
         }
       }
     };
