@@ -76,8 +76,54 @@ struct TwC {   // W_N^J = exp(-2*pi*i*J/N)
 };
 
 // ------------------------------------------------------------------ complex helpers
+// Packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2 work on an aligned register pair, take a scalar or an immediate
+// broadcast to both halves, and swap / negate halves with operand modifiers).  A complex value (re, im) is one
+// such pair, so every butterfly below costs half the issue slots of its scalar form at the same FP32 lane rate
+// (tools/micro/ffma2_rate.cu: 0.49 warp-instructions per clock and sub-partition, 125 lanes per clock and SM,
+// against 0.90-0.96 and 116-123 for FFMA / FADD / FMUL).  The operation order inside every component is the
+// scalar one, so the results are bit-identical.  B2L_PACKED=0 builds the scalar forms (A/B only).
+#ifndef B2L_PACKED
+#define B2L_PACKED 1
+#endif
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 muli2(float2 a) { return make_float2(-a.y, a.x); }    //  i * a
+__device__ __forceinline__ float2 mulni2(float2 a) { return make_float2(a.y, -a.x); }   // -i * a
+#if B2L_PACKED
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+}
+#endif
+
+// a * b = b.x * a + b.y * (i a).  Operand order matters to ptxas: the swapped / half-negated pair must be the FIRST
+// operand of the FFMA2 and the broadcast scalar the second (FFMA2 Rd, -Ra.LO_HI.NP, Rb.F32, Rc); the other way
+// round it builds the pair with a MOV and an FADD.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  return fma2(muli2(a), bc2(b.y), mul2(a, bc2(b.x)));
+}
+// Shared-memory store of a complex value.  ptxas copies the result pair of a packed instruction (two MOVs, half
+// of them IMAD.MOVs on the FMA pipe) in front of an ordinary 64-bit store; it does not for a v2.f32 store written
+// in PTX (nor for 32-bit or 128-bit stores).  saddr: 32-bit shared-window address.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sts_c64(uint32_t saddr, float2 v) {
+  // no "memory" clobber: the statement stays ordered against the barriers (volatile asm, and they do clobber), and
+  // the compiler remains free to move independent loads across it
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(v.x), "f"(v.y));
+}
+// Predicated global store of a complex value: one @p STG.64, never a branch (a branch per bin pair serialises the
+// un-mix loop: ptxas stops interleaving the pairs), and no pair copy after a packed instruction.
+__device__ __forceinline__ void stg_c64_if(float2* p, float2 v, bool ok) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(v.x), "f"(v.y),
+      "r"((int)ok));
 }
 
 // DIT butterfly  (a, b) <- (a + w b, a - w b)  with a compile-time twiddle.
@@ -85,21 +131,19 @@ template <int J, int N>
 __device__ __forceinline__ void bfly(float2& a, float2& b) {
   constexpr int j = ((J % N) + N) % N;
   if constexpr (j == 0) {
-    float2 s = make_float2(a.x + b.x, a.y + b.y);
-    b = make_float2(a.x - b.x, a.y - b.y);
+    float2 s = add2(a, b);
+    b = sub2(a, b);
     a = s;
   } else if constexpr (4 * j == N) {            // w = -i
-    float2 s = make_float2(a.x + b.y, a.y - b.x);
-    b = make_float2(a.x - b.y, a.y + b.x);
+    float2 s = add2(a, mulni2(b));
+    b = add2(a, muli2(b));
     a = s;
   } else {
     constexpr float wr = TwC<j, N>::re, wi = TwC<j, N>::im;
-    float sr = fmaf(wr, b.x, a.x);
-    sr = fmaf(-wi, b.y, sr);
-    float si = fmaf(wr, b.y, a.y);
-    si = fmaf(wi, b.x, si);
-    b = make_float2(fmaf(2.0f, a.x, -sr), fmaf(2.0f, a.y, -si));
-    a = make_float2(sr, si);
+    float2 s = fma2(bc2(wr), b, a);              // a + wr * b
+    s = fma2(bc2(wi), muli2(b), s);              //   + wi * (i b)
+    b = fma2(bc2(2.0f), a, neg2(s));             // a - w b = 2 a - (a + w b)
+    a = s;
   }
 }
 
@@ -197,9 +241,9 @@ __device__ __forceinline__ void load_pass0_windowed(float2 (&v)[Cfg::PPT], int t
       constexpr int ra = bitrevc(2 * j, LOGR), rb = bitrevc(2 * j + 1, LOGR);   // rb == ra + R/2
       const float2 xa = load_x(i + ra * T), xb = load_x(i + rb * T);
       const float2 wa = win(std::integral_constant<int, sa>{}), wb = win(std::integral_constant<int, sb>{});
-      const float pr = xa.x * wa.x, pi = xa.y * wa.y;
-      v[sa] = make_float2(fmaf(xb.x, wb.x, pr), fmaf(xb.y, wb.y, pi));
-      v[sb] = make_float2(fmaf(-xb.x, wb.x, pr), fmaf(-xb.y, wb.y, pi));
+      const float2 pw = mul2(xa, wa);
+      v[sa] = fma2(xb, wb, pw);
+      v[sb] = fma2(neg2(xb), wb, pw);
     });
   });
 }
@@ -374,13 +418,13 @@ __device__ __forceinline__ void fft_forward_tab(float2 (&v)[Cfg::PPT], int t, in
                                  (p == 1 ? (R % 32 == 0) : true) && (TPF % p == 0 || p == 1);
       if constexpr (AFFINE_ST) {
         const int k0 = t & (p - 1);
-        float2* st_base = xbuf + xphys((t - k0) * R + k0);
+        const uint32_t st_base = smem_u32(xbuf + xphys((t - k0) * R + k0));
         static_for<0, NB>([&](auto B) {
           constexpr int b = decltype(B)::value;
           static_for<0, R>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
             constexpr int D = TPF * b * R + q * p;
-            st_base[D + D / 32] = v[b * R + q];
+            sts_c64(st_base + 8u * (D + D / 32), v[b * R + q]);
           });
         });
       } else {
@@ -389,9 +433,10 @@ __device__ __forceinline__ void fft_forward_tab(float2 (&v)[Cfg::PPT], int t, in
           const int i = t + TPF * b;
           const int k = i & (p - 1);
           const int j = (i - k) * R + k;
+          const uint32_t xbuf_s = smem_u32(xbuf);
           static_for<0, R>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
-            xbuf[xphys(j + q * p)] = v[b * R + q];
+            sts_c64(xbuf_s + 8u * xphys(j + q * p), v[b * R + q]);
           });
         });
       }
@@ -435,25 +480,27 @@ __device__ __forceinline__ int spectrum_index(int t, int slot) {
 // One bin pair of the real-input un-mix.  A = Z[k], B = Z[M-k] (Z computed from a window that already
 // carries the factor 1/2), w = exp(-2*pi*i*k/N).  Returns X[k] in xa and X[M-k] in xb.
 __device__ __forceinline__ void r2c_pair(float2 A, float2 B, float2 w, float2& xa, float2& xb) {
-  float er = A.x + B.x, ei = A.y - B.y;
-  float orr = A.y + B.y, oi = B.x - A.x;
-  float pr = fmaf(w.x, orr, -w.y * oi);
-  float pi = fmaf(w.x, oi, w.y * orr);
-  xa = make_float2(er + pr, ei + pi);
-  xb = make_float2(er - pr, pi - ei);
+  // E = A + conj(B), O = -i (A - conj(B)), P = w O;  X[k] = E + P, X[M-k] = conj(E - P)
+  const float2 cb = make_float2(B.x, -B.y);
+  const float2 e = add2(A, cb);
+  const float2 o = mulni2(sub2(A, cb));          // (A.y + B.y, B.x - A.x)
+  const float2 pp = fma2(muli2(o), bc2(w.y), mul2(o, bc2(w.x)));
+  xa = add2(e, pp);
+  xb = make_float2(e.x - pp.x, pp.y - e.y);      // conj(E - P): scalar, the sign flip of one half has no packed form
 }
 
 // Inverse of r2c_pair: from X[k], X[M-k] rebuild Z[k], Z[M-k] (scaled by 2; caller folds 1/2 into its
 // window).  w = exp(-2*pi*i*k/N) as above.
 __device__ __forceinline__ void c2r_pair(float2 xa, float2 xb, float2 w, float2& A, float2& B) {
   // E = (Xa + conj(Xb)), P = (Xa - conj(Xb)) = w*O  ->  O = conj(w) * P
-  float er = xa.x + xb.x, ei = xa.y - xb.y;
-  float pr = xa.x - xb.x, pi = xa.y + xb.y;
-  float orr = fmaf(w.x, pr, w.y * pi);
-  float oi = fmaf(w.x, pi, -w.y * pr);
-  // Z[k] = E + i*O ; Z[M-k] = conj(E) + i*conj(O)
-  A = make_float2(er - oi, ei + orr);
-  B = make_float2(er + oi, orr - ei);
+  const float2 cb = make_float2(xb.x, -xb.y);
+  const float2 e = add2(xa, cb);
+  const float2 pq = sub2(xa, cb);                // (xa.x - xb.x, xa.y + xb.y)
+  const float2 o = fma2(mulni2(pq), bc2(w.y), mul2(pq, bc2(w.x)));   // conj(w) * P
+  // Z[k] = E + i*O ; Z[M-k] = conj(E) + i*conj(O) = conj(E - i*O)
+  A = add2(e, muli2(o));
+  const float2 d = sub2(e, muli2(o));
+  B = make_float2(d.x, -d.y);
 }
 
 }  // namespace b2l

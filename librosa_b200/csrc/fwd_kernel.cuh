@@ -32,9 +32,7 @@
 namespace b2l {
 
 // ------------------------------------------------------------------ mbarrier / TMA (PTX)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
+// smem_u32(): fft_engine.cuh
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -436,8 +434,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         constexpr int slot = decltype(S)::value;
         constexpr int D = spectrum_offset<Cfg>(slot);
         if constexpr (D >= M / 2) {
-          if constexpr (AFFINE_UNMIX && D % 32 == 0) xb_t[D + D / 32] = v[slot];   // xphys(t + D), D a multiple of 32
-          else xbuf[xphys(t + D)] = v[slot];
+          if constexpr (AFFINE_UNMIX && D % 32 == 0) sts_c64(smem_u32(xb_t) + 8u * (D + D / 32), v[slot]);   // xphys(t + D), D a multiple of 32
+          else sts_c64(smem_u32(xbuf) + 8u * xphys(t + D), v[slot]);
         }
       });
     }
@@ -487,16 +485,14 @@ __global__ void __launch_bounds__(NW * 32, 1) fwd_kernel(const FwdArgs a) {
         float2 A, B, xa, xb;
         pair_operands(C, A, B);
         r2c_pair(A, B, unmix_tw(C), xa, xb);
-        if (frame_ok) {
-          orow[k] = xa;
-          orow[M - k] = xb;
-        }
+        stg_c64_if(orow + k, xa, frame_ok);
+        stg_c64_if(orow + (M - k), xb, frame_ok);
       });
       if (t == 0) {
         float2 xa, xb;
         float2 zc = middle_bin();
         r2c_pair(zc, zc, make_float2(0.0f, -1.0f), xa, xb);   // W_N^(M/2) = -i
-        if (frame_ok) orow[M / 2] = xa;
+        stg_c64_if(orow + M / 2, xa, frame_ok);
       }
       group_sync<TPF>(gbar);   // pair reads done before the next tile's exchange writes
     } else {

@@ -133,8 +133,11 @@ def _check(case, golden, oracle, got, want, fixture):
         elif fn in ("onset_strength", "onset_strength_multi"):
             _close(got, ref, 1e-4, 1e-3)          # means of dB differences: same absolute term as mfcc
         elif fn == "spectral_contrast":
+            # dB of the mean of a sub-band's quietest bins (alpha = 2 %: one or two bins in the low bands), 1e3-1e4
+            # below the frame's loudest bin: float32 round-off of the FFT is 1e-7 of THAT bin, i.e. up to 1e-3 of
+            # the valley, 4e-3 dB.  Any reordering of the butterfly arithmetic moves the value that much.
             linear = case["kw"].get("linear", False)
-            _close(got, ref, 1e-4, 1e-6 * scale if linear else 1e-3)
+            _close(got, ref, 1e-4, 1e-6 * scale if linear else 1e-2)
         elif fn == "chroma_stft":
             _close(got, ref, 1e-4, 2e-6)           # values in [0, 1]; same tuning on both sides (mix T, see cases)
         elif fn == "estimate_tuning":
