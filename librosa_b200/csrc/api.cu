@@ -823,7 +823,7 @@ static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, int hw, const b2l
 #define B2L_MEL2_DEFAULT false
 #endif
 #ifndef B2L_DCT_FPL_DEFAULT
-#define B2L_DCT_FPL_DEFAULT 2
+#define B2L_DCT_FPL_DEFAULT 4
 #endif
 #ifndef B2L_TMEM_DEFAULT
 #define B2L_TMEM_DEFAULT true
@@ -1281,6 +1281,29 @@ static int launch_dct(b2l_ctx* c, const b2l_plan* p, const float* d_L, int64_t n
   // frames per lane: 2 halves the shared-memory traffic per FMA (B2L_DCT_FPL=1 selects the two-warp-set form)
   const char* env = getenv("B2L_DCT_FPL");
   const int fpl = env && *env ? atoi(env) : B2L_DCT_FPL_DEFAULT;
+  if (fpl == 4) {
+    // four frames per lane, 128-frame tiles, one tile buffer per block (dct_clamp4_kernel)
+    const size_t smem4 = ((size_t)p->n_mels * 8 * KG + 2 * (size_t)p->n_mels * 64) * 4;
+    // two warp sets over the mel rows (B2L_DCT_KS=1: one) when the partial sums fit in the tile buffer
+    const char* ks_env = getenv("B2L_DCT_KS");
+    const int ks = (ks_env && *ks_env ? atoi(ks_env) : 2) == 2 && KG <= 10 && p->n_mels >= 8 * KG ? 2 : 1;   // 640 threads at most; 32*KG*32 partial sums <= 2*n_mels*64 tile words
+    auto dct_clamp4 = ks == 2 ? dct_clamp4_kernel<2> : dct_clamp4_kernel<1>;
+    const int threads4 = KG * 32 * ks;
+    CUDA_TRY(cudaFuncSetAttribute(dct_clamp4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    const int tiles4 = (int)((T + DCT4_TILE - 1) / DCT4_TILE);
+    const long long total4 = (long long)tiles4 * n_clips;
+    int occ4 = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, dct_clamp4, threads4, smem4));
+    if (occ4 < 1) return fail(B2L_ERR_CUDA, "DCT kernel does not fit on an SM");
+    long long grid4 = (long long)c->sm_count * occ4;
+    if (grid4 > total4) grid4 = total4;
+    dct_clamp4<<<(int)grid4, threads4, smem4, c->stream>>>(d_L, p->d_dct, clamp ? c->d_clip_max : nullptr,
+                                                                  clamp ? p->top_db : -1.0f, p->n_mels, p->n_mfcc, (int)T,
+                                                                  tiles4, total4, tiled, d_out);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return B2L_OK;
+  }
   auto kern = fpl == 2 ? dct_clamp_kernel<2> : dct_clamp_kernel<1>;
   const int threads = fpl == 2 ? KG * 32 : KG * 64;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

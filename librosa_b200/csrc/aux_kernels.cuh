@@ -2,6 +2,7 @@
 // power_to_db for S= inputs, and a batched transpose used as a layout adapter.
 #pragma once
 #include "common.cuh"
+#include "fft_engine.cuh"   // packed FP32 helpers (fma2, bc2)
 
 namespace b2l {
 
@@ -122,6 +123,125 @@ __global__ void dct_clamp_kernel(const float* __restrict__ L, const float* __res
       }
     }
     __syncthreads();   // tile consumed before the buffer is refilled two iterations later
+  }
+}
+
+// Four frames per lane, the shipped form.  The loop above is bound by the shared-memory pipe: a warp-uniform
+// 16-byte load of four DCT coefficients costs four wavefronts, so a mel row costs 8 + FPL wavefronts per warp
+// for 8 * FPL FMAs (0.625 per FMA at FPL = 2).  Here a tile is 128 frames (two 64-frame blocks of the tiled
+// scratch, contiguous in memory), lane l owns frames 4l .. 4l+3 — one 16-byte load per mel row — and the 32
+// accumulators of a lane are 16 register pairs fed by packed FMAs (coefficient broadcast, frame pair): 12
+// wavefronts and 16 FFMA2 per mel row and warp, 0.375 wavefronts per FMA.  One tile buffer per block; two blocks
+// per SM alternate between streaming and multiplying (cp.async), which is what the double buffer did before.
+// KS = 2: two warp sets split the mel rows of a tile and add their partial sums through the (then idle) tile
+// buffer — twice the warps per SM (20 for 40 coefficients, five per scheduler) for one more barrier per tile.
+constexpr int DCT4_TILE = 128;
+template <int KS>
+__global__ void __launch_bounds__(KS == 2 ? 640 : 512) dct_clamp4_kernel(const float* __restrict__ L, const float* __restrict__ dctT,
+                                  const unsigned int* __restrict__ clip_max, float top_db, int n_mels, int n_mfcc,
+                                  int T, int tiles_per_clip, long long total_tiles, int tiled, float* __restrict__ C) {
+  extern __shared__ __align__(16) float s_dyn[];
+  const int KG = (blockDim.x >> 5) / KS, KP = 8 * KG;
+  float* s_dct = s_dyn;                       // [n_mels][KP]
+  float* s_tile = s_dyn + n_mels * KP;        // [2][n_mels][64]
+  const int blk_words = n_mels * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) % KG, kset = (tid >> 5) / KG;
+  const int m_split = KS == 1 ? n_mels : (n_mels + 1) >> 1;
+  const int m_lo = kset == 0 ? 0 : m_split, m_hi = kset == 0 ? m_split : n_mels;
+  for (int i = tid; i < n_mels * KP; i += blockDim.x) s_dct[i] = dctT[i];
+  const bool vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(L) & 15) == 0);
+  const bool vec_out = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  const int blocks64 = (T + 63) >> 6;
+  const float* xlane = s_tile + (lane >> 4) * blk_words + (lane & 15) * 4;
+
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int clip = (int)(tile / tiles_per_clip);
+    const int t0 = (int)(tile % tiles_per_clip) * DCT4_TILE;
+    if (tiled) {
+      const int b0 = t0 >> 6;
+      const int words = (blocks64 - b0 >= 2 ? 2 : 1) * blk_words;   // the clip's last tile may hold one block only
+      const float* Lt = L + ((long long)clip * blocks64 + b0) * blk_words;
+      for (int i = tid; i < words / 4; i += blockDim.x) cp_async16(s_tile + 4 * i, Lt + 4 * i);
+    } else {
+      const float* Lc = L + (long long)clip * n_mels * T + t0;
+      if (vec_ok && t0 + DCT4_TILE <= T) {
+        for (int i = tid; i < 2 * blk_words / 4; i += blockDim.x) {
+          const int sb = i / (blk_words / 4), r = i % (blk_words / 4), m = r >> 4, q = r & 15;
+          cp_async16(s_tile + 4 * i, Lc + (long long)m * T + sb * 64 + 4 * q);
+        }
+      } else {
+        for (int i = tid; i < 2 * blk_words; i += blockDim.x) {
+          const int sb = i / blk_words, r = i % blk_words, m = r >> 6, x = r & 63;
+          if (t0 + sb * 64 + x < T) cp_async4(s_tile + i, Lc + (long long)m * T + sb * 64 + x);
+          else s_tile[i] = 0.0f;
+        }
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    float floor_v = -INFINITY;
+    if (clip_max != nullptr && top_db >= 0.0f) floor_v = key_to_float(clip_max[clip]) - top_db;
+    float2 acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+    for (int m = m_lo; m < m_hi; ++m) {
+      const float4 d0 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp);
+      const float4 d1 = *reinterpret_cast<const float4*>(s_dct + m * KP + 8 * warp + 4);
+      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float4 x = *reinterpret_cast<const float4*>(xlane + m * 64);
+      const float2 xa = make_float2(fmaxf(x.x, floor_v), fmaxf(x.y, floor_v));
+      const float2 xb = make_float2(fmaxf(x.z, floor_v), fmaxf(x.w, floor_v));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j][0] = fma2(bc2(dv[j]), xa, acc[j][0]);
+        acc[j][1] = fma2(bc2(dv[j]), xb, acc[j][1]);
+      }
+    }
+    if constexpr (KS == 2) {
+      // partial sums of the second warp set travel through the tile buffer: word (4j + i) * KG*32 + warp*32 + lane
+      __syncthreads();   // every warp is done with the tile
+      float* s_red = s_tile + warp * 32 + lane;
+      const int rs = KG * 32;
+      if (kset == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s_red[(4 * j + 0) * rs] = acc[j][0].x;
+          s_red[(4 * j + 1) * rs] = acc[j][0].y;
+          s_red[(4 * j + 2) * rs] = acc[j][1].x;
+          s_red[(4 * j + 3) * rs] = acc[j][1].y;
+        }
+      }
+      __syncthreads();
+      if (kset == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j][0].x += s_red[(4 * j + 0) * rs];
+          acc[j][0].y += s_red[(4 * j + 1) * rs];
+          acc[j][1].x += s_red[(4 * j + 2) * rs];
+          acc[j][1].y += s_red[(4 * j + 3) * rs];
+        }
+      }
+    }
+    const int t = t0 + 4 * lane;
+    float* Cc = C + (long long)clip * n_mfcc * T + t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = 8 * warp + j;
+      if (k < n_mfcc && kset == 0) {
+        float* o = Cc + (long long)k * T;
+        if (vec_out && t + 3 < T) {
+          *reinterpret_cast<float4*>(o) = make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y);
+        } else {
+          if (t < T) o[0] = acc[j][0].x;
+          if (t + 1 < T) o[1] = acc[j][0].y;
+          if (t + 2 < T) o[2] = acc[j][1].x;
+          if (t + 3 < T) o[3] = acc[j][1].y;
+        }
+      }
+    }
+    __syncthreads();   // tile consumed before the next one streams in
   }
 }
 
