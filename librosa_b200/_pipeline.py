@@ -171,6 +171,29 @@ def is_pow2(n: int) -> bool:
     return n > 0 and (n & (n - 1)) == 0
 
 
+def mr_covers(n_fft: int) -> bool:
+    """True when the mixed-radix kernel (csrc/mr_kernel.cuh) takes the forward transform: even n_fft that is not a
+    power of two and whose half has no prime factor above 5 (400, 320, 480, 800, 960, 1200, ...).  Mirror of
+    ``mr_factor`` in csrc/api.cu; ``B2L_MR=0`` sends these sizes back to the chirp-z kernels."""
+    n_fft = int(n_fft)
+    if is_pow2(n_fft) or n_fft < 12 or n_fft > MAX_CZT_N_FFT or (n_fft & 1):
+        return False
+    if os.environ.get("B2L_MR", "") not in ("", "1"):
+        return False
+    m = n_fft // 2
+    for q in (5, 3, 2):
+        while m % q == 0:
+            m //= q
+    return m == 1
+
+
+def fused_front_end(n_fft: int) -> bool:
+    """Frame lengths whose melspectrogram / mfcc run as ONE fused kernel (+ the DCT kernel): powers of two
+    (fwd_kernel) and the mixed-radix sizes (mr_kernel).  Everything else composes the spectrogram kernel with the
+    ``S=`` kernels on the device."""
+    return is_pow2(n_fft) or mr_covers(n_fft)
+
+
 def require_supported_n_fft(n_fft: int, inverse: bool = False):
     """Power-of-two n_fft in [8, 8192] runs on the packed real-FFT kernels; any other n_fft in [3, 2047]
     (the reference tests' 501 / 1023 / 1025, the 400 of speech front ends, ...) on the chirp-z kernels

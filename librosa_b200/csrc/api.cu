@@ -19,6 +19,7 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "czt_kernel.cuh"
+#include "mr_kernel.cuh"
 #include "feat_kernels.cuh"
 #include "internal.h"
 #include <complex>
@@ -153,6 +154,12 @@ struct b2l_plan {
   float2* d_czt_hf = nullptr;   // [P] FFT_P(h)/P followed by the engine's inter-pass twiddles
   float2* d_czt_bfull = nullptr;   // [n_fft] b (inverse)
   float2* d_czt_wbi = nullptr;     // [n_fft] conj(b) * window / n_fft (inverse)
+  // mixed-radix forward path for even n_fft whose half is 5-smooth (mr_kernel.cuh); the inverse stays chirp-z
+  int mr = 0, mr_n_pass = 0, mr_tw_count = 0;
+  int mr_radix[kMrMaxPass] = {0}, mr_tw_off[kMrMaxPass] = {0};
+  float* d_mr_win = nullptr;       // [n_fft] window * 1/2
+  float2* d_mr_tw = nullptr;       // pass twiddles
+  float2* d_mr_twn = nullptr;      // [n_fft/4 + 1] exp(-2 pi i k / n_fft)
   // mfcc
   int n_mfcc = 0;
   float* d_dct = nullptr;
@@ -524,6 +531,9 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   cudaFree(p->d_czt_hf);
   cudaFree(p->d_czt_bfull);
   cudaFree(p->d_czt_wbi);
+  cudaFree(p->d_mr_win);
+  cudaFree(p->d_mr_tw);
+  cudaFree(p->d_mr_twn);
   cudaFree(p->d_band);
   for (auto& kv : p->row_tables) {
     cudaFree(kv.second.d_rows);
@@ -533,6 +543,20 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   cudaFree(p->d_dct);
   delete p;
   return B2L_OK;
+}
+
+// Radix schedule of the mixed-radix kernel for n_fft = 2 M: M = 5^c 3^b 2^a as c fives, b threes, then eights and a
+// four / two.  False when n_fft is odd, M has another prime factor, or the schedule / buffers would not fit.
+static bool mr_factor(int n_fft, std::vector<int>& radices) {
+  radices.clear();
+  if (n_fft < 12 || (n_fft & 1) || n_fft > 4096) return false;
+  int m = n_fft / 2;
+  while (m % 5 == 0) { radices.push_back(5); m /= 5; }
+  while (m % 3 == 0) { radices.push_back(3); m /= 3; }
+  while (m % 8 == 0) { radices.push_back(8); m /= 8; }
+  if (m % 4 == 0) { radices.push_back(4); m /= 4; }
+  if (m % 2 == 0) { radices.push_back(2); m /= 2; }
+  return m == 1 && (int)radices.size() <= kMrMaxPass && !radices.empty();
 }
 
 extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** out) {
@@ -613,6 +637,40 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     if ((rc = upload(c, wb, &p->d_czt_wb)) || (rc = upload(c, bk, &p->d_czt_bk)) || (rc = upload(c, hf, &p->d_czt_hf)) ||
         (rc = upload(c, bfull, &p->d_czt_bfull)) || (rc = upload(c, wbi, &p->d_czt_wbi)))
       goto bad;
+    // ---- mixed-radix tables when n_fft = 2 M with M = 2^a 3^b 5^c (odd radices first, see mr_kernel.cuh)
+    {
+      std::vector<int> radices;
+      if (mr_factor(N, radices)) {
+        p->mr = 1;
+        p->mr_n_pass = (int)radices.size();
+        std::vector<float2> tw;
+        int sub = 1;
+        for (int s = 0; s < p->mr_n_pass; ++s) {
+          const int R = radices[s];
+          p->mr_radix[s] = R;
+          p->mr_tw_off[s] = (int)tw.size();
+          if (sub > 1)
+            for (int r = 1; r < R; ++r)
+              for (int k = 0; k < sub; ++k) {
+                const long long num = ((long long)r * k) % ((long long)sub * R);
+                const double ang = -2.0 * pi * (double)num / (double)((long long)sub * R);
+                tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+              }
+          sub *= R;
+        }
+        if (tw.empty()) tw.push_back(make_float2(1.0f, 0.0f));
+        p->mr_tw_count = (int)tw.size();
+        std::vector<float> wf(N);
+        for (int i = 0; i < N; ++i) wf[i] = (float)(d->h_window[i] * 0.5);
+        std::vector<float2> twn((size_t)M / 2 + 1);
+        for (int k = 0; k <= M / 2; ++k) {
+          const double ang = -2.0 * pi * (double)k / (double)N;
+          twn[k] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+        if ((rc = upload(c, wf, &p->d_mr_win)) || (rc = upload(c, tw, &p->d_mr_tw)) || (rc = upload(c, twn, &p->d_mr_twn)))
+          goto bad;
+      }
+    }
   } else {
     HostFftCfg cfg(p->log2m);
     {
@@ -1138,14 +1196,102 @@ static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, in
   return B2L_OK;
 }
 
+// ------------------------------------------------------------------ mixed-radix launch (even n_fft, 5-smooth half)
+// mode 0: complex STFT, 1: |X|^power, 2: mel (log_mode 1: dB values + per-clip maximum for mfcc)
+static bool mr_enabled() {
+  const char* e = getenv("B2L_MR");
+  return !(e && *e) || atoi(e) != 0;
+}
+static int run_mr(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const float* d_y, int64_t n_clips, int64_t n,
+                  int64_t y_stride, float2* out_c, float* out_r) {
+  if (p->ctx != c) return fail(B2L_ERR_INVALID, "plan belongs to another context");
+  if (n_clips < 0 || n < 0 || y_stride < n) return fail(B2L_ERR_INVALID, "bad clip geometry");
+  if (n > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "clips longer than 2^31-1 samples are not supported");
+  const long long T = plan_frames(p, n);
+  if (T <= 0)
+    return fail(B2L_ERR_INVALID, "n_fft=%d is too large for input signal of length=%lld", p->n_fft, (long long)n);
+  if (n_clips == 0) return B2L_OK;
+  if (!d_y || (mode == 0 ? (void*)out_c : (void*)out_r) == nullptr) return fail(B2L_ERR_INVALID, "NULL device pointer");
+  if (mode == 2 && p->n_mels == 0) return fail(B2L_ERR_INVALID, "plan has no mel stage");
+  if (n_clips > 0x7fffffffLL || T > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "batch too large");
+  DeviceGuard g(c->device);
+  MrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.y = d_y;
+  a.clip_stride = y_stride;
+  a.n = (int)n;
+  a.n_clips = (int)n_clips;
+  a.L = p->n_fft;
+  a.M = p->n_fft / 2;
+  a.hop = p->hop;
+  a.pad = p->center ? p->n_fft / 2 : 0;
+  a.pad_mode = p->pad_mode;
+  a.n_frames = (int)T;
+  a.n_bins = 1 + p->n_fft / 2;
+  a.n_pass = p->mr_n_pass;
+  for (int s = 0; s < p->mr_n_pass; ++s) {
+    a.radix[s] = p->mr_radix[s];
+    a.tw_off[s] = p->mr_tw_off[s];
+  }
+  a.tw_count = p->mr_tw_count;
+  a.win = p->d_mr_win;
+  a.tw = p->d_mr_tw;
+  a.twn = p->d_mr_twn;
+  a.out_c = out_c;
+  a.out_r = out_r;
+  a.mode = mode;
+  a.power_mode = p->power_mode;
+  a.power = p->power;
+  a.status = c->d_status;
+  if (mode == 2) {
+    a.band = p->d_band;
+    a.mel_w = p->d_mel_w;
+    a.n_mels = p->n_mels;
+    a.mel_w_count = p->mel_w_count;
+    a.log_mode = log_mode ? 1 : 0;
+    a.amin = p->amin;
+    a.db_sub = 10.0f * log10f(fmaxf(p->amin, fabsf(p->ref_value)));
+    a.clip_max = c->d_clip_max;
+  }
+  const size_t tables = mr_table_bytes(a.L, a.tw_count, a.n_mels, a.mel_w_count);
+  const size_t per_warp = (size_t)2 * a.M * sizeof(float2);
+  // two resident blocks per SM when they fit: at most half of the SM's shared memory each
+  const size_t budget = (c->smem_optin + 1024) / 2 - 1024;
+  int nw = 16;
+  while (nw > 1 && tables + nw * per_warp > budget) --nw;
+  if (tables + nw * per_warp > c->smem_optin)
+    return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", p->n_fft);
+  const size_t smem = tables + nw * per_warp;
+  const unsigned long long kkey = (1ULL << 62);
+  if (c->launch_cache.find(kkey) == c->launch_cache.end()) {
+    CUDA_TRY(cudaFuncSetAttribute(mr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    c->launch_cache[kkey] = 1;
+  }
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mr_kernel, nw * 32, smem));
+  if (occ < 1) return fail(B2L_ERR_CUDA, "mixed-radix kernel does not fit on an SM (smem %zu)", smem);
+  const long long total = (long long)n_clips * T;
+  long long grid = (long long)c->sm_count * occ;
+  const long long need = (total + nw - 1) / nw;
+  if (grid > need) grid = need;
+  mr_kernel<<<(int)grid, nw * 32, smem, c->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_stft(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
                         void* d_D) {
-  if (c && p && p->czt) return run_czt(c, p, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
+  if (c && p && p->czt)
+    return p->mr && mr_enabled() ? run_mr(c, p, 0, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr)
+                                 : run_czt(c, p, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
   return run_forward(c, p, MODE_STFT, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
 }
 extern "C" int b2l_spectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
                                int64_t y_stride, float* d_S) {
-  if (c && p && p->czt) return run_czt(c, p, 1, d_y, n_clips, n, y_stride, nullptr, d_S);
+  if (c && p && p->czt)
+    return p->mr && mr_enabled() ? run_mr(c, p, 1, 0, d_y, n_clips, n, y_stride, nullptr, d_S)
+                                 : run_czt(c, p, 1, d_y, n_clips, n, y_stride, nullptr, d_S);
   return run_forward(c, p, MODE_SPEC, 0, d_y, n_clips, n, y_stride, nullptr, d_S);
 }
 // ------------------------------------------------------------------ frame-wise spectral statistics / framings
@@ -1256,6 +1402,7 @@ extern "C" int b2l_frame_feature(b2l_ctx* c, int32_t what, const float* d_y, int
 
 extern "C" int b2l_melspectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
                                   int64_t y_stride, float* d_mel) {
+  if (c && p && p->czt && p->mr) return run_mr(c, p, 2, 0, d_y, n_clips, n, y_stride, nullptr, d_mel);
   if (p && p->czt)
     return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d: compose b2l_spectrogram + b2l_mel_project for non-power-of-two sizes",
                 p->n_fft);
@@ -1326,7 +1473,7 @@ extern "C" int b2l_mfcc(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t
                         float* d_mfcc, float* d_logmel) {
   if (!c || !p) return fail(B2L_ERR_INVALID, "NULL ctx / plan");
   if (p->n_mfcc == 0) return fail(B2L_ERR_INVALID, "plan has no mfcc stage");
-  if (p->czt)
+  if (p->czt && !p->mr)
     return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d: compose spectrogram, mel_project, power_to_db and dct_project for "
                 "non-power-of-two sizes", p->n_fft);
   if (n_clips <= 0) return n_clips == 0 ? B2L_OK : fail(B2L_ERR_INVALID, "negative n_clips");
@@ -1339,8 +1486,11 @@ extern "C" int b2l_mfcc(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t
   float* scratch = d_logmel;
   // the log-mel scratch is tiled: [clip][ceil(T/64)][n_mels][64] (see dct_clamp_kernel)
   if (!scratch) CUDA_TRY(cudaMalloc((void**)&scratch, (size_t)n_clips * p->n_mels * ((T + 63) / 64 * 64) * sizeof(float)));
-  rc = run_forward(c, p, MODE_MEL, 2, d_y, n_clips, n, y_stride, nullptr, scratch);
-  if (rc == B2L_OK) rc = launch_dct(c, p, scratch, n_clips, T, 1, d_mfcc, 1);
+  // mixed-radix frames (mr_kernel): the dB rows go to the scratch in the plain [clip][mel][frame] layout
+  const int tiled = p->czt ? 0 : 1;
+  rc = p->czt ? run_mr(c, p, 2, 1, d_y, n_clips, n, y_stride, nullptr, scratch)
+              : run_forward(c, p, MODE_MEL, 2, d_y, n_clips, n, y_stride, nullptr, scratch);
+  if (rc == B2L_OK) rc = launch_dct(c, p, scratch, n_clips, T, 1, d_mfcc, tiled);
   if (!d_logmel) {
     cudaStreamSynchronize(c->stream);
     cudaFree(scratch);

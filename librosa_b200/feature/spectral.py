@@ -82,7 +82,7 @@ def melspectrogram(*, y=None, sr: float = 22050, S=None, n_fft: int = 2048, hop_
         res_dtype = np.result_type(req_dtype, basis.dtype)
         return res if res.dtype == res_dtype else res.astype(res_dtype)
     pl.require_supported_n_fft(n_fft)
-    if not pl.is_pow2(n_fft):
+    if not pl.fused_front_end(n_fft):
         # chirp-z frames: |STFT|**power on the device, then the band-sparse projection (two kernels)
         res_dtype = np.result_type(req_dtype, basis.dtype)
         return _compose_nonpow2(y, lambda Sd: melspectrogram(S=Sd, sr=sr, n_fft=n_fft, **kwargs), res_dtype,
@@ -308,7 +308,7 @@ def mfcc(*, y=None, sr: float = 22050, S=None, n_mfcc: int = 20, dct_type: int =
         return res if res.dtype == res_dtype else res.astype(res_dtype)
     dct = _dct_basis(n_mels, n_mfcc, dct_type, norm, lifter)
     pl.require_supported_n_fft(n_fft)
-    if not pl.is_pow2(n_fft):
+    if not pl.fused_front_end(n_fft):
         res_dtype = np.result_type(req_dtype, basis.dtype)
 
         def tail(Sd):

@@ -35,6 +35,16 @@ CASES = [
     dict(name="stft_6_2_A", op="stft", mix="A", shape=(100,), kw=dict(n_fft=6, hop_length=2)),
     dict(name="stft_12_5_edge_A", op="stft", mix="A", shape=(300,), kw=dict(n_fft=12, hop_length=5, pad_mode="edge")),
     dict(name="stft_600_winlen400_hamming_A", op="stft", mix="A", shape=(4000,), kw=dict(n_fft=600, win_length=400, window="hamming")),
+    # even sizes whose half is 5-smooth: the mixed-radix kernel (mr_kernel.cuh) — every radix (5, 3, 8, 4, 2) and
+    # several pass counts, all pad modes, win_length < n_fft, center=False
+    dict(name="stft_320_80_reflect_B", op="stft", mix="B", shape=(4000,), kw=dict(n_fft=320, hop_length=80, pad_mode="reflect")),
+    dict(name="stft_480_120_symmetric_A", op="stft", mix="A", shape=(2, 5000), kw=dict(n_fft=480, hop_length=120, pad_mode="symmetric")),
+    dict(name="stft_486_oddhop_A", op="stft", mix="A", shape=(4001,), kw=dict(n_fft=486, hop_length=97)),
+    dict(name="stft_250_nocenter_B", op="stft", mix="B", shape=(3000,), kw=dict(n_fft=250, hop_length=50, center=False)),
+    dict(name="stft_1200_300_A", op="stft", mix="A", shape=(9000,), kw=dict(n_fft=1200, hop_length=300)),
+    dict(name="stft_96_24_linear_ramp_A", op="stft", mix="A", shape=(1500,), kw=dict(n_fft=96, hop_length=24, pad_mode="linear_ramp")),
+    dict(name="stft_1920_480_C", op="stft", mix="C", shape=(9000,), kw=dict(n_fft=1920, hop_length=480)),
+    dict(name="stft_800_winlen640_edge_A", op="stft", mix="A", shape=(6000,), kw=dict(n_fft=800, win_length=640, hop_length=160, pad_mode="edge")),
     # reference-supported, GPU kernels not built: the CUDA path must refuse loudly (oracle still pinned)
     dict(name="stft_3001_toolarge", op="stft", mix="A", shape=(9000,), kw=dict(n_fft=3001, hop_length=700)),   # beyond the chirp-z range: runs on the FP64 kernels
     # ---- istft: input is the golden stft of the named case
@@ -64,6 +74,9 @@ CASES = [
     dict(name="mel_norm1_fminfmax_B", op="mel", mix="B", shape=(6000,), kw=dict(sr=22050, n_fft=2048, hop_length=512, n_mels=64, fmin=300.0, fmax=8000.0, norm=1)),
     dict(name="mel_16000_400_80_B", op="mel", mix="B", shape=(2, 8000), kw=dict(sr=16000, n_fft=400, hop_length=160, n_mels=80)),
     dict(name="mel_22050_1025_A", op="mel", mix="A", shape=(6000,), kw=dict(sr=22050, n_fft=1025, hop_length=256, n_mels=40)),
+    dict(name="mel_48000_960_64_B", op="mel", mix="B", shape=(2, 9000), kw=dict(sr=48000, n_fft=960, hop_length=480, n_mels=64)),
+    dict(name="mel_16000_800_power1_A", op="mel", mix="A", shape=(7000,), kw=dict(sr=16000, n_fft=800, hop_length=160, n_mels=80, power=1.0)),
+    dict(name="mel_16000_400_128_C", op="mel", mix="C", shape=(3, 6000), kw=dict(sr=16000, n_fft=400, hop_length=160, n_mels=128)),
     dict(name="mel_power3_A", op="mel", mix="A", shape=(4000,), kw=dict(sr=22050, n_fft=512, hop_length=128, n_mels=32, power=3.0)),
     # ---- mfcc
     dict(name="mfcc_16000_1024_A", op="mfcc", mix="A", shape=(8000,), kw=dict(sr=16000, n_mfcc=40, n_fft=1024, hop_length=256)),
@@ -71,6 +84,8 @@ CASES = [
     dict(name="mfcc_22050_2048_C_clamped", op="mfcc", mix="C", shape=(9000,), kw=dict(sr=22050, n_mfcc=20)),
     dict(name="mfcc_stereo_perchannel_max", op="mfcc", mix="C", shape=(2, 9000), kw=dict(sr=22050, n_mfcc=13)),
     dict(name="mfcc_16000_400_C", op="mfcc", mix="C", shape=(2, 8000), kw=dict(sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=40)),
+    dict(name="mfcc_16000_320_A", op="mfcc", mix="A", shape=(7000,), kw=dict(sr=16000, n_mfcc=20, n_fft=320, hop_length=160, n_mels=40)),
+    dict(name="mfcc_16000_400_lifter_B", op="mfcc", mix="B", shape=(2, 8000), kw=dict(sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=80, lifter=22)),
     dict(name="mfcc_lifter22_dct3", op="mfcc", mix="A", shape=(6000,), kw=dict(sr=22050, n_mfcc=13, lifter=22, dct_type=3)),
     dict(name="mfcc_dct1_nonorm", op="mfcc", mix="A", shape=(6000,), kw=dict(sr=22050, n_mfcc=13, dct_type=1, norm=None)),
 ]

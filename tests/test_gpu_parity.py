@@ -112,6 +112,44 @@ def test_case_against_oracle_and_reference_fixture(case, lb, oracle, golden):
         close(got, fixture, **TOL[case["op"]])
 
 
+@pytest.mark.parametrize("name", ["stft_400_160_stereo_A", "stft_2000_500_nocenter_A", "stft_12_5_edge_A",
+                                  "stft_600_winlen400_hamming_A", "stft_486_oddhop_A", "mel_16000_400_80_B",
+                                  "mfcc_16000_400_C", "mfcc_16000_400_lifter_B"])
+def test_even_smooth_sizes_still_pass_on_the_chirpz_kernels(name, lb, oracle, golden, monkeypatch):
+    """Even frame lengths with a 5-smooth half take the mixed-radix kernel by default (mr_kernel.cuh); with
+    B2L_MR=0 they run on the chirp-z kernels (and the composed S= kernels) as before — both stay pinned."""
+    monkeypatch.setenv("B2L_MR", "0")
+    case = BY_NAME[name]
+    got = run_gpu(lb, case, golden)
+    close(got, run_oracle(oracle, case, golden), **TOL[case["op"]])
+    close(got, golden[name], **TOL[case["op"]])
+
+
+def test_mixed_radix_device_resident_and_batch_identity(lb, oracle):
+    """mr_kernel on a DeviceArray batch: every clip equals the single-clip result bit for bit (a warp owns a frame,
+    nothing depends on the batch), non-finite samples are reported like util.valid_audio, and frames at both clip
+    edges (reflect padding, odd hop, clip length that is not a multiple of anything) match the oracle."""
+    import signals
+
+    Y = signals.make("B", (5, 7003), seed=11, sr=16000)
+    kw = dict(n_fft=400, hop_length=161, pad_mode="reflect")
+    Dd = lb.stft(lb.to_device(Y), **kw).get()
+    for c in range(Y.shape[0]):
+        np.testing.assert_array_equal(Dd[c], lb.stft(Y[c], **kw))
+    close(Dd, oracle.stft(Y, **kw), **TOL["stft"])
+    M = lb.feature.melspectrogram(y=lb.to_device(Y), sr=16000, n_fft=400, hop_length=160, n_mels=80).get()
+    close(M, oracle.melspectrogram(y=Y, sr=16000, n_fft=400, hop_length=160, n_mels=80), **TOL["mel"])
+    C_ = lb.feature.mfcc(y=lb.to_device(Y), sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=80).get()
+    close(C_, oracle.mfcc(y=Y, sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=80), **TOL["mfcc"])
+    bad = Y.copy()
+    bad[2, 3000] = np.inf
+    for fn in (lambda a: lb.stft(a, n_fft=400, hop_length=160),
+               lambda a: lb.feature.melspectrogram(y=a, sr=16000, n_fft=400, hop_length=160, n_mels=80),
+               lambda a: lb.feature.mfcc(y=a, sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=80)):
+        with pytest.raises(lb.ParameterError):
+            fn(bad)
+
+
 # ------------------------------------------------------------------ API behaviour on the device path
 def test_stft_layout_and_out(lb, oracle):
     import signals
@@ -443,10 +481,15 @@ def test_two_rank_split_join_on_gpu(lb, oracle):
     close(results["mel"], oracle.melspectrogram(y=Y, sr=22050), **TOL["mel"])
 
 
-def test_chirpz_frames_are_paired_inside_a_clip(lb, oracle):
+@pytest.mark.parametrize("mr", ["0", "1"], ids=["chirpz", "mixed_radix"])
+def test_chirpz_frames_are_paired_inside_a_clip(lb, oracle, monkeypatch, mr):
     """Two frames share one complex chirp-z transform; the pairs must not straddle clips: a clip 80 dB louder
-    (or a non-finite one) next to a quiet clip may not touch the quiet clip's spectrum.  Per-clip tolerance."""
+    (or a non-finite one) next to a quiet clip may not touch the quiet clip's spectrum.  Per-clip tolerance.
+    n_fft = 400 runs on the mixed-radix kernel by default (one warp per frame: nothing is shared between frames);
+    B2L_MR=0 sends it to the chirp-z kernels this test was written for.  The inverse is chirp-z either way."""
     import signals
+
+    monkeypatch.setenv("B2L_MR", mr)
 
     quiet = signals.make("A", (1, 4000), seed=3)[0] * 1e-4
     loud = signals.make("A", (1, 4000), seed=4)[0]
