@@ -165,6 +165,7 @@ def precheck_signal(y, native_ok: bool = False):
 
 MIN_N_FFT, MAX_N_FFT = 8, 8192   # powers of two: kMinLog2M / kMaxLog2M in csrc/internal.h
 MAX_CZT_N_FFT = 2047               # other sizes: Bluestein with P = 2^ceil(log2(2 n_fft - 1)) <= 4096
+MAX_MR_N_FFT = 4096                # even sizes with a 5-smooth half: mixed-radix kernels (forward and inverse)
 
 
 def is_pow2(n: int) -> bool:
@@ -176,7 +177,7 @@ def mr_covers(n_fft: int) -> bool:
     power of two and whose half has no prime factor above 5 (400, 320, 480, 800, 960, 1200, ...).  Mirror of
     ``mr_factor`` in csrc/api.cu; ``B2L_MR=0`` sends these sizes back to the chirp-z kernels."""
     n_fft = int(n_fft)
-    if is_pow2(n_fft) or n_fft < 12 or n_fft > MAX_CZT_N_FFT or (n_fft & 1):
+    if is_pow2(n_fft) or n_fft < 12 or n_fft > MAX_MR_N_FFT or (n_fft & 1):
         return False
     if os.environ.get("B2L_MR", "") not in ("", "1"):
         return False
@@ -195,9 +196,11 @@ def fused_front_end(n_fft: int) -> bool:
 
 
 def require_supported_n_fft(n_fft: int, inverse: bool = False):
-    """Power-of-two n_fft in [8, 8192] runs on the packed real-FFT kernels; any other n_fft in [3, 2047]
-    (the reference tests' 501 / 1023 / 1025, the 400 of speech front ends, ...) on the chirp-z kernels
-    (forward and inverse).  Everything else librosa accepts is refused loudly — there is no CPU fallback."""
+    """Power-of-two n_fft in [8, 8192] runs on the packed real-FFT kernels; even n_fft up to 4096 whose half is
+    5-smooth (400, 480, 960, 1200, 3000, ...) on the mixed-radix kernels; any other n_fft in [3, 2047] (the
+    reference tests' 501 / 1023 / 1025, ...) on the chirp-z kernels (forward and inverse).  Everything else
+    librosa accepts is refused loudly by the float32 path — there is no CPU fallback (host float32 data of such
+    sizes takes the FP64 kernels, see ``wide_route``)."""
     n_fft = int(n_fft)
     if is_pow2(n_fft):
         if MIN_N_FFT <= n_fft <= MAX_N_FFT:
@@ -205,8 +208,9 @@ def require_supported_n_fft(n_fft: int, inverse: bool = False):
         raise nat.UnsupportedOnGPU(
             f"n_fft={n_fft}: the sm_100a kernels are built for powers of two from {MIN_N_FFT} to {MAX_N_FFT} "
             "(no CPU fallback)")
-    if not (3 <= n_fft <= MAX_CZT_N_FFT):
-        raise nat.UnsupportedOnGPU(f"n_fft={n_fft}: non-power-of-two sizes are supported from 3 to {MAX_CZT_N_FFT} "
+    if not (3 <= n_fft <= MAX_CZT_N_FFT) and not mr_covers(n_fft):
+        raise nat.UnsupportedOnGPU(f"n_fft={n_fft}: non-power-of-two sizes are supported from 3 to {MAX_CZT_N_FFT}, and "
+                                   f"even sizes up to {MAX_MR_N_FFT} whose half has no prime factor above 5 "
                                    "(no CPU fallback)")
 
 
@@ -215,7 +219,7 @@ def f32_kernels_cover(n_fft: int) -> bool:
     n_fft = int(n_fft)
     if is_pow2(n_fft):
         return MIN_N_FFT <= n_fft <= MAX_N_FFT
-    return 3 <= n_fft <= MAX_CZT_N_FFT
+    return 3 <= n_fft <= MAX_CZT_N_FFT or mr_covers(n_fft)
 
 
 def wide_route(y, req_dtype, n_fft: int) -> bool:

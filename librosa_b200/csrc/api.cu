@@ -158,6 +158,7 @@ struct b2l_plan {
   int mr = 0, mr_n_pass = 0, mr_tw_count = 0;
   int mr_radix[kMrMaxPass] = {0}, mr_tw_off[kMrMaxPass] = {0};
   float* d_mr_win = nullptr;       // [n_fft] window * 1/2
+  float* d_mr_win_inv = nullptr;   // [n_fft] window / n_fft (inverse)
   float2* d_mr_tw = nullptr;       // pass twiddles
   float2* d_mr_twn = nullptr;      // [n_fft/4 + 1] exp(-2 pi i k / n_fft)
   // mfcc
@@ -532,6 +533,7 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   cudaFree(p->d_czt_bfull);
   cudaFree(p->d_czt_wbi);
   cudaFree(p->d_mr_win);
+  cudaFree(p->d_mr_win_inv);
   cudaFree(p->d_mr_tw);
   cudaFree(p->d_mr_twn);
   cudaFree(p->d_band);
@@ -569,9 +571,11 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     // not a power of two: Bluestein with P = next power of two >= 2*n_fft - 1 (czt_kernel.cuh)
     while ((1 << czt_log2p) < 2 * d->n_fft - 1) ++czt_log2p;
     if (czt_log2p < 5) czt_log2p = 5;
-    if (d->n_fft < 3 || czt_log2p > 12)
+    std::vector<int> probe;
+    if (d->n_fft < 3 || (czt_log2p > 12 && !mr_factor(d->n_fft, probe)))
       return fail(B2L_ERR_UNSUPPORTED,
-                  "n_fft=%d: non-power-of-two sizes are supported from 3 to 2047 (no CPU fallback)", d->n_fft);
+                  "n_fft=%d: non-power-of-two sizes are supported from 3 to 2047, and even sizes up to 4096 whose half "
+                  "has no prime factor above 5 (no CPU fallback)", d->n_fft);
   } else if (l2n - 1 < kMinLog2M || l2n - 1 > kMaxLog2M) {
     return fail(B2L_ERR_UNSUPPORTED,
                 "n_fft=%d: the sm_100a kernels are built for powers of two from %d to %d (no CPU fallback)",
@@ -607,6 +611,8 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     p->log2m = -1;
     const int L = N, P = 1 << czt_log2p;
     const double pi = 3.14159265358979323846264338327950288;
+    if (czt_log2p > 12) p->log2p = 0;   // beyond the chirp-z range: the mixed-radix kernels alone serve this size
+    if (czt_log2p <= 12) {
     std::vector<std::complex<double>> b(L);
     for (int n = 0; n < L; ++n) {
       const long long q = ((long long)n * n) % (2LL * L);          // n^2 mod 2L keeps the phase exact
@@ -637,6 +643,7 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     if ((rc = upload(c, wb, &p->d_czt_wb)) || (rc = upload(c, bk, &p->d_czt_bk)) || (rc = upload(c, hf, &p->d_czt_hf)) ||
         (rc = upload(c, bfull, &p->d_czt_bfull)) || (rc = upload(c, wbi, &p->d_czt_wbi)))
       goto bad;
+    }
     // ---- mixed-radix tables when n_fft = 2 M with M = 2^a 3^b 5^c (odd radices first, see mr_kernel.cuh)
     {
       std::vector<int> radices;
@@ -660,14 +667,18 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
         }
         if (tw.empty()) tw.push_back(make_float2(1.0f, 0.0f));
         p->mr_tw_count = (int)tw.size();
-        std::vector<float> wf(N);
-        for (int i = 0; i < N; ++i) wf[i] = (float)(d->h_window[i] * 0.5);
+        std::vector<float> wf(N), wi(N);
+        for (int i = 0; i < N; ++i) {
+          wf[i] = (float)(d->h_window[i] * 0.5);
+          wi[i] = (float)(d->h_window[i] / (double)N);
+        }
         std::vector<float2> twn((size_t)M / 2 + 1);
         for (int k = 0; k <= M / 2; ++k) {
           const double ang = -2.0 * pi * (double)k / (double)N;
           twn[k] = make_float2((float)cos(ang), (float)sin(ang));
         }
-        if ((rc = upload(c, wf, &p->d_mr_win)) || (rc = upload(c, tw, &p->d_mr_tw)) || (rc = upload(c, twn, &p->d_mr_twn)))
+        if ((rc = upload(c, wf, &p->d_mr_win)) || (rc = upload(c, wi, &p->d_mr_win_inv)) || (rc = upload(c, tw, &p->d_mr_tw)) ||
+            (rc = upload(c, twn, &p->d_mr_twn)))
           goto bad;
       }
     }
@@ -797,9 +808,9 @@ static int get_row_table(b2l_ctx* c, const b2l_plan* p, int H, int hw, const b2l
     *out = &it->second;
     return B2L_OK;
   }
+  const int rsm = H < 4 ? 4 : H, G = rsm / 4;   // row starts: lo_j == 4*(j mod G) (mod rsm)
   const int n_rows = (p->n_mels + H - 1) / H * H;
   const int n_items = n_rows / H;
-  const int rsm = H < 4 ? 4 : H, G = rsm / 4;   // row starts: lo_j == 4*(j mod G) (mod rsm)
   std::vector<MelRow> rows(n_rows);
   std::vector<float> w;
   std::vector<int> item_quads(n_items, 0);
@@ -1198,7 +1209,8 @@ static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, in
 
 // ------------------------------------------------------------------ mixed-radix launch (even n_fft, 5-smooth half)
 // mode 0: complex STFT, 1: |X|^power, 2: mel (log_mode 1: dB values + per-clip maximum for mfcc)
-static bool mr_enabled() {
+static bool mr_enabled(const b2l_plan* p) {
+  if (p->log2p == 0) return true;   // no chirp-z tables for this size
   const char* e = getenv("B2L_MR");
   return !(e && *e) || atoi(e) != 0;
 }
@@ -1262,19 +1274,20 @@ static int run_mr(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const f
   if (tables + nw * per_warp > c->smem_optin)
     return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", p->n_fft);
   const size_t smem = tables + nw * per_warp;
-  const unsigned long long kkey = (1ULL << 62);
+  auto kern = mode == 0 ? mr_kernel<0> : (mode == 1 ? mr_kernel<1> : mr_kernel<2>);
+  const unsigned long long kkey = (1ULL << 62) | (unsigned long long)mode;
   if (c->launch_cache.find(kkey) == c->launch_cache.end()) {
-    CUDA_TRY(cudaFuncSetAttribute(mr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     c->launch_cache[kkey] = 1;
   }
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mr_kernel, nw * 32, smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem));
   if (occ < 1) return fail(B2L_ERR_CUDA, "mixed-radix kernel does not fit on an SM (smem %zu)", smem);
   const long long total = (long long)n_clips * T;
   long long grid = (long long)c->sm_count * occ;
   const long long need = (total + nw - 1) / nw;
   if (grid > need) grid = need;
-  mr_kernel<<<(int)grid, nw * 32, smem, c->stream>>>(a);
+  kern<<<(int)grid, nw * 32, smem, c->stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return B2L_OK;
@@ -1283,14 +1296,14 @@ static int run_mr(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const f
 extern "C" int b2l_stft(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n, int64_t y_stride,
                         void* d_D) {
   if (c && p && p->czt)
-    return p->mr && mr_enabled() ? run_mr(c, p, 0, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr)
+    return p->mr && mr_enabled(p) ? run_mr(c, p, 0, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr)
                                  : run_czt(c, p, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
   return run_forward(c, p, MODE_STFT, 0, d_y, n_clips, n, y_stride, (float2*)d_D, nullptr);
 }
 extern "C" int b2l_spectrogram(b2l_ctx* c, const b2l_plan* p, const float* d_y, int64_t n_clips, int64_t n,
                                int64_t y_stride, float* d_S) {
   if (c && p && p->czt)
-    return p->mr && mr_enabled() ? run_mr(c, p, 1, 0, d_y, n_clips, n, y_stride, nullptr, d_S)
+    return p->mr && mr_enabled(p) ? run_mr(c, p, 1, 0, d_y, n_clips, n, y_stride, nullptr, d_S)
                                  : run_czt(c, p, 1, d_y, n_clips, n, y_stride, nullptr, d_S);
   return run_forward(c, p, MODE_SPEC, 0, d_y, n_clips, n, y_stride, nullptr, d_S);
 }
@@ -1522,6 +1535,51 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
       CUDA_TRY(cudaMalloc((void**)&c->d_scratch, need));
       c->scratch_bytes = need;
     }
+    if (p->mr && mr_enabled(p)) {
+      // mixed-radix inverse frames (mr_inv_kernel) into the scratch array, then the same overlap-add
+      MrInvArgs ma;
+      memset(&ma, 0, sizeof(ma));
+      ma.D = (const float2*)d_D;
+      ma.d_clip_stride = (long long)n_frames_stored * (L / 2 + 1);
+      ma.n_clips = (int)n_clips;
+      ma.n_frames = (int)n_frames_used;
+      ma.L = L;
+      ma.M = L / 2;
+      ma.n_bins = L / 2 + 1;
+      ma.n_pass = p->mr_n_pass;
+      for (int s = 0; s < p->mr_n_pass; ++s) {
+        ma.radix[s] = p->mr_radix[s];
+        ma.tw_off[s] = p->mr_tw_off[s];
+      }
+      ma.tw_count = p->mr_tw_count;
+      ma.win = p->d_mr_win_inv;
+      ma.tw = p->d_mr_tw;
+      ma.twn = p->d_mr_twn;
+      ma.ytmp = c->d_scratch;
+      const size_t tables = mr_table_bytes(L, ma.tw_count, 0, 0);
+      const size_t per_warp = (size_t)2 * ma.M * sizeof(float2);
+      const size_t budget = (c->smem_optin + 1024) / 2 - 1024;
+      int nw = 16;
+      while (nw > 1 && tables + nw * per_warp > budget) --nw;
+      if (tables + nw * per_warp > c->smem_optin)
+        return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", L);
+      const size_t smem = tables + nw * per_warp;
+      const unsigned long long kkey = (1ULL << 62) | 7ULL;
+      if (c->launch_cache.find(kkey) == c->launch_cache.end()) {
+        CUDA_TRY(cudaFuncSetAttribute(mr_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+        c->launch_cache[kkey] = 1;
+      }
+      int occ = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mr_inv_kernel, nw * 32, smem));
+      if (occ < 1) return fail(B2L_ERR_CUDA, "mixed-radix inverse kernel does not fit on an SM (smem %zu)", smem);
+      const long long total = (long long)n_clips * n_frames_used;
+      long long grid = (long long)c->sm_count * occ;
+      const long long need_blocks = (total + nw - 1) / nw;
+      if (grid > need_blocks) grid = need_blocks;
+      mr_inv_kernel<<<(int)grid, nw * 32, smem, c->stream>>>(ma);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+    } else {
     HostFftCfg cfg(p->log2p);
     const int nw = cfg.czt_nw();
     const int G = nw * 32 / cfg.tpf;
@@ -1557,6 +1615,7 @@ extern "C" int b2l_istft(b2l_ctx* c, const b2l_plan* p, const void* d_D, int64_t
     if (grid > steps) grid = steps;
     CUDA_TRY(op(OP_LAUNCH, &a, (int)grid, smem, c->stream, nullptr));
     c->launches++;
+    }
     long long bx = (out_len + 255) / 256;
     const long long cap = (8LL * c->sm_count + n_clips - 1) / n_clips;
     if (bx > cap) bx = cap;

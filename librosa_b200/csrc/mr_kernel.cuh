@@ -77,30 +77,57 @@ __device__ __forceinline__ void mr_dft5(float2 (&u)[5]) {
   u[3] = add2(a2, muli2(b2));
 }
 
-// One Stockham pass of radix R over M points: butterflies i = lane, lane + 32, ... < T = M / R.
-template <int R>
+// One Stockham pass of radix R over M points: butterflies i = lane, lane + 32, ... < T = M / R.  FIRST: sub-length
+// p == 1 (no twiddles, R consecutive outputs per butterfly).  Operand, twiddle and result addresses advance by
+// constant strides (one add per access instead of a multiply-add and a scale).
+template <int R, bool FIRST, int G>
 __device__ __forceinline__ void mr_pass(const float2* __restrict__ src, float2* __restrict__ dst,
                                         const float2* __restrict__ tw, int p, int T, int lane) {
   constexpr bool POW2 = (R & (R - 1)) == 0;
   constexpr int LOGR = ilog2c(R);
-  int k = lane % p;
-  const int kstep = 32 % p;
-  for (int i = lane; i < T; i += 32) {
+  int k = FIRST ? 0 : lane % p;
+  const int kstep = FIRST ? 0 : G % p;
+  for (int i = lane; i < T; i += G) {
     float2 u[R];
+    const float2* sp = src + i;
+    const float2* tp = tw + k;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float2 x = src[i + r * T];
-      if (r > 0 && p > 1) x = cmul(x, tw[(r - 1) * p + k]);
+      float2 x = *sp;
+      sp += T;
+      if (!FIRST && r > 0) {
+        x = cmul(x, *tp);
+        tp += p;
+      }
       u[POW2 ? bitrevc(r, LOGR) : r] = x;
     }
     if constexpr (R == 3) mr_dft3(u);
     else if constexpr (R == 5) mr_dft5(u);
     else dft_reg<R, 0>(u);
-    const int j = (i - k) * R + k;
+    if constexpr (FIRST) {
+      float2* dp = dst + i * R;
 #pragma unroll
-    for (int q = 0; q < R; ++q) dst[j + q * p] = u[q];
-    k += kstep;
-    if (k >= p) k -= p;
+      for (int q = 0; q < R; ++q) dp[q] = u[q];
+    } else {
+      float2* dp = dst + (i - k) * R + k;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        *dp = u[q];
+        dp += p;
+      }
+      k += kstep;
+      if (k >= p) k -= p;
+    }
+  }
+}
+template <bool FIRST, int G>
+__device__ __forceinline__ void mr_pass_any(int R, const float2* src, float2* dst, const float2* tw, int p, int T, int lane) {
+  switch (R) {
+    case 5: mr_pass<5, FIRST, G>(src, dst, tw, p, T, lane); break;
+    case 3: mr_pass<3, FIRST, G>(src, dst, tw, p, T, lane); break;
+    case 8: mr_pass<8, FIRST, G>(src, dst, tw, p, T, lane); break;
+    case 4: mr_pass<4, FIRST, G>(src, dst, tw, p, T, lane); break;
+    default: mr_pass<2, FIRST, G>(src, dst, tw, p, T, lane); break;
   }
 }
 
@@ -112,9 +139,15 @@ __host__ __device__ inline size_t mr_table_bytes(int L, int tw_count, int n_mels
   return (b + 15) & ~(size_t)15;
 }
 
+// MODE 0: complex STFT rows, 1: |X|^power rows, 2: band-sparse mel projection (optionally in dB with the per-clip maximum)
+// G: lanes per frame.  32 = a warp owns a frame; 16 = a warp carries two frames side by side (short frames: 40 radix-5
+// butterflies fill 3 rounds of 16 lanes to 83 % where 2 rounds of 32 lanes reach 62 %).  The lane groups of a warp run
+// in lockstep (__syncwarp); a group past the end of the batch repeats the last frame (identical stores).
+template <int MODE, int G>
 __global__ void __launch_bounds__(512, 2) mr_kernel(const MrArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  constexpr int NG = 32 / G;                      // frames per warp
+  const int tid = threadIdx.x, lane = tid & (G - 1), grp = tid / G, ngroups = blockDim.x / G;
   const int L = a.L, M = a.M;
   float* s_win = reinterpret_cast<float*>(smem);
   float2* s_tw = reinterpret_cast<float2*>(s_win + ((L + 3) & ~3));
@@ -125,45 +158,48 @@ __global__ void __launch_bounds__(512, 2) mr_kernel(const MrArgs a) {
   for (int i = tid; i < L; i += blockDim.x) s_win[i] = a.win[i];
   for (int i = tid; i < a.tw_count; i += blockDim.x) s_tw[i] = a.tw[i];
   for (int i = tid; i <= M / 2; i += blockDim.x) s_twn[i] = a.twn[i];
-  if (a.mode == 2) {
+  if constexpr (MODE == 2) {
     for (int i = tid; i < a.n_mels; i += blockDim.x) s_band[i] = a.band[i];
     for (int i = tid; i < a.mel_w_count; i += blockDim.x) s_melw[i] = a.mel_w[i];
   }
   __syncthreads();
-  float2* buf0 = s_x + (size_t)warp * 2 * M;
+  float2* buf0 = s_x + (size_t)grp * 2 * M;
   float2* buf1 = buf0 + M;
 
   const long long total = (long long)a.n_clips * a.n_frames;
-  const long long stride = (long long)gridDim.x * nwarps;
+  const long long stride = (long long)gridDim.x * ngroups;
   const bool vec_ok = ((a.clip_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 7) == 0);
   float wmax = -INFINITY;
   int wmax_clip = -1;
-  auto flush_max = [&]() {   // per-clip maximum of the dB values this warp produced (log_mode)
+  auto flush_max = [&]() {   // per-clip maximum of the dB values this lane group produced (log_mode)
     if (wmax_clip >= 0) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+      for (int o = G / 2; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
       if (lane == 0 && wmax > -INFINITY) atomicMax(a.clip_max + wmax_clip, float_to_key(wmax));
     }
     wmax = -INFINITY;
   };
-  // (clip, frame) of this warp's frames without a division per frame: advanced by the constant warp stride
-  const long long f0 = (long long)blockIdx.x * nwarps + warp;
-  int clip = (int)(f0 / a.n_frames), frame = (int)(f0 - (long long)clip * a.n_frames);
+  // (clip, frame) of this group's frames without a division per frame: advanced by the constant group stride.  The
+  // loop runs while the FIRST group of the warp has work, so that the warp stays convergent.
+  const long long fw = (long long)blockIdx.x * ngroups + (grp & ~(NG - 1));     // first group of this warp
+  const long long f0 = fw + (grp & (NG - 1));
+  int clip, frame;
+  {
+    const long long fc = f0 < total ? f0 : total - 1;
+    clip = (int)(fc / a.n_frames);
+    frame = (int)(fc - (long long)clip * a.n_frames);
+  }
   const int step_c = (int)(stride / a.n_frames), step_f = (int)(stride - (long long)step_c * a.n_frames);
-  for (long long f = f0; f < total; f += stride, clip += step_c, frame += step_f) {
-    if (frame >= a.n_frames) {
-      frame -= a.n_frames;
-      ++clip;
-    }
+  for (long long f = fw; f < total; f += stride) {
     const float* yc = a.y + (long long)clip * a.clip_stride;
     const long long s0 = (long long)frame * a.hop - a.pad;
     // ---- packed, windowed input
     if (s0 >= 0 && s0 + L <= a.n && vec_ok && (s0 & 1) == 0) {
       const float2* y2 = reinterpret_cast<const float2*>(yc + s0);
       const float2* w2 = reinterpret_cast<const float2*>(s_win);
-      for (int e = lane; e < M; e += 32) buf0[e] = mul2(__ldg(y2 + e), w2[e]);
+      for (int e = lane; e < M; e += G) buf0[e] = mul2(__ldg(y2 + e), w2[e]);
     } else {
-      for (int e = lane; e < M; e += 32) {
+      for (int e = lane; e < M; e += G) {
         const float x0 = load_padded(yc, a.n, s0 + 2 * e, a.pad_mode, a.pad);
         const float x1 = load_padded(yc, a.n, s0 + 2 * e + 1, a.pad_mode, a.pad);
         buf0[e] = make_float2(x0 * s_win[2 * e], x1 * s_win[2 * e + 1]);
@@ -173,63 +209,61 @@ __global__ void __launch_bounds__(512, 2) mr_kernel(const MrArgs a) {
     // ---- Stockham passes
     float2* src = buf0;
     float2* dst = buf1;
-    int p = 1;
-    for (int s = 0; s < a.n_pass; ++s) {
-      const int R = a.radix[s], T = M / R;
-      const float2* tw = s_tw + a.tw_off[s];
-      switch (R) {
-        case 5: mr_pass<5>(src, dst, tw, p, T, lane); break;
-        case 3: mr_pass<3>(src, dst, tw, p, T, lane); break;
-        case 8: mr_pass<8>(src, dst, tw, p, T, lane); break;
-        case 4: mr_pass<4>(src, dst, tw, p, T, lane); break;
-        default: mr_pass<2>(src, dst, tw, p, T, lane); break;
-      }
-      __syncwarp();
+    mr_pass_any<true, G>(a.radix[0], src, dst, s_tw, 1, M / a.radix[0], lane);
+    __syncwarp();
+    int p = a.radix[0];
+    for (int s = 1; s < a.n_pass; ++s) {
       float2* tmp = src;
       src = dst;
       dst = tmp;
+      const int R = a.radix[s];
+      mr_pass_any<false, G>(R, src, dst, s_tw + a.tw_off[s], p, M / R, lane);
+      __syncwarp();
       p *= R;
+    }
+    {
+      float2* tmp = src;
+      src = dst;
+      dst = tmp;
     }
     // ---- real-FFT un-mix and epilogue: src holds Z[0 .. M), dst is free
     const long long orow = ((long long)clip * a.n_frames + frame) * a.n_bins;
     float* prow = reinterpret_cast<float*>(dst);
     bool bad = false;
-    for (int k = lane; k <= M / 2; k += 32) {
-      const float2 A = src[k], B = src[k == 0 ? 0 : M - k];
-      bad = bad || !(fabsf(A.x) + fabsf(A.y) <= 3.0e38f);
-      float2 xa, xb;
-      r2c_pair(A, B, s_twn[k], xa, xb);
-      const bool two = (M - k) != k;
-      if (a.mode == 0) {
-        a.out_c[orow + k] = xa;
-        if (two) a.out_c[orow + M - k] = xb;
-      } else {
-        float pa = sqmag(xa), pb = sqmag(xb);
-        if (a.power_mode == 1) {
-          pa = sqrt_approx(pa);
-          pb = sqrt_approx(pb);
-        } else if (a.power_mode != 2) {
-          pa = power_from_sq(pa, a.power_mode, a.power);
-          pb = power_from_sq(pb, a.power_mode, a.power);
-        }
-        if (a.mode == 1) {
-          a.out_r[orow + k] = pa;
-          if (two) a.out_r[orow + M - k] = pb;
+    auto unmix = [&](auto power_of) {
+      for (int k = lane; k <= M / 2; k += G) {
+        const float2 A = src[k], B = src[k == 0 ? 0 : M - k];
+        bad = bad || !(fabsf(A.x) + fabsf(A.y) <= 3.0e38f);
+        float2 xa, xb;
+        r2c_pair(A, B, s_twn[k], xa, xb);
+        const bool two = (M - k) != k;
+        if constexpr (MODE == 0) {
+          a.out_c[orow + k] = xa;
+          if (two) a.out_c[orow + M - k] = xb;
         } else {
-          prow[k] = pa;
-          if (two) prow[M - k] = pb;
+          const float pa = power_of(sqmag(xa)), pb = power_of(sqmag(xb));
+          if constexpr (MODE == 1) {
+            a.out_r[orow + k] = pa;
+            if (two) a.out_r[orow + M - k] = pb;
+          } else {
+            prow[k] = pa;
+            prow[M - k] = pb;   // k == M - k writes the same value twice: xa == xb there up to the sign of zero
+          }
         }
       }
-    }
+    };
+    if (MODE == 0 || a.power_mode == 2) unmix([](float p2) { return p2; });
+    else if (a.power_mode == 1) unmix([](float p2) { return sqrt_approx(p2); });
+    else unmix([&](float p2) { return power_from_sq(p2, a.power_mode, a.power); });
     if (bad) *a.status = 1;   // util.valid_audio (librosa/util/utils.py:303-306): a non-finite sample poisons every bin
-    if (a.mode == 2) {
+    if constexpr (MODE == 2) {
       __syncwarp();
       if (a.log_mode && clip != wmax_clip) {
-        flush_max();
+        flush_max();            // (executed by every group of the warp or by none: see below)
         wmax_clip = clip;
       }
       float* o = a.out_r + (long long)clip * a.n_mels * a.n_frames + frame;
-      for (int m = lane; m < a.n_mels; m += 32) {
+      for (int m = lane; m < a.n_mels; m += G) {
         const MelBand b = s_band[m];
         const float* w = s_melw + b.off;
         const float* x = prow + b.lo;
@@ -249,8 +283,95 @@ __global__ void __launch_bounds__(512, 2) mr_kernel(const MrArgs a) {
       }
     }
     __syncwarp();   // the rows are consumed before the next frame overwrites the buffers
+    // advance; a group that runs past the end keeps its last frame
+    if (f + (grp & (NG - 1)) + stride < total) {
+      clip += step_c;
+      frame += step_f;
+      if (frame >= a.n_frames) {
+        frame -= a.n_frames;
+        ++clip;
+      }
+    }
   }
-  if (a.mode == 2 && a.log_mode) flush_max();
+  if (MODE == 2 && a.log_mode) flush_max();
+}
+
+// ------------------------------------------------------------------ inverse: irfft of length L per frame
+// scipy.fft.irfft(D, n=L) semantics (Im of the DC and Nyquist bins ignored, 1/L scale; librosa/core/spectrum.py:598):
+// the packed spectrum Z[k] is rebuilt from X[k], X[M-k] (c2r_pair), the inverse transform is the forward engine on
+// re/im-swapped data, and the windowed samples (window / L folded into `win`) go to the scratch array
+// [clip][frame][L] that ola_kernel overlap-adds and normalises — the same contract as czt_inv_kernel, which this
+// replaces for the mixed-radix sizes.
+struct MrInvArgs {
+  const float2* D;          // [clip][frames_stored][n_bins]
+  long long d_clip_stride;
+  int n_clips, n_frames, L, M, n_bins;
+  int n_pass;
+  int radix[kMrMaxPass];
+  int tw_off[kMrMaxPass];
+  int tw_count;
+  const float* win;         // [L] window / L
+  const float2* tw;
+  const float2* twn;
+  float* ytmp;              // [clip][n_frames][L]
+};
+
+__global__ void __launch_bounds__(512, 2) mr_inv_kernel(const MrInvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int L = a.L, M = a.M;
+  float* s_win = reinterpret_cast<float*>(smem);
+  float2* s_tw = reinterpret_cast<float2*>(s_win + ((L + 3) & ~3));
+  float2* s_twn = s_tw + ((a.tw_count + 1) & ~1);
+  float2* s_x = reinterpret_cast<float2*>(smem + mr_table_bytes(L, a.tw_count, 0, 0));
+  for (int i = tid; i < L; i += blockDim.x) s_win[i] = a.win[i];
+  for (int i = tid; i < a.tw_count; i += blockDim.x) s_tw[i] = a.tw[i];
+  for (int i = tid; i <= M / 2; i += blockDim.x) s_twn[i] = a.twn[i];
+  __syncthreads();
+  float2* buf0 = s_x + (size_t)warp * 2 * M;
+  float2* buf1 = buf0 + M;
+  const long long total = (long long)a.n_clips * a.n_frames;
+  const long long stride = (long long)gridDim.x * nwarps;
+  const long long f0 = (long long)blockIdx.x * nwarps + warp;
+  int clip = (int)(f0 / a.n_frames), frame = (int)(f0 - (long long)clip * a.n_frames);
+  const int step_c = (int)(stride / a.n_frames), step_f = (int)(stride - (long long)step_c * a.n_frames);
+  for (long long f = f0; f < total; f += stride, clip += step_c, frame += step_f) {
+    if (frame >= a.n_frames) {
+      frame -= a.n_frames;
+      ++clip;
+    }
+    const float2* row = a.D + (long long)clip * a.d_clip_stride + (long long)frame * a.n_bins;
+    for (int k = lane; k <= M / 2; k += 32) {
+      float2 xa = __ldg(row + k), xb = __ldg(row + M - k);
+      if (k == 0) xa.y = xb.y = 0.0f;                       // DC and Nyquist: imaginary parts ignored
+      float2 A, B;
+      c2r_pair(xa, xb, s_twn[k], A, B);
+      buf0[k] = make_float2(A.y, A.x);                      // swapped: the inverse runs as a forward transform
+      if (k != 0 && M - k != k) buf0[M - k] = make_float2(B.y, B.x);
+    }
+    __syncwarp();
+    float2* src = buf0;
+    float2* dst = buf1;
+    mr_pass_any<true, 32>(a.radix[0], src, dst, s_tw, 1, M / a.radix[0], lane);
+    __syncwarp();
+    int p = a.radix[0];
+    for (int s = 1; s < a.n_pass; ++s) {
+      float2* tmp = src;
+      src = dst;
+      dst = tmp;
+      const int R = a.radix[s];
+      mr_pass_any<false, 32>(R, src, dst, s_tw + a.tw_off[s], p, M / R, lane);
+      __syncwarp();
+      p *= R;
+    }
+    float2* out = reinterpret_cast<float2*>(a.ytmp + ((long long)clip * a.n_frames + frame) * L);
+    const float2* w2 = reinterpret_cast<const float2*>(s_win);
+    for (int n = lane; n < M; n += 32) {
+      const float2 r = dst[n];                              // z[n] = (r.y, r.x) = x[2n] + i x[2n+1]
+      out[n] = mul2(make_float2(r.y, r.x), w2[n]);
+    }
+    __syncwarp();
+  }
 }
 
 }  // namespace b2l

@@ -45,6 +45,9 @@ CASES = [
     dict(name="stft_96_24_linear_ramp_A", op="stft", mix="A", shape=(1500,), kw=dict(n_fft=96, hop_length=24, pad_mode="linear_ramp")),
     dict(name="stft_1920_480_C", op="stft", mix="C", shape=(9000,), kw=dict(n_fft=1920, hop_length=480)),
     dict(name="stft_800_winlen640_edge_A", op="stft", mix="A", shape=(6000,), kw=dict(n_fft=800, win_length=640, hop_length=160, pad_mode="edge")),
+    # beyond the chirp-z range (n_fft > 2047): served by the mixed-radix kernels alone
+    dict(name="stft_3000_750_A", op="stft", mix="A", shape=(2, 12000), kw=dict(n_fft=3000, hop_length=750)),
+    dict(name="stft_4000_1000_nocenter_B", op="stft", mix="B", shape=(15000,), kw=dict(n_fft=4000, hop_length=1000, center=False)),
     # reference-supported, GPU kernels not built: the CUDA path must refuse loudly (oracle still pinned)
     dict(name="stft_3001_toolarge", op="stft", mix="A", shape=(9000,), kw=dict(n_fft=3001, hop_length=700)),   # beyond the chirp-z range: runs on the FP64 kernels
     # ---- istft: input is the golden stft of the named case
@@ -60,6 +63,12 @@ CASES = [
     dict(name="istft_501_length", op="istft", src="stft_501_nonpow2", kw=dict(hop_length=128, n_fft=501, length=3000)),
     dict(name="istft_400_160_stereo", op="istft", src="stft_400_160_stereo_A", kw=dict(hop_length=160, length=8000)),
     dict(name="istft_2000_nocenter", op="istft", src="stft_2000_500_nocenter_A", kw=dict(hop_length=500, center=False)),
+    dict(name="istft_1200_300", op="istft", src="stft_1200_300_A", kw=dict(hop_length=300, length=9000)),
+    dict(name="istft_480_120_stereo", op="istft", src="stft_480_120_symmetric_A", kw=dict(hop_length=120)),
+    dict(name="istft_250_nocenter", op="istft", src="stft_250_nocenter_B", kw=dict(hop_length=50, center=False)),
+    dict(name="istft_486_oddhop", op="istft", src="stft_486_oddhop_A", kw=dict(hop_length=97, length=4001)),
+    dict(name="istft_800_winlen640", op="istft", src="stft_800_winlen640_edge_A", kw=dict(hop_length=160, win_length=640, length=6000)),
+    dict(name="istft_3000_750", op="istft", src="stft_3000_750_A", kw=dict(hop_length=750, length=12000)),
     dict(name="istft_6_2", op="istft", src="stft_6_2_A", kw=dict(hop_length=2)),
     dict(name="istft_8192_2048", op="istft", src="stft_8192_2048_A", kw=dict(hop_length=2048, length=30000)),
     dict(name="istft_4096_1024_short_length", op="istft", src="stft_4096_1024_A", kw=dict(hop_length=1024, length=7000)),
@@ -77,6 +86,7 @@ CASES = [
     dict(name="mel_48000_960_64_B", op="mel", mix="B", shape=(2, 9000), kw=dict(sr=48000, n_fft=960, hop_length=480, n_mels=64)),
     dict(name="mel_16000_800_power1_A", op="mel", mix="A", shape=(7000,), kw=dict(sr=16000, n_fft=800, hop_length=160, n_mels=80, power=1.0)),
     dict(name="mel_16000_400_128_C", op="mel", mix="C", shape=(3, 6000), kw=dict(sr=16000, n_fft=400, hop_length=160, n_mels=128)),
+    dict(name="mel_44100_2400_64_B", op="mel", mix="B", shape=(14000,), kw=dict(sr=44100, n_fft=2400, hop_length=600, n_mels=64)),
     dict(name="mel_power3_A", op="mel", mix="A", shape=(4000,), kw=dict(sr=22050, n_fft=512, hop_length=128, n_mels=32, power=3.0)),
     # ---- mfcc
     dict(name="mfcc_16000_1024_A", op="mfcc", mix="A", shape=(8000,), kw=dict(sr=16000, n_mfcc=40, n_fft=1024, hop_length=256)),
@@ -85,7 +95,7 @@ CASES = [
     dict(name="mfcc_stereo_perchannel_max", op="mfcc", mix="C", shape=(2, 9000), kw=dict(sr=22050, n_mfcc=13)),
     dict(name="mfcc_16000_400_C", op="mfcc", mix="C", shape=(2, 8000), kw=dict(sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=40)),
     dict(name="mfcc_16000_320_A", op="mfcc", mix="A", shape=(7000,), kw=dict(sr=16000, n_mfcc=20, n_fft=320, hop_length=160, n_mels=40)),
-    dict(name="mfcc_16000_400_lifter_B", op="mfcc", mix="B", shape=(2, 8000), kw=dict(sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=80, lifter=22)),
+    dict(name="mfcc_16000_400_lifter_A", op="mfcc", mix="A", shape=(2, 8000), kw=dict(sr=16000, n_mfcc=13, n_fft=400, hop_length=160, n_mels=80, lifter=22)),
     dict(name="mfcc_lifter22_dct3", op="mfcc", mix="A", shape=(6000,), kw=dict(sr=22050, n_mfcc=13, lifter=22, dct_type=3)),
     dict(name="mfcc_dct1_nonorm", op="mfcc", mix="A", shape=(6000,), kw=dict(sr=22050, n_mfcc=13, dct_type=1, norm=None)),
 ]

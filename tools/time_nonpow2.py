@@ -14,6 +14,8 @@ cases = [("mel 400/160/80", lambda: lb.feature.melspectrogram(y=yd, sr=16000, n_
          ("spectral_centroid 400/160", lambda: lb.feature.spectral_centroid(y=yd, sr=16000, n_fft=400, hop_length=160)),
          ("mel 800/160/80", lambda: lb.feature.melspectrogram(y=yd, sr=16000, n_fft=800, hop_length=160, n_mels=80)),
          ("mel 512/160/80", lambda: lb.feature.melspectrogram(y=yd, sr=16000, n_fft=512, hop_length=160, n_mels=80))]
+Dd = lb.stft(yd, n_fft=400, hop_length=160)
+cases.insert(3, ("istft 400/160", lambda: lb.istft(Dd, hop_length=160, n_fft=400, length=160000)))
 for mr in ("1", "0"):
     os.environ["B2L_MR"] = mr
     for name, fn in cases:
