@@ -52,7 +52,7 @@ typedef struct b2l_event b2l_event;
  * float64 expressions as the reference (filters.get_window + util.pad_center, filters.mel, the
  * scipy.fft.dct matrix), uploaded once per plan. */
 typedef struct b2l_plan_desc {
-  int32_t n_fft;             /* power of two, 8 .. 8192                     core/spectrum.py:58-69   */
+  int32_t n_fft;             /* 2^k in 8..8192; even <= 4096 with a 5-smooth half (mixed radix); any 3..2047 (chirp-z)  core/spectrum.py:58-69 */
   int32_t hop_length;        /* >= 1                                        core/spectrum.py:235-237 */
   int32_t center;            /* 0 / 1                                       core/spectrum.py:252     */
   int32_t pad_mode;          /* enum b2l_pad_mode                           core/spectrum.py:287     */

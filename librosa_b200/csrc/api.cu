@@ -1209,6 +1209,13 @@ static int run_czt(b2l_ctx* c, const b2l_plan* p, int mode, const float* d_y, in
 
 // ------------------------------------------------------------------ mixed-radix launch (even n_fft, 5-smooth half)
 // mode 0: complex STFT, 1: |X|^power, 2: mel (log_mode 1: dB values + per-clip maximum for mfcc)
+// frames per warp of mr_kernel: 2 (16 lanes each) for short frames, else 1; B2L_MR_LANES = 16 / 32 forces one (A/B)
+static int mr_frames_per_warp(int M) {
+  int lanes = M <= 512 ? 16 : 32;
+  const char* e = getenv("B2L_MR_LANES");
+  if (e && *e && (atoi(e) == 16 || atoi(e) == 32)) lanes = atoi(e);
+  return 32 / lanes;
+}
 static bool mr_enabled(const b2l_plan* p) {
   if (p->log2p == 0) return true;   // no chirp-z tables for this size
   const char* e = getenv("B2L_MR");
@@ -1266,7 +1273,7 @@ static int run_mr(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const f
     a.clip_max = c->d_clip_max;
   }
   const size_t tables = mr_table_bytes(a.L, a.tw_count, a.n_mels, a.mel_w_count);
-  const size_t per_warp = (size_t)2 * a.M * sizeof(float2);
+  const size_t per_warp = (size_t)2 * a.M * sizeof(float2) * (size_t)mr_frames_per_warp(a.M);
   // two resident blocks per SM when they fit: at most half of the SM's shared memory each
   const size_t budget = (c->smem_optin + 1024) / 2 - 1024;
   int nw = 16;
@@ -1274,8 +1281,12 @@ static int run_mr(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const f
   if (tables + nw * per_warp > c->smem_optin)
     return fail(B2L_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than one SM has", p->n_fft);
   const size_t smem = tables + nw * per_warp;
-  auto kern = mode == 0 ? mr_kernel<0> : (mode == 1 ? mr_kernel<1> : mr_kernel<2>);
-  const unsigned long long kkey = (1ULL << 62) | (unsigned long long)mode;
+  // lanes per frame: short frames ride two to a warp (their butterfly rounds fill 16 lanes better than 32)
+  const int fpw = mr_frames_per_warp(a.M);
+  const int lanes = 32 / fpw;
+  auto kern = lanes == 16 ? (mode == 0 ? mr_kernel<0, 16> : (mode == 1 ? mr_kernel<1, 16> : mr_kernel<2, 16>))
+                          : (mode == 0 ? mr_kernel<0, 32> : (mode == 1 ? mr_kernel<1, 32> : mr_kernel<2, 32>));
+  const unsigned long long kkey = (1ULL << 62) | (unsigned long long)(mode + 8 * fpw);
   if (c->launch_cache.find(kkey) == c->launch_cache.end()) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     c->launch_cache[kkey] = 1;
@@ -1285,7 +1296,7 @@ static int run_mr(b2l_ctx* c, const b2l_plan* p, int mode, int log_mode, const f
   if (occ < 1) return fail(B2L_ERR_CUDA, "mixed-radix kernel does not fit on an SM (smem %zu)", smem);
   const long long total = (long long)n_clips * T;
   long long grid = (long long)c->sm_count * occ;
-  const long long need = (total + nw - 1) / nw;
+  const long long need = (total + (long long)nw * fpw - 1) / ((long long)nw * fpw);
   if (grid > need) grid = need;
   kern<<<(int)grid, nw * 32, smem, c->stream>>>(a);
   CUDA_TRY(cudaGetLastError());

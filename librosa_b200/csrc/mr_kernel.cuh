@@ -171,10 +171,12 @@ __global__ void __launch_bounds__(512, 2) mr_kernel(const MrArgs a) {
   const bool vec_ok = ((a.clip_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 7) == 0);
   float wmax = -INFINITY;
   int wmax_clip = -1;
+  // the lanes of this group (the groups of a warp may sit in different clips, so they reduce separately)
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   auto flush_max = [&]() {   // per-clip maximum of the dB values this lane group produced (log_mode)
     if (wmax_clip >= 0) {
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+      for (int o = G / 2; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(gmask, wmax, o));
       if (lane == 0 && wmax > -INFINITY) atomicMax(a.clip_max + wmax_clip, float_to_key(wmax));
     }
     wmax = -INFINITY;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(512, 2) mr_kernel(const MrArgs a) {
     if constexpr (MODE == 2) {
       __syncwarp();
       if (a.log_mode && clip != wmax_clip) {
-        flush_max();            // (executed by every group of the warp or by none: see below)
+        flush_max();
         wmax_clip = clip;
       }
       float* o = a.out_r + (long long)clip * a.n_mels * a.n_frames + frame;

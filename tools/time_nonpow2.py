@@ -17,6 +17,8 @@ cases = [("mel 400/160/80", lambda: lb.feature.melspectrogram(y=yd, sr=16000, n_
 Dd = lb.stft(yd, n_fft=400, hop_length=160)
 cases.insert(3, ("istft 400/160", lambda: lb.istft(Dd, hop_length=160, n_fft=400, length=160000)))
 for mr in ("1", "0"):
+    if mr == "0" and os.environ.get("B2L_SKIP_CZT"):
+        continue
     os.environ["B2L_MR"] = mr
     for name, fn in cases:
         if mr == "0" and "512" in name:
@@ -27,4 +29,4 @@ for mr in ("1", "0"):
         e0.record()
         for _ in range(10): fn().free()
         e1.record(); ctx.synchronize()
-        print(json.dumps({"what": name, "B2L_MR": mr, "ms": round(e0.elapsed_ms(e1) / 10, 3), "frames": 1024 * 1001}), flush=True)
+        print(json.dumps({"what": name, "B2L_MR": mr, "lanes": os.environ.get("B2L_MR_LANES", ""), "ms": round(e0.elapsed_ms(e1) / 10, 3), "frames": 1024 * 1001}), flush=True)
