@@ -160,6 +160,40 @@ def test_mixed_radix_device_resident_and_batch_identity(lb, oracle):
             fn(bad)
 
 
+def _smooth_even_sizes(limit=4096):
+    out = []
+    for n in range(12, limit + 1, 2):
+        m = n // 2
+        for q in (2, 3, 5):
+            while m % q == 0:
+                m //= q
+        if m == 1 and n & (n - 1):
+            out.append(n)
+    return out
+
+
+def test_mixed_radix_every_size(lb, oracle):
+    """All 96 frame lengths mr_kernel / mr_inv_kernel serve (even, 12 .. 4096, half = 2^a 3^b 5^c, not a power of
+    two) — every radix schedule the host can produce: stft against the oracle, and istft of the oracle's spectrum
+    (length given) against the signal at the float32 bound the power-of-two path is held to (SNR >= 60 dB)."""
+    import signals
+
+    sizes = _smooth_even_sizes()
+    assert len(sizes) == 96
+    for idx, n_fft in enumerate(sizes):
+        hop = max(1, n_fft // 4 - (idx % 3))                 # also hops that do not divide n_fft
+        y = signals.make("AB"[idx % 2], (2, 3 * n_fft + 17 * (idx % 5)), seed=100 + idx)
+        kw = dict(n_fft=n_fft, hop_length=hop, pad_mode=("constant", "reflect", "edge")[idx % 3])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            D, Do = lb.stft(y, **kw), oracle.stft(y, **kw)
+        close(D, Do, **TOL["stft"])
+        yr = lb.istft(Do, hop_length=hop, n_fft=n_fft, length=y.shape[-1])
+        err = yr - y
+        snr = 10 * np.log10(float((y ** 2).sum()) / max(float((err ** 2).sum()), 1e-30))
+        assert snr >= 60.0, (n_fft, hop, snr)
+
+
 # ------------------------------------------------------------------ API behaviour on the device path
 def test_stft_layout_and_out(lb, oracle):
     import signals
