@@ -1905,7 +1905,7 @@ extern "C" int b2l_spectral_contrast(b2l_ctx* c, const b2l_contrast_desc* d, con
     a.k[b] = d->k[b];
     max_count = std::max(max_count, d->count[b]);
   }
-  int cap = 1;
+  int cap = 32;   // at least one entry per lane: the short-tail path parks 32 sorted runs in the scratch
   while (cap < max_count) cap <<= 1;
   DeviceGuard g(c->device);
   const size_t per_warp = ((size_t)((n_bins + 3) & ~3) + cap) * 4;

@@ -326,6 +326,28 @@ struct ContrastArgs {
   int lo[16], count[16], k[16];   // first bin, bins in the sub-band, tail length (>= 1)
   int n_bands;
 };
+// Bitonic network on the first N entries of a register array of order-preserving keys (ascending), fully unrolled.
+template <int N>
+__device__ __forceinline__ void sort_keys(unsigned int (&v)[16]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int p = i ^ j;
+        if (p > i) {
+          const unsigned int x = v[i], y = v[p];
+          const unsigned int lo = min(x, y), hi = max(x, y);
+          const bool up = (i & k) == 0;
+          v[i] = up ? lo : hi;
+          v[p] = up ? hi : lo;
+        }
+      }
+    }
+  }
+}
+
 __global__ void contrast_kernel(const float* __restrict__ S, long long n_rows, int n_frames, int F, int sort_cap,
                                 ContrastArgs a, float* __restrict__ peak, float* __restrict__ valley) {
   extern __shared__ __align__(16) float s_dyn[];
@@ -342,11 +364,67 @@ __global__ void contrast_kernel(const float* __restrict__ S, long long n_rows, i
       const int n = a.count[b];
       const int kk = min(a.k[b], n);
       float lo_sum = 0.0f, hi_sum = 0.0f;
-      if (kk <= 16) {
-        // short tails (the default quantile 0.02 gives k <= 9 for n_fft = 2048): extract the k extremes one
-        // at a time — lane-local scan of the lane's strided elements, one warp reduction on the
-        // order-preserving keys, the owning lane knocks its element out.  ~40 instructions per extreme
-        // instead of a full sort of the band.
+      if (kk <= 16 && n <= 512) {
+        // short tails of a band of at most 512 bins (the default quantile 0.02 gives k <= 9 for n_fft = 2048): lane l
+        // owns the bins l, l + 32, ... of the band, sorts its (at most 16) order-preserving keys once in registers and
+        // parks the sorted run in shared memory; the k smallest / largest of the band then come off the heads / tails
+        // of the 32 runs — one warp reduction per extreme, and only the owning lane advances its pointer and
+        // reloads.  (Round 1 rescanned the lane's elements for every extreme: 4 x as many instructions.)
+        unsigned int v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = lane + 32 * j;
+          v[j] = i < n ? float_to_key(s_row[a.lo[b] + i]) : 0xffffffffu;   // padding sorts last
+        }
+        const int per = (n + 31) >> 5;                 // warp-uniform: entries per lane (the last ones may be padding)
+        if (per > 8) sort_keys<16>(v);
+        else if (per > 4) sort_keys<8>(v);
+        else if (per > 2) sort_keys<4>(v);
+        else if (per > 1) sort_keys<2>(v);
+        unsigned int* s_keys = reinterpret_cast<unsigned int*>(s_sort);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < per) s_keys[lane + 32 * j] = v[j];
+        const int mine = lane < n ? (n - lane + 31) >> 5 : 0;   // valid entries of this lane
+        __syncwarp();
+        {
+          int h = 0;
+          unsigned int cand = mine > 0 ? v[0] : 0xffffffffu;
+          float acc = 0.0f;
+          for (int e = 0; e < kk; ++e) {
+            const unsigned int win = __reduce_min_sync(0xffffffffu, cand);
+            const unsigned int owners = __ballot_sync(0xffffffffu, cand == win && h < mine);
+            if (owners == 0u) break;                              // fewer than k candidates left
+            if (lane == __ffs(owners) - 1) {
+              ++h;
+              cand = h < mine ? s_keys[lane + 32 * h] : 0xffffffffu;
+            }
+            acc += key_to_float(win);
+          }
+          lo_sum = acc;
+        }
+        {
+          // the largest come off the tails of the runs: `used` entries of this lane are gone, the next one sits at
+          // s_top[-32 * used]  (an index form that counts up: ptxas 12.9 mis-addressed the count-down form by one entry)
+          const unsigned int* s_top = s_keys + lane + 32 * (mine > 0 ? mine - 1 : 0);
+          int used = 0;
+          unsigned int cand = mine > 0 ? s_top[0] : 0u;
+          float acc = 0.0f;
+          for (int e = 0; e < kk; ++e) {
+            const unsigned int win = __reduce_max_sync(0xffffffffu, cand);
+            const unsigned int owners = __ballot_sync(0xffffffffu, cand == win && used < mine);
+            if (owners == 0u) break;
+            if (lane == __ffs(owners) - 1) {
+              ++used;
+              cand = used < mine ? s_top[-32 * used] : 0u;
+            }
+            acc += key_to_float(win);
+          }
+          hi_sum = acc;
+        }
+      } else if (kk <= 16) {
+        // short tails of a longer band: extract the k extremes one at a time — lane-local scan of the lane's strided
+        // elements, one warp reduction on the order-preserving keys, the owning lane knocks its element out
         for (int pass = 0; pass < 2; ++pass) {                  // 0: valley (minima), 1: peak (maxima)
           for (int i = lane; i < n; i += 32) s_sort[i] = s_row[a.lo[b] + i];
           __syncwarp();
