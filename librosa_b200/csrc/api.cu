@@ -141,6 +141,7 @@ struct b2l_plan {
   int n_mels = 0, mel_w_count = 0;
   float* d_mel_w = nullptr;
   MelBand* d_band = nullptr;
+  float* d_mel_wT = nullptr;     // n_mels <= 16: dense transposed weights [bin][16] (dense_project_kernel)
   std::vector<MelBand> h_band;
   std::vector<float> h_mel_w;
   struct RowTable { MelRow* d_rows = nullptr; float* d_w = nullptr; unsigned short* d_order = nullptr; int n_rows = 0, w_count = 0, list_len = 0; };
@@ -527,6 +528,7 @@ extern "C" int b2l_plan_destroy(b2l_plan* p) {
   cudaFree(p->d_tw);
   cudaFree(p->d_twn);
   cudaFree(p->d_mel_w);
+  cudaFree(p->d_mel_wT);
   cudaFree(p->d_czt_wb);
   cudaFree(p->d_czt_bk);
   cudaFree(p->d_czt_hf);
@@ -734,6 +736,12 @@ extern "C" int b2l_plan_create(b2l_ctx* c, const b2l_plan_desc* d, b2l_plan** ou
     p->h_band = bands;
     p->h_mel_w = w;
     if ((rc = upload(c, w, &p->d_mel_w)) || (rc = upload(c, bands, &p->d_band))) goto bad;
+    if (d->n_mels <= 16) {
+      std::vector<float> wT((size_t)F * 16, 0.0f);
+      for (int m = 0; m < d->n_mels; ++m)
+        for (int k = 0; k < F; ++k) wT[(size_t)k * 16 + m] = d->h_mel_basis[(size_t)m * F + k];
+      if ((rc = upload(c, wT, &p->d_mel_wT))) goto bad;
+    }
   }
   if (d->n_mfcc > 0) {
     // transposed and zero padded to 8-coefficient groups: dctT[m][8*KG] (dct_clamp_kernel)
@@ -1775,6 +1783,25 @@ extern "C" int b2l_mel_project(b2l_ctx* c, const b2l_plan* p, const float* d_S, 
   if (n_clips <= 0 || n_frames <= 0) return B2L_OK;
   DeviceGuard g(c->device);
   const int F = p->n_fft / 2 + 1;
+  {
+    // a few rows whose bands cover most of the spectrum (chroma): dense_project_kernel (B2L_DENSE_PROJECT=0: off)
+    const char* e = getenv("B2L_DENSE_PROJECT");
+    const size_t dsmem = ((((size_t)F * 33 + 3) & ~(size_t)3) + (size_t)F * 16 + 8 * 16 * 32) * 4;
+    if (p->d_mel_wT && (long long)p->mel_w_count * 4 >= (long long)p->n_mels * F && dsmem <= c->smem_optin &&
+        !(e && *e && atoi(e) == 0)) {
+      const int r4 = (p->n_mels + 3) / 4;
+      auto kern = r4 == 1 ? dense_project_kernel<1> : r4 == 2 ? dense_project_kernel<2> : r4 == 3 ? dense_project_kernel<3> : dense_project_kernel<4>;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+      const int tiles_d = (int)((n_frames + 31) / 32);
+      const long long total = (long long)tiles_d * n_clips;
+      long long grid_d = c->sm_count;
+      if (grid_d > total) grid_d = total;
+      kern<<<(int)grid_d, 256, dsmem, c->stream>>>(d_S, p->d_mel_wT, p->n_mels, F, (int)n_frames, tiles_d, total, d_mel);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+      return B2L_OK;
+    }
+  }
   size_t smem = (size_t)F * 33 * 4;
   if (smem > c->smem_optin) return fail(B2L_ERR_UNSUPPORTED, "n_fft too large for mel_project");
   CUDA_TRY(cudaFuncSetAttribute(mel_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -299,6 +299,62 @@ __global__ void mel_project_kernel(const float* __restrict__ S, const float* __r
   }
 }
 
+
+// ------------------------------------------------------------------ projection onto a FEW dense rows (chroma)
+// filters.chroma gives 12 rows that are dense over all 1 + n_fft/2 bins (librosa/feature/spectral.py:1283-1285,
+// einsum "cf,...ft->...ct"): mel_project_kernel's one-warp-per-row walk is a 1025-long dependent FMA chain on 12 of
+// a CTA's warps.  Here a persistent CTA keeps the transposed weights wT[bin][16] (rows zero padded to 16) in shared
+// memory next to a [F][33] tile of 32 frames; warp w takes the bins w, w + NW, ...: one tile read and three / four
+// broadcast 16-byte weight reads feed 12 / 16 FMAs into lane-private accumulators (lane = frame); the NW partial
+// sums meet in shared memory and are written along the frame axis.  S [n_clips][T][F] -> out [n_clips][rows][T].
+template <int ROWS4>   // rows / 4 rounded up: 1 .. 4
+__global__ void __launch_bounds__(256, 1) dense_project_kernel(const float* __restrict__ S, const float* __restrict__ wT,
+                                                               int rows, int F, int T, int tiles_per_clip,
+                                                               long long total_tiles, float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_dense[];
+  constexpr int NW = 8;
+  float* s_tile = s_dense;                                 // [F][33]
+  float4* s_w = reinterpret_cast<float4*>(s_dense + (((size_t)F * 33 + 3) & ~(size_t)3));   // [F][4] float4
+  float* s_part = reinterpret_cast<float*>(s_w + (size_t)F * 4);                             // [NW][16][32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < F * 4; i += 256) s_w[i] = reinterpret_cast<const float4*>(wT)[i];
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int clip = (int)(tile / tiles_per_clip);
+    const int t0 = (int)(tile - (long long)clip * tiles_per_clip) * 32;
+    const float* Sc = S + ((long long)clip * T + t0) * F;
+    __syncthreads();                                       // previous tile consumed (and the weights staged)
+    for (int f = warp; f < 32; f += NW) {
+      const bool ok = t0 + f < T;
+      for (int k = lane; k < F; k += 32) s_tile[k * 33 + f] = ok ? __ldg(Sc + (long long)f * F + k) : 0.0f;
+    }
+    __syncthreads();
+    float acc[4 * ROWS4];
+#pragma unroll
+    for (int r = 0; r < 4 * ROWS4; ++r) acc[r] = 0.0f;
+    for (int k = warp; k < F; k += NW) {
+      const float x = s_tile[k * 33 + lane];
+#pragma unroll
+      for (int q = 0; q < ROWS4; ++q) {
+        const float4 w = s_w[k * 4 + q];
+        acc[4 * q + 0] = fmaf(w.x, x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(w.y, x, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(w.z, x, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(w.w, x, acc[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4 * ROWS4; ++r) s_part[(warp * 16 + r) * 32 + lane] = acc[r];
+    __syncthreads();
+    for (int o = tid; o < rows * 32; o += 256) {
+      const int r = o >> 5, f = o & 31;
+      float v = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) v += s_part[(w * 16 + r) * 32 + f];
+      if (t0 + f < T) out[((long long)clip * rows + r) * T + t0 + f] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ power_to_db
 __global__ void db_kernel(const float* __restrict__ in, long long per_clip, float amin, float db_sub,
                           unsigned int* __restrict__ clip_max, float* __restrict__ out) {
