@@ -194,6 +194,13 @@ typedef struct b2l_contrast_desc {
 } b2l_contrast_desc;
 int b2l_spectral_contrast(b2l_ctx* ctx, const b2l_contrast_desc* desc, const float* d_S, int64_t n_clips,
                           int64_t n_frames, int32_t n_bins, float* d_peak, float* d_valley);
+/* librosa.resample(res_type="polyphase") (core/audio.py:1129-1145 -> scipy.signal.resample_poly): d_x [n_clips][x_stride]
+ * (n_in valid samples per row) -> d_out [n_clips][n_total].  d_h: the zero-padded float32 low-pass * up (n_h taps, device),
+ * designed on the host as SciPy does; output sample j < n_keep is sum_m x[m] h[(n_pre_remove + j) * down - m * up],
+ * samples n_keep .. n_total-1 are the zeros of util.fix_length (:1172-1173); out_scale = 1 / sqrt(ratio) for scale=True. */
+int b2l_resample_poly(b2l_ctx* ctx, const float* d_x, int64_t n_clips, int64_t n_in, int64_t x_stride, const float* d_h,
+                      int32_t n_h, int32_t up, int32_t down, int64_t n_pre_remove, int64_t n_keep, int64_t n_total,
+                      float out_scale, float* d_out);
 /* out = x - y over n floats */
 int b2l_sub(b2l_ctx* ctx, const float* d_x, const float* d_y, int64_t n, float* d_out);
 /* Tuning estimation for chroma_stft (feature/spectral.py:1137-1293): librosa.estimate_tuning

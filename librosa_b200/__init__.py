@@ -17,7 +17,7 @@ from ._native import (
     device_count,
     pinned_empty,
 )
-from .core.audio import stream
+from .core.audio import resample, stream
 from .core.convert import fft_frequencies, hz_to_mel, hz_to_octs, mel_frequencies, mel_to_hz
 from .core.pitch import estimate_tuning
 from .core.spectrum import (_spectrogram, amplitude_to_db, db_to_amplitude, db_to_power, griffinlim, istft,
@@ -45,7 +45,7 @@ def to_device(arr, device=None):
 
 
 __all__ = [
-    "stream", "stft", "istft", "griffinlim", "power_to_db", "amplitude_to_db", "pcen", "phase_vocoder", "reassigned_spectrogram", "db_to_power", "db_to_amplitude", "_spectrogram", "feature", "filters", "util", "core", "onset", "decompose", "effects",
+    "stream", "resample", "stft", "istft", "griffinlim", "power_to_db", "amplitude_to_db", "pcen", "phase_vocoder", "reassigned_spectrogram", "db_to_power", "db_to_amplitude", "_spectrogram", "feature", "filters", "util", "core", "onset", "decompose", "effects",
     "hz_to_mel", "mel_to_hz", "hz_to_octs", "estimate_tuning", "mel_frequencies", "fft_frequencies", "ParameterError", "LibrosaError",
     "Context", "DeviceArray", "default_context", "device_count", "pinned_empty", "to_device", "device_copy",
     "NativeLibraryError", "UnsupportedOnGPU", "bind_host_to_device",

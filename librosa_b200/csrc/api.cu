@@ -1815,6 +1815,27 @@ extern "C" int b2l_mel_project(b2l_ctx* c, const b2l_plan* p, const float* d_S, 
   return B2L_OK;
 }
 
+// ------------------------------------------------------------------ polyphase resampling
+extern "C" int b2l_resample_poly(b2l_ctx* c, const float* d_x, int64_t n_clips, int64_t n_in, int64_t x_stride,
+                                 const float* d_h, int32_t n_h, int32_t up, int32_t down, int64_t n_pre_remove,
+                                 int64_t n_keep, int64_t n_total, float out_scale, float* d_out) {
+  if (!c || !d_x || !d_h || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
+  if (up < 1 || down < 1 || n_h < 1 || n_pre_remove < 0 || n_keep < 0 || n_total < n_keep || x_stride < n_in)
+    return fail(B2L_ERR_INVALID, "bad resampling geometry");
+  if (n_clips <= 0 || n_total <= 0) return B2L_OK;
+  if (n_in > 0x7fffffffLL || n_total > 0x7fffffffLL) return fail(B2L_ERR_UNSUPPORTED, "signals longer than 2^31-1 samples");
+  DeviceGuard g(c->device);
+  const long long total = (long long)n_clips * n_total;
+  long long grid = (total + 255) / 256;
+  const long long cap = (long long)c->sm_count * 32;
+  if (grid > cap) grid = cap;
+  resample_poly_kernel<<<(int)grid, 256, 0, c->stream>>>(d_x, x_stride, (int)n_in, d_h, n_h, up, down, n_pre_remove,
+                                                          (int)n_keep, (int)n_total, n_clips, out_scale, d_out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return B2L_OK;
+}
+
 extern "C" int b2l_power_to_db(b2l_ctx* c, const float* d_in, int64_t n_clips, int64_t per_clip, float amin,
                                float ref_value, float top_db, float* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");

@@ -355,6 +355,37 @@ __global__ void __launch_bounds__(256, 1) dense_project_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------ polyphase resampling
+// librosa.resample(res_type="polyphase") = scipy.signal.resample_poly(y, up, down) (librosa/core/audio.py:1129-1145):
+// upfirdn(h, x, up, down) cropped to [n_pre_remove, n_pre_remove + n_out) with the zero-padded low-pass h the host
+// designs exactly as SciPy does (firwin(2 * 10 * max(up, down) + 1, 1 / max(up, down), window=("kaiser", 5.0)) * up,
+// float32 for float32 data).  Output sample j is
+//     y[j] = sum_m x[m] * h[(n_pre_remove + j) * down - m * up],
+// accumulated over increasing m like SciPy's upfirdn loop; one thread per output sample (about 20 * max(1, down / up)
+// taps each).  Samples j >= n_keep of a row are the zeros of util.fix_length; out_scale carries 1 / sqrt(ratio).
+__global__ void resample_poly_kernel(const float* __restrict__ x, long long x_stride, int n_in, const float* __restrict__ h,
+                                     int n_h, int up, int down, long long n_pre_remove, int n_keep, int n_total,
+                                     long long n_clips, float out_scale, float* __restrict__ out) {
+  const long long total = n_clips * n_total;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const long long clip = o / n_total;
+    const int j = (int)(o - clip * n_total);
+    float acc = 0.0f;
+    if (j < n_keep) {
+      const long long t = (n_pre_remove + j) * (long long)down;          // position in the up-sampled stream
+      long long m_hi = t / up;
+      if (m_hi > n_in - 1) m_hi = n_in - 1;
+      long long m_lo = t - (n_h - 1);                                    // smallest m with t - m * up <= n_h - 1
+      m_lo = m_lo <= 0 ? 0 : (m_lo + up - 1) / up;
+      const float* xc = x + clip * x_stride;
+      long long k = t - m_lo * up;
+      for (long long m = m_lo; m <= m_hi; ++m, k -= up) acc = fmaf(__ldg(h + k), __ldg(xc + m), acc);
+      acc *= out_scale;
+    }
+    out[o] = acc;
+  }
+}
+
 // ------------------------------------------------------------------ power_to_db
 __global__ void db_kernel(const float* __restrict__ in, long long per_clip, float amin, float db_sub,
                           unsigned int* __restrict__ clip_max, float* __restrict__ out) {

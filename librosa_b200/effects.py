@@ -3,7 +3,10 @@ librosa/effects.py:58-131, :134-206, :209-281): stft -> decompose.hpss -> istft,
 device (one upload of the signal, one download per returned component)."""
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
+
+import numpy as np
 
 from . import _native as nat
 from . import _pipeline as pl
@@ -11,7 +14,7 @@ from .core.spectrum import istft, phase_vocoder, stft
 from .decompose import _hpss_device
 from .util.exceptions import ParameterError
 
-__all__ = ["hpss", "harmonic", "percussive", "time_stretch"]
+__all__ = ["hpss", "harmonic", "percussive", "time_stretch", "pitch_shift"]
 
 
 def _separate(y, want, *, kernel_size, power, mask, margin, n_fft, hop_length, win_length, window, center, pad_mode):
@@ -90,3 +93,54 @@ def time_stretch(y, *, rate: float, **kwargs):
     out = istft(Ds, length=round(n / rate), **kwargs)
     Ds.free()
     return out if on_device else pl.finish(ctx, out, True, req, validate=True)
+
+
+def pitch_shift(y, *, sr: float, n_steps: float, bins_per_octave: int = 12, res_type: str = "soxr_hq",
+                scale: bool = False, **kwargs):
+    """Shift the pitch of ``y`` by ``n_steps`` steps; same contract as ``librosa.effects.pitch_shift``
+    (effects.py:487-574): time_stretch by ``2**(-n_steps / bins_per_octave)``, resample from ``sr / rate`` back to
+    ``sr``, crop / zero-pad to the input length — all on the device.  Only ``res_type="polyphase"`` runs on the GPU
+    (see ``resample``); like the reference it needs an integer ``sr / rate`` (whole octaves, ...) and raises
+    ``ParameterError`` otherwise.  ``kwargs`` go to ``stft`` / ``istft``."""
+    from .core.audio import resample
+    from .util.utils import is_positive_int
+
+    if not is_positive_int(bins_per_octave):
+        raise ParameterError(f"bins_per_octave={bins_per_octave} must be a positive integer.")
+    rate = 2.0 ** (-float(n_steps) / bins_per_octave)
+    n, req = pl.precheck_signal(y)
+    on_device = isinstance(y, nat.DeviceArray)
+    yd = y if on_device else nat.default_context().to_device(np.ascontiguousarray(y, dtype=np.float32))
+    if not on_device:
+        ctx = yd.ctx
+        nat.check(nat.lib().b2l_status_reset(ctx.handle))
+        lead = yd.shape[:-1]
+        n_clips = int(np.prod(lead, dtype=np.int64)) if lead else 1
+        if n_clips and n:
+            nat.check(nat.lib().b2l_scan_finite(ctx.handle, C.c_void_p(yd.ptr), n_clips, n, n, 0))
+    stretched = time_stretch(yd, rate=rate, **kwargs)
+    try:
+        shifted = resample(stretched, orig_sr=float(sr) / rate, target_sr=sr, res_type=res_type, scale=scale)
+    finally:
+        stretched.free()
+        if not on_device and "shifted" not in locals():
+            yd.free()
+    # util.fix_length(y_shift, size=y.shape[-1]) on the device
+    m = shifted.shape[-1]
+    if m == n:
+        out = shifted
+    else:
+        ctx = shifted.ctx
+        lead = shifted.shape[:-1]
+        rows = int(np.prod(lead, dtype=np.int64)) if lead else 1
+        out = nat.DeviceArray.empty(ctx, tuple(lead) + (n,), np.float32)
+        L = nat.lib()
+        if m < n:
+            nat.check(L.b2l_memset(ctx.handle, C.c_void_p(out.ptr), 0, out.nbytes))
+        if rows and min(m, n):
+            nat.check(L.b2l_copy2d(ctx.handle, C.c_void_p(out.ptr), n * 4, C.c_void_p(shifted.ptr), m * 4,
+                                   min(m, n) * 4, rows))
+        shifted.free()
+    if not on_device:
+        yd.free()
+    return out if on_device else pl.finish(out.ctx, out, True, req, validate=True)

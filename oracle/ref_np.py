@@ -938,6 +938,44 @@ def magphase(D, power=1):
     return mag, phase
 
 
+def resample(y, orig_sr, target_sr, res_type="polyphase", fix=True, scale=False, axis=-1):
+    """librosa.resample (librosa/core/audio.py:1002-1179) for the resamplers whose arithmetic lives in SciPy:
+    ``polyphase`` = scipy.signal.resample_poly(y, target_sr // gcd, orig_sr // gcd) (:1129-1145, integer rates only) and
+    ``fft`` / ``scipy`` = scipy.signal.resample (:1125-1128); then fix_length to ceil(n * ratio) (:1172-1173), the
+    optional 1 / sqrt(ratio) scale (:1175-1176) and a cast back to the input dtype (:1179).  The other resamplers
+    (soxr, resampy, samplerate) are third-party libraries that are not vendored with the reference."""
+    import scipy.signal
+
+    if orig_sr == target_sr:
+        return y
+    ratio = float(target_sr) / orig_sr
+    n_samples = int(np.ceil(y.shape[axis] * ratio))
+    if res_type in ("scipy", "fft"):
+        y_hat = scipy.signal.resample(y, n_samples, axis=axis)
+    elif res_type == "polyphase":
+        if int(orig_sr) != orig_sr or int(target_sr) != target_sr:
+            raise ParameterError("polyphase resampling is only supported for integer-valued sampling rates.")
+        orig_sr, target_sr = int(orig_sr), int(target_sr)
+        gcd = np.gcd(orig_sr, target_sr)
+        y_hat = scipy.signal.resample_poly(y, target_sr // gcd, orig_sr // gcd, axis=axis)
+    else:
+        raise ParameterError(f"the oracle restates only the SciPy resamplers, not res_type={res_type!r}")
+    if fix:
+        y_hat = fix_length(y_hat, size=n_samples, axis=axis)
+    if scale:
+        y_hat /= np.sqrt(ratio)
+    return np.asarray(y_hat, dtype=y.dtype)
+
+
+def effects_pitch_shift(y, sr, n_steps, bins_per_octave=12, res_type="polyphase", scale=False, **kwargs):
+    """librosa.effects.pitch_shift (librosa/effects.py:487-574): time_stretch by 2^(-n_steps / bins_per_octave), resample
+    from sr / rate back to sr, crop / pad to the input length."""
+    rate = 2.0 ** (-float(n_steps) / bins_per_octave)
+    y_shift = resample(effects_time_stretch(y, rate=rate, **kwargs), orig_sr=float(sr) / rate, target_sr=sr,
+                       res_type=res_type, scale=scale)
+    return fix_length(y_shift, size=y.shape[-1])
+
+
 def decompose_hpss(S, kernel_size=31, power=2.0, mask=False, margin=1.0):
     """librosa/decompose.py:338-389."""
     from scipy.ndimage import median_filter

@@ -147,6 +147,17 @@ FEATURE_CASES += [
     dict(name="time_stretch_07_T", fn="time_stretch", ns="effects", mix="T", seed=6, shape=(20000,), pos=True, kw=dict(rate=0.7)),
 ]
 
+FEATURE_CASES += [
+    # ---- resample (top level, polyphase = scipy.signal.resample_poly) and effects.pitch_shift on top of it
+    dict(name="resample_poly_22050_16000_A", fn="resample", ns="top", mix="A", shape=(9000,), pos=True, kw=dict(orig_sr=22050, target_sr=16000, res_type="polyphase")),
+    dict(name="resample_poly_44100_16000_stereo_B", fn="resample", ns="top", mix="B", shape=(2, 12000), pos=True, kw=dict(orig_sr=44100, target_sr=16000, res_type="polyphase")),
+    dict(name="resample_poly_up_8000_22050_A", fn="resample", ns="top", mix="A", shape=(3000,), pos=True, kw=dict(orig_sr=8000, target_sr=22050, res_type="polyphase")),
+    dict(name="resample_poly_nofix_scale_B", fn="resample", ns="top", mix="B", shape=(5001,), pos=True, kw=dict(orig_sr=22050, target_sr=11025, res_type="polyphase", fix=False, scale=True)),
+    dict(name="resample_poly_48000_44100_C", fn="resample", ns="top", mix="C", shape=(3, 6000), pos=True, kw=dict(orig_sr=48000, target_sr=44100, res_type="polyphase")),
+    dict(name="pitch_shift_up12_B", fn="pitch_shift", ns="effects", mix="B", shape=(2, 12000), pos=True, kw=dict(sr=22050, n_steps=12, res_type="polyphase", n_fft=1024)),
+    dict(name="pitch_shift_down12_T", fn="pitch_shift", ns="effects", mix="T", seed=9, shape=(20000,), pos=True, kw=dict(sr=22050, n_steps=-12, res_type="polyphase")),
+]
+
 FEATURE_BY_NAME = {c["name"]: c for c in FEATURE_CASES}
 
 

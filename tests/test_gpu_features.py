@@ -152,6 +152,10 @@ def _check(case, golden, oracle, got, want, fixture):
             _close(got, ref, 1e-4, 1e-5 * scale)  # identical input STFT; float32 running phase sum + atan2f / sincosf
         elif case.get("ns") == "decompose":
             _close(got, ref, 1e-4, 1e-6 * scale)  # identical input array: medians are selections, masks smooth
+        elif fn == "resample":
+            _close(got, ref, 1e-4, 2e-6 * scale)  # ~25 float32 multiply-adds per sample; SciPy rounds each product
+        elif fn == "pitch_shift":
+            _close(got, ref, 1e-4, 2e-3 * scale)  # time_stretch's bound (below) carried through the FIR
         elif fn == "time_stretch":
             # The reference keeps the unwrapped phase of every bin as a float32 running sum (np.cumsum); after
             # some tens of frames it reaches hundreds of radians (ulp 3e-5 rad), and two STFTs that differ in

@@ -288,3 +288,21 @@ def test_stream_blocks_line_up_with_frames():
         next(lb.stream("song.wav", block_length=4, frame_length=64, hop_length=16))
     with pytest.raises(lb.ParameterError):
         next(lb.stream(y, block_length=0, frame_length=64, hop_length=16))
+
+
+def test_resample_argument_handling_without_a_gpu():
+    """librosa.resample's host-side contract (core/audio.py:1115-1133): equal rates return the input itself, polyphase
+    needs integer rates, and the resamplers this library does not implement are refused loudly."""
+    import librosa_b200 as lb
+
+    y = np.zeros(100, dtype=np.float32)
+    assert lb.resample(y, orig_sr=22050, target_sr=22050) is y
+    with pytest.raises(lb.ParameterError):
+        lb.resample(y, orig_sr=22050.5, target_sr=16000, res_type="polyphase")
+    for res_type in ("soxr_hq", "kaiser_best", "fft", "scipy", "linear"):
+        with pytest.raises(lb.UnsupportedOnGPU):
+            lb.resample(y, orig_sr=22050, target_sr=16000, res_type=res_type)
+    with pytest.raises(lb.ParameterError):
+        lb.resample([0.0, 1.0], orig_sr=22050, target_sr=16000, res_type="polyphase")
+    with pytest.raises(lb.ParameterError):
+        lb.effects.pitch_shift(y, sr=22050, n_steps=1, bins_per_octave=0, res_type="polyphase")
