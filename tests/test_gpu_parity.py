@@ -422,23 +422,45 @@ def test_cfg5_round_trip_snr(lb):
     assert snr.min() >= 60.0, snr.min()
 
 
-def test_cfg3_cfg4_sampled(lb, oracle):
-    """cfg 3 (stereo 44.1 kHz stft 4096/1024) and cfg 4 (mfcc 16 kHz 1024/256) on a shard-sized sample,
-    with linearity of the stft as the size-independent property."""
-    Y = _block(64, 441000, seed=3).reshape(32, 2, 441000)
+def _fetch_clip(lb, dev, index, per_clip_shape, dtype):
+    """One clip's block of a device-resident result (memory layout [clip][...]) without downloading the rest."""
+    import ctypes as C
+
+    from librosa_b200 import _native as nat
+
+    host = np.empty(per_clip_shape, dtype=dtype)
+    nat.check(nat.lib().b2l_d2h(dev.ctx.handle, host.ctypes.data_as(C.c_void_p), C.c_void_p(dev.ptr + index * host.nbytes),
+                                host.nbytes))
+    dev.ctx.synchronize()
+    return host
+
+
+def test_cfg3_cfg4_full_shards_sampled(lb, oracle):
+    """cfg 3 and cfg 4 at the per-GPU shard sizes of BASELINE.json — ONE launch over 2 048 channel-clips (1 024 stereo
+    clips x 10 s @ 44.1 kHz, stft 4096/1024: 3.6 GB in, 14.5 GB out, device resident) and ONE over 512 clips x 30 s
+    @ 16 kHz (mfcc 40 / 128 mels, 1024/256) — with clips sampled from the start, the middle and the end of the launch
+    compared against the oracle, and stft linearity as the size-independent property."""
+    Y = _block(2048, 441000, seed=3).reshape(1024, 2, 441000)
     d = lb.to_device(Y)
     D = lb.stft(d, n_fft=4096, hop_length=1024)
-    assert D.shape == (32, 2, 2049, 431)
-    Dh = D.get()
-    close(Dh[3, 1], oracle.stft(Y[3, 1], n_fft=4096, hop_length=1024), **TOL["stft"])
-    both = lb.stft(Y[0, 0] + Y[5, 1], n_fft=4096, hop_length=1024)
+    assert D.shape == (1024, 2, 2049, 431)
+    picks = {}
+    for flat in (0, 67, 1023, 1500, 2047):                      # channel-clip index in launch order
+        blk = _fetch_clip(lb, D, flat, (431, 2049), np.complex64)   # native layout [frame][bin]
+        picks[flat] = blk.T
+        close(picks[flat], oracle.stft(Y.reshape(2048, -1)[flat], n_fft=4096, hop_length=1024), **TOL["stft"])
+    D.free()
+    d.free()
+    flatY = Y.reshape(2048, -1)
+    both = lb.stft(flatY[0] + flatY[1500], n_fft=4096, hop_length=1024)
     scale = float(np.abs(both).max())
-    np.testing.assert_allclose(both, Dh[0, 0] + Dh[5, 1], rtol=1e-4, atol=2e-6 * scale)
-    Z = _block(32, 480000, seed=4)
-    C = lb.feature.mfcc(y=lb.to_device(Z), sr=16000, n_mfcc=40, n_fft=1024, hop_length=256).get()
-    assert C.shape == (32, 40, 1876)
-    for i in (0, 31):
-        close(C[i], oracle.mfcc(y=Z[i], sr=16000, n_mfcc=40, n_fft=1024, hop_length=256), **TOL["mfcc"])
+    np.testing.assert_allclose(both, picks[0] + picks[1500], rtol=1e-4, atol=2e-6 * scale)
+    del Y, flatY
+    Z = _block(512, 480000, seed=4)
+    C_ = lb.feature.mfcc(y=lb.to_device(Z), sr=16000, n_mfcc=40, n_fft=1024, hop_length=256).get()
+    assert C_.shape == (512, 40, 1876)
+    for i in (0, 129, 300, 511):
+        close(C_[i], oracle.mfcc(y=Z[i], sr=16000, n_mfcc=40, n_fft=1024, hop_length=256), **TOL["mfcc"])
 
 
 def test_pinned_host_end_to_end(lb, oracle):
