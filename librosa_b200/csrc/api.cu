@@ -1841,24 +1841,27 @@ extern "C" int b2l_power_to_db(b2l_ctx* c, const float* d_in, int64_t n_clips, i
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (!(amin > 0.0f)) return fail(B2L_ERR_INVALID, "amin must be strictly positive");
   if (n_clips <= 0 || per_clip <= 0) return B2L_OK;
-  if (n_clips > 65535) return fail(B2L_ERR_UNSUPPORTED, "power_to_db: more than 65535 leading indices");
   DeviceGuard g(c->device);
   int rc = ensure_clip_max(c, (size_t)n_clips);
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(c->d_clip_max, 0, (size_t)n_clips * sizeof(unsigned int), c->stream));
-  long long bx = (per_clip + 256LL * 8 - 1) / (256LL * 8);
-  long long cap = (4LL * c->sm_count + n_clips - 1) / n_clips;
-  if (bx > cap) bx = cap;
-  if (bx < 1) bx = 1;
-  dim3 grid((unsigned)bx, (unsigned)n_clips);
   const float db_sub = 10.0f * log10f(fmaxf(amin, fabsf(ref_value)));
-  db_kernel<<<grid, 256, 0, c->stream>>>(d_in, per_clip, amin, db_sub, c->d_clip_max, d_out);
-  CUDA_TRY(cudaGetLastError());
-  c->launches++;
-  if (top_db >= 0.0f) {
-    db_clamp_kernel<<<grid, 256, 0, c->stream>>>(d_out, per_clip, c->d_clip_max, top_db);
+  // the clip index rides in grid.y (at most 65535): larger batches go in slices, like the kernels they accompany
+  for (int64_t c0 = 0; c0 < n_clips; c0 += 65535) {
+    const int64_t m = std::min<int64_t>(65535, n_clips - c0);
+    long long bx = (per_clip + 256LL * 8 - 1) / (256LL * 8);
+    long long cap = (4LL * c->sm_count + m - 1) / m;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)m);
+    db_kernel<<<grid, 256, 0, c->stream>>>(d_in + c0 * per_clip, per_clip, amin, db_sub, c->d_clip_max + c0, d_out + c0 * per_clip);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
+    if (top_db >= 0.0f) {
+      db_clamp_kernel<<<grid, 256, 0, c->stream>>>(d_out + c0 * per_clip, per_clip, c->d_clip_max + c0, top_db);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+    }
   }
   return B2L_OK;
 }
@@ -2191,18 +2194,20 @@ extern "C" int b2l_transpose(b2l_ctx* c, const void* d_in, int64_t n_clips, int6
                              int32_t elem_bytes, void* d_out) {
   if (!c || !d_in || !d_out) return fail(B2L_ERR_INVALID, "NULL argument");
   if (n_clips <= 0 || rows <= 0 || cols <= 0) return B2L_OK;
-  if (n_clips > 65535) return fail(B2L_ERR_UNSUPPORTED, "transpose: more than 65535 leading indices");
+  if (elem_bytes != 4 && elem_bytes != 8) return fail(B2L_ERR_INVALID, "elem_bytes must be 4 or 8");
   DeviceGuard g(c->device);
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)n_clips);
   dim3 block(32, 8);
-  if (elem_bytes == 4)
-    transpose_kernel<float><<<grid, block, 0, c->stream>>>((const float*)d_in, (int)rows, (int)cols, (float*)d_out);
-  else if (elem_bytes == 8)
-    transpose_kernel<float2><<<grid, block, 0, c->stream>>>((const float2*)d_in, (int)rows, (int)cols, (float2*)d_out);
-  else
-    return fail(B2L_ERR_INVALID, "elem_bytes must be 4 or 8");
-  CUDA_TRY(cudaGetLastError());
-  c->launches++;
+  for (int64_t c0 = 0; c0 < n_clips; c0 += 65535) {   // the clip index rides in grid.z: larger batches go in slices
+    const int64_t m = std::min<int64_t>(65535, n_clips - c0);
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)m);
+    const size_t off = (size_t)c0 * (size_t)rows * (size_t)cols;
+    if (elem_bytes == 4)
+      transpose_kernel<float><<<grid, block, 0, c->stream>>>((const float*)d_in + off, (int)rows, (int)cols, (float*)d_out + off);
+    else
+      transpose_kernel<float2><<<grid, block, 0, c->stream>>>((const float2*)d_in + off, (int)rows, (int)cols, (float2*)d_out + off);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+  }
   return B2L_OK;
 }
 

@@ -463,6 +463,23 @@ def test_cfg3_cfg4_full_shards_sampled(lb, oracle):
         close(C_[i], oracle.mfcc(y=Z[i], sr=16000, n_mfcc=40, n_fft=1024, hop_length=256), **TOL["mfcc"])
 
 
+def test_more_than_65535_clips_through_the_helpers(lb, oracle):
+    """Batches of more than 65 535 (short) clips: the main kernels walk (clip, tile) pairs in grid.x and always took
+    them; the helpers around them (finite scan, layout transpose of a C-ordered STFT, power_to_db with its per-clip
+    maximum) carry the clip index in grid.y / grid.z and now run in slices."""
+    rng = np.random.default_rng(3)
+    y = (0.1 * rng.standard_normal((70001, 96))).astype(np.float32)
+    kw = dict(n_fft=32, hop_length=8)
+    D = lb.stft(y, **kw)
+    Do = oracle.stft(y, **kw)
+    close(D, Do, **TOL["stft"])
+    yr = lb.istft(np.ascontiguousarray(Do), hop_length=8, length=96)      # C-ordered host matrix
+    assert yr.shape == y.shape
+    np.testing.assert_allclose(yr, y, atol=2e-6)
+    S = (np.abs(Do[:, :, :6]) ** 2).astype(np.float32)                   # (70001, 17, 6): 70 001 leading indices
+    close(lb.power_to_db(S, top_db=30.0), oracle.power_to_db(S, top_db=30.0), rtol=1e-5, atol_abs=1e-4)
+
+
 def test_pinned_host_end_to_end(lb, oracle):
     import signals
 
