@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the librosa FFT time-frequency hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5|stats|speech400]
 
 Metric (BASELINE.json): mel-spectrogram frames/sec, n_fft=2048, hop=512, n_mels=128, float32, on
 BASELINE.json configs[1] — batch = 1024 clips x 10 s mono @ 22050 Hz per GPU.  One "step" is one pass of
@@ -16,7 +16,8 @@ One JSON line on stdout (rank 0).  Extra keys beyond the base contract:
   e2e           same metric through the public drop-in call with HOST (pinned) buffers, H2D + D2H inside;
                 `pageable` = the same call on an ordinary ndarray; `h2d_ceiling_gbs_per_gpu` = plain upload
                 bandwidth with every rank transferring at once (the floor of the end-to-end step)
-  secondary     device-resident ms / frames/s / roofline of BASELINE.json configs 3, 4, 5 (per-GPU shards)
+  secondary     device-resident ms / frames/s / roofline of BASELINE.json configs 3, 4, 5 (per-GPU shards) and of the
+                n_fft = 400 speech front end (`speech400`, mixed-radix kernel; not a BASELINE.json config)
   clocks        NVML samples taken during the timed region
 """
 from __future__ import annotations
@@ -626,7 +627,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 / cfg4 / cfg5 secondary numbers")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 / cfg4 / cfg5 / speech400 secondary numbers")
     ap.add_argument("--no-join", action="store_true", help="skip the NCCL scatter -> mel -> gather leg (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
