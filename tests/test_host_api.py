@@ -4,6 +4,8 @@ validation that must raise exactly like the reference *before* any GPU work
 tests/test_core.py:295-314, tests/test_failures.py:76-127, tests/test_features.py:890-894)."""
 import warnings
 
+import os
+
 import numpy as np
 import pytest
 import scipy.signal
@@ -306,3 +308,31 @@ def test_resample_argument_handling_without_a_gpu():
         lb.resample([0.0, 1.0], orig_sr=22050, target_sr=16000, res_type="polyphase")
     with pytest.raises(lb.ParameterError):
         lb.effects.pitch_shift(y, sr=22050, n_steps=1, bins_per_octave=0, res_type="polyphase")
+
+
+def test_frame_length_routing_table():
+    """Which kernels a frame length goes to (host mirror of csrc/api.cu: b2l_plan_create / mr_factor): powers of two
+    8 .. 8192 -> fwd_kernel, the 96 even sizes 12 .. 4096 with a 5-smooth half -> the mixed-radix kernels (unless
+    B2L_MR=0), any other size up to 2047 -> chirp-z; the rest is refused by the float32 path."""
+    from librosa_b200 import _pipeline as pl
+
+    smooth = [n for n in range(2, 5000) if pl.mr_covers(n)]
+    assert len(smooth) == 96 and smooth[0] == 12 and smooth[-1] == 4050
+    assert all(n % 2 == 0 and not pl.is_pow2(n) for n in smooth)
+    for n in (400, 320, 480, 800, 960, 1200, 3000, 4000):
+        assert pl.mr_covers(n) and pl.fused_front_end(n) and pl.f32_kernels_cover(n)
+    for n in (401, 1025, 14, 2 * 7 * 25, 4098, 2048):
+        assert not pl.mr_covers(n)
+    for n in (8, 2048, 8192):
+        assert pl.fused_front_end(n)
+        pl.require_supported_n_fft(n)
+    for n in (501, 1023, 2047, 3000):
+        pl.require_supported_n_fft(n)
+    for n in (3001, 2049, 16384, 4102):
+        with pytest.raises(UnsupportedOnGPU):
+            pl.require_supported_n_fft(n)
+    os.environ["B2L_MR"] = "0"
+    try:
+        assert not pl.mr_covers(400) and pl.f32_kernels_cover(400) and not pl.f32_kernels_cover(3000)
+    finally:
+        del os.environ["B2L_MR"]
