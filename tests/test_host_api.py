@@ -336,3 +336,28 @@ def test_frame_length_routing_table():
         assert not pl.mr_covers(400) and pl.f32_kernels_cover(400) and not pl.f32_kernels_cover(3000)
     finally:
         del os.environ["B2L_MR"]
+
+
+def test_polyphase_filter_bookkeeping_matches_scipy():
+    """The host half of resample(res_type="polyphase"): the zero-padded low-pass and the crop offset handed to
+    b2l_resample_poly, checked by evaluating the kernel's formula  y[j] = sum_m x[m] h[(n_pre_remove + j) down - m up]
+    in NumPy against scipy.signal.resample_poly itself (float64 accumulation here: only the bookkeeping is under test)."""
+    import scipy.signal
+
+    from librosa_b200.core.audio import _poly_filter
+
+    rng = np.random.default_rng(2)
+    for up, down, n in ((320, 441, 700), (160, 441, 1000), (441, 160, 300), (1, 2, 501), (3, 1, 50), (147, 160, 999)):
+        x = rng.standard_normal(n).astype(np.float32)
+        h, n_pre_remove = _poly_filter(up, down)
+        n_out = (n * up + down - 1) // down
+        got = np.zeros(n_out)
+        for j in range(n_out):
+            t = (n_pre_remove + j) * down
+            m_hi = min(t // up, n - 1)
+            m_lo = max(0, -(-(t - (len(h) - 1)) // up))
+            m = np.arange(m_lo, m_hi + 1)
+            got[j] = np.dot(x[m].astype(np.float64), h[t - m * up].astype(np.float64))
+        want = scipy.signal.resample_poly(x, up, down)
+        assert want.shape == (n_out,)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-6 * float(np.abs(want).max()))
